@@ -1,0 +1,163 @@
+/*
+ * psi_b200.h -- C ABI of libpsi_b200.so: the PSI fitting hot path on B200 (sm_100a).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_`;
+ *   - FP32 values, int32 indices, row-major, innermost dimension contiguous;
+ *   - batch strides are in ELEMENTS (floats); a batch stride of 0 shares one cloud /
+ *     one scene across the whole batch (the reference replicates them B times:
+ *     source/fitting_proxe.py:90,96);
+ *   - outputs are caller-owned and OVERWRITTEN (no pre-zero contract, unlike
+ *     chamfer_pytorch/chamfer.cu:177-178 whose memsets are commented out);
+ *   - work is enqueued on `stream` (a cudaStream_t) and the call returns without
+ *     synchronising; no global state, re-entrant, never prints;
+ *   - return value: 0 = ok, >0 = a cudaError_t from the launch, <0 = PSI_ERR_*.
+ *
+ * Each entry point names the reference interface it replaces.
+ */
+#ifndef PSI_B200_H
+#define PSI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *psi_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define PSI_API __attribute__((visibility("default")))
+#else
+#define PSI_API
+#endif
+
+#define PSI_OK 0
+#define PSI_ERR_BAD_ARG (-1)      /* null pointer, negative size, bad alignment */
+#define PSI_ERR_WORKSPACE (-2)    /* workspace too small */
+#define PSI_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels were built for */
+#define PSI_ERR_ALLOC (-4)        /* device allocation failed (model upload only) */
+
+#define PSI_ABI_VERSION 1
+
+/* ABI version of the loaded library (PSI_ABI_VERSION it was built with). */
+PSI_API int psi_abi_version(void);
+/* Static string for a PSI_ERR_* or cudaError_t value. */
+PSI_API const char *psi_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Chamfer / nearest neighbour.
+ * Replaces: chamfer.forward / chamfer.backward (chamfer_pytorch/chamfer_cuda.cpp:17-33,
+ * kernels chamfer_pytorch/chamfer.cu:12-195), reached from
+ * chamfer_pytorch/dist_chamfer.py:15-46 and dist_chamfer_idx.py:11-46.
+ *
+ * Distance definition (bit-exact with the reference build):
+ *   dx = s.x - q.x ...;  d = fma(dz,dz, fma(dx,dx, rn(dy*dy)));  first minimum wins
+ *   (lowest index on ties).  Inputs must be finite.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch psi_nn_fwd / psi_chamfer_fwd need for these sizes (may be 0). */
+PSI_API size_t psi_nn_workspace_bytes(int B, int n, int m);
+
+/* One direction: for every query q[b,j] (j<n) the nearest of s[b,0..m): squared distance
+ * and index.  q_bstride / s_bstride in floats (0 = shared).  dist,idx: [B,n].
+ * idx may be NULL.  m == 0 leaves outputs untouched (as the reference's loops do). */
+PSI_API int psi_nn_fwd(const float *q, long q_bstride, int B, int n,
+               const float *s, long s_bstride, int m,
+               float *dist, int *idx,
+               void *workspace, size_t workspace_bytes, psi_stream_t stream);
+
+/* Both directions, the reference signature: xyz1 [B,n,3], xyz2 [B,m,3] contiguous.
+ * dist2/idx2 may both be NULL to skip the xyz2->xyz1 direction (the fitting loss
+ * discards it: source/fitting_habitat.py:138). */
+PSI_API int psi_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int n, int m,
+                    float *dist1, float *dist2, int *idx1, int *idx2,
+                    void *workspace, size_t workspace_bytes, psi_stream_t stream);
+
+/* Gradient of sum_j graddist[b,j]*dist[b,j] w.r.t. the queries only (a deterministic
+ * gather): grad_q[b,j] = 2*graddist[b,j]*(q[b,j]-s[b,idx[b,j]]).  grad_q: [B,n,3]. */
+PSI_API int psi_nn_bwd(const float *q, long q_bstride, int B, int n,
+               const float *s, long s_bstride, int m,
+               const float *graddist, const int *idx, float *grad_q, psi_stream_t stream);
+
+/* The reference backward: both clouds receive gradient from both directions
+ * (chamfer.cu:155-195).  gradxyz1 [B,n,3], gradxyz2 [B,m,3] are OVERWRITTEN (zeroed
+ * here, then accumulated; the scatter into the other cloud uses float atomics exactly as
+ * the reference does, so its rounding is order-dependent).  graddist2/idx2 may be NULL. */
+PSI_API int psi_chamfer_bwd(const float *xyz1, const float *xyz2, int B, int n, int m,
+                    const float *graddist1, const float *graddist2,
+                    const int *idx1, const int *idx2,
+                    float *gradxyz1, float *gradxyz2, psi_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scene SDF lookup.
+ * Replaces: the normalise + F.grid_sample(sdf, grid[...,[2,1,0]], padding_mode='border')
+ * block at source/fitting_habitat.py:145-152, fitting_proxe.py:144-151, train_s2.py:182-189,
+ * utils/utils_eval_collision_habitat.py:121-128, with torch-1.2 semantics
+ * (align_corners=True).
+ *
+ * sdf: S grids [S,D,D,D], index [x][y][z], z contiguous.  h_grid_min/h_grid_max: HOST
+ * arrays [S,3].  verts [B,V,3] in the scene frame.  body_scene: device int[B] giving the
+ * grid of each body, or NULL (all bodies use grid 0).  out [B,V]; grad [B,V,3] =
+ * d out / d verts (may be NULL).  partial: NULL or float[B, psi_sdf_num_partials(V), 2]
+ * receiving per-chunk (sum of -sdf over sdf<0, count of sdf<0) in a fixed order
+ * (the collision reduction of fitting_habitat.py:155-160, reduced deterministically).
+ * ---------------------------------------------------------------------------------------- */
+PSI_API int psi_sdf_num_partials(int V);
+PSI_API int psi_sdf_fwd(const float *sdf, int S, int D, const float *h_grid_min, const float *h_grid_max,
+                const float *verts, int B, int V, const int *body_scene,
+                float *out, float *grad, float *partial, psi_stream_t stream);
+
+/* grad_verts[b,v,:] = grad_out[b,v] * grad[b,v,:]  (the backward of psi_sdf_fwd). */
+PSI_API int psi_sdf_bwd(const float *grad_out, const float *grad, long count, float *grad_verts,
+                psi_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SMPL-X linear blend skinning.
+ * Replaces: smplx.SMPLX.forward -> smplx.lbs.lbs (pip smplx==0.1.13; math vendored at
+ * human_body_prior/body_model/lbs.py:34-262; call sites source/fitting_habitat.py:126-129)
+ * fused with the translation (body_model.py:246-247) and with
+ * GeometryTransformer.verts_transform (source/cvae.py:141-149).
+ *
+ * The model handle owns device copies of the constants in the kernels' own layout.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct psi_lbs_model psi_lbs_model;
+
+/* Host arrays in the reference's layout: v_template [V,3], shapedirs [V,3,NB],
+ * posedirs [P,V*3] with P=(J-1)*9 (body_model.py:123-125), J_regressor [J,V],
+ * weights [V,J], parents int[J] (parents[0] ignored).  Uploads on `stream`, returns after
+ * the upload completed. */
+PSI_API int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB,
+                         const float *h_v_template, const float *h_shapedirs,
+                         const float *h_posedirs, const float *h_J_regressor,
+                         const float *h_weights, const int *h_parents, psi_stream_t stream);
+PSI_API void psi_lbs_model_destroy(psi_lbs_model *m);
+/* Bytes of constants resident in HBM for this model (for roofline accounting). */
+PSI_API size_t psi_lbs_model_bytes(const psi_lbs_model *m);
+
+/* Floats of per-call state psi_lbs_fwd saves for psi_lbs_bwd. */
+PSI_API size_t psi_lbs_saved_floats(const psi_lbs_model *m, int B);
+
+/* betas [B,NB] (shape+expression), pose [B,J*3] axis-angle (after hand PCA + pose_mean),
+ * transl [B,3] or NULL, cam [B,12] rows of a 3x4 rigid transform applied last
+ * (cam_bstride floats between bodies, 0 = shared) or NULL.  verts [B,V,3]; joints [B,J,3]
+ * (posed joints + transl, camera frame) or NULL; saved: psi_lbs_saved_floats floats. */
+PSI_API int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                const float *transl, const float *cam, long cam_bstride,
+                float *verts, float *joints, float *saved, psi_stream_t stream);
+
+/* Given grad_verts [B,V,3] (and grad_joints [B,J,3] or NULL): grad_betas [B,NB],
+ * grad_pose [B,J*3], grad_transl [B,3] (may be NULL).  workspace:
+ * psi_lbs_bwd_workspace_bytes bytes. */
+PSI_API size_t psi_lbs_bwd_workspace_bytes(const psi_lbs_model *m, int B);
+PSI_API int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                const float *cam, long cam_bstride, const float *saved,
+                const float *grad_verts, const float *grad_joints,
+                float *grad_betas, float *grad_pose, float *grad_transl,
+                void *workspace, size_t workspace_bytes, psi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSI_B200_H */

@@ -1,0 +1,21 @@
+// ABI version and error strings for libpsi_b200.
+#include "common.cuh"
+
+extern "C" {
+
+int psi_abi_version(void) { return PSI_ABI_VERSION; }
+
+const char *psi_error_string(int code) {
+    switch (code) {
+        case PSI_OK: return "ok";
+        case PSI_ERR_BAD_ARG: return "psi: bad argument (null pointer, negative size or misaligned buffer)";
+        case PSI_ERR_WORKSPACE: return "psi: workspace too small";
+        case PSI_ERR_UNSUPPORTED: return "psi: shape not supported by this build";
+        case PSI_ERR_ALLOC: return "psi: device allocation failed";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "psi: unknown error";
+}
+
+}  // extern "C"

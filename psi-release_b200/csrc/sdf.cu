@@ -1,0 +1,174 @@
+// Scene-SDF trilinear lookup with analytic gradient and fused collision partial sums.
+//
+// Replaces the normalise + F.grid_sample(..., padding_mode='border') block of
+// source/fitting_habitat.py:145-152 (torch-1.2 semantics: align_corners=True)
+// and the reduction inputs of :155-160.
+//
+// One grid per SCENE (the reference replicates 64 MiB per body, fitting_proxe.py:90): a
+// 256^3 grid (64 MiB) stays resident in B200's 126 MB L2 across bodies and iterations.
+// One thread per vertex: 8 read-only gathers (4 pairs adjacent in z), trilerp and d/dv in
+// registers; per-(body, chunk) partial sums of (-sdf, 1) over sdf<0 are reduced in a fixed
+// order (shuffle tree + fixed-order smem pass) so the collision term is reproducible.
+#include "common.cuh"
+
+namespace psi {
+
+constexpr int kSdfThreads = 256;
+constexpr int kSdfPerThread = 4;
+constexpr int kSdfChunk = kSdfThreads * kSdfPerThread;  // vertices per CTA
+constexpr int kMaxScenes = 16;
+
+struct SdfScenes {
+    float gmin[kMaxScenes][3];
+    float inv_extent[kMaxScenes][3];  // 1/(max-min)
+    float gscale[kMaxScenes][3];      // (D-1)/2 * 2/(max-min): d f / d v inside the grid
+};
+
+__global__ void __launch_bounds__(kSdfThreads)
+sdf_fwd_kernel(const float *__restrict__ sdf, int D, const SdfScenes sc,
+               const float *__restrict__ verts, int V, const int *__restrict__ body_scene,
+               float *__restrict__ out, float *__restrict__ grad, float *__restrict__ partial,
+               int num_partials) {
+    const int b = blockIdx.y;
+    const int scene = body_scene ? body_scene[b] : 0;
+    const float *__restrict__ grid = sdf + (size_t)scene * D * D * D;
+    const float dm1 = (float)(D - 1);
+    float neg_sum = 0.f, neg_cnt = 0.f;
+
+#pragma unroll
+    for (int r = 0; r < kSdfPerThread; ++r) {
+        const int v = blockIdx.x * kSdfChunk + r * kSdfThreads + threadIdx.x;
+        if (v >= V) continue;
+        const size_t o = (size_t)b * V + v;
+        float f[3], gm[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float x = __ldg(verts + o * 3 + a);
+            // reference operation order: (v-min)/(max-min)*2-1, then ((u+1)/2)*(D-1)
+            const float u = (x - sc.gmin[scene][a]) * sc.inv_extent[scene][a] * 2.0f - 1.0f;
+            float c = ((u + 1.0f) * 0.5f) * dm1;
+            float mult = sc.gscale[scene][a];
+            if (!(c > 0.0f)) { c = 0.0f; mult = 0.0f; }          // border clamp, zero gradient
+            else if (c >= dm1) { c = dm1; mult = 0.0f; }
+            f[a] = c;
+            gm[a] = mult;
+        }
+        int i0[3];
+        float w0[3], w1[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float fl = floorf(f[a]);
+            i0[a] = (int)fl;
+            w1[a] = f[a] - fl;
+            w0[a] = (fl + 1.0f) - f[a];
+        }
+        const int x1 = min(i0[0] + 1, D - 1), y1 = min(i0[1] + 1, D - 1), z1 = min(i0[2] + 1, D - 1);
+        // corners past the border carry weight 0 (f is clamped to D-1 => w1 == 0): clamping the
+        // index keeps the load in bounds without changing the value.
+        const size_t r00 = ((size_t)i0[0] * D + i0[1]) * D, r01 = ((size_t)i0[0] * D + y1) * D;
+        const size_t r10 = ((size_t)x1 * D + i0[1]) * D, r11 = ((size_t)x1 * D + y1) * D;
+        const float s000 = __ldg(grid + r00 + i0[2]), s001 = __ldg(grid + r00 + z1);
+        const float s010 = __ldg(grid + r01 + i0[2]), s011 = __ldg(grid + r01 + z1);
+        const float s100 = __ldg(grid + r10 + i0[2]), s101 = __ldg(grid + r10 + z1);
+        const float s110 = __ldg(grid + r11 + i0[2]), s111 = __ldg(grid + r11 + z1);
+        const bool xin = i0[0] + 1 <= D - 1, yin = i0[1] + 1 <= D - 1, zin = i0[2] + 1 <= D - 1;
+        const float wx0 = w0[0], wx1 = xin ? w1[0] : 0.f;
+        const float wy0 = w0[1], wy1 = yin ? w1[1] : 0.f;
+        const float wz0 = w0[2], wz1 = zin ? w1[2] : 0.f;
+        // interpolate along z, then y, then x
+        const float c00 = s000 * wz0 + s001 * wz1, c01 = s010 * wz0 + s011 * wz1;
+        const float c10 = s100 * wz0 + s101 * wz1, c11 = s110 * wz0 + s111 * wz1;
+        const float c0 = c00 * wy0 + c01 * wy1, c1 = c10 * wy0 + c11 * wy1;
+        const float val = c0 * wx0 + c1 * wx1;
+        out[o] = val;
+        if (grad) {
+            const float gx = xin ? (c1 - c0) : 0.f;
+            const float gy = yin ? ((c01 - c00) * wx0 + (c11 - c10) * wx1) : 0.f;
+            const float d00 = zin ? (s001 - s000) : 0.f, d01 = zin ? (s011 - s010) : 0.f;
+            const float d10 = zin ? (s101 - s100) : 0.f, d11 = zin ? (s111 - s110) : 0.f;
+            const float gz = (d00 * wy0 + d01 * wy1) * wx0 + (d10 * wy0 + d11 * wy1) * wx1;
+            grad[o * 3 + 0] = gx * gm[0];
+            grad[o * 3 + 1] = gy * gm[1];
+            grad[o * 3 + 2] = gz * gm[2];
+        }
+        if (val < 0.f) {
+            neg_sum -= val;
+            neg_cnt += 1.f;
+        }
+    }
+
+    if (partial) {
+        __shared__ float red[2][kSdfThreads / 32];
+        neg_sum = warp_sum(neg_sum);
+        neg_cnt = warp_sum(neg_cnt);
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) {
+            red[0][w] = neg_sum;
+            red[1][w] = neg_cnt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f, c = 0.f;
+#pragma unroll
+            for (int i = 0; i < kSdfThreads / 32; ++i) {
+                s += red[0][i];
+                c += red[1][i];
+            }
+            partial[((size_t)b * num_partials + blockIdx.x) * 2 + 0] = s;
+            partial[((size_t)b * num_partials + blockIdx.x) * 2 + 1] = c;
+        }
+    }
+}
+
+__global__ void sdf_bwd_kernel(const float *__restrict__ go, const float *__restrict__ grad,
+                               long count, float *__restrict__ gv) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float g = go[i];
+    gv[i * 3 + 0] = g * grad[i * 3 + 0];
+    gv[i * 3 + 1] = g * grad[i * 3 + 1];
+    gv[i * 3 + 2] = g * grad[i * 3 + 2];
+}
+
+}  // namespace psi
+
+extern "C" {
+
+int psi_sdf_num_partials(int V) { return V <= 0 ? 0 : (V + psi::kSdfChunk - 1) / psi::kSdfChunk; }
+
+int psi_sdf_fwd(const float *sdf, int S, int D, const float *h_grid_min, const float *h_grid_max,
+                const float *verts, int B, int V, const int *body_scene, float *out, float *grad,
+                float *partial, psi_stream_t stream) {
+    if (B < 0 || V < 0 || D < 1 || S < 1) return PSI_ERR_BAD_ARG;
+    if (S > psi::kMaxScenes) return PSI_ERR_UNSUPPORTED;
+    if (B == 0 || V == 0) return PSI_OK;
+    if (!sdf || !h_grid_min || !h_grid_max || !verts || !out) return PSI_ERR_BAD_ARG;
+    if (B > 65535) return PSI_ERR_UNSUPPORTED;
+    psi::SdfScenes sc;
+    for (int s = 0; s < S; ++s)
+        for (int a = 0; a < 3; ++a) {
+            const float ext = h_grid_max[s * 3 + a] - h_grid_min[s * 3 + a];
+            sc.gmin[s][a] = h_grid_min[s * 3 + a];
+            sc.inv_extent[s][a] = 1.0f / ext;
+            sc.gscale[s][a] = (float)(D - 1) / 2.0f * (2.0f / ext);
+        }
+    const int np = psi_sdf_num_partials(V);
+    dim3 grid((unsigned)np, (unsigned)B);
+    psi::sdf_fwd_kernel<<<grid, psi::kSdfThreads, 0, (cudaStream_t)stream>>>(
+        sdf, D, sc, verts, V, body_scene, out, grad, partial, np);
+    PSI_RETURN_IF_LAUNCH_FAILED();
+    return PSI_OK;
+}
+
+int psi_sdf_bwd(const float *grad_out, const float *grad, long count, float *grad_verts,
+                psi_stream_t stream) {
+    if (count < 0) return PSI_ERR_BAD_ARG;
+    if (count == 0) return PSI_OK;
+    if (!grad_out || !grad || !grad_verts) return PSI_ERR_BAD_ARG;
+    psi::sdf_bwd_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        grad_out, grad, count, grad_verts);
+    PSI_RETURN_IF_LAUNCH_FAILED();
+    return PSI_OK;
+}
+
+}  // extern "C"

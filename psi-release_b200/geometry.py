@@ -1,0 +1,237 @@
+"""Host-side glue of the fitting loop: rotation representations, GeometryTransformer,
+BodyParamParser and the VPoser decoder -- device-agnostic torch restatements of
+
+  source/cvae.py:36-95     ContinousRotReprDecoder (6D <-> matrix <-> axis-angle)
+  source/cvae.py:97-206    GeometryTransformer
+  source/cvae.py:225-334   BodyParamParser
+  human_body_prior/train/vposer_smpl.py:107-121,153-171  VPoser.decode / matrot2aa
+
+The reference delegates matrix<->axis-angle to torchgeometry==0.1.2 (requirements.txt:103,
+absent here); `rotation_matrix_to_angle_axis` / `angle_axis_to_rotation_matrix` restate its
+published algorithm, branch structure included.  The reference hard-codes `.cuda()`
+(cvae.py:299,326-332); here tensors stay on the device of their inputs.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+# ------------------------------------------------------------------ torchgeometry 0.1.2 pieces
+def rotation_matrix_to_quaternion(R, eps: float = 1e-6):
+    """[N,3,3] -> [N,4] (w,x,y,z); torchgeometry works on the transposed matrix."""
+    rt = R.transpose(1, 2)
+    m00, m11, m22 = rt[:, 0, 0], rt[:, 1, 1], rt[:, 2, 2]
+    mask_d2 = m22 < eps
+    mask_d0_d1 = m00 > m11
+    mask_d0_nd1 = m00 < -m11
+    t0 = 1 + m00 - m11 - m22
+    q0 = torch.stack([rt[:, 1, 2] - rt[:, 2, 1], t0, rt[:, 0, 1] + rt[:, 1, 0], rt[:, 2, 0] + rt[:, 0, 2]], -1)
+    t1 = 1 - m00 + m11 - m22
+    q1 = torch.stack([rt[:, 2, 0] - rt[:, 0, 2], rt[:, 0, 1] + rt[:, 1, 0], t1, rt[:, 1, 2] + rt[:, 2, 1]], -1)
+    t2 = 1 - m00 - m11 + m22
+    q2 = torch.stack([rt[:, 0, 1] - rt[:, 1, 0], rt[:, 2, 0] + rt[:, 0, 2], rt[:, 1, 2] + rt[:, 2, 1], t2], -1)
+    t3 = 1 + m00 + m11 + m22
+    q3 = torch.stack([t3, rt[:, 1, 2] - rt[:, 2, 1], rt[:, 2, 0] - rt[:, 0, 2], rt[:, 0, 1] - rt[:, 1, 0]], -1)
+    c0 = (mask_d2 & mask_d0_d1).unsqueeze(-1).to(R.dtype)
+    c1 = (mask_d2 & ~mask_d0_d1).unsqueeze(-1).to(R.dtype)
+    c2 = (~mask_d2 & mask_d0_nd1).unsqueeze(-1).to(R.dtype)
+    c3 = (~mask_d2 & ~mask_d0_nd1).unsqueeze(-1).to(R.dtype)
+    q = q0 * c0 + q1 * c1 + q2 * c2 + q3 * c3
+    q = q / torch.sqrt(t0.unsqueeze(-1) * c0 + t1.unsqueeze(-1) * c1 + t2.unsqueeze(-1) * c2
+                       + t3.unsqueeze(-1) * c3)
+    return q * 0.5
+
+
+def quaternion_to_angle_axis(q):
+    q1, q2, q3 = q[..., 1], q[..., 2], q[..., 3]
+    sin_sq = q1 * q1 + q2 * q2 + q3 * q3
+    sin_t = torch.sqrt(sin_sq)
+    cos_t = q[..., 0]
+    two_theta = 2.0 * torch.where(cos_t < 0.0, torch.atan2(-sin_t, -cos_t), torch.atan2(sin_t, cos_t))
+    k = torch.where(sin_sq > 0.0, two_theta / sin_t, 2.0 * torch.ones_like(sin_t))
+    return torch.stack([q1 * k, q2 * k, q3 * k], dim=-1)
+
+
+def rotation_matrix_to_angle_axis(R):
+    """[N,3,3] (the reference pads to 3x4 first, cvae.py:78) -> [N,3]."""
+    return quaternion_to_angle_axis(rotation_matrix_to_quaternion(R[:, :3, :3]))
+
+
+def angle_axis_to_rotation_matrix(aa, eps: float = 1e-6):
+    """[N,3] -> [N,3,3] with torchgeometry's first-order branch for tiny angles."""
+    theta2 = torch.sum(aa * aa, dim=1)
+    theta = torch.sqrt(theta2)
+    w = aa / (theta.unsqueeze(1) + eps)
+    wx, wy, wz = w[:, 0], w[:, 1], w[:, 2]
+    c, s = torch.cos(theta), torch.sin(theta)
+    normal = torch.stack([
+        c + wx * wx * (1.0 - c), wx * wy * (1.0 - c) - wz * s, wy * s + wx * wz * (1.0 - c),
+        wz * s + wx * wy * (1.0 - c), c + wy * wy * (1.0 - c), -wx * s + wy * wz * (1.0 - c),
+        -wy * s + wx * wz * (1.0 - c), wx * s + wy * wz * (1.0 - c), c + wz * wz * (1.0 - c)],
+        dim=1).view(-1, 3, 3)
+    rx, ry, rz = aa[:, 0], aa[:, 1], aa[:, 2]
+    one = torch.ones_like(rx)
+    taylor = torch.stack([one, -rz, ry, rz, one, -rx, -ry, rx, one], dim=1).view(-1, 3, 3)
+    mask = (theta2 > eps).view(-1, 1, 1).to(aa.dtype)
+    return mask * normal + (1 - mask) * taylor
+
+
+class ContinousRotReprDecoder(nn.Module):
+    """cvae.py:36-95 (spelling as in the reference)."""
+
+    def forward(self, module_input):
+        return self.decode(module_input)
+
+    @staticmethod
+    def decode(module_input):
+        x = module_input.reshape(-1, 3, 2)
+        b1 = F.normalize(x[:, :, 0], dim=1)
+        dot = torch.sum(b1 * x[:, :, 1], dim=1, keepdim=True)
+        b2 = F.normalize(x[:, :, 1] - dot * b1, dim=-1)
+        b3 = torch.cross(b1, b2, dim=1)
+        return torch.stack([b1, b2, b3], dim=-1)
+
+    @staticmethod
+    def matrot2aa(pose_matrot):
+        return rotation_matrix_to_angle_axis(pose_matrot.reshape(-1, 3, 3)).reshape(-1, 3).contiguous()
+
+    @staticmethod
+    def aa2matrot(pose):
+        return angle_axis_to_rotation_matrix(pose.reshape(-1, 3)).contiguous()
+
+
+class GeometryTransformer:
+    """cvae.py:97-206."""
+
+    @staticmethod
+    def get_contact_id(body_segments_folder, contact_body_parts=("L_Hand", "R_Hand")):
+        """cvae.py:99-115: per part `list(set(verts_ind))`, concatenated (duplicates across
+        parts kept).  The reference re-reads the JSON files every iteration (T10); callers here
+        hoist the call out of the loop."""
+        verts, faces = [], []
+        for part in contact_body_parts:
+            with open(os.path.join(body_segments_folder, part + ".json"), "r") as f:
+                data = json.load(f)
+            verts.append(list(set(data["verts_ind"])))
+            faces.append(list(set(data["faces_ind"])))
+        return np.concatenate(verts), np.concatenate(faces)
+
+    @staticmethod
+    def convert_to_6D_rot(x_batch):
+        xt, xr, xb = x_batch[:, :3], x_batch[:, 3:6], x_batch[:, 6:]
+        xr_mat = ContinousRotReprDecoder.aa2matrot(xr)
+        return torch.cat([xt, xr_mat[:, :, :-1].reshape(-1, 6), xb], dim=-1)
+
+    @staticmethod
+    def convert_to_3D_rot(x_batch):
+        xt, xr, xb = x_batch[:, :3], x_batch[:, 3:9], x_batch[:, 9:]
+        xr_aa = ContinousRotReprDecoder.matrot2aa(ContinousRotReprDecoder.decode(xr))
+        return torch.cat([xt, xr_aa, xb], dim=-1)
+
+    @staticmethod
+    def verts_transform(verts_batch, cam_ext_batch):
+        """cvae.py:141-149.  (The fitting loop fuses this into the LBS kernel; this stand-alone
+        form serves unchanged reference code and evaluation scripts.)"""
+        vh = F.pad(verts_batch, (0, 1), mode="constant", value=1)
+        return torch.matmul(vh, cam_ext_batch.permute(0, 2, 1))[:, :, :-1]
+
+    @staticmethod
+    def recover_global_T(x_batch, cam_intrisic, max_depth):
+        xt, xr = x_batch[:, :3], x_batch[:, 3:]
+        fx, fy = cam_intrisic[:, 0, 0], cam_intrisic[:, 1, 1]
+        px, py = cam_intrisic[:, 0, 2], cam_intrisic[:, 1, 2]
+        s_ = 1.0 / torch.max(px, py)
+        z = (xt[:, 2] + 1.0) / 2.0 * max_depth
+        x = xt[:, 0] * z / s_ / fx
+        y = xt[:, 1] * z / s_ / fy
+        return torch.cat([torch.stack([x, y, z], dim=-1), xr], dim=-1)
+
+    @staticmethod
+    def normalize_global_T(x_batch, cam_intrisic, max_depth):
+        xt, xr = x_batch[:, :3], x_batch[:, 3:]
+        fx, fy = cam_intrisic[:, 0, 0], cam_intrisic[:, 1, 1]
+        px, py = cam_intrisic[:, 0, 2], cam_intrisic[:, 1, 2]
+        s_ = 1.0 / torch.max(px, py)
+        x = s_ * xt[:, 0] * fx / (xt[:, 2] + 1e-6)
+        y = s_ * xt[:, 1] * fy / (xt[:, 2] + 1e-6)
+        z = 2.0 * xt[:, 2] / max_depth - 1.0
+        return torch.cat([torch.stack([x, y, z], dim=-1), xr], dim=-1)
+
+
+_KEYS = (("transl", 0, 3), ("global_orient", 3, 6), ("betas", 6, 16), ("body_pose", 16, 48),
+         ("left_hand_pose", 48, 60), ("right_hand_pose", 60, 72))
+
+
+class BodyParamParser:
+    """cvae.py:225-334: the 72-D body vector <-> the pickle dictionary."""
+
+    @staticmethod
+    def body_params_encapsulate(x_body_rec):
+        x = x_body_rec.detach().cpu().numpy()
+        return [{k: x[b:b + 1, s:e] for k, s, e in _KEYS} for b in range(x.shape[0])]
+
+    @staticmethod
+    def body_params_encapsulate_batch(x_body_rec):
+        d = {k: x_body_rec[:, s:e] for k, s, e in _KEYS}
+        d["body_pose_vp"] = d.pop("body_pose")
+        return d
+
+    @staticmethod
+    def body_params_encapsulate_latent(x_body_rec, eps=None):
+        out = BodyParamParser.body_params_encapsulate(x_body_rec)
+        e = eps.detach().cpu().numpy()
+        for b, d in enumerate(out):
+            d["z"] = e[b:b + 1, :]
+        return out
+
+    @staticmethod
+    def body_params_parse(body_params_batch, device="cuda"):
+        x = np.concatenate([body_params_batch[k] for k, _, _ in _KEYS], axis=-1)
+        return torch.tensor(x, dtype=torch.float32, device=device)
+
+    @staticmethod
+    def body_params_parse_fitting(body_params_batch, device="cuda"):
+        x = BodyParamParser.body_params_parse(body_params_batch, device)
+        cam_ext = torch.tensor(body_params_batch["cam_ext"], dtype=torch.float32, device=device)
+        cam_int = torch.tensor(body_params_batch["cam_int"], dtype=torch.float32, device=device)
+        return x, cam_ext, cam_int
+
+
+class VPoserDecoder(nn.Module):
+    """The decode half of VPoser (vposer_smpl.py:83-121): 32 -> 512 -> 512 -> 21*6, leaky 0.2,
+    dropout inactive in eval, 6D -> matrix -> axis-angle.  Parameter names follow the
+    reference so a real VPoser state_dict loads with strict=False."""
+
+    def __init__(self, num_neurons=512, latentD=32, num_joints=21):
+        super().__init__()
+        self.latentD, self.num_joints = latentD, num_joints
+        self.bodyprior_dec_fc1 = nn.Linear(latentD, num_neurons)
+        self.bodyprior_dec_fc2 = nn.Linear(num_neurons, num_neurons)
+        self.bodyprior_dec_out = nn.Linear(num_neurons, num_joints * 6)
+        self.dropout = nn.Dropout(p=0.1)
+        self.rot_decoder = ContinousRotReprDecoder()
+
+    @classmethod
+    def from_weights(cls, weights: dict):
+        m = cls(num_neurons=weights["bodyprior_dec_fc1.weight"].shape[0],
+                latentD=weights["bodyprior_dec_fc1.weight"].shape[1],
+                num_joints=weights["bodyprior_dec_out.weight"].shape[0] // 6)
+        m.load_state_dict({k: torch.as_tensor(v) for k, v in weights.items()}, strict=True)
+        return m.eval()
+
+    def decode(self, Zin, output_type="matrot"):
+        assert output_type in ("matrot", "aa")
+        x = F.leaky_relu(self.bodyprior_dec_fc1(Zin), negative_slope=0.2)
+        x = self.dropout(x)
+        x = F.leaky_relu(self.bodyprior_dec_fc2(x), negative_slope=0.2)
+        x = self.bodyprior_dec_out(x)
+        R = self.rot_decoder(x).view(-1, 1, self.num_joints, 9)
+        if output_type == "aa":
+            return rotation_matrix_to_angle_axis(R.reshape(-1, 3, 3)).view(Zin.shape[0], 1, -1, 3).contiguous()
+        return R
