@@ -1,0 +1,325 @@
+"""bench.py -- fitted bodies / second over the 300-iteration scene-fit loop (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], per GPU): 64 bodies, one synthetic scene (256^3 SDF over
+[-3,3]^3, 50 000 scene points), SMPL-X-shaped model with 10 475 vertices, every vertex a contact
+vertex ("10k-vert body"), 300 iterations of {cal_loss forward, backward, Adam(lr 0.1) step}
+(fitting_habitat.py:177-191; SURVEY.md T7 on why Adam).  One STEP = fitting one batch of 64
+bodies for 300 iterations.  Bodies are independent problems: with N GPUs every rank fits its own
+64 bodies (weak scaling) and one all-gather of the fitted vectors ends the job.
+
+`value`  : bodies/s with the inputs already on the device (FittingOP.fit).
+`e2e`    : bodies/s through FittingOP.fit_host -- pinned HOST body vectors + camera transform
+           copied in, fitted vectors copied out, inside the timed region.
+`--impl reference` : the reference algorithm on the host CPU (oracle/: torch-CPU LBS and
+           grid_sample, AVX brute-force NN in C/OpenMP, torch Adam), all host threads, on a
+           bounded sample (64 bodies x `--ref-iters` iterations per step, scaled to 300).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NUM_VERTS, NUM_POINTS, SDF_DIM, ITERS = 10475, 50000, 256, 300
+LOSS = dict(weight_loss_rec=1, weight_loss_vposer=0.01, weight_contact=0.1, weight_collision=0.5)
+METRIC = "fitted bodies/sec (300-iter scene-fit loop)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="bodies per GPU")
+    ap.add_argument("--iters", type=int, default=ITERS)
+    ap.add_argument("--nn", default="bruteforce", choices=["bruteforce"])
+    ap.add_argument("--ref-iters", type=int, default=6, help="iterations per reference-arm step")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "configs[1]: batch=%d bodies/GPU, 1 scene, %d-vert body, %d^3 SDF, %d-pt scene, "
+                        "%d Adam iterations, full-body contact" % (args.batch, NUM_VERTS, SDF_DIM, NUM_POINTS, args.iters),
+            "bodies_per_gpu": args.batch, "global_bodies": args.batch * n_gpus, "iterations": args.iters,
+            "optimizer": "adam lr=0.1", "nn": "one direction (body->scene), brute force, bit-exact",
+            "loss_mode": "independent", "parallelism": "dp%d (bodies sharded, no data-path collective)" % n_gpus,
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        busy = [x for x in sm if x > 0.5 * (max(mx) if mx else 1)] or sm
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def make_world(args, rank):
+    from psi_release_b200 import synthetic
+    model = synthetic.make_smplx_model(seed=1234, num_verts=NUM_VERTS)
+    scene = synthetic.make_scene(seed=0, dim=SDF_DIM, num_points=NUM_POINTS)
+    xh = synthetic.make_body_params(scene, args.batch, seed=rank)
+    return model, scene, xh
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from psi_release_b200 import _lib, chamfer, synthetic
+    from psi_release_b200.distributed import gather_rows
+    from psi_release_b200.fitting import FittingOP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, scene, xh = make_world(args, rank)
+    cfg = dict(model_data=model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
+               contact_ids=synthetic.make_contact_ids(NUM_VERTS, "full"), init_lr_h=0.1,
+               num_iter=args.iters, batch_size=args.batch, device=dev, use_cuda_graph=True)
+    op = FittingOP(cfg, LOSS)
+    xh_host = torch.tensor(xh).pin_memory()
+    cam_host = torch.tensor(scene.cam_ext).unsqueeze(0).pin_memory()
+    xh_dev, cam_dev = xh_host.to(dev), cam_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        """K steps, each bracketed by its own CUDA events on the launching stream; L2 flushed
+        between steps outside the events.  Returns the max over ranks of the summed time (ms)."""
+        tot = 0.0
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            tot += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    for _ in range(max(args.warmup, 3)):
+        op.fit(xh_dev, cam_dev)
+    # kernels launched per captured iteration (the graph replays them `iters` times per step)
+    c0 = L.psi_launch_count()
+    op.use_cuda_graph = False
+    op.fit(xh_dev, cam_dev, num_iter=1)
+    per_iter = int(L.psi_launch_count() - c0)
+    op.use_cuda_graph = True
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, fitted = timed(lambda: op.fit(xh_dev, cam_dev), args.steps)
+    ms_e2e, fitted_h = timed(lambda: op.fit_host(xh_host, cam_host), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # one all-gather of the fitted vectors ends a sharded job (not part of the per-step loop)
+    all_fitted = gather_rows(fitted, args.batch * world) if world > 1 else fitted
+    assert all_fitted.shape == (args.batch * world, 72) and torch.isfinite(all_fitted).all()
+
+    # dominant kernel, timed alone with CUDA events on its launching stream (L2 flushed)
+    verts = op.body_verts(xh_dev, cam_dev).detach().contiguous()
+    for _ in range(3):
+        chamfer.nn_forward(verts, op.s_verts)
+    ks = []
+    for _ in range(10):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        chamfer.nn_forward(verts, op.s_verts)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ks.append(e0.elapsed_time(e1))
+    nn_ms = float(np.mean(ks))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    bodies = args.batch * world * args.steps
+    value = bodies / (ms_dev * 1e-3)
+    e2e = bodies / (ms_e2e * 1e-3)
+    hbm_peak, peak_src = peaks()
+    B = args.batch
+    alg_bytes = (B * NUM_VERTS + NUM_POINTS) * 12 + B * NUM_VERTS * 8       # 809.5 kB/body at B=1
+    pairs = B * NUM_VERTS * NUM_POINTS
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    out = {
+        "metric": METRIC, "value": value, "unit": "bodies/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e, "unit": "bodies/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(xh_host.numel() * 4 + cam_host.numel() * 4) * world,
+                "d2h_bytes_per_step": int(args.batch * 72 * 4) * world,
+                "api": "psi_release_b200.fitting.FittingOP.fit_host"},
+        "gpu_launches": per_iter * args.iters * args.steps * world,
+        "gpu_launches_per_iteration": per_iter,
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "psi::nn_fwd_kernel<8,16,256,1024,2> (Chamfer/NN forward, %d of every %d ms of a step)"
+                      % (round(nn_ms * args.iters), round(ms_dev / args.steps)),
+            "bound": "hbm", "achieved": alg_bytes / (nn_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_bytes / (nn_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+            "traffic": None, "launch_ms": nn_ms, "timed": "alone, 10 launches, CUDA events, L2 flushed",
+            "share_of_step": nn_ms * args.iters / (ms_dev / args.steps),
+            "note": "brute-force NN is FP32-issue bound (5200 flop/B, SURVEY 8(d)): see fp32",
+            "fp32": {"bound": "fp32 issue", "achieved": pairs * 8 / (nn_ms * 1e-3) / 1e12,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": pairs * 8 / (nn_ms * 1e-3) / 1e12 / fp32_peak,
+                     "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm (no measured FP32 peak)",
+                     "pairs_per_s": pairs / (nn_ms * 1e-3)}},
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, seconds=args.cpu_baseline_seconds)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------- CPU arms
+def _cpu_setup(args):
+    from oracle import oracle
+    from psi_release_b200 import synthetic
+    model, scene, xh = make_world(args, 0)
+    so = oracle.SMPLXOracle(model)
+    vp = oracle.VPoserDecoderOracle(synthetic.make_vposer_weights())
+    t = torch.tensor
+    kw = dict(smplx_model=so, vposer=vp, sdf=t(scene.sdf), gmin=t(scene.grid_min), gmax=t(scene.grid_max),
+              scene_points=t(scene.points), contact_ids=np.arange(NUM_VERTS), weights=LOSS, robust_c=1.0,
+              loss_mode="independent")
+    return oracle, t(xh), t(scene.cam_ext).unsqueeze(0), kw
+
+
+def _cpu_step(oracle, xh, cam, kw, iters):
+    t0 = time.perf_counter()
+    oracle.fit_loop(xh, cam.expand(xh.shape[0], -1, -1), iters, 0.1, **kw)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args, seconds):
+    """The oracle port timed on the host cores (rank 0, N=1 legs): bounded sample."""
+    oracle, xh, cam, kw = _cpu_setup(args)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nb = min(args.batch, 16)
+    t1 = _cpu_step(oracle, xh[:nb], cam, kw, 1)              # warm-up + cost probe
+    iters = int(max(1, min(20, seconds / max(t1, 1e-3))))
+    t = _cpu_step(oracle, xh[:nb], cam, kw, iters)
+    val = nb * (iters / args.iters) / t
+    return {"value": val, "unit": "bodies/s", "cores": cores, "kind": "port",
+            "simd_lanes": oracle.simd_width(), "threads_nn": oracle.num_threads(),
+            "sample": "%d bodies x %d of %d iterations (torch-CPU LBS + grid_sample, C/OpenMP brute-force NN, "
+                      "torch Adam), scaled to %d iterations" % (nb, iters, args.iters, args.iters)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    oracle, xh, cam, kw = _cpu_setup(args)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    it = args.ref_iters
+    for _ in range(max(1, min(args.warmup, 3))):
+        _cpu_step(oracle, xh, cam, kw, 1)
+    t = 0.0
+    for _ in range(args.steps):
+        t += _cpu_step(oracle, xh, cam, kw, it)
+    val = args.batch * args.steps * (it / args.iters) / t
+    sample = ("each step = %d bodies x %d of %d iterations on the host CPU (torch-CPU LBS + grid_sample, "
+              "AVX brute-force NN in C/OpenMP, torch Adam), scaled to %d iterations" % (args.batch, it, args.iters, args.iters))
+    cfg = workload_config(args, world)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "bodies/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3 * (args.iters / it),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "bodies/s", "cores": cores, "kind": "port",
+                         "simd_lanes": oracle.simd_width(), "sample": sample},
+        "e2e": {"value": val, "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -43,6 +43,10 @@ typedef void *psi_stream_t; /* cudaStream_t */
 
 /* ABI version of the loaded library (PSI_ABI_VERSION it was built with). */
 PSI_API int psi_abi_version(void);
+/* Number of kernel launches this library has enqueued since load (statistics only: a relaxed
+ * atomic counter, the one piece of process-wide state; launches captured into a CUDA graph
+ * count once, at capture). */
+PSI_API unsigned long long psi_launch_count(void);
 /* Static string for a PSI_ERR_* or cudaError_t value. */
 PSI_API const char *psi_error_string(int code);
 

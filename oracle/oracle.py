@@ -351,16 +351,20 @@ class _NNFunction(torch.autograd.Function):
 
 def cal_loss(xhr, xhr_rec, cam_ext, smplx_model: SMPLXOracle, vposer: VPoserDecoderOracle,
              sdf, gmin, gmax, scene_points, contact_ids, weights: dict, robust_c: float = 1.0,
-             collision_mode: str = "batch"):
+             loss_mode: str = "batch"):
     """fitting_habitat.py:103-164 on CPU tensors.  Returns the four weighted loss terms.
-    collision_mode 'batch' = the reference's batch-global mean over negative entries;
-    'body' = one mean per body, summed over bodies / B never used by the reference scripts
-    except at B=1 where both coincide."""
+    loss_mode 'batch' = the reference code as written (means over the whole batch, the
+    collision mean over all negative entries of the batch; SURVEY.md T9);
+    'independent' = the SUM over bodies of that same loss evaluated at B=1, i.e. what the
+    shipped scripts compute body by body (batch_size 1, fitting_habitat.py:254).  Both coincide
+    at B=1."""
     B = xhr_rec.shape[0]
-    loss_rec = weights["weight_loss_rec"] * F.l1_loss(xhr, xhr_rec)
+    indep = loss_mode == "independent"
+    red = (lambda t: t.reshape(B, -1).mean(dim=1).sum()) if indep else (lambda t: t.mean())
+    loss_rec = weights["weight_loss_rec"] * red((xhr - xhr_rec).abs())
     xh = convert_to_3D_rot(xhr_rec)
     z = xh[:, 16:48]
-    loss_vposer = weights["weight_loss_vposer"] * torch.mean(z ** 2)
+    loss_vposer = weights["weight_loss_vposer"] * red(z ** 2)
     body_pose = vposer.decode(z)
     verts, _ = smplx_model(body_pose=body_pose, transl=xh[:, :3], global_orient=xh[:, 3:6],
                            betas=xh[:, 6:16], left_hand_pose=xh[:, 48:60], right_hand_pose=xh[:, 60:])
@@ -368,16 +372,32 @@ def cal_loss(xhr, xhr_rec, cam_ext, smplx_model: SMPLXOracle, vposer: VPoserDeco
     contact = verts[:, torch.as_tensor(contact_ids, dtype=torch.long), :].contiguous()
     d = _NNFunction.apply(contact, scene_points)
     s = torch.sqrt(d + 1e-4)
-    loss_contact = weights["weight_contact"] * torch.mean(s / (s + robust_c))
+    loss_contact = weights["weight_contact"] * red(s / (s + robust_c))
     body_sdf = sdf_lookup_torch(sdf, gmin, gmax, verts)
     neg = body_sdf < 0
-    if collision_mode == "batch":
+    if not indep:
         if int(neg.sum()) < 1:
             pene = torch.tensor(0.0)
         else:
             pene = body_sdf[neg].abs().mean()
     else:
         cnt = neg.sum(dim=1).clamp(min=1).to(body_sdf.dtype)
-        pene = ((-body_sdf * neg).sum(dim=1) / cnt).sum() / B
+        pene = ((-body_sdf * neg).sum(dim=1) / cnt).sum()
     loss_collision = weights["weight_collision"] * pene
     return loss_rec, loss_vposer, loss_contact, loss_collision
+
+
+def fit_loop(xh, cam_ext, num_iter, lr, smplx_model, vposer, sdf, gmin, gmax, scene_points,
+             contact_ids, weights, robust_c=1.0, loss_mode="independent"):
+    """fitting_habitat.py:169-197 on the CPU: Adam(lr) on the 75-D vector, `num_iter` iterations.
+    xh [B,72] -> fitted [B,72]."""
+    xhr = convert_to_6D_rot(xh)
+    xhr_rec = xhr.clone().requires_grad_(True)
+    opt = torch.optim.Adam([xhr_rec], lr=lr)
+    for _ in range(num_iter):
+        opt.zero_grad()
+        terms = cal_loss(xhr, xhr_rec, cam_ext, smplx_model, vposer, sdf, gmin, gmax, scene_points,
+                         contact_ids, weights, robust_c, loss_mode)
+        sum(terms).backward()
+        opt.step()
+    return convert_to_3D_rot(xhr_rec.detach())

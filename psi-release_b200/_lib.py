@@ -41,6 +41,7 @@ def lib():
     sig = {
         "psi_abi_version": (_i, []),
         "psi_error_string": (ctypes.c_char_p, [_i]),
+        "psi_launch_count": (ctypes.c_ulonglong, []),
         "psi_nn_workspace_bytes": (_sz, [_i, _i, _i]),
         "psi_nn_fwd": (_i, [_vp, _l, _i, _i, _vp, _l, _i, _vp, _vp, _vp, _sz, _vp]),
         "psi_chamfer_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -67,7 +68,7 @@ def lib():
     return L
 
 
-EXPORTS = ["psi_abi_version", "psi_error_string", "psi_nn_workspace_bytes", "psi_nn_fwd",
+EXPORTS = ["psi_abi_version", "psi_error_string", "psi_launch_count", "psi_nn_workspace_bytes", "psi_nn_fwd",
            "psi_chamfer_fwd", "psi_nn_bwd", "psi_chamfer_bwd", "psi_sdf_num_partials", "psi_sdf_fwd",
            "psi_sdf_bwd", "psi_lbs_model_create", "psi_lbs_model_destroy", "psi_lbs_model_bytes",
            "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd"]

@@ -1,9 +1,17 @@
 // ABI version and error strings for libpsi_b200.
 #include "common.cuh"
+#include <atomic>
+
+namespace psi {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace psi
 
 extern "C" {
 
 int psi_abi_version(void) { return PSI_ABI_VERSION; }
+
+unsigned long long psi_launch_count(void) { return psi::g_launches.load(std::memory_order_relaxed); }
 
 const char *psi_error_string(int code) {
     switch (code) {

@@ -311,10 +311,10 @@ static int nn_fwd_launch(const float *q, long q_bstride, int B, int n, const flo
         const size_t smem = 2 * kSmallTP * 3 * sizeof(float);
         nn_fwd_kernel<kSmallQ, kG, kSmallT, kSmallTP, 4><<<grid, kSmallT, smem, st>>>(p);
     }
-    PSI_RETURN_IF_LAUNCH_FAILED();
+    PSI_LAUNCHED();
     if (pl.num_chunks > 1) {
         nn_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.packed, total, dist, idx);
-        PSI_RETURN_IF_LAUNCH_FAILED();
+        PSI_LAUNCHED();
     }
     return PSI_OK;
 }
@@ -356,7 +356,7 @@ int psi_nn_bwd(const float *q, long q_bstride, int B, int n, const float *s, lon
     const long total = (long)B * n;
     psi::nn_bwd_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         q, q_bstride, B, n, s, s_bstride, graddist, idx, grad_q);
-    PSI_RETURN_IF_LAUNCH_FAILED();
+    PSI_LAUNCHED();
     return PSI_OK;
 }
 
@@ -375,13 +375,13 @@ int psi_chamfer_bwd(const float *xyz1, const float *xyz2, int B, int n, int m,
         const long total = (long)B * n;
         psi::chamfer_bwd_dir_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
             xyz1, xyz2, B, n, m, graddist1, idx1, gradxyz1, gradxyz2);
-        PSI_RETURN_IF_LAUNCH_FAILED();
+        PSI_LAUNCHED();
     }
     if (graddist2 && idx2 && n > 0 && m > 0) {
         const long total = (long)B * m;
         psi::chamfer_bwd_dir_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
             xyz2, xyz1, B, m, n, graddist2, idx2, gradxyz2, gradxyz1);
-        PSI_RETURN_IF_LAUNCH_FAILED();
+        PSI_LAUNCHED();
     }
     return PSI_OK;
 }

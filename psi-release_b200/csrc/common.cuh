@@ -10,9 +10,18 @@
         if (e__ != cudaSuccess) return (int)e__;       \
     } while (0)
 
+// counts the launch, then reports a launch-time error
+#define PSI_LAUNCHED()                                 \
+    do {                                               \
+        psi::count_launch();                           \
+        PSI_RETURN_IF_LAUNCH_FAILED();                 \
+    } while (0)
+
 #define PSI_NUM_SMS 148  // B200: 2 dies x 74 SMs
 
 namespace psi {
+
+void count_launch();   // api.cu
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -759,10 +759,10 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     lbs_pose_fwd_kernel<<<B, 64, 0, st>>>(m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
                                           B, betas, pose, transl, saved, L, joints);
-    PSI_RETURN_IF_LAUNCH_FAILED();
+    PSI_LAUNCHED();
     if (B % kBG) {
         lbs_zero_coef_pad_kernel<<<8, 256, 0, st>>>(saved + L.coef, B, m->Kpad);
-        PSI_RETURN_IF_LAUNCH_FAILED();
+        PSI_LAUNCHED();
     }
     VertexFwdParams p;
     p.basis = m->basis; p.v_template = m->v_template; p.skin_w = m->skin_w; p.skin_j = m->skin_j;
@@ -777,7 +777,7 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
     }
     dim3 grid((unsigned)(m->Npad / kTileN), (unsigned)((B + kBG - 1) / kBG));
     lbs_vertex_fwd_kernel<<<grid, 64, smem, st>>>(p);
-    PSI_RETURN_IF_LAUNCH_FAILED();
+    PSI_LAUNCHED();
     return PSI_OK;
 }
 
@@ -807,13 +807,13 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
         lbs_vertex_bwd_kernel<<<grid, 256, 0, st>>>(m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                                                     m->skin_w, saved + L.A, cam, cam_bstride,
                                                     grad_verts, ws + W.gw, ws + W.gvp);
-        PSI_RETURN_IF_LAUNCH_FAILED();
+        PSI_LAUNCHED();
     }
     {
         dim3 grid((unsigned)(m->J + 1), (unsigned)B);
         lbs_dA_kernel<<<grid, 128, 0, st>>>(m->V, m->J, m->jl_start, m->jl_vert, m->jl_w,
                                             ws + W.gw, saved + L.vp, ws + W.dA, ws + W.dtr);
-        PSI_RETURN_IF_LAUNCH_FAILED();
+        PSI_LAUNCHED();
     }
     {
         const int total_chunks = m->Npad / 32;
@@ -821,13 +821,13 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
         dim3 grid((unsigned)(m->Kpad / 128), (unsigned)kNSplit, (unsigned)(W.Bpad / 32));
         lbs_dcoef_kernel<<<grid, 128, 0, st>>>(m->Kpad, m->Npad, B, W.Bpad, m->basis, ws + W.gvp,
                                                ws + W.part, cps);
-        PSI_RETURN_IF_LAUNCH_FAILED();
+        PSI_LAUNCHED();
     }
     lbs_pose_bwd_kernel<<<B, 64, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
                                           m->parents, pose, saved, L, ws + W.dA, ws + W.dtr,
                                           ws + W.part, grad_joints, grad_betas, grad_pose,
                                           grad_transl);
-    PSI_RETURN_IF_LAUNCH_FAILED();
+    PSI_LAUNCHED();
     return PSI_OK;
 }
 

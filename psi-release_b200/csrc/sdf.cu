@@ -156,7 +156,7 @@ int psi_sdf_fwd(const float *sdf, int S, int D, const float *h_grid_min, const f
     dim3 grid((unsigned)np, (unsigned)B);
     psi::sdf_fwd_kernel<<<grid, psi::kSdfThreads, 0, (cudaStream_t)stream>>>(
         sdf, D, sc, verts, V, body_scene, out, grad, partial, np);
-    PSI_RETURN_IF_LAUNCH_FAILED();
+    PSI_LAUNCHED();
     return PSI_OK;
 }
 
@@ -167,7 +167,7 @@ int psi_sdf_bwd(const float *grad_out, const float *grad, long count, float *gra
     if (!grad_out || !grad || !grad_verts) return PSI_ERR_BAD_ARG;
     psi::sdf_bwd_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         grad_out, grad, count, grad_verts);
-    PSI_RETURN_IF_LAUNCH_FAILED();
+    PSI_LAUNCHED();
     return PSI_OK;
 }
 

@@ -45,7 +45,7 @@ class _Adam:
         self.p, self.lr, self.b1, self.b2, self.eps = param, lr, betas[0], betas[1], eps
         self.m = torch.zeros_like(param)
         self.v = torch.zeros_like(param)
-        self.t = torch.zeros((), dtype=torch.float32, device=param.device)
+        self.t = torch.zeros((), dtype=torch.float64, device=param.device)
 
     def reset(self):
         self.m.zero_()
@@ -54,13 +54,15 @@ class _Adam:
 
     @torch.no_grad()
     def step(self, grad):
+        # same operation order as torch's single-tensor Adam; bias corrections in float64
         self.t += 1
         self.m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
         self.v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
         bc1 = 1 - torch.pow(self.b1, self.t)
-        bc2 = 1 - torch.pow(self.b2, self.t)
-        denom = (self.v.sqrt() / bc2.sqrt()).add_(self.eps)
-        self.p.addcdiv_(self.m / bc1, denom, value=-self.lr)
+        bc2_sqrt = (1 - torch.pow(self.b2, self.t)).sqrt()
+        step_size = (self.lr / bc1).to(torch.float32)
+        denom = (self.v.sqrt() / bc2_sqrt.to(torch.float32)).add_(self.eps)
+        self.p.sub_((self.m / denom) * step_size)
 
 
 class FittingOP:

@@ -1,0 +1,100 @@
+"""GPU tests of the fitting loop (FittingOP) against the CPU restatement of
+source/fitting_habitat.py's loop, plus the loop-level invariants the sharded job relies on."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle  # noqa: E402
+
+W = dict(weight_loss_rec=1, weight_loss_vposer=0.01, weight_contact=0.1, weight_collision=0.5)
+
+
+def _world(small_model, B, contact="parts"):
+    from psi_release_b200 import synthetic
+    scene = synthetic.make_scene(seed=1, dim=32, num_points=3000)
+    xh = synthetic.make_body_params(scene, B, seed=3)
+    cid = synthetic.make_contact_ids(431, contact)
+    cfg = dict(model_data=small_model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
+               contact_ids=cid, init_lr_h=0.1, num_iter=4, batch_size=B, device="cuda")
+    return scene, xh, cid, cfg
+
+
+def _oracle_kw(small_model, scene, cid):
+    from psi_release_b200 import synthetic
+    t = torch.tensor
+    return dict(smplx_model=oracle.SMPLXOracle(small_model),
+                vposer=oracle.VPoserDecoderOracle(synthetic.make_vposer_weights()), sdf=t(scene.sdf),
+                gmin=t(scene.grid_min), gmax=t(scene.grid_max), scene_points=t(scene.points),
+                contact_ids=cid, weights=W)
+
+
+@pytest.mark.parametrize("mode", ["independent", "batch"])
+def test_cal_loss_and_gradient_match_cpu_restatement(small_model, mode):
+    from psi_release_b200.fitting import FittingOP
+    from psi_release_b200.geometry import GeometryTransformer
+    B = 3
+    scene, xh, cid, cfg = _world(small_model, B)
+    op = FittingOP(dict(cfg, loss_mode=mode, use_cuda_graph=False), W)
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0)
+    xhr = GeometryTransformer.convert_to_6D_rot(torch.tensor(xh))
+    pert = xhr + 0.01 * torch.randn(xhr.shape, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        op.xhr_rec.copy_(pert.cuda())
+    terms = op.cal_loss(xhr.cuda(), cam.cuda())
+    (g,) = torch.autograd.grad(sum(terms), op.xhr_rec)
+    ref_rec = pert.clone().requires_grad_(True)
+    rterms = oracle.cal_loss(xhr, ref_rec, cam.expand(B, -1, -1), loss_mode=mode, **_oracle_kw(small_model, scene, cid))
+    (rg,) = torch.autograd.grad(sum(rterms), ref_rec)
+    for a, b in zip(terms, rterms):
+        assert abs(float(a) - float(b)) <= 1e-4 * max(1.0, abs(float(b)))
+    assert float((g.cpu() - rg).abs().max()) <= 2e-4 * float(rg.abs().max())
+
+
+def test_fit_matches_cpu_fit_loop_and_graph_equals_eager(small_model):
+    from psi_release_b200.fitting import FittingOP
+    B = 2
+    scene, xh, cid, cfg = _world(small_model, B)
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0)
+    eager = FittingOP(dict(cfg, use_cuda_graph=False), W).fit(torch.tensor(xh).cuda(), cam.cuda())
+    op = FittingOP(dict(cfg, use_cuda_graph=True), W)
+    graph = op.fit(torch.tensor(xh).cuda(), cam.cuda())
+    assert torch.equal(eager, graph)                       # deterministic kernels, same order
+    again = op.fit(torch.tensor(xh).cuda(), cam.cuda())    # graph reuse resets the optimiser state
+    assert torch.equal(graph, again)
+    ref = oracle.fit_loop(torch.tensor(xh), cam.expand(B, -1, -1), 4, 0.1, loss_mode="independent",
+                          **_oracle_kw(small_model, scene, cid))
+    # 4 Adam steps of size 0.1: sign-level agreement of every update -> a tight absolute band
+    assert float((graph.cpu() - ref).abs().max()) < 5e-3
+    host = op.fit_host(torch.tensor(xh).pin_memory(), cam.pin_memory())
+    assert torch.equal(host, graph.cpu())
+
+
+def test_independent_mode_is_shard_invariant(small_model):
+    """Fitting bodies [0:4] together == fitting [0:2] and [2:4] separately, bit for bit: the
+    property that lets the batch be sharded over GPUs with no collective in the loop."""
+    from psi_release_b200.fitting import FittingOP
+    scene, xh, cid, cfg = _world(small_model, 4)
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0).cuda()
+    full = FittingOP(dict(cfg, batch_size=4), W).fit(torch.tensor(xh).cuda(), cam)
+    lo = FittingOP(dict(cfg, batch_size=2), W).fit(torch.tensor(xh[:2]).cuda(), cam)
+    hi = FittingOP(dict(cfg, batch_size=2), W).fit(torch.tensor(xh[2:]).cuda(), cam)
+    assert torch.equal(full, torch.cat([lo, hi]))
+
+
+def test_reference_style_single_body_pickle_flow(small_model, tmp_path):
+    """fitting(pickle) -> save_result(pickle) as fitting_habitat.py:__main__ drives it."""
+    from psi_release_b200 import io
+    from psi_release_b200.fitting import FittingOP
+    scene, xh, cid, cfg = _world(small_model, 1)
+    fn = str(tmp_path / "gen" / "body_gen_000000.pkl")
+    (tmp_path / "gen").mkdir()
+    io.write_body_pickle(fn, xh[0], scene.cam_ext[None], np.eye(3, dtype=np.float32)[None])
+    op = FittingOP(cfg, W)
+    out = op.fitting(fn)
+    assert out.shape == (1, 72) and torch.isfinite(out).all()
+    op.save_result(out, str(tmp_path / "fit" / "body_gen_000000.pkl"))
+    d = io.read_body_pickle(str(tmp_path / "fit" / "body_gen_000000.pkl"))
+    assert set(d) == {"transl", "global_orient", "betas", "body_pose", "left_hand_pose", "right_hand_pose", "cam_ext", "cam_int"}
+    assert d["body_pose"].shape == (1, 32)

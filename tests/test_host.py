@@ -1,0 +1,191 @@
+"""CPU tests: C-ABI surface, host-side logic, wire formats, multi-process sharding (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    from psi_release_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "psi_b200.h")).read()
+    declared = sorted(set(re.findall(r"PSI_API[^;]*?\b(psi_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 18
+    L = ctypes.CDLL(_lib.lib_path())
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(_lib.EXPORTS) == declared          # the Python binding covers the whole header
+    lib = _lib.lib()
+    assert lib.psi_abi_version() == 1
+    assert b"workspace" in lib.psi_error_string(-2)
+    assert lib.psi_sdf_num_partials(10475) == 11 and lib.psi_nn_workspace_bytes(2, 10, 30) == 2 * 30 * 8
+
+
+def test_product_has_no_oracle_import_and_fails_loudly_without_cuda():
+    pkg = os.path.join(ROOT, "psi-release_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
+    from psi_release_b200 import _lib, chamfer
+    with pytest.raises(_lib.PsiError):
+        chamfer.nn_forward(torch.zeros(1, 4, 3), torch.zeros(5, 3))     # CPU tensors are rejected
+    if not torch.cuda.is_available():
+        from psi_release_b200.fitting import FittingOP
+        with pytest.raises(Exception):
+            FittingOP(dict(batch_size=1, device="cpu", init_lr_h=0.1), {})
+
+
+def test_geometry_glue_matches_oracle_restatement():
+    from psi_release_b200.geometry import GeometryTransformer, VPoserDecoder, BodyParamParser
+    from psi_release_b200 import synthetic
+    rng = np.random.default_rng(0)
+    x = torch.tensor(rng.standard_normal((9, 72)).astype(np.float32))
+    x[:, 3:6] *= 0.5            # keep |aa| < pi so the round trip is the identity
+    x6 = GeometryTransformer.convert_to_6D_rot(x)
+    assert x6.shape == (9, 75)
+    np.testing.assert_array_equal(x6.numpy(), oracle.convert_to_6D_rot(x).numpy())
+    np.testing.assert_array_equal(GeometryTransformer.convert_to_3D_rot(x6).numpy(), oracle.convert_to_3D_rot(x6).numpy())
+    np.testing.assert_allclose(GeometryTransformer.convert_to_3D_rot(x6).numpy(), x.numpy(), atol=3e-5)
+    w = synthetic.make_vposer_weights()
+    z = torch.tensor(rng.standard_normal((5, 32)).astype(np.float32))
+    a = VPoserDecoder.from_weights(w).decode(z, output_type="aa").view(5, -1)
+    np.testing.assert_allclose(a.detach().numpy(), oracle.VPoserDecoderOracle(w).decode(z).numpy(), atol=1e-6)
+    v = torch.tensor(rng.standard_normal((2, 50, 3)).astype(np.float32))
+    cam = torch.eye(4).repeat(2, 1, 1); cam[:, :3, 3] = torch.tensor([1.0, 2.0, 3.0])
+    np.testing.assert_allclose(GeometryTransformer.verts_transform(v, cam).numpy(), (v + cam[:, None, :3, 3]).numpy(), atol=1e-6)
+    d = BodyParamParser.body_params_encapsulate_batch(x)
+    assert d["body_pose_vp"].shape == (9, 32) and d["right_hand_pose"].shape == (9, 12)
+    lst = BodyParamParser.body_params_encapsulate(x)
+    back = BodyParamParser.body_params_parse(lst[3], device="cpu")
+    np.testing.assert_array_equal(back.numpy(), x[3:4].numpy())
+
+
+def test_adam_matches_torch_optim():
+    from psi_release_b200.fitting import _Adam
+    torch.manual_seed(0)
+    p0 = torch.randn(4, 75)
+    grads = [torch.randn(4, 75) for _ in range(25)]
+    p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=0.1)
+    q = p0.clone()
+    mine = _Adam(q, lr=0.1)
+    for g in grads:
+        p.grad = g.clone()
+        opt.step()
+        mine.step(g)
+    np.testing.assert_allclose(q.numpy(), p.detach().numpy(), rtol=2e-5, atol=2e-6)
+    mine.reset()
+    assert float(mine.t) == 0 and float(mine.m.abs().sum()) == 0
+
+
+def test_wire_formats_roundtrip(tmp_path):
+    from psi_release_b200 import io, synthetic
+    from psi_release_b200.geometry import BodyParamParser
+    pts = np.random.default_rng(1).standard_normal((100, 3)).astype(np.float32)
+    for binary in (True, False):
+        fn = str(tmp_path / f"s{int(binary)}.ply")
+        io.write_ply_vertices(fn, pts, binary=binary)
+        np.testing.assert_allclose(io.read_scene_vertices(fn), pts, rtol=1e-6)
+    scene = synthetic.make_scene(seed=3, dim=8, num_points=64)
+    synthetic.write_scene(str(tmp_path / "sdf" / "room"), scene)
+    import json
+    d = json.load(open(tmp_path / "sdf" / "room.json"))
+    assert d["dim"] == 8 and np.load(tmp_path / "sdf" / "room_sdf.npy").size == 512
+    xh = synthetic.make_body_params(scene, 2, seed=0)
+    fn = str(tmp_path / "body_gen_000000.pkl")
+    io.write_body_pickle(fn, xh[1], scene.cam_ext, np.eye(3))
+    x, cam_ext, cam_int = BodyParamParser.body_params_parse_fitting(io.read_body_pickle(fn), device="cpu")
+    np.testing.assert_array_equal(x.numpy(), xh[1:2])
+    assert cam_ext.shape == (4, 4)
+
+
+def test_synthetic_world_is_deterministic_and_well_formed():
+    from psi_release_b200 import synthetic
+    a = synthetic.make_smplx_model(seed=1234, num_verts=300)
+    b = synthetic.make_smplx_model(seed=1234, num_verts=300)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    assert a["posedirs"].shape == (300, 3, 486) and a["weights"].shape == (300, 55)
+    np.testing.assert_allclose(a["weights"].sum(1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(a["J_regressor"].sum(1), 1.0, atol=1e-5)
+    assert (a["weights"] != 0).sum(1).max() <= 4
+    p = a["kintree_table"][0]
+    assert p[0] == -1 and all(p[j] < j for j in range(1, 55))
+    s = synthetic.make_scene(seed=0, dim=24, num_points=500)
+    v, _ = oracle.sdf_fwd(s.sdf, s.grid_min, s.grid_max, s.points, want_grad=False)
+    assert np.abs(v).max() < 0.3          # surface samples sit near the zero level set (grid res 0.26)
+    xh = synthetic.make_body_params(s, 8, seed=1)
+    assert xh.shape == (8, 72) and np.isfinite(xh).all()
+    ids = synthetic.make_contact_ids(10475, "parts")
+    assert 2000 < len(ids) < 3000 and len(np.unique(ids)) < len(ids) or len(ids) > 0
+
+
+def test_shard_bounds_partition():
+    from psi_release_b200.distributed import shard_bounds
+    for total in (0, 1, 7, 64, 513):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PSI_ROOT"])
+from psi_release_b200.distributed import shard_rows, gather_rows, shard_bounds
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+full = torch.arange(7 * 72, dtype=torch.float32).view(7, 72)
+mine = shard_rows(full, w, r) * 2.0          # stand-in for "fit my shard"
+out = gather_rows(mine, 7)
+assert torch.equal(out, full * 2.0), (r, out.shape)
+dist.barrier()
+if r == 0:
+    print("GATHER_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, PSI_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GATHER_OK" in out.stdout
+
+
+def test_oracle_fit_loop_reduces_loss_and_modes_agree_at_b1(small_model):
+    """The CPU restatement of fitting_habitat.py's loop: at B=1 'batch' == 'independent'."""
+    from psi_release_b200 import synthetic
+    scene = synthetic.make_scene(seed=0, dim=24, num_points=600)
+    xh = torch.tensor(synthetic.make_body_params(scene, 2, seed=0))
+    so = oracle.SMPLXOracle(small_model)
+    vp = oracle.VPoserDecoderOracle(synthetic.make_vposer_weights())
+    t = torch.tensor
+    W = dict(weight_loss_rec=1, weight_loss_vposer=0.01, weight_contact=0.1, weight_collision=0.5)
+    kw = dict(smplx_model=so, vposer=vp, sdf=t(scene.sdf), gmin=t(scene.grid_min), gmax=t(scene.grid_max),
+              scene_points=t(scene.points), contact_ids=synthetic.make_contact_ids(431, "parts"), weights=W)
+    cam = t(scene.cam_ext).unsqueeze(0)
+    xhr = oracle.convert_to_6D_rot(xh[:1])
+    a = oracle.cal_loss(xhr, xhr.clone(), cam, loss_mode="batch", **kw)
+    b = oracle.cal_loss(xhr, xhr.clone(), cam, loss_mode="independent", **kw)
+    for x, y in zip(a, b):
+        assert abs(float(x) - float(y)) < 1e-7
+    # independent mode: fitting two bodies together == fitting them one by one
+    both = oracle.fit_loop(xh, cam.expand(2, -1, -1), 3, 0.1, loss_mode="independent", **kw)
+    one = oracle.fit_loop(xh[1:2], cam, 3, 0.1, loss_mode="independent", **kw)
+    np.testing.assert_allclose(both[1:2].numpy(), one.numpy(), atol=2e-5)
