@@ -94,6 +94,19 @@ PSI_API int psi_chamfer_bwd(const float *xyz1, const float *xyz2, int B, int n, 
                     const int *idx1, const int *idx2,
                     float *gradxyz1, float *gradxyz2, psi_stream_t stream);
 
+/* Exact NN against a STATIC scene through a cluster index (same outputs as psi_nn_fwd with
+ * s_bstride == 0, bit for bit: the index only skips clusters whose floating-point lower bound
+ * exceeds a distance already seen).  The fitting loop queries the same scene points
+ * (self.s_verts_batch, source/fitting_habitat.py:93-96) 300 x B times; the index is built once.
+ * h_points: HOST array [m,3], finite values.  Returns after the upload completed. */
+typedef struct psi_nn_index psi_nn_index;
+PSI_API int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_stream_t stream);
+PSI_API void psi_nn_index_destroy(psi_nn_index *ix);
+PSI_API size_t psi_nn_index_bytes(const psi_nn_index *ix);
+/* q [B,n,3] (q_bstride floats between bodies) -> dist, idx [B,n]; idx (original point order) may be NULL. */
+PSI_API int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                       float *dist, int *idx, psi_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Scene SDF lookup.
  * Replaces: the normalise + F.grid_sample(sdf, grid[...,[2,1,0]], padding_mode='border')

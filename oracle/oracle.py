@@ -50,6 +50,8 @@ def lib():
         L.psi_oracle_chamfer_fwd.argtypes = [fp, fp, it, it, it, fp, ip, fp, ip]
         L.psi_oracle_chamfer_bwd.argtypes = [fp, fp, it, it, it, fp, ip, fp, ip, fp, fp]
         L.psi_oracle_sdf_fwd.argtypes = [fp, it, fp, fp, fp, lg, fp, fp]
+        L.psi_oracle_set_threads.argtypes = [it]
+        L.psi_oracle_set_threads.restype = None
         for f in (L.psi_oracle_nn_fwd, L.psi_oracle_chamfer_fwd, L.psi_oracle_chamfer_bwd,
                   L.psi_oracle_sdf_fwd, L.psi_oracle_num_threads, L.psi_oracle_simd_width):
             f.restype = it
@@ -71,6 +73,10 @@ def _f32(a):
 
 def num_threads() -> int:
     return int(lib().psi_oracle_num_threads())
+
+
+def set_threads(n: int) -> None:
+    lib().psi_oracle_set_threads(int(n))
 
 
 def simd_width() -> int:

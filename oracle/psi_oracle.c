@@ -45,6 +45,14 @@ int psi_oracle_num_threads(void) {
 #endif
 }
 
+void psi_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* the reference distance, scalar form (chamfer.cu:31-35 under nvcc's contraction) */
 static inline float ref_dist(float qx, float qy, float qz, float sx, float sy, float sz) {
     float dx = sx - qx, dy = sy - qy, dz = sz - qz;

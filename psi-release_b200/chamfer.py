@@ -122,9 +122,53 @@ class chamferDist(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
+class SceneIndex:
+    """Cluster index over a STATIC scene cloud (psi_nn_index_*): nn_forward / nn_distance against
+    it return exactly what the brute-force kernel returns (same distances, same indices into
+    the ORIGINAL point order), skipping clusters that provably cannot hold the minimum."""
+
+    def __init__(self, points):
+        import ctypes
+        pts = points.detach().to("cpu", torch.float32).contiguous()
+        if pts.dim() != 2 or pts.shape[1] != 3:
+            raise ValueError(f"scene points must be [M,3], got {tuple(pts.shape)}")
+        if not points.is_cuda:
+            raise _lib.PsiError("SceneIndex needs the scene points on a CUDA device")
+        self.points = points.contiguous()          # original order, used by the backward gather
+        self.device = points.device
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().psi_nn_index_create(ctypes.byref(h), _lib.ptr(pts), pts.shape[0], _lib.stream_ptr())
+        _lib.check(rc, "psi_nn_index_create")
+        self.h = h
+
+    def nbytes(self) -> int:
+        return int(_lib.lib().psi_nn_index_bytes(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().psi_nn_index_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 def nn_forward(query, scene):
-    """query [B,N,3]; scene [M,3] (shared by the batch) or [B,M,3] -> dist [B,N], idx [B,N]."""
+    """query [B,N,3]; scene [M,3] (shared by the batch), [B,M,3] or a SceneIndex
+    -> dist [B,N], idx [B,N]."""
     _check_cloud(query, "query")
+    if isinstance(scene, SceneIndex):
+        _lib.require_cuda(query)
+        query = query.contiguous()
+        B, n, _ = query.shape
+        dist = torch.empty(B, n, dtype=torch.float32, device=query.device)
+        idx = torch.empty(B, n, dtype=torch.int32, device=query.device)
+        with torch.cuda.device(query.device):
+            rc = _lib.lib().psi_nn_index_query(scene.h, _lib.ptr(query), n * 3, B, n, _lib.ptr(dist),
+                                               _lib.ptr(idx), _lib.stream_ptr())
+        _lib.check(rc, "psi_nn_index_query")
+        return dist, idx
     _lib.require_cuda(query, scene)
     query = query.contiguous()
     scene = scene.contiguous()
@@ -149,8 +193,13 @@ def nn_forward(query, scene):
 class _NNDistance(Function):
     @staticmethod
     def forward(ctx, query, scene):
-        query, scene = query.contiguous(), scene.contiguous()
-        dist, idx = nn_forward(query, scene)
+        query = query.contiguous()
+        if isinstance(scene, SceneIndex):
+            dist, idx = nn_forward(query, scene)
+            scene = scene.points
+        else:
+            scene = scene.contiguous()
+            dist, idx = nn_forward(query, scene)
         ctx.save_for_backward(query, scene, idx)
         ctx.mark_non_differentiable(idx)
         return dist, idx

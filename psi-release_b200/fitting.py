@@ -113,6 +113,11 @@ class FittingOP:
             self.scene_sdf = sdf_mod.SceneSDF.from_files(self.scene_sdf_path, device=self.device)
             pts = read_scene_vertices(self.scene_verts_path)
         self.s_verts = torch.tensor(np.asarray(pts), dtype=torch.float32, device=self.device).contiguous()
+        # 'index': exact cluster-pruned NN over the static scene (same outputs as 'bruteforce')
+        self.nn_mode = getattr(self, "nn", "index")
+        if self.nn_mode not in ("index", "bruteforce"):
+            raise ValueError("fittingconfig['nn'] must be 'index' or 'bruteforce'")
+        self.s_index = chamfer.SceneIndex(self.s_verts) if self.nn_mode == "index" else None
 
         # --- contact vertex ids, read ONCE (cvae.py:99-115)
         cid = getattr(self, "contact_ids", None)
@@ -151,7 +156,8 @@ class FittingOP:
 
         body_verts = self.body_verts(xh_rec, cam_ext)                        # [B,V,3], scene frame
         contact = body_verts if self._full_contact else body_verts[:, self.contact_ids, :]
-        contact_dist, _ = chamfer.nn_distance(contact.contiguous(), self.s_verts)
+        contact_dist, _ = chamfer.nn_distance(contact.contiguous(),
+                                              self.s_index if self.s_index is not None else self.s_verts)
         s = torch.sqrt(contact_dist + 1e-4)
         loss_contact = self.weight_contact * red(s / (s + self.robust_c))
 

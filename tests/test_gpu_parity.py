@@ -60,6 +60,49 @@ def test_nn_big_variant_and_chunk_merge_bit_exact():
     assert np.array_equal(_bits(d.cpu().numpy()), _bits(d_o))
 
 
+@pytest.mark.parametrize("B,n,m", [(1, 1, 1), (2, 300, 31), (3, 257, 1003), (2, 1000, 5000), (1, 64, 40000)])
+def test_nn_index_is_bit_identical_to_bruteforce_and_oracle(B, n, m):
+    """The cluster-pruned exact NN: same distances, same ORIGINAL indices, ties included."""
+    from psi_release_b200 import chamfer
+    rng = np.random.default_rng(B * 77 + n + m)
+    # surface-like scene (points on box faces) + queries both far from and on top of the surfaces
+    s = rng.uniform(-2, 2, (m, 3)).astype(np.float32)
+    s[: m // 2, 2] = -1.5
+    q = rng.uniform(-2.5, 2.5, (B, n, 3)).astype(np.float32)
+    if m > 40:
+        s[m // 3] = s[7]; s[m - 2] = s[7]          # exact duplicates: lowest original index wins
+        q[:, 0] = s[7]
+        q[:, 1] = 0.5 * (s[3] + s[4])              # equidistant-ish
+    ix = chamfer.SceneIndex(_cuda(s))
+    d, i = chamfer.nn_forward(_cuda(q), ix)
+    d_o, i_o = oracle.nn_fwd(q, s)
+    assert np.array_equal(i.cpu().numpy(), i_o)
+    assert np.array_equal(_bits(d.cpu().numpy()), _bits(d_o))
+    d_b, i_b = chamfer.nn_forward(_cuda(q), _cuda(s))
+    assert torch.equal(i, i_b) and torch.equal(d.view(torch.int32), d_b.view(torch.int32))
+    # gradient path through the index == through the brute force
+    tq = _cuda(q).requires_grad_(True)
+    dd, _ = chamfer.nn_distance(tq, ix)
+    dd.sum().backward()
+    tq2 = _cuda(q).requires_grad_(True)
+    dd2, _ = chamfer.nn_distance(tq2, _cuda(s))
+    dd2.sum().backward()
+    assert torch.equal(tq.grad, tq2.grad)
+
+
+def test_nn_index_grid_aligned_ties():
+    """Scene on a regular lattice and queries at cell centres: many exact ties."""
+    from psi_release_b200 import chamfer
+    g = np.arange(-4, 5, dtype=np.float32) * 0.25
+    s = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(3)
+    s = s[rng.permutation(len(s))].copy()
+    q = (s[:500] + np.float32(0.125))[None]
+    d, i = chamfer.nn_forward(_cuda(q), chamfer.SceneIndex(_cuda(s)))
+    d_o, i_o = oracle.nn_fwd(q, s)
+    assert np.array_equal(i.cpu().numpy(), i_o) and np.array_equal(_bits(d.cpu().numpy()), _bits(d_o))
+
+
 def test_nn_unaligned_scene_pointer_falls_back_to_plain_loads():
     from psi_release_b200 import chamfer
     rng = np.random.default_rng(8)

@@ -62,6 +62,14 @@ def main():
     out["nn_pairs_per_s"] = pairs / (mn * 1e-3)
     out["nn_alg_GBps"] = (B * V * 12 + M * 12 + B * V * 8) / (mn * 1e-3) / 1e9
 
+    ix = chamfer.SceneIndex(pts)
+    med, mn = timeit(lambda: chamfer.nn_forward(verts, ix), flush=flush)
+    out["nn_index_ms"] = med
+    out["nn_index_min_ms"] = mn
+    di, ii = chamfer.nn_forward(verts, ix)
+    db, ib = chamfer.nn_forward(verts, pts)
+    out["nn_index_equal_bruteforce"] = bool(torch.equal(ii, ib) and torch.equal(di.view(torch.int32), db.view(torch.int32)))
+
     med, mn = timeit(lambda: body_model.lbs(betas, pose, h, transl=transl, cam=cam), flush=flush)
     out["lbs_fwd_ms"] = med
     out["lbs_fwd_min_ms"] = mn
