@@ -103,9 +103,12 @@ typedef struct psi_nn_index psi_nn_index;
 PSI_API int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_stream_t stream);
 PSI_API void psi_nn_index_destroy(psi_nn_index *ix);
 PSI_API size_t psi_nn_index_bytes(const psi_nn_index *ix);
-/* q [B,n,3] (q_bstride floats between bodies) -> dist, idx [B,n]; idx (original point order) may be NULL. */
+/* Query j of body b is q[b*q_bstride + 3*(qsel ? qsel[j] : j)]: qsel (device int[n], or NULL)
+ * selects rows of a larger per-body array, e.g. the contact vertices of the body mesh
+ * (body_verts_batch[:, vid, :], source/fitting_habitat.py:135) without a gather pass.
+ * -> dist, idx [B,n]; idx (original point order) may be NULL. */
 PSI_API int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
-                       float *dist, int *idx, psi_stream_t stream);
+                       const int *qsel, float *dist, int *idx, psi_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scene SDF lookup.
@@ -158,21 +161,68 @@ PSI_API size_t psi_lbs_saved_floats(const psi_lbs_model *m, int B);
 
 /* betas [B,NB] (shape+expression), pose [B,J*3] axis-angle (after hand PCA + pose_mean),
  * transl [B,3] or NULL, cam [B,12] rows of a 3x4 rigid transform applied last
- * (cam_bstride floats between bodies, 0 = shared) or NULL.  verts [B,V,3]; joints [B,J,3]
- * (posed joints + transl, camera frame) or NULL; saved: psi_lbs_saved_floats floats. */
+ * (cam_bstride floats between bodies, 0 = shared) or NULL.  rot_in [B,num_rot,9] (or NULL with
+ * num_rot 0): row-major rotation matrices used for joints 0..num_rot-1 INSTEAD of
+ * Rodrigues(pose) -- the fused fitting loop hands VPoser's / the 6D global rotation over
+ * without the matrix -> axis-angle -> matrix round trip (cvae.py:72-80 + lbs.py:165-192).
+ * verts [B,V,3]; joints [B,J,3] (posed joints + transl, camera frame) or NULL;
+ * saved: psi_lbs_saved_floats floats. */
 PSI_API int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
                 const float *transl, const float *cam, long cam_bstride,
+                const float *rot_in, int num_rot,
                 float *verts, float *joints, float *saved, psi_stream_t stream);
 
 /* Given grad_verts [B,V,3] (and grad_joints [B,J,3] or NULL): grad_betas [B,NB],
- * grad_pose [B,J*3], grad_transl [B,3] (may be NULL).  workspace:
+ * grad_pose [B,J*3] (zero for joints < num_rot), grad_transl [B,3] (may be NULL),
+ * grad_rot [B,num_rot,9] = d loss / d rot_in (NULL with num_rot 0).  workspace:
  * psi_lbs_bwd_workspace_bytes bytes. */
 PSI_API size_t psi_lbs_bwd_workspace_bytes(const psi_lbs_model *m, int B);
 PSI_API int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
                 const float *cam, long cam_bstride, const float *saved,
                 const float *grad_verts, const float *grad_joints,
                 float *grad_betas, float *grad_pose, float *grad_transl,
+                float *grad_rot, int num_rot,
                 void *workspace, size_t workspace_bytes, psi_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The fused fitting loop.
+ * Replaces: FittingOP.cal_loss + loss.backward + optimizer.step, i.e. the body of the loop at
+ * source/fitting_habitat.py:177-191 (cal_loss :103-164; Adam :76), for a batch of bodies in one
+ * scene, as 11 kernel launches per iteration replayed from a CUDA graph.  Loss = the SUM over
+ * bodies of the reference's B=1 loss (bodies never interact).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct psi_fit_config {
+    int B;                /* bodies in the batch */
+    int use_graph;        /* capture one iteration into a CUDA graph and replay it */
+    float w_rec, w_vposer, w_contact, w_collision;   /* lossconfig, fitting_habitat.py:261-266 */
+    float robust_c;       /* 1.0 (fitting_habitat.py:141) or 0.01 (fitting_proxe.py:139) */
+    float lr, beta1, beta2, eps;                     /* torch.optim.Adam: init_lr_h, .9, .999, 1e-8 */
+} psi_fit_config;
+
+typedef struct psi_fit_ctx psi_fit_ctx;
+
+/* model/index/scene_points [m,3]/sdf [D,D,D] are borrowed (device objects that must outlive the
+ * context; V,J,NB = the model's sizes).  VPoser decoder weights in the reference's nn.Linear
+ * layout: h_W1 [hidden,latent], h_W2 [hidden,hidden], h_W3 [nbody*6,hidden] (+ biases);
+ * hand PCA components h_hand_l/r [ncomp,45] and pose_mean [J*3] as smplx holds them;
+ * h_contact_ids: the concatenated contact vertex ids (duplicates allowed, cvae.py:105-112). */
+PSI_API int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, int NB,
+                   const psi_nn_index *index, const float *scene_points, const float *sdf, int D,
+                   const float *h_grid_min, const float *h_grid_max,
+                   const float *h_W1, const float *h_b1, const float *h_W2, const float *h_b2,
+                   const float *h_W3, const float *h_b3, int latent, int hidden, int nbody,
+                   const float *h_hand_l, const float *h_hand_r, const float *h_pose_mean, int ncomp,
+                   const int *h_contact_ids, int num_contact, const psi_fit_config *cfg,
+                   psi_stream_t stream);
+PSI_API void psi_fit_destroy(psi_fit_ctx *c);
+/* xhr_init [B,75] = [transl 3 | rot6d 6 | betas 10 | vposer z 32 | lhand 12 | rhand 12]
+ * (GeometryTransformer.convert_to_6D_rot of the generated body, fitting_habitat.py:174-175);
+ * cam [B,12] rows of the 3x4 camera->scene transform (cam_bstride 0 = one for all bodies).
+ * Runs num_iter iterations; xhr_out [B,75] = fitted vector; losses_out [B,4] (may be NULL) =
+ * the four weighted terms of the last evaluated iteration.  Device pointers. */
+PSI_API int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride,
+                int num_iter, float *xhr_out, float *losses_out, psi_stream_t stream);
+PSI_API int psi_fit_launches_per_iteration(void);
 
 #ifdef __cplusplus
 }

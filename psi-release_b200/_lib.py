@@ -16,6 +16,13 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _l = ctypes.c_long
 _sz = ctypes.c_size_t
+_f = ctypes.c_float
+
+
+class FitConfig(ctypes.Structure):
+    """struct psi_fit_config (include/psi_b200.h)."""
+    _fields_ = [("B", _i), ("use_graph", _i), ("w_rec", _f), ("w_vposer", _f), ("w_contact", _f),
+                ("w_collision", _f), ("robust_c", _f), ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f)]
 
 
 class PsiError(RuntimeError):
@@ -50,7 +57,7 @@ def lib():
         "psi_nn_index_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _vp]),
         "psi_nn_index_destroy": (None, [_vp]),
         "psi_nn_index_bytes": (_sz, [_vp]),
-        "psi_nn_index_query": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp]),
+        "psi_nn_index_query": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _vp]),
         "psi_sdf_num_partials": (_i, [_i]),
         "psi_sdf_fwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
         "psi_sdf_bwd": (_i, [_vp, _vp, _l, _vp, _vp]),
@@ -58,9 +65,15 @@ def lib():
         "psi_lbs_model_destroy": (None, [_vp]),
         "psi_lbs_model_bytes": (_sz, [_vp]),
         "psi_lbs_saved_floats": (_sz, [_vp, _i]),
-        "psi_lbs_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp]),
+        "psi_lbs_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _l, _vp, _i, _vp, _vp, _vp, _vp]),
         "psi_lbs_bwd_workspace_bytes": (_sz, [_vp, _i]),
-        "psi_lbs_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+        "psi_lbs_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+        "psi_fit_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i,
+                                ctypes.POINTER(FitConfig), _vp]),
+        "psi_fit_destroy": (None, [_vp]),
+        "psi_fit_run": (_i, [_vp, _vp, _vp, _l, _i, _vp, _vp, _vp]),
+        "psi_fit_launches_per_iteration": (_i, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)      # AttributeError here = header / library mismatch
@@ -76,7 +89,8 @@ EXPORTS = ["psi_abi_version", "psi_error_string", "psi_launch_count", "psi_nn_wo
            "psi_chamfer_fwd", "psi_nn_bwd", "psi_chamfer_bwd", "psi_nn_index_create", "psi_nn_index_destroy",
            "psi_nn_index_bytes", "psi_nn_index_query", "psi_sdf_num_partials", "psi_sdf_fwd",
            "psi_sdf_bwd", "psi_lbs_model_create", "psi_lbs_model_destroy", "psi_lbs_model_bytes",
-           "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd"]
+           "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd",
+           "psi_fit_create", "psi_fit_destroy", "psi_fit_run", "psi_fit_launches_per_iteration"]
 
 
 def check(rc: int, what: str) -> None:

@@ -89,7 +89,7 @@ class _LBS(Function):
         saved = torch.empty(int(L.psi_lbs_saved_floats(handle.h, B)), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = L.psi_lbs_fwd(handle.h, B, _lib.ptr(betas), _lib.ptr(pose), _lib.ptr(transl_c),
-                               _lib.ptr(cam_c), cam_stride, _lib.ptr(verts), _lib.ptr(joints),
+                               _lib.ptr(cam_c), cam_stride, None, 0, _lib.ptr(verts), _lib.ptr(joints),
                                _lib.ptr(saved), _lib.stream_ptr())
         _lib.check(rc, "psi_lbs_fwd")
         ctx.handle = handle
@@ -120,7 +120,7 @@ class _LBS(Function):
         with torch.cuda.device(dev):
             rc = L.psi_lbs_bwd(handle.h, B, _lib.ptr(betas), _lib.ptr(pose), _lib.ptr(cam_c),
                                ctx.cam_stride, _lib.ptr(saved), _lib.ptr(gverts), _lib.ptr(gj),
-                               _lib.ptr(gbetas), _lib.ptr(gpose), _lib.ptr(gtransl), _lib.ptr(ws),
+                               _lib.ptr(gbetas), _lib.ptr(gpose), _lib.ptr(gtransl), None, 0, _lib.ptr(ws),
                                ws.numel() * 4, _lib.stream_ptr())
         _lib.check(rc, "psi_lbs_bwd")
         return gbetas, gpose, gtransl, None, None, None

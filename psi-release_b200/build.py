@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "chamfer.cu", "nn_index.cu", "sdf.cu", "lbs.cu"]
+SOURCES = ["api.cu", "chamfer.cu", "nn_index.cu", "sdf.cu", "lbs.cu", "fit.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

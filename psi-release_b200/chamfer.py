@@ -165,7 +165,7 @@ def nn_forward(query, scene):
         dist = torch.empty(B, n, dtype=torch.float32, device=query.device)
         idx = torch.empty(B, n, dtype=torch.int32, device=query.device)
         with torch.cuda.device(query.device):
-            rc = _lib.lib().psi_nn_index_query(scene.h, _lib.ptr(query), n * 3, B, n, _lib.ptr(dist),
+            rc = _lib.lib().psi_nn_index_query(scene.h, _lib.ptr(query), n * 3, B, n, None, _lib.ptr(dist),
                                                _lib.ptr(idx), _lib.stream_ptr())
         _lib.check(rc, "psi_nn_index_query")
         return dist, idx

@@ -99,10 +99,17 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ Jdirs, const int *__restrict__ parents, int B,
                     const float *__restrict__ betas, const float *__restrict__ pose,
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
-                    float *__restrict__ joints_out) {
+                    float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
     const int b = blockIdx.x, tid = threadIdx.x;
-    for (int j = tid; j < J; j += blockDim.x) rodrigues(pose + ((size_t)b * J + j) * 3, sR + j * 9);
+    for (int j = tid; j < J; j += blockDim.x) {
+        if (j < num_rot) {   // rotation matrices handed over directly (no axis-angle round trip)
+#pragma unroll
+            for (int e = 0; e < 9; ++e) sR[j * 9 + e] = rot_in[((size_t)b * num_rot + j) * 9 + e];
+        } else {
+            rodrigues(pose + ((size_t)b * J + j) * 3, sR + j * 9);
+        }
+    }
     for (int e = tid; e < J * 3; e += blockDim.x) {
         float v = Jt[e];
         for (int l = 0; l < NB; ++l) v = fmaf(Jdirs[(size_t)e * NB + l], betas[(size_t)b * NB + l], v);
@@ -464,7 +471,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     const float *__restrict__ dA, const float *__restrict__ dtr,
                     const float *__restrict__ part, const float *__restrict__ gjoints,
                     float *__restrict__ gbetas, float *__restrict__ gpose,
-                    float *__restrict__ gtransl) {
+                    float *__restrict__ gtransl, float *__restrict__ grot, int num_rot) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
     __shared__ float dbeta_direct[64];
@@ -531,8 +538,15 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
         for (int e = 0; e < 3; ++e) dJ[e] += dGt[e];
     }
     __syncthreads();
-    // Rodrigues backward (lbs.py:177-191)
+    // Rodrigues backward (lbs.py:177-191); joints given as matrices export dR itself
     for (int j = tid; j < J; j += blockDim.x) {
+        float *o = gpose + ((size_t)b * J + j) * 3;
+        if (j < num_rot) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) grot[((size_t)b * num_rot + j) * 9 + e] = dR[j * 9 + e];
+            o[0] = o[1] = o[2] = 0.f;
+            continue;
+        }
         const float *r = pose + ((size_t)b * J + j) * 3;
         const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
         const float a = sqrtf(ex * ex + ey * ey + ez * ez);
@@ -564,7 +578,6 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
             }
         const float dn0 = dK[7] - dK[5], dn1 = dK[2] - dK[6], dn2 = dK[3] - dK[1];
         da += -(dn0 * r[0] + dn1 * r[1] + dn2 * r[2]) / (a * a);
-        float *o = gpose + ((size_t)b * J + j) * 3;
         o[0] = dn0 / a + da * ex / a;
         o[1] = dn1 / a + da * ey / a;
         o[2] = dn2 / a + da * ez / a;
@@ -748,17 +761,18 @@ size_t psi_lbs_saved_floats(const psi_lbs_model *m, int B) {
 }
 
 int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
-                const float *transl, const float *cam, long cam_bstride, float *verts,
-                float *joints, float *saved, psi_stream_t stream) {
+                const float *transl, const float *cam, long cam_bstride, const float *rot_in,
+                int num_rot, float *verts, float *joints, float *saved, psi_stream_t stream) {
     using namespace psi;
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!betas || !pose || !verts || !saved) return PSI_ERR_BAD_ARG;
+    if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !rot_in)) return PSI_ERR_BAD_ARG;
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     lbs_pose_fwd_kernel<<<B, 64, 0, st>>>(m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints);
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot);
     PSI_LAUNCHED();
     if (B % kBG) {
         lbs_zero_coef_pad_kernel<<<8, 256, 0, st>>>(saved + L.coef, B, m->Kpad);
@@ -789,12 +803,14 @@ size_t psi_lbs_bwd_workspace_bytes(const psi_lbs_model *m, int B) {
 int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
                 const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
                 const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
-                void *workspace, size_t workspace_bytes, psi_stream_t stream) {
+                float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
+                psi_stream_t stream) {
     using namespace psi;
     (void)betas;
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!pose || !saved || !grad_verts || !grad_betas || !grad_pose || !workspace) return PSI_ERR_BAD_ARG;
+    if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !grad_rot)) return PSI_ERR_BAD_ARG;
     if (B > 65535) return PSI_ERR_UNSUPPORTED;
     const BwdLayout W = bwd_layout(m, B);
     if (workspace_bytes < W.total * sizeof(float)) return PSI_ERR_WORKSPACE;
@@ -826,7 +842,7 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
     lbs_pose_bwd_kernel<<<B, 64, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
                                           m->parents, pose, saved, L, ws + W.dA, ws + W.dtr,
                                           ws + W.part, grad_joints, grad_betas, grad_pose,
-                                          grad_transl);
+                                          grad_transl, grad_rot, num_rot);
     PSI_LAUNCHED();
     return PSI_OK;
 }

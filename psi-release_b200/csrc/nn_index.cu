@@ -104,7 +104,8 @@ __device__ __forceinline__ unsigned visit_super(const psi_nn_index &ix, const fl
 template <bool SMEM>
 __global__ void __launch_bounds__(kIdxThreads)
 nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q, long q_bstride, int n,
-                      long total, float *__restrict__ dist, int *__restrict__ idx) {
+                      const int *__restrict__ qsel, long total, float *__restrict__ dist,
+                      int *__restrict__ idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float4 *sbox = ix.sbox, *cbox = ix.cbox;
     if (SMEM) {
@@ -120,7 +121,8 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q, long q
     const long warps = (long)gridDim.x * (blockDim.x >> 5);
     for (long t = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += warps) {
         const long b = t / n;
-        const float *qp = q + b * q_bstride + (t - b * n) * 3;
+        const long j = t - b * n;
+        const float *qp = q + b * q_bstride + (qsel ? (long)__ldg(qsel + j) : j) * 3;
         const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
         LaneBest lb;
         lb.d = CUDART_INF_F;
@@ -281,7 +283,7 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
 
 size_t psi_nn_index_bytes(const psi_nn_index *ix) { return ix ? ix->bytes : 0; }
 
-int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n, const int *qsel,
                        float *dist, int *idx, psi_stream_t stream) {
     using namespace psi;
     if (!ix || B < 0 || n < 0) return PSI_ERR_BAD_ARG;
@@ -301,9 +303,9 @@ int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, i
             cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
             attr = true;
         }
-        nn_index_query_kernel<true><<<(unsigned)blocks, kIdxThreads, box_bytes, st>>>(*ix, q, q_bstride, n, total, dist, idx);
+        nn_index_query_kernel<true><<<(unsigned)blocks, kIdxThreads, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx);
     } else {
-        nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, total, dist, idx);
+        nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx);
     }
     PSI_LAUNCHED();
     return PSI_OK;

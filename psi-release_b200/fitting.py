@@ -126,6 +126,22 @@ class FittingOP:
         self.contact_ids = torch.as_tensor(np.asarray(cid), dtype=torch.long, device=self.device)
         self._full_contact = bool(self.contact_ids.numel() == self.body_mesh_model.handle(self.device).V and
                                   torch.equal(self.contact_ids, torch.arange(self.contact_ids.numel(), device=self.device)))
+        # 'fused': the whole iteration in libpsi_b200 (psi_fit_run, 11 launches/iteration);
+        # 'autograd': torch autograd over the psi ops (any loss_mode, any nn mode)
+        self.engine = getattr(self, "engine", "fused" if (self.loss_mode == "independent" and
+                                                          self.nn_mode == "index") else "autograd")
+        if self.engine not in ("fused", "autograd"):
+            raise ValueError("fittingconfig['engine'] must be 'fused' or 'autograd'")
+        self._fused = None
+        if self.engine == "fused":
+            if self.loss_mode != "independent" or self.nn_mode != "index":
+                raise ValueError("engine='fused' needs loss_mode='independent' and nn='index'")
+            from .fused import FusedFit
+            lossw = {k: getattr(self, k) for k in ("weight_loss_rec", "weight_loss_vposer", "weight_contact",
+                                                   "weight_collision")}
+            self._fused = FusedFit(B, self.body_mesh_model.handle(self.device), self.body_mesh_model,
+                                   self.s_index, self.scene_sdf, self.vposer, self.contact_ids.cpu().numpy(),
+                                   lossw, self.robust_c, self.init_lr_h, use_graph=self.use_cuda_graph)
         self._graph = None
         self._static_xhr = None
         self._static_cam = None
@@ -205,6 +221,12 @@ class FittingOP:
         with torch.cuda.device(self.device):
             xhr = GeometryTransformer.convert_to_6D_rot(xh)
             self._xhr_init, self._cam_init, self._cam_shape = xhr, cam_ext, tuple(cam_ext.shape)
+            if self._fused is not None:
+                fitted, losses = self._fused.run(xhr, cam_ext, num_iter)
+                with torch.no_grad():
+                    self.xhr_rec.copy_(fitted)
+                self.last_losses = losses.sum(dim=0)
+                return GeometryTransformer.convert_to_3D_rot(fitted)
             if self.use_cuda_graph:
                 if self._graph is None or self._static_cam.shape != cam_ext.shape:
                     self._build_graph()

@@ -73,16 +73,43 @@ def test_fit_matches_cpu_fit_loop_and_graph_equals_eager(small_model):
 
 def test_independent_mode_is_shard_invariant(small_model):
     """Fitting bodies [0:4] together == fitting [0:2] and [2:4] separately: the property that
-    lets the batch be sharded over GPUs with no collective in the loop.  The psi kernels are
-    batch-size invariant bit for bit; the torch/cuBLAS VPoser MLP in front of them picks
-    batch-dependent GEMM tilings, hence a (tight) tolerance instead of torch.equal."""
+    lets the batch be sharded over GPUs with no collective in the loop."""
     from psi_release_b200.fitting import FittingOP
     scene, xh, cid, cfg = _world(small_model, 4)
     cam = torch.tensor(scene.cam_ext).unsqueeze(0).cuda()
     full = FittingOP(dict(cfg, batch_size=4), W).fit(torch.tensor(xh).cuda(), cam)
     lo = FittingOP(dict(cfg, batch_size=2), W).fit(torch.tensor(xh[:2]).cuda(), cam)
     hi = FittingOP(dict(cfg, batch_size=2), W).fit(torch.tensor(xh[2:]).cuda(), cam)
-    assert float((full - torch.cat([lo, hi])).abs().max()) < 1e-4
+    # fused engine: every kernel is per-body deterministic -> bit-identical whatever the batch split
+    assert torch.equal(full, torch.cat([lo, hi]))
+    # autograd engine: the torch/cuBLAS VPoser MLP picks batch-dependent tilings -> tight tolerance
+    a_full = FittingOP(dict(cfg, batch_size=4, engine="autograd"), W).fit(torch.tensor(xh).cuda(), cam)
+    a_lo = FittingOP(dict(cfg, batch_size=2, engine="autograd"), W).fit(torch.tensor(xh[:2]).cuda(), cam)
+    assert float((a_full[:2] - a_lo).abs().max()) < 1e-4
+
+
+def test_fused_engine_matches_autograd_engine_and_cpu_loop(small_model):
+    """psi_fit_run (11 launches/iteration) vs torch autograd over the psi ops vs the CPU restatement.
+    The fused path hands rotation matrices to LBS instead of the reference's matrix -> axis-angle ->
+    Rodrigues round trip (identity on SO(3) up to rounding), hence tolerances, not equality."""
+    from psi_release_b200.fitting import FittingOP
+    for contact in ("parts", "full"):
+        scene, xh, cid, cfg = _world(small_model, 3, contact)
+        cam = torch.tensor(scene.cam_ext).unsqueeze(0)
+        fused = FittingOP(dict(cfg, engine="fused", num_iter=6), W)
+        auto = FittingOP(dict(cfg, engine="autograd", num_iter=6), W)
+        # one iteration: the Adam step is lr*sign(g) -> any sign disagreement shows up as 0.2
+        f1 = fused.fit(torch.tensor(xh).cuda(), cam.cuda(), num_iter=1)
+        a1 = auto.fit(torch.tensor(xh).cuda(), cam.cuda(), num_iter=1)
+        assert float((f1 - a1).abs().max()) < 2e-3
+        ff = fused.fit(torch.tensor(xh).cuda(), cam.cuda())
+        aa = auto.fit(torch.tensor(xh).cuda(), cam.cuda())
+        assert float((ff - aa).abs().max()) < 2e-2
+        ref = oracle.fit_loop(torch.tensor(xh), cam.expand(3, -1, -1), 6, 0.1, loss_mode="independent",
+                              **_oracle_kw(small_model, scene, cid))
+        assert float((ff.cpu() - ref).abs().max()) < 2e-2
+        # loss values of the last iteration agree with the autograd engine's
+        np.testing.assert_allclose(fused.last_losses.cpu().numpy(), auto.last_losses.cpu().numpy(), rtol=2e-2, atol=1e-4)
 
 
 def test_reference_style_single_body_pickle_flow(small_model, tmp_path):
