@@ -37,6 +37,8 @@ struct psi_fit_ctx {
     int *nni, *step;
     size_t lbs_ws_bytes;
     cudaGraphExec_t exec;
+    cudaStream_t gstream;          // graphs cannot be captured on the legacy default stream
+    cudaEvent_t ev_in, ev_out;
     std::vector<void *> owned;
 };
 
@@ -392,6 +394,9 @@ extern "C" {
 void psi_fit_destroy(psi_fit_ctx *c) {
     if (!c) return;
     if (c->exec) cudaGraphExecDestroy(c->exec);
+    if (c->gstream) cudaStreamDestroy(c->gstream);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
     for (void *p : c->owned) cudaFree(p);
     delete c;
 }
@@ -418,7 +423,13 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->model = model; c->index = index; c->cfg = *cfg;
     c->B = cfg->B; c->V = V; c->J = J; c->NB = NB; c->latent = latent; c->hidden = hidden; c->nbody = nbody;
     c->ncomp = ncomp; c->num_rot = nbody + 1; c->D = D; c->sdf = sdf; c->scene_pts = scene_points;
-    c->num_contact = num_contact; c->exec = nullptr;
+    c->num_contact = num_contact; c->exec = nullptr; c->gstream = nullptr; c->ev_in = c->ev_out = nullptr;
+    if (cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        psi_fit_destroy(c);
+        return PSI_ERR_ALLOC;
+    }
     for (int a = 0; a < 3; ++a) { c->gmin[a] = h_grid_min[a]; c->gmax[a] = h_grid_max[a]; }
     c->np_sdf = psi_sdf_num_partials(V);
     c->nchunk = (V + 255) / 256;
@@ -502,30 +513,37 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
     if (c->cfg.use_graph && cs == cudaStreamCaptureStatusNone && num_iter > 1) {
+        // the loop runs on the context's own stream, ordered after / before the caller's stream
+        cudaStream_t gs = c->gstream;
+        e = cudaEventRecord(c->ev_in, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(gs, c->ev_in, 0);
+        if (e != cudaSuccess) return (int)e;
         if (!c->exec) {
-            // warm the lazily-initialised pieces outside the capture (results are overwritten below)
-            int rc = enqueue_iteration(c, st);
+            // warm the lazily-initialised pieces outside the capture (state is reset below)
+            int rc = enqueue_iteration(c, gs);
             if (rc) return rc;
             cudaGraph_t graph = nullptr;
-            e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal);
             if (e != cudaSuccess) return (int)e;
-            rc = enqueue_iteration(c, st);
-            e = cudaStreamEndCapture(st, &graph);
+            rc = enqueue_iteration(c, gs);
+            e = cudaStreamEndCapture(gs, &graph);
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (e != cudaSuccess) return (int)e;
             e = cudaGraphInstantiate(&c->exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return (int)e;
-            // undo the warm-up iteration
-            e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, gs);
             if (e != cudaSuccess) return (int)e;
-            fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B);
+            fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gs>>>(c->am, c->av, c->step, (long)n, c->B);
             PSI_LAUNCHED();
         }
         for (int it = 0; it < num_iter; ++it) {
-            e = cudaGraphLaunch(c->exec, st);
+            e = cudaGraphLaunch(c->exec, gs);
             if (e != cudaSuccess) return (int)e;
         }
+        e = cudaEventRecord(c->ev_out, gs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_out, 0);
+        if (e != cudaSuccess) return (int)e;
     } else {
         for (int it = 0; it < num_iter; ++it) {
             const int rc = enqueue_iteration(c, st);
