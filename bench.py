@@ -61,7 +61,7 @@ def workload_config(args, n_gpus):
     return {"workload": "configs[1]: batch=%d bodies/GPU, 1 scene, %d-vert body, %d^3 SDF, %d-pt scene, "
                         "%d Adam iterations, full-body contact" % (args.batch, NUM_VERTS, SDF_DIM, NUM_POINTS, args.iters),
             "bodies_per_gpu": args.batch, "global_bodies": args.batch * n_gpus, "iterations": args.iters,
-            "optimizer": "adam lr=0.1", "nn": "one direction (body->scene), brute force, bit-exact",
+            "optimizer": "adam lr=0.1", "nn": "one direction (body->scene), %s, bit-exact" % ("exact cluster index" if args.nn == "index" else "brute force"),
             "loss_mode": "independent", "parallelism": "dp%d (bodies sharded, no data-path collective)" % n_gpus,
             "l2": "flushed between timed steps (256 MiB write)"}
 
@@ -177,11 +177,14 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         op.fit(xh_dev, cam_dev)
     # kernels launched per captured iteration (the graph replays them `iters` times per step)
-    c0 = L.psi_launch_count()
-    op.use_cuda_graph = False
-    op.fit(xh_dev, cam_dev, num_iter=1)
-    per_iter = int(L.psi_launch_count() - c0)
-    op.use_cuda_graph = True
+    if op.engine == "fused":
+        per_iter = int(L.psi_fit_launches_per_iteration())
+    else:
+        c0 = L.psi_launch_count()
+        op.use_cuda_graph = False
+        op.fit(xh_dev, cam_dev, num_iter=1)
+        per_iter = int(L.psi_launch_count() - c0)
+        op.use_cuda_graph = True
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -194,21 +197,40 @@ def run_ours(args):
     all_fitted = gather_rows(fitted, args.batch * world) if world > 1 else fitted
     assert all_fitted.shape == (args.batch * world, 72) and torch.isfinite(all_fitted).all()
 
-    # dominant kernel, timed alone with CUDA events on its launching stream (L2 flushed)
+    # the psi kernels of one iteration, each timed ALONE with CUDA events on its launching stream
+    # (10 launches, L2 flushed in between); the slowest one carries `roofline`
+    from psi_release_b200 import body_model as bm, sdf as sdf_mod
     verts = op.body_verts(xh_dev, cam_dev).detach().contiguous()
-    for _ in range(3):
-        chamfer.nn_forward(verts, op.s_verts)
-    ks = []
-    for _ in range(10):
-        flush.zero_()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        chamfer.nn_forward(verts, op.s_verts)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ks.append(e0.elapsed_time(e1))
-    nn_ms = float(np.mean(ks))
+    h = op.body_mesh_model.handle(dev)
+    rng = np.random.default_rng(0)
+    betas = torch.tensor(rng.standard_normal((args.batch, 20)).astype(np.float32), device=dev)
+    pose = torch.tensor((rng.standard_normal((args.batch, 165)) * 0.3).astype(np.float32), device=dev)
+    bq, pq = betas.clone().requires_grad_(True), pose.clone().requires_grad_(True)
+    vq, _ = bm.lbs(bq, pq, h, cam=cam_dev)
+    gq = torch.randn_like(vq)
+
+    def alone(fn):
+        for _ in range(3):
+            fn()
+        ks = []
+        for _ in range(10):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ks.append(e0.elapsed_time(e1))
+        return float(np.mean(ks))
+
+    nn_target = op.s_index if op.s_index is not None else op.s_verts
+    kernel_ms = {
+        "nn": alone(lambda: chamfer.nn_forward(verts, nn_target)),
+        "lbs_fwd": alone(lambda: bm.lbs(betas, pose, h, cam=cam_dev)),
+        "lbs_bwd": alone(lambda: torch.autograd.grad(vq, (bq, pq), gq, retain_graph=True)),
+        "sdf": alone(lambda: sdf_mod.sdf_forward(op.scene_sdf, verts, want_grad=True, want_partials=True)),
+    }
 
     if rank != 0:
         if world > 1:
@@ -219,10 +241,45 @@ def run_ours(args):
     e2e = bodies / (ms_e2e * 1e-3)
     hbm_peak, peak_src = peaks()
     B = args.batch
-    alg_bytes = (B * NUM_VERTS + NUM_POINTS) * 12 + B * NUM_VERTS * 8       # 809.5 kB/body at B=1
     pairs = B * NUM_VERTS * NUM_POINTS
     sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    model_bytes = h.nbytes()
+    # algorithmic bytes per launch (SURVEY.md 8(d) per-body figures x B)
+    alg = {
+        "nn": (B * NUM_VERTS * 12 + B * NUM_VERTS * 8 + NUM_POINTS * 12),
+        "lbs_fwd": model_bytes + B * (740 + NUM_VERTS * 12),
+        "lbs_bwd": model_bytes + B * (NUM_VERTS * 24 + 740),
+        "sdf": B * NUM_VERTS * (32 + 12 + 4 + 12),
+    }
+    names = {"nn": ("psi::nn_index_query_kernel<true> (exact cluster-pruned NN)" if op.s_index is not None
+                    else "psi::nn_fwd_kernel<8,16,256,1024,2> (brute-force NN)"),
+             "lbs_fwd": "psi::lbs_pose_fwd_kernel + psi::lbs_vertex_fwd_kernel",
+             "lbs_bwd": "psi::lbs_vertex_bwd/dA/dcoef/pose_bwd kernels", "sdf": "psi::sdf_fwd_kernel"}
+    top = max(kernel_ms, key=kernel_ms.get)
+    step_ms = ms_dev / args.steps
+
+    def roof(k):
+        ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
+        return {"kernel": names[k], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "peak_source": peak_src, "traffic": None, "launch_ms": kernel_ms[k],
+                "algorithmic_bytes_per_launch": alg[k],
+                "share_of_step": kernel_ms[k] * args.iters / step_ms}
+
+    roofline = roof(top)
+    roofline["timed"] = "alone, 10 launches, CUDA events on the launching stream, L2 flushed"
+    roofline["others"] = {k: roof(k) for k in kernel_ms if k != top}
+    if op.s_index is None:
+        roofline["fp32"] = {"bound": "fp32 issue", "achieved": pairs * 8 / (kernel_ms["nn"] * 1e-3) / 1e12,
+                            "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": pairs * 8 / (kernel_ms["nn"] * 1e-3) / 1e12 / fp32_peak,
+                            "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm (no measured FP32 peak)",
+                            "pairs_per_s": pairs / (kernel_ms["nn"] * 1e-3)}
+    else:
+        roofline["note"] = ("the pruned NN evaluates ~2 of 1563 clusters per query: its cost is a chain of "
+                            "dependent L2 reads, neither HBM- nor tensor-bound; brute-force equivalent rate = "
+                            "%.3g pair/s" % (pairs / (kernel_ms["nn"] * 1e-3)))
+    roofline["lbs_fwd_fp32_frac"] = 49.3e6 * B / (kernel_ms["lbs_fwd"] * 1e-3) / 1e12 / fp32_peak
     out = {
         "metric": METRIC, "value": value, "unit": "bodies/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -235,18 +292,8 @@ def run_ours(args):
         "gpu_launches": per_iter * args.iters * args.steps * world,
         "gpu_launches_per_iteration": per_iter,
         "clocks": clocks,
-        "roofline": {
-            "kernel": "psi::nn_fwd_kernel<8,16,256,1024,2> (Chamfer/NN forward, %d of every %d ms of a step)"
-                      % (round(nn_ms * args.iters), round(ms_dev / args.steps)),
-            "bound": "hbm", "achieved": alg_bytes / (nn_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / (nn_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
-            "traffic": None, "launch_ms": nn_ms, "timed": "alone, 10 launches, CUDA events, L2 flushed",
-            "share_of_step": nn_ms * args.iters / (ms_dev / args.steps),
-            "note": "brute-force NN is FP32-issue bound (5200 flop/B, SURVEY 8(d)): see fp32",
-            "fp32": {"bound": "fp32 issue", "achieved": pairs * 8 / (nn_ms * 1e-3) / 1e12,
-                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": pairs * 8 / (nn_ms * 1e-3) / 1e12 / fp32_peak,
-                     "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm (no measured FP32 peak)",
-                     "pairs_per_s": pairs / (nn_ms * 1e-3)}},
+        "roofline": roofline,
+        "engine": op.engine,
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, seconds=args.cpu_baseline_seconds)
