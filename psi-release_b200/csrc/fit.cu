@@ -27,7 +27,7 @@ struct psi_fit_ctx {
     psi_fit_config cfg;
     int B, V, J, NB, latent, hidden, nbody, ncomp, num_rot, nu, num_contact, D, np_sdf, nchunk;
     // constants
-    float *W1, *W1T, *b1, *W2, *W2T, *b2, *W3, *W3T, *b3, *hand_l, *hand_r, *pose_mean, *cweight;
+    float *W1, *W1T, *b1, *W2, *W2T, *b2, *W3, *W3T, *W3Tp, *b3, *hand_l, *hand_r, *pose_mean, *cweight;
     int *csel, *cslot;
     const float *sdf, *scene_pts;
     float gmin[3], gmax[3];
@@ -100,6 +100,10 @@ __device__ void gs_bwd(const float *x6, const float *dR, float *dx6) {
 struct FitDims {
     int B, V, J, NB, latent, hidden, nbody, ncomp, num_rot;
 };
+
+}  // namespace psi
+#include "fit_mlp.cuh"
+namespace psi {
 
 // x layout [75]: t3 | 6D | betas10 | z32 | lh12 | rh12   (cvae.py:28-33 after convert_to_6D_rot)
 __global__ void __launch_bounds__(256)
@@ -355,7 +359,7 @@ __global__ void fit_cam_kernel(const float *cam, long stride, int B, float *out)
 
 static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     const FitDims d = {c->B, c->V, c->J, c->NB, c->latent, c->hidden, c->nbody, c->ncomp, c->num_rot};
-    fit_prologue_kernel<<<c->B, 256, 0, st>>>(d, c->x0, c->x, c->W1T, c->b1, c->W2T, c->b2, c->W3T, c->b3,
+    fit_prologue2_kernel<<<c->B, kMlpThreads, sizeof(MlpSmem), st>>>(d, c->x0, c->x, c->W1T, c->b1, c->W2T, c->b2, c->W3Tp, c->b3,
                                               c->hand_l, c->hand_r, c->pose_mean, c->cfg.w_rec,
                                               c->cfg.w_vposer, c->rot, c->pose, c->shape, c->transl,
                                               c->h1pre, c->h2pre, c->o6, c->losses);
@@ -379,7 +383,7 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     rc = psi_lbs_bwd(c->model, c->B, c->shape, c->pose, c->cam, 12, c->saved, c->gverts, nullptr, c->gshape,
                      c->gpose, c->gtransl, c->grot, c->num_rot, c->lbs_ws, c->lbs_ws_bytes, st);
     if (rc) return rc;
-    fit_epilogue_kernel<<<c->B, 256, 0, st>>>(d, c->cfg, c->np_sdf, c->nchunk, c->num_contact, c->x0, c->x,
+    fit_epilogue2_kernel<<<c->B, kMlpThreads, sizeof(MlpSmem), st>>>(d, c->cfg, c->np_sdf, c->nchunk, c->num_contact, c->x0, c->x,
                                               c->am, c->av, c->step, c->W1, c->W2, c->W3, c->hand_l,
                                               c->hand_r, c->h1pre, c->h2pre, c->o6, c->grot, c->gpose,
                                               c->gshape, c->gtransl, c->partial, c->cpart, c->losses);
@@ -414,7 +418,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         !h_W2 || !h_b2 || !h_W3 || !h_b3 || !h_hand_l || !h_hand_r || !h_pose_mean || !h_contact_ids || !cfg)
         return PSI_ERR_BAD_ARG;
     if (cfg->B < 1 || num_contact < 1 || D < 1 || V < 1) return PSI_ERR_BAD_ARG;
-    if (hidden != 512 || latent > 32 || latent < 1 || nbody * 6 > 128 || nbody + 1 > J || ncomp > 16 ||
+    if (hidden != 512 || latent != 32 || nbody * 6 > 128 || nbody + 1 > J || ncomp > 16 ||
         J < 31 || NB < 10 || hidden % 32)
         return PSI_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -474,6 +478,15 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
                                         std::vector<float>(h_pose_mean, h_pose_mean + (size_t)J * 3)};
     c->W1 = upload_f(W1); c->W2 = upload_f(W2); c->W3 = upload_f(W3);
     c->W1T = upload_f(W1T); c->W2T = upload_f(W2T); c->W3T = upload_f(W3T);
+    {   // output layer transposed and padded to 128 columns (16-byte aligned rows for the bulk copies)
+        std::vector<float> W3Tp((size_t)H * 128, 0.f);
+        for (int o = 0; o < NO; ++o) for (int i = 0; i < H; ++i) W3Tp[(size_t)i * 128 + o] = W3[(size_t)o * H + i];
+        c->W3Tp = upload_f(W3Tp);
+        if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;   // W3Tp dies here
+    }
+    if (cudaFuncSetAttribute(fit_prologue2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(fit_epilogue2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem)) != cudaSuccess)
+        rc = PSI_ERR_UNSUPPORTED;
     c->b1 = upload_f(keep_alive[0]); c->b2 = upload_f(keep_alive[1]); c->b3 = upload_f(keep_alive[2]);
     c->hand_l = upload_f(keep_alive[3]); c->hand_r = upload_f(keep_alive[4]); c->pose_mean = upload_f(keep_alive[5]);
     c->cweight = upload_f(cweight); c->csel = upload_i(csel); c->cslot = upload_i(cslot);

@@ -35,15 +35,22 @@
 namespace psi {
 
 constexpr int kMaxJ = 64;
-constexpr int kKT = 32;         // basis rows per pipeline stage
+constexpr int kKT = 16;         // basis rows per pipeline stage
 constexpr int kTileN = 96;      // basis columns per CTA = 32 vertices
-constexpr int kBG = 32;         // bodies per CTA (2 warps x 16)
+constexpr int kBG = 64;         // bodies per CTA (4 warps x 16)
 constexpr int kStages = 3;
 constexpr int kNSplit = 41;     // dcoef split of the N reduction (Npad/32 chunks / 41)
 
 }  // namespace psi
 
+struct psi_lbs_tree {          // kinematic tree by levels (root = level 0) + children lists (device)
+    int nlev;
+    const int *lvl_start, *lvl_joint, *child_start, *child_list;
+};
+
 struct psi_lbs_model {
+    psi_lbs_tree tree;
+    int *tree_buf;
     int V, J, NB, P, K, Kpad, Npad, KW;
     long nnz;
     float *basis, *v_template, *Jt, *Jdirs, *skin_w, *jl_w;
@@ -94,12 +101,13 @@ __device__ __forceinline__ void rodrigues(const float *r, float *R) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt,
                     const float *__restrict__ Jdirs, const int *__restrict__ parents, int B,
                     const float *__restrict__ betas, const float *__restrict__ pose,
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
-                    float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot) {
+                    float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
+                    const psi_lbs_tree tree) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int j = tid; j < J; j += blockDim.x) {
@@ -116,10 +124,15 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
         sJ[e] = v;
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int e = 0; e < 9; ++e) sGr[e] = sR[e];
-        for (int e = 0; e < 3; ++e) sGt[e] = sJ[e];
-        for (int j = 1; j < J; ++j) {
+    // kinematic chain, one tree level at a time (joints of a level are independent)
+    for (int l = 0; l < tree.nlev; ++l) {
+        for (int q = tree.lvl_start[l] + tid; q < tree.lvl_start[l + 1]; q += blockDim.x) {
+            const int j = tree.lvl_joint[q];
+            if (j == 0) {
+                for (int e = 0; e < 9; ++e) sGr[e] = sR[e];
+                for (int e = 0; e < 3; ++e) sGt[e] = sJ[e];
+                continue;
+            }
             const int p = parents[j];
             const float *Gp = sGr + p * 9, *Rj = sR + j * 9;
             float rel[3] = {sJ[j * 3] - sJ[p * 3], sJ[j * 3 + 1] - sJ[p * 3 + 1],
@@ -134,8 +147,8 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     Gp[r * 3] * rel[0] + Gp[r * 3 + 1] * rel[1] + Gp[r * 3 + 2] * rel[2] + sGt[p * 3 + r];
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
     float *oR = saved + L.R + (size_t)b * J * 9, *oJ = saved + L.Jr + (size_t)b * J * 3;
     float *oGr = saved + L.Gr + (size_t)b * J * 9, *oGt = saved + L.Gt + (size_t)b * J * 3;
     float *oA = saved + L.A + (size_t)b * J * 12;
@@ -192,7 +205,7 @@ struct VertexFwdParams {
     int V, J, Kpad, Npad, KW, B;
 };
 
-__global__ void __launch_bounds__(64, 6) lbs_vertex_fwd_kernel(const VertexFwdParams p) {
+__global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sm = reinterpret_cast<float *>(smem_raw);
     constexpr int kStageFloats = kKT * kTileN + kKT * kBG;  // 4096 floats = 16 KB
@@ -219,10 +232,11 @@ __global__ void __launch_bounds__(64, 6) lbs_vertex_fwd_kernel(const VertexFwdPa
             tma_load_1d(dstC, coef_g + (size_t)chunk * kKT * kBG, kKT * kBG * 4, &full[st]);
         }
         __syncwarp();
-        // lane l moves basis row (chunk*32 + l): 96 contiguous floats
-        tma_load_1d(dstB + lane * kTileN,
-                    p.basis + (size_t)(chunk * kKT + lane) * p.Npad + (size_t)tile * kTileN,
-                    kTileN * 4, &full[st]);
+        // lane l < kKT moves basis row (chunk*kKT + l): 96 contiguous floats
+        if (lane < kKT)
+            tma_load_1d(dstB + lane * kTileN,
+                        p.basis + (size_t)(chunk * kKT + lane) * p.Npad + (size_t)tile * kTileN,
+                        kTileN * 4, &full[st]);
     };
 
     if (w == 0) {
@@ -238,11 +252,11 @@ __global__ void __launch_bounds__(64, 6) lbs_vertex_fwd_kernel(const VertexFwdPa
         const int st = c % kStages;
         mbar_wait(&full[st], (uint32_t)((c / kStages) & 1));
         const float *bs = sm + st * kStageFloats + 3 * lane;
-        const float4 *cs = reinterpret_cast<const float4 *>(sm + st * kStageFloats + kKT * kTileN) + 4 * w;
+        const float4 *cs = reinterpret_cast<const float4 *>(sm + st * kStageFloats + kKT * kTileN) + 4 * w;  // [kk][64 bodies]
 #pragma unroll 4
         for (int kk = 0; kk < kKT; ++kk) {
             const float b0 = bs[kk * kTileN], b1 = bs[kk * kTileN + 1], b2 = bs[kk * kTileN + 2];
-            const float4 c0 = cs[kk * 8 + 0], c1 = cs[kk * 8 + 1], c2 = cs[kk * 8 + 2], c3 = cs[kk * 8 + 3];
+            const float4 c0 = cs[kk * (kBG / 4) + 0], c1 = cs[kk * (kBG / 4) + 1], c2 = cs[kk * (kBG / 4) + 2], c3 = cs[kk * (kBG / 4) + 3];
             const float cf[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w,
                                   c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
 #pragma unroll
@@ -464,15 +478,16 @@ lbs_dcoef_kernel(int Kpad, int Npad, int B, int Bpad, const float *__restrict__ 
 }
 
 // per body: reduce the d coef partials, run the chain and Rodrigues backward
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     const float *__restrict__ Jdirs, const int *__restrict__ parents,
                     const float *__restrict__ pose, const float *__restrict__ saved, SavedLayout L,
                     const float *__restrict__ dA, const float *__restrict__ dtr,
                     const float *__restrict__ part, const float *__restrict__ gjoints,
                     float *__restrict__ gbetas, float *__restrict__ gpose,
-                    float *__restrict__ gtransl, float *__restrict__ grot, int num_rot) {
-    __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9];
+                    float *__restrict__ gtransl, float *__restrict__ grot, int num_rot,
+                    const psi_lbs_tree tree) {
+    __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], drel_s[kMaxJ * 3];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
     __shared__ float dbeta_direct[64];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -504,40 +519,54 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
             dJ[j * 3 + c] = -(sGr[j * 9 + c] * at[0] + sGr[j * 9 + 3 + c] * at[1] + sGr[j * 9 + 6 + c] * at[2]);
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int j = J - 1; j >= 1; --j) {
-            const int p = parents[j];
-            const float *Rj = sR + j * 9, *Gp = sGr + p * 9;
-            const float rel[3] = {sJ[j * 3] - sJ[p * 3], sJ[j * 3 + 1] - sJ[p * 3 + 1], sJ[j * 3 + 2] - sJ[p * 3 + 2]};
-            float g[9], gt[3];
+    // chain backward, deepest tree level first.  A joint first PULLS from its children (fixed
+    // child order: deterministic, race free), then finishes its own dR / d rel.
+    for (int l = tree.nlev - 1; l >= 0; --l) {
+        for (int q = tree.lvl_start[l] + tid; q < tree.lvl_start[l + 1]; q += blockDim.x) {
+            const int j = tree.lvl_joint[q];
+            float g[9], gt[3], dj[3];
 #pragma unroll
             for (int e = 0; e < 9; ++e) g[e] = dGr[j * 9 + e];
 #pragma unroll
-            for (int e = 0; e < 3; ++e) gt[e] = dGt[j * 3 + e];
+            for (int e = 0; e < 3; ++e) { gt[e] = dGt[j * 3 + e]; dj[e] = dJ[j * 3 + e]; }
+            for (int ci = tree.child_start[j]; ci < tree.child_start[j + 1]; ++ci) {
+                const int c = tree.child_list[ci];
+                const float *Rc = sR + c * 9, *gc = dGr + c * 9, *gtc = dGt + c * 3;
+                const float rel[3] = {sJ[c * 3] - sJ[j * 3], sJ[c * 3 + 1] - sJ[j * 3 + 1], sJ[c * 3 + 2] - sJ[j * 3 + 2]};
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+                for (int r = 0; r < 3; ++r) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    // dGr[p] += dGr[j] Rj^T + dGt[j] rel^T
-                    dGr[p * 9 + r * 3 + c] += g[r * 3] * Rj[c * 3] + g[r * 3 + 1] * Rj[c * 3 + 1] +
-                                              g[r * 3 + 2] * Rj[c * 3 + 2] + gt[r] * rel[c];
-                    // dR[j] += Gp^T dGr[j]
-                    dR[j * 9 + r * 3 + c] += Gp[r] * g[c] + Gp[3 + r] * g[3 + c] + Gp[6 + r] * g[6 + c];
+                    for (int cc = 0; cc < 3; ++cc)   // dGr[j] += dGr[c] Rc^T + dGt[c] rel^T
+                        g[r * 3 + cc] += gc[r * 3] * Rc[cc * 3] + gc[r * 3 + 1] * Rc[cc * 3 + 1] +
+                                         gc[r * 3 + 2] * Rc[cc * 3 + 2] + gtc[r] * rel[cc];
+                    gt[r] += gtc[r];
+                    dj[r] -= drel_s[c * 3 + r];
                 }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float drel = Gp[r] * gt[0] + Gp[3 + r] * gt[1] + Gp[6 + r] * gt[2];
-                dJ[j * 3 + r] += drel;
-                dJ[p * 3 + r] -= drel;
-                dGt[p * 3 + r] += gt[r];
             }
+#pragma unroll
+            for (int e = 0; e < 9; ++e) dGr[j * 9 + e] = g[e];
+            if (j == 0) {
+#pragma unroll
+                for (int e = 0; e < 9; ++e) dR[e] += g[e];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) dj[e] += gt[e];
+            } else {
+                const float *Gp = sGr + parents[j] * 9;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)   // dR[j] += Gp^T dGr[j]
+                        dR[j * 9 + r * 3 + cc] += Gp[r] * g[cc] + Gp[3 + r] * g[3 + cc] + Gp[6 + r] * g[6 + cc];
+                    const float drel = Gp[r] * gt[0] + Gp[3 + r] * gt[1] + Gp[6 + r] * gt[2];
+                    drel_s[j * 3 + r] = drel;
+                    dj[r] += drel;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) { dGt[j * 3 + e] = gt[e]; dJ[j * 3 + e] = dj[e]; }
         }
-#pragma unroll
-        for (int e = 0; e < 9; ++e) dR[e] += dGr[e];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) dJ[e] += dGt[e];
+        __syncthreads();
     }
-    __syncthreads();
     // Rodrigues backward (lbs.py:177-191); joints given as matrices export dR itself
     for (int j = tid; j < J; j += blockDim.x) {
         float *o = gpose + ((size_t)b * J + j) * 3;
@@ -635,7 +664,7 @@ void psi_lbs_model_destroy(psi_lbs_model *m) {
     if (!m) return;
     cudaFree(m->basis); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
     cudaFree(m->skin_w); cudaFree(m->jl_w); cudaFree(m->skin_j); cudaFree(m->parents);
-    cudaFree(m->jl_start); cudaFree(m->jl_vert);
+    cudaFree(m->jl_start); cudaFree(m->jl_vert); cudaFree(m->tree_buf);
     delete m;
 }
 
@@ -729,6 +758,21 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
         }
     std::vector<int> parents(h_parents, h_parents + J);
     parents[0] = -1;
+    // tree levels and children lists, packed: [lvl_start (J+1) | lvl_joint (J) | child_start (J+1) | child_list (J)]
+    std::vector<int> level(J, 0), treebuf((size_t)4 * J + 2, 0);
+    int nlev = 1;
+    for (int j = 1; j < J; ++j) { level[j] = level[parents[j]] + 1; nlev = level[j] + 1 > nlev ? level[j] + 1 : nlev; }
+    {
+        int *lvl_start = treebuf.data(), *lvl_joint = lvl_start + J + 1, *child_start = lvl_joint + J, *child_list = child_start + J + 1;
+        for (int j = 0; j < J; ++j) ++lvl_start[level[j] + 1];
+        for (int l = 0; l < J; ++l) lvl_start[l + 1] += lvl_start[l];
+        std::vector<int> fillp(lvl_start, lvl_start + J);
+        for (int j = 0; j < J; ++j) lvl_joint[fillp[level[j]]++] = j;
+        for (int j = 1; j < J; ++j) ++child_start[parents[j] + 1];
+        for (int j = 0; j < J; ++j) child_start[j + 1] += child_start[j];
+        std::vector<int> fillc(child_start, child_start + J);
+        for (int j = 1; j < J; ++j) child_list[fillc[parents[j]]++] = j;
+    }
 
     int rc = PSI_OK;
     if (rc == PSI_OK) rc = upload(&m->basis, basis, st, &m->bytes);
@@ -741,6 +785,14 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     if (rc == PSI_OK) rc = upload(&m->jl_start, jl_start, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->jl_vert, jl_vert, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->jl_w, jl_w, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->tree_buf, treebuf, st, &m->bytes);
+    if (rc == PSI_OK) {
+        m->tree.nlev = nlev;
+        m->tree.lvl_start = m->tree_buf;
+        m->tree.lvl_joint = m->tree_buf + J + 1;
+        m->tree.child_start = m->tree_buf + 2 * J + 1;
+        m->tree.child_list = m->tree_buf + 3 * J + 2;
+    }
     if (rc == PSI_OK) {
         cudaError_t e = cudaStreamSynchronize(st);   // host vectors die with this scope
         if (e != cudaSuccess) rc = (int)e;
@@ -771,8 +823,8 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
-    lbs_pose_fwd_kernel<<<B, 64, 0, st>>>(m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot);
+    lbs_pose_fwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, m->tree);
     PSI_LAUNCHED();
     if (B % kBG) {
         lbs_zero_coef_pad_kernel<<<8, 256, 0, st>>>(saved + L.coef, B, m->Kpad);
@@ -790,7 +842,7 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
         attr_set = true;
     }
     dim3 grid((unsigned)(m->Npad / kTileN), (unsigned)((B + kBG - 1) / kBG));
-    lbs_vertex_fwd_kernel<<<grid, 64, smem, st>>>(p);
+    lbs_vertex_fwd_kernel<<<grid, 128, smem, st>>>(p);
     PSI_LAUNCHED();
     return PSI_OK;
 }
@@ -839,10 +891,10 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
                                                ws + W.part, cps);
         PSI_LAUNCHED();
     }
-    lbs_pose_bwd_kernel<<<B, 64, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
+    lbs_pose_bwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
                                           m->parents, pose, saved, L, ws + W.dA, ws + W.dtr,
                                           ws + W.part, grad_joints, grad_betas, grad_pose,
-                                          grad_transl, grad_rot, num_rot);
+                                          grad_transl, grad_rot, num_rot, m->tree);
     PSI_LAUNCHED();
     return PSI_OK;
 }

@@ -38,8 +38,8 @@ constexpr int kIdxThreads = 512;
 struct psi_nn_index {
     int m, num_clusters, num_supers, spad, rounds;
     float4 *pts;    // [num_supers*8*32] (x,y,z,orig index bits); pads = +inf / INT_MAX
-    float4 *cbox;   // [num_supers*8][2] lo,hi ; pad clusters lo=hi=+inf
-    float4 *sbox;   // [spad][2], spad = rounds*32
+    float4 *cbox;   // [2][num_supers*8]: every lo, then every hi ; pad clusters lo=hi=+inf
+    float4 *sbox;   // [2][spad], spad = rounds*32
     size_t bytes;
 };
 
@@ -81,8 +81,8 @@ __device__ __forceinline__ unsigned visit_super(const psi_nn_index &ix, const fl
     unsigned clb = 0x7f800000u;
     if (lane < kFan) {
         const int c = s * kFan + lane;
-        const float4 lo = SMEM ? cbox[c * 2] : __ldg(cbox + (size_t)c * 2);
-        const float4 hi = SMEM ? cbox[c * 2 + 1] : __ldg(cbox + (size_t)c * 2 + 1);
+        const float4 lo = SMEM ? cbox[c] : __ldg(cbox + c);                       // SoA: all lo, then all hi
+        const float4 hi = SMEM ? cbox[ix.num_clusters + c] : __ldg(cbox + ix.num_clusters + c);
         clb = __float_as_uint(box_lb(lo, hi, qx, qy, qz));
     }
     int skip = -1;
@@ -136,8 +136,8 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q, long q
             slb[r] = 0x7f800000u;
             if (r < ix.rounds) {
                 const int s = r * 32 + lane;
-                const float4 lo = SMEM ? sbox[s * 2] : __ldg(sbox + (size_t)s * 2);
-                const float4 hi = SMEM ? sbox[s * 2 + 1] : __ldg(sbox + (size_t)s * 2 + 1);
+                const float4 lo = SMEM ? sbox[s] : __ldg(sbox + s);
+                const float4 hi = SMEM ? sbox[ix.spad + s] : __ldg(sbox + ix.spad + s);
                 slb[r] = __float_as_uint(box_lb(lo, hi, qx, qy, qz));
                 const unsigned mn = __reduce_min_sync(0xffffffffu, slb[r]);
                 if (mn < best_lb) {
@@ -255,9 +255,9 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
         }
         if (!any) { l = make_float4(inf, inf, inf, 0.f); h = l; }   // empty: bound = +inf, never admitted
     };
-    for (size_t c = 0; c < ncl; ++c) box_of(c * kLeaf, kLeaf, cbox[c * 2], cbox[c * 2 + 1]);
+    for (size_t c = 0; c < ncl; ++c) box_of(c * kLeaf, kLeaf, cbox[c], cbox[ncl + c]);
     for (int s = 0; s < ix->spad; ++s)
-        box_of((size_t)s * kLeaf * kFan, s < num_supers ? (size_t)kLeaf * kFan : 0, sbox[(size_t)s * 2], sbox[(size_t)s * 2 + 1]);
+        box_of((size_t)s * kLeaf * kFan, s < num_supers ? (size_t)kLeaf * kFan : 0, sbox[(size_t)s], sbox[(size_t)ix->spad + s]);
     ix->bytes = 0;
     auto up = [&](float4 **dst, const std::vector<float4> &h) -> int {
         const size_t nb = h.size() * sizeof(float4);
