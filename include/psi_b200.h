@@ -109,6 +109,11 @@ PSI_API size_t psi_nn_index_bytes(const psi_nn_index *ix);
  * -> dist, idx [B,n]; idx (original point order) may be NULL. */
 PSI_API int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
                        const int *qsel, float *dist, int *idx, psi_stream_t stream);
+/* Same, with a per-query HINT buffer (device int[B*n], in/out): on entry the cluster that held the
+ * query's nearest neighbour last time (or -1), on exit this call's.  It only seeds the pruning
+ * bound (that cluster is visited first) -- results are identical with any hint contents. */
+PSI_API int psi_nn_index_query_hint(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                            const int *qsel, float *dist, int *idx, int *hint, psi_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scene SDF lookup.

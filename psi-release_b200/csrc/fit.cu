@@ -34,7 +34,7 @@ struct psi_fit_ctx {
     // state + scratch
     float *x0, *x, *am, *av, *cam, *rot, *pose, *shape, *transl, *h1pre, *h2pre, *o6, *verts, *saved,
         *sdfv, *sdfg, *partial, *nnd, *gverts, *cpart, *gshape, *gpose, *grot, *gtransl, *lbs_ws, *losses;
-    int *nni, *step;
+    int *nni, *step, *nnhint;
     size_t lbs_ws_bytes;
     cudaGraphExec_t exec;
     cudaStream_t gstream;          // graphs cannot be captured on the legacy default stream
@@ -367,7 +367,8 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     int rc = psi_lbs_fwd(c->model, c->B, c->shape, c->pose, c->transl, c->cam, 12, c->rot, c->num_rot,
                          c->verts, nullptr, c->saved, st);
     if (rc) return rc;
-    rc = psi_nn_index_query(c->index, c->verts, (long)c->V * 3, c->B, c->nu, c->csel, c->nnd, c->nni, st);
+    rc = psi_nn_index_query_hint(c->index, c->verts, (long)c->V * 3, c->B, c->nu, c->csel, c->nnd, c->nni,
+                                 c->nnhint, st);
     if (rc) return rc;
     rc = psi_sdf_fwd(c->sdf, 1, c->D, c->gmin, c->gmax, c->verts, c->B, c->V, nullptr, c->sdfv, c->sdfg,
                      c->partial, st);
@@ -497,7 +498,8 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->transl = fbuf(B * 3); c->h1pre = fbuf(B * H); c->h2pre = fbuf(B * H); c->o6 = fbuf(B * NO);
     c->verts = fbuf(B * V * 3); c->saved = fbuf(psi_lbs_saved_floats(model, c->B) + 64);
     c->sdfv = fbuf(B * V); c->sdfg = fbuf(B * V * 3); c->partial = fbuf(B * c->np_sdf * 2);
-    c->nnd = fbuf(B * c->nu); c->nni = (int *)dev_alloc(B * c->nu * sizeof(int)); c->gverts = fbuf(B * V * 3);
+    c->nnd = fbuf(B * c->nu); c->nni = (int *)dev_alloc(B * c->nu * sizeof(int));
+    c->nnhint = (int *)dev_alloc(B * c->nu * sizeof(int)); c->gverts = fbuf(B * V * 3);
     c->cpart = fbuf(B * c->nchunk); c->gshape = fbuf(B * NB); c->gpose = fbuf(B * J * 3);
     c->grot = fbuf(B * c->num_rot * 9); c->gtransl = fbuf(B * 3); c->losses = fbuf(B * 4);
     c->step = (int *)dev_alloc(B * sizeof(int));
@@ -517,6 +519,8 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
     const size_t xd = 9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp, n = (size_t)c->B * xd;
     cudaError_t e = cudaMemcpyAsync(c->x0, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(c->nnhint, 0xff, (size_t)c->B * c->nu * sizeof(int), st);   // -1: no hint yet
     if (e != cudaSuccess) return (int)e;
     // one [3x4] transform per body (stride 0 broadcasts a shared one)
     fit_cam_kernel<<<(unsigned)((c->B * 12 + 255) / 256), 256, 0, st>>>(cam, cam_bstride, c->B, c->cam);

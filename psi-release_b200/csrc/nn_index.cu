@@ -1,172 +1,208 @@
-// Exact nearest neighbour against a STATIC scene through a two-level box index.
+// Exact nearest neighbour against a STATIC scene through a three-level box index.
 //
 // Same contract as psi_nn_fwd with a shared scene (chamfer_pytorch/chamfer.cu:12-134 semantics:
 // d = fma(dz,dz,fma(dx,dx,rn(dy*dy))), lowest ORIGINAL index wins ties) -- the outputs are
 // bit-identical to the brute-force kernel; only provably irrelevant pair evaluations are skipped.
 //
-// Index (built once per scene on the host): a balanced kd bisection (longest axis, sizes kept
-// multiples of the leaf) orders the points so that every 32 consecutive points form a compact
-// CLUSTER and every 8 consecutive clusters a compact SUPER-cluster, each with an axis-aligned box.
+// Index (built once per scene on the host): a balanced kd bisection (longest axis, part sizes kept
+// multiples of the level below) orders the points so that 32 consecutive points form a compact
+// CLUSTER, 8 clusters a SUPER (256 points), 8 supers a MEGA (2048 points); every node has an
+// axis-aligned box.  Boxes are stored SoA (all lo, then all hi) and live in shared memory.
 //
 // Why it is exact.  For a query q and a box [lo,hi], g_a = max(fl(lo_a-q_a), fl(q_a-hi_a), 0)
 // satisfies g_a <= |fl(s_a-q_a)| for every point s in the box (rounding is monotone), and
 // fma(gz,gz,fma(gx,gx,rn(gy*gy))) is monotone in |g|, so lb(q,box) <= d(q,s) IN FLOATING POINT for
-// every s in the box.  A box is skipped only if lb > ub where ub is a distance already seen, so every
-// skipped point has d > final minimum and cannot win or tie.  Visited points are compared
-// lexicographically on (d, original index).
+// every s in the box.  A box is skipped only if lb > ub where ub is the distance of a point
+// already evaluated, so every skipped point has d > final minimum and cannot win or tie.
+// Visited points are compared lexicographically on (d, original index).
 //
-// Execution: one warp per query, boxes resident in shared memory (6 kB + 50 kB at 50 000 points).
-// Lanes evaluate 32 super boxes per round (bounds kept in registers), then for every admitted
-// super its 8 cluster boxes, then the 32 points of an admitted cluster with ONE coalesced 512-byte
-// load; the running upper bound is a warp-wide redux.sync.min on the distance bits (d >= 0, so the
-// IEEE pattern is monotone).  A best-first seed (nearest super, its nearest cluster) tightens the
-// bound before the ordered sweep.
+// Execution: one warp per query.  A 32-lane round evaluates 32 mega boxes, or the 8 children of
+// up to 4 admitted parents at once (lane = parent slot*8 + child); an admitted cluster is ONE
+// coalesced 512-byte load, one point per lane; the running bound is a warp-wide redux.sync.min on
+// the distance bits (d >= 0: the IEEE pattern is monotone).  The bound is seeded either
+// best-first (nearest mega -> super -> cluster) or from a HINT: the cluster that held the
+// nearest neighbour of the same query in the previous fitting iteration (bodies move little per
+// Adam step), which is just another visited cluster, so exactness does not depend on it.
 #include "common.cuh"
 #include <algorithm>
 #include <math.h>
 #include <math_constants.h>
 #include <new>
+#include <stdlib.h>
 #include <vector>
 
 namespace psi {
-constexpr int kLeaf = 32;        // points per cluster (one per lane)
-constexpr int kFan = 8;          // clusters per super-cluster
-constexpr int kMaxRounds = 16;   // super bounds kept in registers: up to 16*32 supers = 131 072 points
+constexpr int kLeaf = 32;         // points per cluster (one per lane)
+constexpr int kFan = 8;           // children per super / mega
+constexpr int kMaxMegaRounds = 8; // mega bounds kept in registers: 8*32 megas = 524 288 points
 constexpr int kIdxThreads = 512;
+constexpr size_t kIdxSmemMax = 72 * 1024;
 }  // namespace psi
 
 struct psi_nn_index {
-    int m, num_clusters, num_supers, spad, rounds;
-    float4 *pts;    // [num_supers*8*32] (x,y,z,orig index bits); pads = +inf / INT_MAX
-    float4 *cbox;   // [2][num_supers*8]: every lo, then every hi ; pad clusters lo=hi=+inf
-    float4 *sbox;   // [2][spad], spad = rounds*32
+    int m, num_megas, num_supers, num_clusters, mpad, rounds;
+    float4 *pts;    // [num_clusters*32] (x,y,z,orig index bits); pads = +inf / INT_MAX
+    float4 *boxes;  // SoA: [lo: mega(mpad) | super | cluster][hi: same]; empty nodes lo=hi=+inf
+    int *pos_of;    // sorted position of every original point (index -> cluster, for the hint)
+    int nbox;       // mpad + num_supers + num_clusters
     size_t bytes;
 };
 
 namespace psi {
 
-__device__ __forceinline__ float box_lb(const float4 lo, const float4 hi, float qx, float qy, float qz) {
+__device__ __forceinline__ unsigned box_lb(const float4 lo, const float4 hi, float qx, float qy, float qz) {
     const float gx = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
     const float gy = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
     const float gz = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
-    return __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+    return __float_as_uint(__fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy))));
 }
 
-struct LaneBest {
-    float d;
-    int i;
+struct Query {
+    float x, y, z;
+    float bd;        // lane-local best distance
+    int bi;          // ... and its original index
+    unsigned ub;     // warp-uniform bound (bits of a distance already seen)
+    int lane;
 };
 
-// all lanes: the 32 points of cluster c -> lane-local best; returns the tightened bound
-__device__ __forceinline__ unsigned visit_cluster(const float4 *__restrict__ pts, int c, int lane,
-                                                  float qx, float qy, float qz, LaneBest &lb,
-                                                  unsigned ub_bits) {
-    const float4 p = __ldg(pts + (size_t)c * kLeaf + lane);
-    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
-    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-    const int oi = __float_as_int(p.w);
-    if (d < lb.d || (d == lb.d && oi < lb.i)) {
-        lb.d = d;
-        lb.i = oi;
-    }
-    return min(ub_bits, __reduce_min_sync(0xffffffffu, __float_as_uint(d)));
+template <bool SMEM>
+__device__ __forceinline__ unsigned node_lb(const psi_nn_index &ix, const float4 *boxes, int node,
+                                            const Query &q) {
+    const float4 lo = SMEM ? boxes[node] : __ldg(boxes + node);
+    const float4 hi = SMEM ? boxes[ix.nbox + node] : __ldg(boxes + ix.nbox + node);
+    return box_lb(lo, hi, q.x, q.y, q.z);
 }
 
-// all lanes: the clusters of super s that the bound admits (lanes 0..7 hold one cluster box each).
-// seed: visit the nearest cluster first.  `done` = a cluster already visited (or -1).
+// all lanes: the 32 points of cluster c
+__device__ __forceinline__ void visit_cluster(const float4 *__restrict__ pts, int c, Query &q) {
+    const float4 p = __ldg(pts + (size_t)c * kLeaf + q.lane);
+    const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const int oi = __float_as_int(p.w);
+    if (d < q.bd || (d == q.bd && oi < q.bi)) {
+        q.bd = d;
+        q.bi = oi;
+    }
+    q.ub = min(q.ub, __reduce_min_sync(0xffffffffu, __float_as_uint(d)));
+}
+
+// take up to 4 set bits out of a warp-uniform mask; lane group g = lane/8 gets the g-th one (or -1)
+__device__ __forceinline__ int take4(unsigned &mask, int lane) {
+    int pos[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pos[k] = __ffs(mask) - 1;          // -1 when the mask is empty
+        mask &= mask - (mask != 0);
+    }
+    const int g = lane >> 3;
+    return g == 0 ? pos[0] : (g == 1 ? pos[1] : (g == 2 ? pos[2] : pos[3]));
+}
+
+// Expand admitted supers (bits of `smask` over lanes holding `my_super`) into clusters and visit.
 template <bool SMEM>
-__device__ __forceinline__ unsigned visit_super(const psi_nn_index &ix, const float4 *cbox, int s,
-                                                int lane, float qx, float qy, float qz, LaneBest &lb,
-                                                unsigned ub_bits, bool seed) {
-    unsigned clb = 0x7f800000u;
-    if (lane < kFan) {
-        const int c = s * kFan + lane;
-        const float4 lo = SMEM ? cbox[c] : __ldg(cbox + c);                       // SoA: all lo, then all hi
-        const float4 hi = SMEM ? cbox[ix.num_clusters + c] : __ldg(cbox + ix.num_clusters + c);
-        clb = __float_as_uint(box_lb(lo, hi, qx, qy, qz));
+__device__ __forceinline__ void sweep_supers(const psi_nn_index &ix, const float4 *boxes, unsigned smask,
+                                             unsigned slb, int my_super, int skip_cluster, Query &q) {
+    const int cbase = ix.mpad + ix.num_supers;
+    while (smask) {
+        const int src = take4(smask, q.lane);                       // lane that holds my parent super
+        const int sid = __shfl_sync(0xffffffffu, my_super, src < 0 ? 0 : src);
+        const int cid = sid * kFan + (q.lane & 7);
+        unsigned clb = 0x7f800000u;
+        if (src >= 0) clb = node_lb<SMEM>(ix, boxes, cbase + cid, q);
+        unsigned cmask = __ballot_sync(0xffffffffu, clb <= q.ub && cid != skip_cluster && src >= 0);
+        while (cmask) {
+            const int cl = __ffs(cmask) - 1;
+            cmask &= cmask - 1;
+            visit_cluster(ix.pts, __shfl_sync(0xffffffffu, cid, cl), q);
+            cmask &= __ballot_sync(0xffffffffu, clb <= q.ub);       // the bound may have tightened
+        }
+        smask &= __ballot_sync(0xffffffffu, slb <= q.ub);
     }
-    int skip = -1;
-    if (seed) {
-        const unsigned mn = __reduce_min_sync(0xffffffffu, clb);
-        skip = __ffs(__ballot_sync(0xffffffffu, clb == mn)) - 1;
-        ub_bits = visit_cluster(ix.pts, s * kFan + skip, lane, qx, qy, qz, lb, ub_bits);
-    }
-    unsigned mask = __ballot_sync(0xffffffffu, clb <= ub_bits && lane != skip && lane < kFan);
-    while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        ub_bits = visit_cluster(ix.pts, s * kFan + k, lane, qx, qy, qz, lb, ub_bits);
-        mask &= __ballot_sync(0xffffffffu, clb <= ub_bits);   // the bound may have tightened
-    }
-    return ub_bits;
 }
 
 template <bool SMEM>
 __global__ void __launch_bounds__(kIdxThreads)
-nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q, long q_bstride, int n,
+nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q_in, long q_bstride, int n,
                       const int *__restrict__ qsel, long total, float *__restrict__ dist,
-                      int *__restrict__ idx) {
+                      int *__restrict__ idx, int *__restrict__ hint) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const float4 *sbox = ix.sbox, *cbox = ix.cbox;
+    const float4 *boxes = ix.boxes;
     if (SMEM) {
         float4 *s4 = reinterpret_cast<float4 *>(smem_raw);
-        const int ns = ix.spad * 2, nc = ix.num_supers * kFan * 2;
-        for (int i = threadIdx.x; i < ns; i += blockDim.x) s4[i] = __ldg(ix.sbox + i);
-        for (int i = threadIdx.x; i < nc; i += blockDim.x) s4[ns + i] = __ldg(ix.cbox + i);
+        for (int i = threadIdx.x; i < 2 * ix.nbox; i += blockDim.x) s4[i] = __ldg(ix.boxes + i);
         __syncthreads();
-        sbox = s4;
-        cbox = s4 + ns;
+        boxes = s4;
     }
     const int lane = threadIdx.x & 31;
     const long warps = (long)gridDim.x * (blockDim.x >> 5);
     for (long t = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += warps) {
         const long b = t / n;
         const long j = t - b * n;
-        const float *qp = q + b * q_bstride + (qsel ? (long)__ldg(qsel + j) : j) * 3;
-        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-        LaneBest lb;
-        lb.d = CUDART_INF_F;
-        lb.i = 0x7fffffff;
-        // level 1: every super-cluster bound, 32 per round, kept in registers
-        unsigned slb[kMaxRounds];
-        unsigned best_lb = 0xffffffffu;
-        int s0 = 0;
+        const float *qp = q_in + b * q_bstride + (qsel ? (long)__ldg(qsel + j) : j) * 3;
+        Query q;
+        q.x = __ldg(qp); q.y = __ldg(qp + 1); q.z = __ldg(qp + 2);
+        q.bd = CUDART_INF_F;
+        q.bi = 0x7fffffff;
+        q.ub = 0x7f800000u;
+        q.lane = lane;
+        // level 0: every mega bound (32 per round), kept in registers
+        unsigned mlb[kMaxMegaRounds];
 #pragma unroll
-        for (int r = 0; r < kMaxRounds; ++r) {
-            slb[r] = 0x7f800000u;
-            if (r < ix.rounds) {
-                const int s = r * 32 + lane;
-                const float4 lo = SMEM ? sbox[s] : __ldg(sbox + s);
-                const float4 hi = SMEM ? sbox[ix.spad + s] : __ldg(sbox + ix.spad + s);
-                slb[r] = __float_as_uint(box_lb(lo, hi, qx, qy, qz));
-                const unsigned mn = __reduce_min_sync(0xffffffffu, slb[r]);
-                if (mn < best_lb) {
-                    best_lb = mn;
-                    s0 = r * 32 + __ffs(__ballot_sync(0xffffffffu, slb[r] == mn)) - 1;
-                }
-            }
+        for (int r = 0; r < kMaxMegaRounds; ++r) {
+            mlb[r] = 0x7f800000u;
+            if (r < ix.rounds) mlb[r] = node_lb<SMEM>(ix, boxes, r * 32 + lane, q);
         }
-        // seed, then the ordered sweep over the admitted supers
-        unsigned ub = visit_super<SMEM>(ix, cbox, s0, lane, qx, qy, qz, lb, 0x7f800000u, true);
+        // seed the bound
+        int seeded;
+        const int h = hint ? hint[t] : -1;
+        if (h >= 0 && h < ix.num_clusters) {
+            seeded = h;                                             // last iteration's winning cluster
+        } else {                                                    // best-first descent
+            unsigned best = 0xffffffffu;
+            int m0 = 0;
 #pragma unroll
-        for (int r = 0; r < kMaxRounds; ++r) {
+            for (int r = 0; r < kMaxMegaRounds; ++r)
+                if (r < ix.rounds) {
+                    const unsigned mn = __reduce_min_sync(0xffffffffu, mlb[r]);
+                    if (mn < best) {
+                        best = mn;
+                        m0 = r * 32 + __ffs(__ballot_sync(0xffffffffu, mlb[r] == mn)) - 1;
+                    }
+                }
+            unsigned lb8 = 0x7f800000u;
+            if (lane < kFan) lb8 = node_lb<SMEM>(ix, boxes, ix.mpad + m0 * kFan + lane, q);
+            unsigned mn = __reduce_min_sync(0xffffffffu, lb8);
+            const int s0 = m0 * kFan + __ffs(__ballot_sync(0xffffffffu, lb8 == mn)) - 1;
+            lb8 = 0x7f800000u;
+            if (lane < kFan) lb8 = node_lb<SMEM>(ix, boxes, ix.mpad + ix.num_supers + s0 * kFan + lane, q);
+            mn = __reduce_min_sync(0xffffffffu, lb8);
+            seeded = s0 * kFan + __ffs(__ballot_sync(0xffffffffu, lb8 == mn)) - 1;
+        }
+        visit_cluster(ix.pts, seeded, q);
+        // sweep: megas -> supers -> clusters, 4 parents per 32-lane round
+#pragma unroll
+        for (int r = 0; r < kMaxMegaRounds; ++r) {
             if (r < ix.rounds) {
-                unsigned mask = __ballot_sync(0xffffffffu, slb[r] <= ub && (r * 32 + lane) != s0);
-                while (mask) {
-                    const int k = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    ub = visit_super<SMEM>(ix, cbox, r * 32 + k, lane, qx, qy, qz, lb, ub, false);
-                    mask &= __ballot_sync(0xffffffffu, slb[r] <= ub);
+                unsigned mmask = __ballot_sync(0xffffffffu, mlb[r] <= q.ub);
+                while (mmask) {
+                    const int src = take4(mmask, lane);
+                    const int my_super = (r * 32 + (src < 0 ? 0 : src)) * kFan + (lane & 7);
+                    unsigned slb = 0x7f800000u;
+                    if (src >= 0) slb = node_lb<SMEM>(ix, boxes, ix.mpad + my_super, q);
+                    const unsigned smask = __ballot_sync(0xffffffffu, slb <= q.ub && src >= 0);
+                    sweep_supers<SMEM>(ix, boxes, smask, slb, my_super, seeded, q);
+                    mmask &= __ballot_sync(0xffffffffu, mlb[r] <= q.ub);
                 }
             }
         }
         // lexicographic (d, original index) minimum over the lanes
-        const unsigned dmin = __reduce_min_sync(0xffffffffu, __float_as_uint(lb.d));
-        const unsigned imin = __reduce_min_sync(
-            0xffffffffu, (__float_as_uint(lb.d) == dmin) ? (unsigned)lb.i : 0x7fffffffu);
+        const unsigned dmin = __reduce_min_sync(0xffffffffu, __float_as_uint(q.bd));
+        const bool win = __float_as_uint(q.bd) == dmin;
+        const unsigned imin = __reduce_min_sync(0xffffffffu, win ? (unsigned)q.bi : 0x7fffffffu);
         if (lane == 0) {
             dist[t] = __uint_as_float(dmin);
             if (idx) idx[t] = (int)imin;
+            if (hint) hint[t] = (imin < (unsigned)ix.m) ? __ldg(ix.pos_of + imin) / kLeaf : -1;
         }
     }
 }
@@ -200,8 +236,8 @@ extern "C" {
 void psi_nn_index_destroy(psi_nn_index *ix) {
     if (!ix) return;
     cudaFree(ix->pts);
-    cudaFree(ix->cbox);
-    cudaFree(ix->sbox);
+    cudaFree(ix->boxes);
+    cudaFree(ix->pos_of);
     delete ix;
 }
 
@@ -213,29 +249,32 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
         const float v = h_points[i];
         if (!(v == v) || v == HUGE_VALF || v == -HUGE_VALF) return PSI_ERR_BAD_ARG;  // finite only
     }
-    const int num_supers = (m + kLeaf * kFan - 1) / (kLeaf * kFan);
-    const int rounds = (num_supers + 31) / 32;
-    if (rounds > kMaxRounds) return PSI_ERR_UNSUPPORTED;
+    const int mega_pts = kLeaf * kFan * kFan, super_pts = kLeaf * kFan;
+    const int num_megas = (m + mega_pts - 1) / mega_pts;
+    const int rounds = (num_megas + 31) / 32;
+    if (rounds > kMaxMegaRounds) return PSI_ERR_UNSUPPORTED;
     std::vector<int> ids((size_t)m);
     for (int i = 0; i < m; ++i) ids[i] = i;
-    kd_order(h_points, ids.data(), m, kLeaf * kFan);                       // supers
-    for (int s = 0; s < num_supers; ++s) {                                  // clusters inside a super
-        const int b = s * kLeaf * kFan, e = std::min(m, b + kLeaf * kFan);
-        kd_order(h_points, ids.data() + b, e - b, kLeaf);
-    }
+    kd_order(h_points, ids.data(), m, mega_pts);
+    for (int b = 0; b < m; b += mega_pts) kd_order(h_points, ids.data() + b, std::min(mega_pts, m - b), super_pts);
+    for (int b = 0; b < m; b += super_pts) kd_order(h_points, ids.data() + b, std::min(super_pts, m - b), kLeaf);
     psi_nn_index *ix = new (std::nothrow) psi_nn_index();
     if (!ix) return PSI_ERR_ALLOC;
+    ix->pts = nullptr; ix->boxes = nullptr; ix->pos_of = nullptr;
     ix->m = m;
-    ix->num_supers = num_supers;
-    ix->num_clusters = num_supers * kFan;
+    ix->num_megas = num_megas;
     ix->rounds = rounds;
-    ix->spad = rounds * 32;
-    const size_t ncl = (size_t)ix->num_clusters;
+    ix->mpad = rounds * 32;
+    ix->num_supers = num_megas * kFan;
+    ix->num_clusters = ix->num_supers * kFan;
+    ix->nbox = ix->mpad + ix->num_supers + ix->num_clusters;
     const float inf = HUGE_VALF;
-    std::vector<float4> pts(ncl * kLeaf), cbox(ncl * 2), sbox((size_t)ix->spad * 2);
+    std::vector<float4> pts((size_t)ix->num_clusters * kLeaf), boxes((size_t)2 * ix->nbox);
+    std::vector<int> pos_of((size_t)m);
     for (size_t i = 0; i < pts.size(); ++i) {
         if (i < (size_t)m) {
             const int oi = ids[i];
+            pos_of[oi] = (int)i;
             pts[i] = make_float4(h_points[(size_t)oi * 3], h_points[(size_t)oi * 3 + 1], h_points[(size_t)oi * 3 + 2], 0.f);
             reinterpret_cast<int &>(pts[i].w) = oi;
         } else {
@@ -243,9 +282,8 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
             reinterpret_cast<int &>(pts[i].w) = 0x7fffffff;
         }
     }
-    auto box_of = [&](size_t first, size_t count, float4 &l, float4 &h) {
-        l = make_float4(inf, inf, inf, 0.f);
-        h = make_float4(-inf, -inf, -inf, 0.f);
+    auto box_of = [&](size_t first, size_t count, int node) {
+        float4 l = make_float4(inf, inf, inf, 0.f), h = make_float4(-inf, -inf, -inf, 0.f);
         bool any = false;
         for (size_t i = first; i < first + count && i < (size_t)m; ++i) {
             const float4 &p = pts[i];
@@ -254,25 +292,24 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
             any = true;
         }
         if (!any) { l = make_float4(inf, inf, inf, 0.f); h = l; }   // empty: bound = +inf, never admitted
+        boxes[node] = l;
+        boxes[(size_t)ix->nbox + node] = h;
     };
-    for (size_t c = 0; c < ncl; ++c) box_of(c * kLeaf, kLeaf, cbox[c], cbox[ncl + c]);
-    for (int s = 0; s < ix->spad; ++s)
-        box_of((size_t)s * kLeaf * kFan, s < num_supers ? (size_t)kLeaf * kFan : 0, sbox[(size_t)s], sbox[(size_t)ix->spad + s]);
+    for (int g = 0; g < ix->mpad; ++g) box_of((size_t)g * mega_pts, g < num_megas ? mega_pts : 0, g);
+    for (int s = 0; s < ix->num_supers; ++s) box_of((size_t)s * super_pts, super_pts, ix->mpad + s);
+    for (int c = 0; c < ix->num_clusters; ++c) box_of((size_t)c * kLeaf, kLeaf, ix->mpad + ix->num_supers + c);
     ix->bytes = 0;
-    auto up = [&](float4 **dst, const std::vector<float4> &h) -> int {
-        const size_t nb = h.size() * sizeof(float4);
-        if (cudaMalloc((void **)dst, nb) != cudaSuccess) return PSI_ERR_ALLOC;
-        cudaError_t e = cudaMemcpyAsync(*dst, h.data(), nb, cudaMemcpyHostToDevice, st);
+    int rc = PSI_OK;
+    auto up = [&](void **dst, const void *src, size_t nb) {
+        if (rc != PSI_OK) return;
+        if (cudaMalloc(dst, nb) != cudaSuccess) { rc = PSI_ERR_ALLOC; return; }
+        if (cudaMemcpyAsync(*dst, src, nb, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = PSI_ERR_ALLOC;
         ix->bytes += nb;
-        return e == cudaSuccess ? PSI_OK : (int)e;
     };
-    int rc = up(&ix->pts, pts);
-    if (rc == PSI_OK) rc = up(&ix->cbox, cbox);
-    if (rc == PSI_OK) rc = up(&ix->sbox, sbox);
-    if (rc == PSI_OK) {
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) rc = (int)e;
-    }
+    up((void **)&ix->pts, pts.data(), pts.size() * sizeof(float4));
+    up((void **)&ix->boxes, boxes.data(), boxes.size() * sizeof(float4));
+    up((void **)&ix->pos_of, pos_of.data(), pos_of.size() * sizeof(int));
+    if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;
     if (rc != PSI_OK) {
         psi_nn_index_destroy(ix);
         return rc;
@@ -283,32 +320,37 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
 
 size_t psi_nn_index_bytes(const psi_nn_index *ix) { return ix ? ix->bytes : 0; }
 
-int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n, const int *qsel,
-                       float *dist, int *idx, psi_stream_t stream) {
+int psi_nn_index_query_hint(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                            const int *qsel, float *dist, int *idx, int *hint, psi_stream_t stream) {
     using namespace psi;
     if (!ix || B < 0 || n < 0) return PSI_ERR_BAD_ARG;
     if (B == 0 || n == 0) return PSI_OK;
     if (!q || !dist) return PSI_ERR_BAD_ARG;
     const long total = (long)B * n;
     const int wpb = kIdxThreads / 32;
-    const size_t box_bytes = ((size_t)ix->spad * 2 + (size_t)ix->num_clusters * 2) * sizeof(float4);
-    const bool smem = box_bytes <= 56 * 1024;     // 4 CTAs of 16 warps per SM stay resident
+    const size_t box_bytes = (size_t)2 * ix->nbox * sizeof(float4);
+    const bool smem = box_bytes <= kIdxSmemMax;
     long blocks = (total + wpb - 1) / wpb;
-    const long cap = (long)PSI_NUM_SMS * 4;
+    const long cap = (long)PSI_NUM_SMS * (smem ? 3 : 4);
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
     if (smem) {
         static bool attr = false;
         if (!attr) {
-            cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+            cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
             attr = true;
         }
-        nn_index_query_kernel<true><<<(unsigned)blocks, kIdxThreads, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx);
+        nn_index_query_kernel<true><<<(unsigned)blocks, kIdxThreads, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     } else {
-        nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx);
+        nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     }
     PSI_LAUNCHED();
     return PSI_OK;
+}
+
+int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                       const int *qsel, float *dist, int *idx, psi_stream_t stream) {
+    return psi_nn_index_query_hint(ix, q, q_bstride, B, n, qsel, dist, idx, nullptr, stream);
 }
 
 }  // extern "C"
