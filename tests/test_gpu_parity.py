@@ -317,3 +317,43 @@ def test_product_ops_reject_cpu_tensors():
     from psi_release_b200 import chamfer, _lib
     with pytest.raises(_lib.PsiError):
         chamfer.nn_forward(torch.zeros(1, 4, 3), torch.zeros(5, 3))
+
+
+def test_nn_index_hints_never_change_results_and_multi_round_megas():
+    """Any hint contents (none, stale, random, out of range) give the same bits; 70 000 points
+    need more than one 32-mega round."""
+    from psi_release_b200 import chamfer, _lib
+    rng = np.random.default_rng(21)
+    m, B, n = 70000, 2, 3000
+    s = rng.uniform(-3, 3, (m, 3)).astype(np.float32)
+    s[:, 2] = np.where(rng.random(m) < 0.6, -1.4, s[:, 2])
+    q = rng.uniform(-2, 2, (B, n, 3)).astype(np.float32)
+    ix = chamfer.SceneIndex(_cuda(s))
+    d_o, i_o = oracle.nn_fwd(q, s)
+    tq = _cuda(q)
+    L = _lib.lib()
+    hint = None
+    for mode in ("none", "self", "random", "garbage"):
+        dist = torch.empty(B, n, device="cuda")
+        idx = torch.empty(B, n, dtype=torch.int32, device="cuda")
+        if mode == "none":
+            hint = torch.full((B, n), -1, dtype=torch.int32, device="cuda")
+        elif mode == "random":
+            hint = torch.randint(0, m // 32, (B, n), dtype=torch.int32, device="cuda")
+        elif mode == "garbage":
+            hint = torch.randint(-5, 1 << 30, (B, n), dtype=torch.int32, device="cuda")
+        # mode "self": reuse the hints the previous call wrote
+        rc = L.psi_nn_index_query_hint(ix.h, _lib.ptr(tq), n * 3, B, n, None, _lib.ptr(dist), _lib.ptr(idx),
+                                       _lib.ptr(hint), _lib.stream_ptr())
+        assert rc == 0
+        assert np.array_equal(idx.cpu().numpy(), i_o), mode
+        assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o)), mode
+    # qsel: query a subset of rows in place
+    sel_np = rng.choice(n, 500, replace=False).astype(np.int32)
+    sel = torch.tensor(sel_np, device="cuda")
+    dist = torch.empty(B, 500, device="cuda")
+    idx = torch.empty(B, 500, dtype=torch.int32, device="cuda")
+    rc = L.psi_nn_index_query(ix.h, _lib.ptr(tq), n * 3, B, 500, _lib.ptr(sel), _lib.ptr(dist), _lib.ptr(idx),
+                              _lib.stream_ptr())
+    assert rc == 0
+    assert np.array_equal(idx.cpu().numpy(), i_o[:, sel_np])
