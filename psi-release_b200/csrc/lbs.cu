@@ -38,7 +38,7 @@ constexpr int kMaxJ = 64;
 constexpr int kKT = 16;         // basis rows per pipeline stage
 constexpr int kTileN = 96;      // basis columns per CTA = 32 vertices
 constexpr int kBG = 64;         // bodies per CTA (4 warps x 16)
-constexpr int kStages = 3;
+constexpr int kStages = 6;        // 6 x 10 kB ring: 5 stages of prefetch cover the L2->smem latency
 constexpr int kNSplit = 41;     // dcoef split of the N reduction (Npad/32 chunks / 41)
 
 }  // namespace psi
