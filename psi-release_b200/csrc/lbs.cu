@@ -39,7 +39,7 @@ constexpr int kKT = 16;         // basis rows per pipeline stage
 constexpr int kTileN = 96;      // basis columns per CTA = 32 vertices
 constexpr int kBG = 64;         // bodies per CTA (4 warps x 16)
 constexpr int kStages = 6;        // 6 x 10 kB ring: 5 stages of prefetch cover the L2->smem latency
-constexpr int kNSplit = 41;     // dcoef split of the N reduction (Npad/32 chunks / 41)
+constexpr int kNSplit = 74;     // dcoef split of the N reduction: 4 k-tiles x 74 x (B/32) CTAs = 4 per SM at B=64
 
 }  // namespace psi
 
@@ -206,49 +206,46 @@ struct VertexFwdParams {
 };
 
 __global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdParams p) {
+    // 4 warps (16 bodies each, lane = vertex).  full[st]: bytes landed; empty[st]: all 4 warps
+    // released the stage.  Lane 0 of warp 0 refills a stage kStages-2 chunks ahead, so there is no
+    // block-wide barrier inside the K loop: warps may drift a chunk apart.
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sm = reinterpret_cast<float *>(smem_raw);
-    constexpr int kStageFloats = kKT * kTileN + kKT * kBG;  // 4096 floats = 16 KB
-    __shared__ __align__(8) uint64_t full[kStages];
+    constexpr int kStageFloats = kKT * kTileN + kKT * kBG;  // 2560 floats = 10 kB
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int tile = blockIdx.x, bg = blockIdx.y;
     const int nchunks = p.Kpad / kKT;
+    // the basis is stored tile-major [tile][Kpad][96]: a stage is ONE contiguous 6 kB block
+    const float *__restrict__ basis_t = p.basis + (size_t)tile * p.Kpad * kTileN;
     const float *__restrict__ coef_g = p.coef + (size_t)bg * p.Kpad * kBG;
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kStages; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    auto issue = [&](int chunk) {   // called by warp 0 only
-        const int st = chunk % kStages;
+    auto issue = [&](int c) {   // warp 0, lane 0 only
+        const int st = c % kStages;
+        mbar_wait(&empty[st], (uint32_t)(((c / kStages) & 1) ^ 1));   // first use: passes at once
         float *dstB = sm + st * kStageFloats;
-        float *dstC = dstB + kKT * kTileN;
-        if (lane == 0) {
-            mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageFloats * 4));
-            tma_load_1d(dstC, coef_g + (size_t)chunk * kKT * kBG, kKT * kBG * 4, &full[st]);
-        }
-        __syncwarp();
-        // lane l < kKT moves basis row (chunk*kKT + l): 96 contiguous floats
-        if (lane < kKT)
-            tma_load_1d(dstB + lane * kTileN,
-                        p.basis + (size_t)(chunk * kKT + lane) * p.Npad + (size_t)tile * kTileN,
-                        kTileN * 4, &full[st]);
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageFloats * 4));
+        tma_load_1d(dstB, basis_t + (size_t)c * kKT * kTileN, kKT * kTileN * 4, &full[st]);
+        tma_load_1d(dstB + kKT * kTileN, coef_g + (size_t)c * kKT * kBG, kKT * kBG * 4, &full[st]);
     };
-
-    if (w == 0) {
-        for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
-    }
+    if (tid == 0)
+        for (int c = 0; c < kStages - 2 && c < nchunks; ++c) issue(c);
 
     float acc[16][3];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
 
     for (int c = 0; c < nchunks; ++c) {
-        if (w == 0 && c + kStages - 1 < nchunks) issue(c + kStages - 1);
+        if (tid == 0 && c + kStages - 2 < nchunks) issue(c + kStages - 2);
+        __syncwarp();
         const int st = c % kStages;
         mbar_wait(&full[st], (uint32_t)((c / kStages) & 1));
         const float *bs = sm + st * kStageFloats + 3 * lane;
@@ -266,7 +263,8 @@ __global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdP
                 acc[i][2] = fmaf(cf[i], b2, acc[i][2]);
             }
         }
-        __syncthreads();   // every warp is done with stage st before it is refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);   // this warp is done with stage st
     }
 
     const int v = tile * 32 + lane;
@@ -428,8 +426,8 @@ lbs_dcoef_kernel(int Kpad, int Npad, int B, int Bpad, const float *__restrict__ 
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     const int total_chunks = Npad / 32;
-    const int c_begin = ns * chunks_per_split;
-    const int c_end = min(total_chunks, c_begin + chunks_per_split);
+    const int c_begin = (int)((long)ns * total_chunks / chunks_per_split);           // balanced partition (chunks_per_split = number of splits)
+    const int c_end = (int)((long)(ns + 1) * total_chunks / chunks_per_split);
     for (int c = c_begin; c < c_end; ++c) {
         const int n0 = c * 32;
         __syncthreads();
@@ -437,7 +435,7 @@ lbs_dcoef_kernel(int Kpad, int Npad, int B, int Bpad, const float *__restrict__ 
         for (int r = 0; r < 8; ++r) {
             const int row = r * 16 + (tid >> 3), col4 = tid & 7;
             const float4 vv = __ldg(reinterpret_cast<const float4 *>(
-                basis + (size_t)(kbase + row) * Npad + n0 + col4 * 4));
+                basis + (size_t)(n0 / kTileN) * Kpad * kTileN + (size_t)(kbase + row) * kTileN + (n0 % kTileN) + col4 * 4));
             BsT[col4 * 4 + 0][row] = vv.x; BsT[col4 * 4 + 1][row] = vv.y;
             BsT[col4 * 4 + 2][row] = vv.z; BsT[col4 * 4 + 3][row] = vv.w;
         }
@@ -497,8 +495,16 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     for (int e = tid; e < J * 3; e += blockDim.x) sJ[e] = iJ[e];
     // d pose-feature (added to dR below) and the direct d beta, summed over splits in order
     for (int k = tid; k < P + NB; k += blockDim.x) {
-        float s = 0.f;
-        for (int ns = 0; ns < nsplit; ++ns) s += part[((size_t)ns * Bpad + b) * Kpad + k];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // fixed order: 4 interleaved partial sums
+        int ns = 0;
+        for (; ns + 4 <= nsplit; ns += 4) {
+            s0 += part[((size_t)ns * Bpad + b) * Kpad + k];
+            s1 += part[((size_t)(ns + 1) * Bpad + b) * Kpad + k];
+            s2 += part[((size_t)(ns + 2) * Bpad + b) * Kpad + k];
+            s3 += part[((size_t)(ns + 3) * Bpad + b) * Kpad + k];
+        }
+        for (; ns < nsplit; ++ns) s0 += part[((size_t)ns * Bpad + b) * Kpad + k];
+        const float s = (s0 + s1) + (s2 + s3);
         if (k < P) dR[9 + k] = s;           // joint j = k/9+1, entry k%9
         else dbeta_direct[k - P] = s;
     }
@@ -689,11 +695,13 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     const int P = m->P, Kpad = m->Kpad, Npad = m->Npad;
     const size_t N = (size_t)3 * V;
 
+    // tile-major: element (k, n) lives at [n / 96][k][n % 96]
     std::vector<float> basis((size_t)Kpad * Npad, 0.f);
+    auto bidx = [&](int k, size_t n) { return (n / kTileN) * (size_t)Kpad * kTileN + (size_t)k * kTileN + (n % kTileN); };
     for (int k = 0; k < P; ++k)
-        for (size_t n = 0; n < N; ++n) basis[(size_t)k * Npad + n] = h_posedirs[(size_t)k * N + n];
+        for (size_t n = 0; n < N; ++n) basis[bidx(k, n)] = h_posedirs[(size_t)k * N + n];
     for (int l = 0; l < NB; ++l)
-        for (size_t n = 0; n < N; ++n) basis[(size_t)(P + l) * Npad + n] = h_shapedirs[n * NB + l];
+        for (size_t n = 0; n < N; ++n) basis[bidx(P + l, n)] = h_shapedirs[n * NB + l];
     std::vector<float> vt((size_t)Npad, 0.f);
     for (size_t n = 0; n < N; ++n) vt[n] = h_v_template[n];
 
@@ -885,7 +893,7 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
     }
     {
         const int total_chunks = m->Npad / 32;
-        const int cps = (total_chunks + kNSplit - 1) / kNSplit;
+        const int cps = kNSplit;
         dim3 grid((unsigned)(m->Kpad / 128), (unsigned)kNSplit, (unsigned)(W.Bpad / 32));
         lbs_dcoef_kernel<<<grid, 128, 0, st>>>(m->Kpad, m->Npad, B, W.Bpad, m->basis, ws + W.gvp,
                                                ws + W.part, cps);
