@@ -114,6 +114,12 @@ PSI_API int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bs
  * bound (that cluster is visited first) -- results are identical with any hint contents. */
 PSI_API int psi_nn_index_query_hint(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
                             const int *qsel, float *dist, int *idx, int *hint, psi_stream_t stream);
+/* Same, choosing the schedule: mode 0 = by query count (the two above), 1 = one warp per query,
+ * 2 = one thread per query (fast when consecutive queries are spatial neighbours).  All modes
+ * return identical bits. */
+PSI_API int psi_nn_index_query_mode(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                            const int *qsel, float *dist, int *idx, int *hint, int mode,
+                            psi_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scene SDF lookup.

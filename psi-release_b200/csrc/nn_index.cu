@@ -207,6 +207,100 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Thread-per-query walk of the same index, for LARGE, SPATIALLY COHERENT query sets (the fitting
+// loop orders the contact vertices along a kd curve of the template mesh, so the 32 queries of
+// a warp are neighbours on the body and walk nearly the same nodes: loop control, box loads
+// (shared-memory broadcasts) and leaf loads (same 512-byte leaf) are shared by the warp).
+// Same pruning rule, same lexicographic (d, original index) minimum => same bits as the
+// warp-per-query kernel and as the brute force; only the schedule differs.
+template <bool SMEM>
+__device__ __forceinline__ float node_lbf(const psi_nn_index &ix, const float4 *boxes, int node,
+                                          float qx, float qy, float qz) {
+    const float4 lo = SMEM ? boxes[node] : __ldg(boxes + node);
+    const float4 hi = SMEM ? boxes[ix.nbox + node] : __ldg(boxes + ix.nbox + node);
+    return __uint_as_float(box_lb(lo, hi, qx, qy, qz));
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, long q_bstride, int n,
+                       const int *__restrict__ qsel, long total, float *__restrict__ dist,
+                       int *__restrict__ idx, int *__restrict__ hint) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float4 *boxes = ix.boxes;
+    if (SMEM) {
+        float4 *s4 = reinterpret_cast<float4 *>(smem_raw);
+        for (int i = threadIdx.x; i < 2 * ix.nbox; i += blockDim.x) s4[i] = __ldg(ix.boxes + i);
+        __syncthreads();
+        boxes = s4;
+    }
+    const int sbase = ix.mpad, cbase = ix.mpad + ix.num_supers;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / n;
+        const long j = t - b * n;
+        const float *qp = q_in + b * q_bstride + (qsel ? (long)__ldg(qsel + j) : j) * 3;
+        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        float bd = CUDART_INF_F;
+        int bi = 0x7fffffff;
+        auto visit = [&](int c) {
+            const float4 *p = ix.pts + (size_t)c * kLeaf;
+#pragma unroll 8
+            for (int i = 0; i < kLeaf; ++i) {
+                const float4 pt = __ldg(p + i);
+                const float dx = __fsub_rn(pt.x, qx), dy = __fsub_rn(pt.y, qy), dz = __fsub_rn(pt.z, qz);
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                const int oi = __float_as_int(pt.w);
+                if (d < bd || (d == bd && oi < bi)) {
+                    bd = d;
+                    bi = oi;
+                }
+            }
+        };
+        // seed: hinted leaf, else greedy descent (nearest mega -> super -> cluster)
+        int seeded = hint ? hint[t] : -1;
+        if (seeded < 0 || seeded >= ix.num_clusters) {
+            float best = CUDART_INF_F;
+            int m0 = 0;
+            for (int g = 0; g < ix.num_megas; ++g) {
+                const float lb = node_lbf<SMEM>(ix, boxes, g, qx, qy, qz);
+                if (lb < best) { best = lb; m0 = g; }
+            }
+            best = CUDART_INF_F;
+            int s0 = m0 * kFan;
+            for (int s = m0 * kFan; s < m0 * kFan + kFan; ++s) {
+                const float lb = node_lbf<SMEM>(ix, boxes, sbase + s, qx, qy, qz);
+                if (lb < best) { best = lb; s0 = s; }
+            }
+            best = CUDART_INF_F;
+            seeded = s0 * kFan;
+            for (int c = s0 * kFan; c < s0 * kFan + kFan; ++c) {
+                const float lb = node_lbf<SMEM>(ix, boxes, cbase + c, qx, qy, qz);
+                if (lb < best) { best = lb; seeded = c; }
+            }
+        }
+        visit(seeded);
+        // ordered sweep with pruning against this query's best distance so far
+#pragma unroll 1
+        for (int g = 0; g < ix.num_megas; ++g) {
+            if (node_lbf<SMEM>(ix, boxes, g, qx, qy, qz) > bd) continue;
+#pragma unroll 1
+            for (int s = g * kFan; s < g * kFan + kFan; ++s) {
+                if (node_lbf<SMEM>(ix, boxes, sbase + s, qx, qy, qz) > bd) continue;
+#pragma unroll 1
+                for (int c = s * kFan; c < s * kFan + kFan; ++c) {
+                    if (c == seeded) continue;
+                    if (node_lbf<SMEM>(ix, boxes, cbase + c, qx, qy, qz) > bd) continue;
+                    visit(c);
+                }
+            }
+        }
+        dist[t] = bd;
+        if (idx) idx[t] = bi;
+        if (hint) hint[t] = ((unsigned)bi < (unsigned)ix.m) ? __ldg(ix.pos_of + bi) / kLeaf : -1;
+    }
+}
+
 // balanced kd bisection: reorder ids[0..n) so that consecutive runs of `leaf` are compact
 static void kd_order(const float *P, int *ids, int n, int leaf) {
     if (n <= leaf) return;
@@ -320,8 +414,10 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
 
 size_t psi_nn_index_bytes(const psi_nn_index *ix) { return ix ? ix->bytes : 0; }
 
-int psi_nn_index_query_hint(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
-                            const int *qsel, float *dist, int *idx, int *hint, psi_stream_t stream) {
+// mode 0: pick by query count; 1: warp per query; 2: thread per query
+static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                               const int *qsel, float *dist, int *idx, int *hint, int mode,
+                               psi_stream_t stream) {
     using namespace psi;
     if (!ix || B < 0 || n < 0) return PSI_ERR_BAD_ARG;
     if (B == 0 || n == 0) return PSI_OK;
@@ -330,27 +426,49 @@ int psi_nn_index_query_hint(const psi_nn_index *ix, const float *q, long q_bstri
     const int wpb = kIdxThreads / 32;
     const size_t box_bytes = (size_t)2 * ix->nbox * sizeof(float4);
     const bool smem = box_bytes <= kIdxSmemMax;
-    long blocks = (total + wpb - 1) / wpb;
-    const long cap = (long)PSI_NUM_SMS * (smem ? 3 : 4);
-    if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
-    if (smem) {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
-            attr = true;
-        }
-        nn_index_query_kernel<true><<<(unsigned)blocks, kIdxThreads, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
+        cudaFuncSetAttribute(nn_index_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
+        attr = true;
+    }
+    if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
+        // one thread per query: enough queries to fill the machine with 256-thread CTAs
+        long blocks = (total + 255) / 256;
+        const long cap = (long)PSI_NUM_SMS * 3;
+        if (blocks > cap) blocks = cap;
+        if (smem)
+            nn_index_thread_kernel<true><<<(unsigned)blocks, 256, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+        else
+            nn_index_thread_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     } else {
-        nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+        long blocks = (total + wpb - 1) / wpb;
+        const long cap = (long)PSI_NUM_SMS * (smem ? 3 : 4);
+        if (blocks > cap) blocks = cap;
+        if (smem)
+            nn_index_query_kernel<true><<<(unsigned)blocks, kIdxThreads, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+        else
+            nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     }
     PSI_LAUNCHED();
     return PSI_OK;
 }
 
+int psi_nn_index_query_hint(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                            const int *qsel, float *dist, int *idx, int *hint, psi_stream_t stream) {
+    return nn_index_query_impl(ix, q, q_bstride, B, n, qsel, dist, idx, hint, 0, stream);
+}
+
+int psi_nn_index_query_mode(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
+                            const int *qsel, float *dist, int *idx, int *hint, int mode,
+                            psi_stream_t stream) {
+    return nn_index_query_impl(ix, q, q_bstride, B, n, qsel, dist, idx, hint, mode, stream);
+}
+
 int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
                        const int *qsel, float *dist, int *idx, psi_stream_t stream) {
-    return psi_nn_index_query_hint(ix, q, q_bstride, B, n, qsel, dist, idx, nullptr, stream);
+    return nn_index_query_impl(ix, q, q_bstride, B, n, qsel, dist, idx, nullptr, 0, stream);
 }
 
 }  // extern "C"

@@ -29,7 +29,22 @@ class FusedFit:
         W3, b3 = sd["bodyprior_dec_out.weight"], sd["bodyprior_dec_out.bias"]
         hl, hr = f32(body_model.left_hand_components), f32(body_model.right_hand_components)
         pm = f32(body_model.pose_mean)
-        cid = np.ascontiguousarray(np.asarray(contact_ids, dtype=np.int32))
+        # Query order = order of first appearance in this list.  Sorting the ids along a Morton curve
+        # of the template mesh makes the 32 queries of a warp neighbours on the body, which the
+        # thread-per-query NN kernel needs to be fast; the result does not depend on the order.
+        cid = np.asarray(contact_ids, dtype=np.int64)
+        vt = np.asarray(body_model._model_data["v_template"], dtype=np.float64)
+        cell = ((vt - vt.min(0)) / np.maximum(vt.max(0) - vt.min(0), 1e-12) * 1023.0 + 0.5).astype(np.int64)
+
+        def _spread(v):
+            v = v & 0x3FF
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            return (v | (v << 2)) & 0x09249249
+
+        rank = _spread(cell[:, 0]) | (_spread(cell[:, 1]) << 1) | (_spread(cell[:, 2]) << 2)
+        cid = np.ascontiguousarray(cid[np.argsort(rank[cid], kind="stable")].astype(np.int32))
         cfg = _lib.FitConfig(B=self.B, use_graph=1 if use_graph else 0,
                              w_rec=float(weights["weight_loss_rec"]), w_vposer=float(weights["weight_loss_vposer"]),
                              w_contact=float(weights["weight_contact"]), w_collision=float(weights["weight_collision"]),

@@ -357,3 +357,29 @@ def test_nn_index_hints_never_change_results_and_multi_round_megas():
                               _lib.stream_ptr())
     assert rc == 0
     assert np.array_equal(idx.cpu().numpy(), i_o[:, sel_np])
+
+
+def test_nn_index_schedules_agree_bit_for_bit():
+    """Warp-per-query and thread-per-query walks of the index return the same bits (and the oracle's)."""
+    from psi_release_b200 import chamfer, _lib
+    rng = np.random.default_rng(31)
+    m, B, n = 30000, 3, 2000
+    s = rng.uniform(-2.5, 2.5, (m, 3)).astype(np.float32)
+    s[: m // 2, 1] = 2.0
+    s[100] = s[5]; s[20000] = s[5]
+    q = rng.uniform(-2.5, 2.5, (B, n, 3)).astype(np.float32)
+    q[:, 0] = s[5]
+    ix = chamfer.SceneIndex(_cuda(s))
+    d_o, i_o = oracle.nn_fwd(q, s)
+    L = _lib.lib()
+    tq = _cuda(q)
+    for mode in (1, 2):
+        for use_hint in (False, True):
+            dist = torch.empty(B, n, device="cuda"); idx = torch.empty(B, n, dtype=torch.int32, device="cuda")
+            hint = torch.randint(-3, m // 32 + 5, (B, n), dtype=torch.int32, device="cuda") if use_hint else None
+            for _ in range(2):      # the second pass runs on the hints written by the first
+                rc = L.psi_nn_index_query_mode(ix.h, _lib.ptr(tq), n * 3, B, n, None, _lib.ptr(dist), _lib.ptr(idx),
+                                               _lib.ptr(hint), mode, _lib.stream_ptr())
+                assert rc == 0
+                assert np.array_equal(idx.cpu().numpy(), i_o), (mode, use_hint)
+                assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o)), (mode, use_hint)

@@ -70,6 +70,29 @@ def main():
     db, ib = chamfer.nn_forward(verts, pts)
     out["nn_index_equal_bruteforce"] = bool(torch.equal(ii, ib) and torch.equal(di.view(torch.int32), db.view(torch.int32)))
 
+    # index query schedules: 1 = warp per query, 2 = thread per query; with / without coherent order + hints
+    from psi_release_b200 import _lib
+    L = _lib.lib()
+    vt = model["v_template"].astype(np.float64)
+    cell = ((vt - vt.min(0)) / (vt.max(0) - vt.min(0)) * 1023 + 0.5).astype(np.int64)
+    def spread(v):
+        v = v & 0x3FF; v = (v | (v << 16)) & 0x030000FF; v = (v | (v << 8)) & 0x0300F00F; v = (v | (v << 4)) & 0x030C30C3
+        return (v | (v << 2)) & 0x09249249
+    rank = spread(cell[:, 0]) | (spread(cell[:, 1]) << 1) | (spread(cell[:, 2]) << 2)
+    sel_sorted = torch.tensor(np.argsort(rank, kind="stable").astype(np.int32), device=dev)
+    dq = torch.empty(B, V, device=dev); iq = torch.empty(B, V, dtype=torch.int32, device=dev)
+    hint = torch.full((B, V), -1, dtype=torch.int32, device=dev)
+    def run(mode, sel, hnt):
+        rc = L.psi_nn_index_query_mode(ix.h, _lib.ptr(verts), V * 3, B, V, _lib.ptr(sel), _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(hnt), mode, _lib.stream_ptr())
+        assert rc == 0
+    for mode in (1, 2):
+        for name, sel in (("natural", None), ("sorted", sel_sorted)):
+            out["nn_mode%d_%s_nohint_ms" % (mode, name)] = timeit(lambda: run(mode, sel, None), flush=flush)[0]
+            hint.fill_(-1); run(mode, sel, hint)
+            out["nn_mode%d_%s_hint_ms" % (mode, name)] = timeit(lambda: run(mode, sel, hint), flush=flush)[0]
+    run(2, None, None)
+    out["nn_mode2_equal_bruteforce"] = bool(torch.equal(iq, ib) and torch.equal(dq.view(torch.int32), db.view(torch.int32)))
+
     med, mn = timeit(lambda: body_model.lbs(betas, pose, h, transl=transl, cam=cam), flush=flush)
     out["lbs_fwd_ms"] = med
     out["lbs_fwd_min_ms"] = mn
