@@ -233,6 +233,12 @@ PSI_API void psi_fit_destroy(psi_fit_ctx *c);
  * the four weighted terms of the last evaluated iteration.  Device pointers. */
 PSI_API int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride,
                 int num_iter, float *xhr_out, float *losses_out, psi_stream_t stream);
+/* The same call split in two, so that several contexts (e.g. two halves of a batch) can run
+ * their loops CONCURRENTLY on their own streams: psi_fit_begin enqueues everything and returns;
+ * psi_fit_end makes `stream` wait for the loop and copies the results out. */
+PSI_API int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride,
+                  int num_iter, psi_stream_t stream);
+PSI_API int psi_fit_end(psi_fit_ctx *c, float *xhr_out, float *losses_out, psi_stream_t stream);
 PSI_API int psi_fit_launches_per_iteration(void);
 
 #ifdef __cplusplus

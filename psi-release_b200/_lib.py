@@ -75,6 +75,8 @@ def lib():
                                 ctypes.POINTER(FitConfig), _vp]),
         "psi_fit_destroy": (None, [_vp]),
         "psi_fit_run": (_i, [_vp, _vp, _vp, _l, _i, _vp, _vp, _vp]),
+        "psi_fit_begin": (_i, [_vp, _vp, _vp, _l, _i, _vp]),
+        "psi_fit_end": (_i, [_vp, _vp, _vp, _vp]),
         "psi_fit_launches_per_iteration": (_i, []),
     }
     for name, (res, args) in sig.items():
@@ -92,7 +94,8 @@ EXPORTS = ["psi_abi_version", "psi_error_string", "psi_launch_count", "psi_nn_wo
            "psi_nn_index_bytes", "psi_nn_index_query", "psi_nn_index_query_hint", "psi_nn_index_query_mode", "psi_sdf_num_partials", "psi_sdf_fwd",
            "psi_sdf_bwd", "psi_lbs_model_create", "psi_lbs_model_destroy", "psi_lbs_model_bytes",
            "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd",
-           "psi_fit_create", "psi_fit_destroy", "psi_fit_run", "psi_fit_launches_per_iteration"]
+           "psi_fit_create", "psi_fit_destroy", "psi_fit_run", "psi_fit_begin", "psi_fit_end",
+           "psi_fit_launches_per_iteration"]
 
 
 def check(rc: int, what: str) -> None:

@@ -37,6 +37,7 @@ struct psi_fit_ctx {
     int *nni, *step, *nnhint;
     size_t lbs_ws_bytes;
     cudaGraphExec_t exec;
+    int pending_join;
     cudaStream_t gstream;          // graphs cannot be captured on the legacy default stream
     cudaEvent_t ev_in, ev_out;
     std::vector<void *> owned;
@@ -428,7 +429,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->model = model; c->index = index; c->cfg = *cfg;
     c->B = cfg->B; c->V = V; c->J = J; c->NB = NB; c->latent = latent; c->hidden = hidden; c->nbody = nbody;
     c->ncomp = ncomp; c->num_rot = nbody + 1; c->D = D; c->sdf = sdf; c->scene_pts = scene_points;
-    c->num_contact = num_contact; c->exec = nullptr; c->gstream = nullptr; c->ev_in = c->ev_out = nullptr;
+    c->num_contact = num_contact; c->exec = nullptr; c->pending_join = 0; c->gstream = nullptr; c->ev_in = c->ev_out = nullptr;
     if (cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -511,10 +512,10 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     return PSI_OK;
 }
 
-int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int num_iter,
-                float *xhr_out, float *losses_out, psi_stream_t stream) {
+int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int num_iter,
+                  psi_stream_t stream) {
     using namespace psi;
-    if (!c || !xhr_init || !cam || !xhr_out || num_iter < 0) return PSI_ERR_BAD_ARG;
+    if (!c || !xhr_init || !cam || num_iter < 0) return PSI_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t xd = 9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp, n = (size_t)c->B * xd;
     cudaError_t e = cudaMemcpyAsync(c->x0, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -559,20 +560,42 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
             if (e != cudaSuccess) return (int)e;
         }
         e = cudaEventRecord(c->ev_out, gs);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_out, 0);
         if (e != cudaSuccess) return (int)e;
+        c->pending_join = 1;
     } else {
         for (int it = 0; it < num_iter; ++it) {
             const int rc = enqueue_iteration(c, st);
             if (rc) return rc;
         }
+        c->pending_join = 0;
     }
+    return PSI_OK;
+}
+
+int psi_fit_end(psi_fit_ctx *c, float *xhr_out, float *losses_out, psi_stream_t stream) {
+    if (!c || !xhr_out) return PSI_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (c->pending_join) {
+        e = cudaStreamWaitEvent(st, c->ev_out, 0);
+        if (e != cudaSuccess) return (int)e;
+        c->pending_join = 0;
+    }
+    const size_t n = (size_t)c->B * (9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp);
     e = cudaMemcpyAsync(xhr_out, c->x, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess && losses_out)
         e = cudaMemcpyAsync(losses_out, c->losses, (size_t)c->B * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
     return e == cudaSuccess ? PSI_OK : (int)e;
 }
 
-int psi_fit_launches_per_iteration(void) { return 11; }
+int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int num_iter,
+                float *xhr_out, float *losses_out, psi_stream_t stream) {
+    if (!xhr_out) return PSI_ERR_BAD_ARG;
+    const int rc = psi_fit_begin(c, xhr_init, cam, cam_bstride, num_iter, stream);
+    if (rc) return rc;
+    return psi_fit_end(c, xhr_out, losses_out, stream);
+}
+
+int psi_fit_launches_per_iteration(void) { return 12; }
 
 }  // extern "C"

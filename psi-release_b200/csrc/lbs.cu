@@ -428,27 +428,42 @@ lbs_dcoef_kernel(int Kpad, int Npad, int B, int Bpad, const float *__restrict__ 
     const int total_chunks = Npad / 32;
     const int c_begin = (int)((long)ns * total_chunks / chunks_per_split);           // balanced partition (chunks_per_split = number of splits)
     const int c_end = (int)((long)(ns + 1) * total_chunks / chunks_per_split);
-    for (int c = c_begin; c < c_end; ++c) {
+    // software pipeline: the next chunk's global loads are in flight while this one is computed.
+    // store mapping: lanes run over 16 rows (k or body) x 2 column groups -> conflict-free
+    // transposed stores ((4n + row) % 32 covers all banks).
+    const int lrow = tid & 15, col4 = tid >> 4;
+    float4 pb[8], pg[2];
+    auto fetch = [&](int c) {
         const int n0 = c * 32;
+        const float *bt = basis + (size_t)(n0 / kTileN) * Kpad * kTileN + (n0 % kTileN) + col4 * 4;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            pb[r] = __ldg(reinterpret_cast<const float4 *>(bt + (size_t)(kbase + r * 16 + lrow) * kTileN));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = r * 16 + lrow;
+            pg[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bbase + row < B)
+                pg[r] = __ldg(reinterpret_cast<const float4 *>(gvp + (size_t)(bbase + row) * Npad + n0 + col4 * 4));
+        }
+    };
+    if (c_begin < c_end) fetch(c_begin);
+    for (int c = c_begin; c < c_end; ++c) {
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int row = r * 16 + (tid >> 3), col4 = tid & 7;
-            const float4 vv = __ldg(reinterpret_cast<const float4 *>(
-                basis + (size_t)(n0 / kTileN) * Kpad * kTileN + (size_t)(kbase + row) * kTileN + (n0 % kTileN) + col4 * 4));
-            BsT[col4 * 4 + 0][row] = vv.x; BsT[col4 * 4 + 1][row] = vv.y;
-            BsT[col4 * 4 + 2][row] = vv.z; BsT[col4 * 4 + 3][row] = vv.w;
+            const int row = r * 16 + lrow;
+            BsT[col4 * 4 + 0][row] = pb[r].x; BsT[col4 * 4 + 1][row] = pb[r].y;
+            BsT[col4 * 4 + 2][row] = pb[r].z; BsT[col4 * 4 + 3][row] = pb[r].w;
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const int row = r * 16 + (tid >> 3), col4 = tid & 7;
-            float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bbase + row < B)
-                vv = __ldg(reinterpret_cast<const float4 *>(gvp + (size_t)(bbase + row) * Npad + n0 + col4 * 4));
-            GT[col4 * 4 + 0][row] = vv.x; GT[col4 * 4 + 1][row] = vv.y;
-            GT[col4 * 4 + 2][row] = vv.z; GT[col4 * 4 + 3][row] = vv.w;
+            const int row = r * 16 + lrow;
+            GT[col4 * 4 + 0][row] = pg[r].x; GT[col4 * 4 + 1][row] = pg[r].y;
+            GT[col4 * 4 + 2][row] = pg[r].z; GT[col4 * 4 + 3][row] = pg[r].w;
         }
         __syncthreads();
+        if (c + 1 < c_end) fetch(c + 1);
 #pragma unroll 8
         for (int n = 0; n < 32; ++n) {
             const float4 a0 = *reinterpret_cast<const float4 *>(&BsT[n][4 * tk]);
@@ -475,7 +490,24 @@ lbs_dcoef_kernel(int Kpad, int Npad, int B, int Bpad, const float *__restrict__ 
     }
 }
 
-// per body: reduce the d coef partials, run the chain and Rodrigues backward
+// dsum[b][k] = sum over the N-splits, in a fixed order (4 interleaved partial sums)
+__global__ void __launch_bounds__(256)
+lbs_dcoef_reduce_kernel(const float *__restrict__ part, int nsplit, long per_split, float *__restrict__ dsum) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_split) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int ns = 0;
+    for (; ns + 4 <= nsplit; ns += 4) {
+        s0 += part[(size_t)ns * per_split + i];
+        s1 += part[(size_t)(ns + 1) * per_split + i];
+        s2 += part[(size_t)(ns + 2) * per_split + i];
+        s3 += part[(size_t)(ns + 3) * per_split + i];
+    }
+    for (; ns < nsplit; ++ns) s0 += part[(size_t)ns * per_split + i];
+    dsum[i] = (s0 + s1) + (s2 + s3);
+}
+
+// per body: run the chain and Rodrigues backward on the reduced d coef
 __global__ void __launch_bounds__(128)
 lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     const float *__restrict__ Jdirs, const int *__restrict__ parents,
@@ -495,16 +527,8 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     for (int e = tid; e < J * 3; e += blockDim.x) sJ[e] = iJ[e];
     // d pose-feature (added to dR below) and the direct d beta, summed over splits in order
     for (int k = tid; k < P + NB; k += blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // fixed order: 4 interleaved partial sums
-        int ns = 0;
-        for (; ns + 4 <= nsplit; ns += 4) {
-            s0 += part[((size_t)ns * Bpad + b) * Kpad + k];
-            s1 += part[((size_t)(ns + 1) * Bpad + b) * Kpad + k];
-            s2 += part[((size_t)(ns + 2) * Bpad + b) * Kpad + k];
-            s3 += part[((size_t)(ns + 3) * Bpad + b) * Kpad + k];
-        }
-        for (; ns < nsplit; ++ns) s0 += part[((size_t)ns * Bpad + b) * Kpad + k];
-        const float s = (s0 + s1) + (s2 + s3);
+        const float s = part[(size_t)b * Kpad + k];          // already summed over the splits
+        (void)nsplit; (void)Bpad;
         if (k < P) dR[9 + k] = s;           // joint j = k/9+1, entry k%9
         else dbeta_direct[k - P] = s;
     }
@@ -631,7 +655,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
 }
 
 struct BwdLayout {
-    size_t gw, gvp, dA, dtr, part, total;  // in floats
+    size_t gw, gvp, dA, dtr, part, dsum, total;  // in floats
     int Bpad;
 };
 static BwdLayout bwd_layout(const psi_lbs_model *m, int B) {
@@ -645,6 +669,7 @@ static BwdLayout bwd_layout(const psi_lbs_model *m, int B) {
     l.dtr = o;  o += (size_t)B * 3;
     o = (o + 3) & ~(size_t)3;
     l.part = o; o += (size_t)kNSplit * l.Bpad * m->Kpad;
+    l.dsum = o; o += (size_t)l.Bpad * m->Kpad;
     l.total = o;
     return l;
 }
@@ -898,10 +923,13 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
         lbs_dcoef_kernel<<<grid, 128, 0, st>>>(m->Kpad, m->Npad, B, W.Bpad, m->basis, ws + W.gvp,
                                                ws + W.part, cps);
         PSI_LAUNCHED();
+        const long per_split = (long)W.Bpad * m->Kpad;
+        lbs_dcoef_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(ws + W.part, kNSplit, per_split, ws + W.dsum);
+        PSI_LAUNCHED();
     }
     lbs_pose_bwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
                                           m->parents, pose, saved, L, ws + W.dA, ws + W.dtr,
-                                          ws + W.part, grad_joints, grad_betas, grad_pose,
+                                          ws + W.dsum, grad_joints, grad_betas, grad_pose,
                                           grad_transl, grad_rot, num_rot, m->tree);
     PSI_LAUNCHED();
     return PSI_OK;

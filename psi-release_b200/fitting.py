@@ -141,7 +141,8 @@ class FittingOP:
                                                    "weight_collision")}
             self._fused = FusedFit(B, self.body_mesh_model.handle(self.device), self.body_mesh_model,
                                    self.s_index, self.scene_sdf, self.vposer, self.contact_ids.cpu().numpy(),
-                                   lossw, self.robust_c, self.init_lr_h, use_graph=self.use_cuda_graph)
+                                   lossw, self.robust_c, self.init_lr_h, use_graph=self.use_cuda_graph,
+                                   num_streams=getattr(self, "num_streams", None))
         self._graph = None
         self._static_xhr = None
         self._static_cam = None
