@@ -278,15 +278,14 @@ __global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdP
         sj[k] = (k < kw) ? p.skin_j[(size_t)v * kw + k] : 0;
         sw[k] = (k < kw) ? p.skin_w[(size_t)v * kw + k] : 0.f;
     }
-#pragma unroll 1
+    // fully unrolled over the warp's 16 bodies: compile-time accumulator indices and the skinning
+    // loads of several bodies in flight at once (this epilogue was a third of the kernel's stalls
+    // when it ran one body at a time)
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int b = bg * kBG + w * 16 + i;
-        if (b >= p.B) break;
-        float x = 0.f, y = 0.f, z = 0.f;
-#pragma unroll
-        for (int ii = 0; ii < 16; ++ii)
-            if (ii == i) { x = acc[ii][0]; y = acc[ii][1]; z = acc[ii][2]; }
-        x += t0; y += t1; z += t2;
+        if (b >= p.B) continue;
+        float x = acc[i][0] + t0, y = acc[i][1] + t1, z = acc[i][2] + t2;
         p.vp_out[((size_t)b * p.V + v) * 3 + 0] = x;
         p.vp_out[((size_t)b * p.V + v) * 3 + 1] = y;
         p.vp_out[((size_t)b * p.V + v) * 3 + 2] = z;
