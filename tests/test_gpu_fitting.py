@@ -127,3 +127,48 @@ def test_reference_style_single_body_pickle_flow(small_model, tmp_path):
     d = io.read_body_pickle(str(tmp_path / "fit" / "body_gen_000000.pkl"))
     assert set(d) == {"transl", "global_orient", "betas", "body_pose", "left_hand_pose", "right_hand_pose", "cam_ext", "cam_int"}
     assert d["body_pose"].shape == (1, 32)
+
+
+def test_evaluation_scores_match_reference_definition(small_model):
+    """utils_eval_collision_habitat.py:121-138 evaluated on the CPU restatement."""
+    from psi_release_b200 import evaluate
+    from psi_release_b200.fitting import FittingOP
+    B = 6
+    scene, xh, cid, cfg = _world(small_model, B)
+    op = FittingOP(dict(cfg, engine="autograd"), W)
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0)
+    nc, ct = evaluate.collision_scores(op, torch.tensor(xh).cuda(), cam.cuda())
+    kw = _oracle_kw(small_model, scene, cid)
+    cx = torch.tensor(xh)
+    v, _ = kw["smplx_model"](body_pose=kw["vposer"].decode(cx[:, 16:48]), transl=cx[:, :3], global_orient=cx[:, 3:6],
+                             betas=cx[:, 6:16], left_hand_pose=cx[:, 48:60], right_hand_pose=cx[:, 60:])
+    v = oracle.verts_transform(v, cam.expand(B, -1, -1))
+    s = oracle.sdf_lookup_torch(kw["sdf"], kw["gmin"], kw["gmax"], v)
+    for b in range(B):
+        if int((s[b] < 0).sum()) < 1:
+            ref_nc, ref_ct = 1.0, 0.0
+        else:
+            ref_nc, ref_ct = float((s[b] > 0).sum()) / s.shape[1], 1.0
+        assert abs(float(nc[b]) - ref_nc) <= 2.0 / s.shape[1]      # a vertex within rounding of sdf == 0
+        assert float(ct[b]) == ref_ct
+    assert 0 < float(ct.sum()) <= B
+
+
+def test_multi_scene_fit_equals_per_scene_fits(small_model):
+    """distributed.fit_scenes on one rank: two scenes, ragged body counts."""
+    from psi_release_b200 import synthetic
+    from psi_release_b200.distributed import fit_scenes
+    from psi_release_b200.fitting import FittingOP
+    scenes = [synthetic.make_scene(seed=s, dim=24, num_points=1500) for s in (4, 5)]
+    xhs = [torch.tensor(synthetic.make_body_params(sc, n, seed=9 + i)) for i, (sc, n) in enumerate(zip(scenes, (3, 2)))]
+    cams = [torch.tensor(sc.cam_ext).unsqueeze(0) for sc in scenes]
+    cid = synthetic.make_contact_ids(431, "parts")
+
+    def make(s, batch):
+        return FittingOP(dict(model_data=small_model, scene=scenes[s], vposer_weights=synthetic.make_vposer_weights(),
+                              contact_ids=cid, init_lr_h=0.1, num_iter=3, batch_size=batch, device="cuda"), W)
+
+    out = fit_scenes(make, xhs, cams)
+    assert out.shape == (5, 72)
+    ref = torch.cat([make(s, xhs[s].shape[0]).fit(xhs[s].cuda(), cams[s].cuda()) for s in range(2)])
+    assert torch.equal(out, ref)

@@ -140,6 +140,18 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_scene_shard_plan_config3():
+    from psi_release_b200.distributed import plan_scene_shards
+    plan = plan_scene_shards([128, 128, 128, 128], 8)            # BASELINE configs[2]
+    assert [sum(b - a for _, a, b in items) for items in plan] == [64] * 8
+    assert all(len(items) == 1 for items in plan)                 # a rank never straddles scenes here
+    assert plan[3] == [(1, 64, 128)]
+    plan = plan_scene_shards([5, 1, 7], 4)                        # ragged: 13 bodies over 4 ranks
+    flat = [(s, i) for items in plan for s, a, b in items for i in range(a, b)]
+    assert flat == [(0, i) for i in range(5)] + [(1, 0)] + [(2, i) for i in range(7)]
+    assert max(sum(b - a for _, a, b in it) for it in plan) - min(sum(b - a for _, a, b in it) for it in plan) <= 1
+
+
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["PSI_ROOT"])
