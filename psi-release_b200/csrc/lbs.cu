@@ -205,7 +205,10 @@ struct VertexFwdParams {
     int V, J, Kpad, Npad, KW, B;
 };
 
-__global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdParams p) {
+constexpr int kBPT = 8;                   // bodies per thread (24 accumulators); kBG / kBPT warps per CTA
+constexpr int kVfWarps = kBG / kBPT;      // 8 warps = 256 threads, 3 CTAs per SM: 17.7 warps/SM at B=64
+
+__global__ void __launch_bounds__(kVfWarps * 32, 3) lbs_vertex_fwd_kernel(const VertexFwdParams p) {
     // 4 warps (16 bodies each, lane = vertex).  full[st]: bytes landed; empty[st]: all 4 warps
     // released the stage.  Lane 0 of warp 0 refills a stage kStages-2 chunks ahead, so there is no
     // block-wide barrier inside the K loop: warps may drift a chunk apart.
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdP
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kVfWarps); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -239,9 +242,9 @@ __global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdP
     if (tid == 0)
         for (int c = 0; c < kStages - 2 && c < nchunks; ++c) issue(c);
 
-    float acc[16][3];
+    float acc[kBPT][3];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+    for (int i = 0; i < kBPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
 
     for (int c = 0; c < nchunks; ++c) {
         if (tid == 0 && c + kStages - 2 < nchunks) issue(c + kStages - 2);
@@ -249,15 +252,18 @@ __global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdP
         const int st = c % kStages;
         mbar_wait(&full[st], (uint32_t)((c / kStages) & 1));
         const float *bs = sm + st * kStageFloats + 3 * lane;
-        const float4 *cs = reinterpret_cast<const float4 *>(sm + st * kStageFloats + kKT * kTileN) + 4 * w;  // [kk][64 bodies]
+        const float4 *cs = reinterpret_cast<const float4 *>(sm + st * kStageFloats + kKT * kTileN) + (kBPT / 4) * w;  // [kk][64 bodies]
 #pragma unroll 4
         for (int kk = 0; kk < kKT; ++kk) {
             const float b0 = bs[kk * kTileN], b1 = bs[kk * kTileN + 1], b2 = bs[kk * kTileN + 2];
-            const float4 c0 = cs[kk * (kBG / 4) + 0], c1 = cs[kk * (kBG / 4) + 1], c2 = cs[kk * (kBG / 4) + 2], c3 = cs[kk * (kBG / 4) + 3];
-            const float cf[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w,
-                                  c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+            float cf[kBPT];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int u = 0; u < kBPT / 4; ++u) {
+                const float4 cc = cs[kk * (kBG / 4) + u];
+                cf[4 * u] = cc.x; cf[4 * u + 1] = cc.y; cf[4 * u + 2] = cc.z; cf[4 * u + 3] = cc.w;
+            }
+#pragma unroll
+            for (int i = 0; i < kBPT; ++i) {
                 acc[i][0] = fmaf(cf[i], b0, acc[i][0]);
                 acc[i][1] = fmaf(cf[i], b1, acc[i][1]);
                 acc[i][2] = fmaf(cf[i], b2, acc[i][2]);
@@ -278,17 +284,24 @@ __global__ void __launch_bounds__(128, 3) lbs_vertex_fwd_kernel(const VertexFwdP
         sj[k] = (k < kw) ? p.skin_j[(size_t)v * kw + k] : 0;
         sw[k] = (k < kw) ? p.skin_w[(size_t)v * kw + k] : 0.f;
     }
-    // fully unrolled over the warp's 16 bodies: compile-time accumulator indices and the skinning
-    // loads of several bodies in flight at once (this epilogue was a third of the kernel's stalls
-    // when it ran one body at a time)
+    // phase A (unrolled, compile-time accumulator indices): v_posed = blend + template, stored once
+    // (the backward needs it anyway); phase B (rolled): skinning reads it back, so the 24
+    // accumulators are dead before the register-hungry part starts
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int b = bg * kBG + w * 16 + i;
+    for (int i = 0; i < kBPT; ++i) {
+        const int b = bg * kBG + w * kBPT + i;
         if (b >= p.B) continue;
-        float x = acc[i][0] + t0, y = acc[i][1] + t1, z = acc[i][2] + t2;
-        p.vp_out[((size_t)b * p.V + v) * 3 + 0] = x;
-        p.vp_out[((size_t)b * p.V + v) * 3 + 1] = y;
-        p.vp_out[((size_t)b * p.V + v) * 3 + 2] = z;
+        float *vp = p.vp_out + ((size_t)b * p.V + v) * 3;
+        vp[0] = acc[i][0] + t0;
+        vp[1] = acc[i][1] + t1;
+        vp[2] = acc[i][2] + t2;
+    }
+#pragma unroll 1
+    for (int i = 0; i < kBPT; ++i) {
+        const int b = bg * kBG + w * kBPT + i;
+        if (b >= p.B) break;
+        const float *vp = p.vp_out + ((size_t)b * p.V + v) * 3;
+        const float x = vp[0], y = vp[1], z = vp[2];
         float T[12];
 #pragma unroll
         for (int e = 0; e < 12; ++e) T[e] = 0.f;
@@ -874,7 +887,7 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
         attr_set = true;
     }
     dim3 grid((unsigned)(m->Npad / kTileN), (unsigned)((B + kBG - 1) / kBG));
-    lbs_vertex_fwd_kernel<<<grid, 128, smem, st>>>(p);
+    lbs_vertex_fwd_kernel<<<grid, kVfWarps * 32, smem, st>>>(p);
     PSI_LAUNCHED();
     return PSI_OK;
 }

@@ -227,14 +227,30 @@ __global__ void __launch_bounds__(256)
 nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, long q_bstride, int n,
                        const int *__restrict__ qsel, long total, float *__restrict__ dist,
                        int *__restrict__ idx, int *__restrict__ hint) {
+    // Only the mega + super boxes (7 kB at 50 000 points) are staged in shared memory: 8 CTAs stay
+    // resident per SM (64 warps) -- this walk is latency bound; the cluster boxes (50 kB) come
+    // through L1, where the coherent warps hit.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const float4 *boxes = ix.boxes;
+    const int ntop = ix.mpad + ix.num_supers;
+    float4 *s4 = reinterpret_cast<float4 *>(smem_raw);
     if (SMEM) {
-        float4 *s4 = reinterpret_cast<float4 *>(smem_raw);
-        for (int i = threadIdx.x; i < 2 * ix.nbox; i += blockDim.x) s4[i] = __ldg(ix.boxes + i);
+        for (int i = threadIdx.x; i < ntop; i += blockDim.x) {
+            s4[i] = __ldg(ix.boxes + i);
+            s4[ntop + i] = __ldg(ix.boxes + ix.nbox + i);
+        }
         __syncthreads();
-        boxes = s4;
     }
+    auto lbf = [&](int node, float qx, float qy, float qz) -> float {
+        float4 lo, hi;
+        if (SMEM && node < ntop) {
+            lo = s4[node];
+            hi = s4[ntop + node];
+        } else {
+            lo = __ldg(ix.boxes + node);
+            hi = __ldg(ix.boxes + ix.nbox + node);
+        }
+        return __uint_as_float(box_lb(lo, hi, qx, qy, qz));
+    };
     const int sbase = ix.mpad, cbase = ix.mpad + ix.num_supers;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
         const long b = t / n;
@@ -263,19 +279,19 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
             float best = CUDART_INF_F;
             int m0 = 0;
             for (int g = 0; g < ix.num_megas; ++g) {
-                const float lb = node_lbf<SMEM>(ix, boxes, g, qx, qy, qz);
+                const float lb = lbf(g, qx, qy, qz);
                 if (lb < best) { best = lb; m0 = g; }
             }
             best = CUDART_INF_F;
             int s0 = m0 * kFan;
             for (int s = m0 * kFan; s < m0 * kFan + kFan; ++s) {
-                const float lb = node_lbf<SMEM>(ix, boxes, sbase + s, qx, qy, qz);
+                const float lb = lbf(sbase + s, qx, qy, qz);
                 if (lb < best) { best = lb; s0 = s; }
             }
             best = CUDART_INF_F;
             seeded = s0 * kFan;
             for (int c = s0 * kFan; c < s0 * kFan + kFan; ++c) {
-                const float lb = node_lbf<SMEM>(ix, boxes, cbase + c, qx, qy, qz);
+                const float lb = lbf(cbase + c, qx, qy, qz);
                 if (lb < best) { best = lb; seeded = c; }
             }
         }
@@ -283,14 +299,14 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
         // ordered sweep with pruning against this query's best distance so far
 #pragma unroll 1
         for (int g = 0; g < ix.num_megas; ++g) {
-            if (node_lbf<SMEM>(ix, boxes, g, qx, qy, qz) > bd) continue;
+            if (lbf(g, qx, qy, qz) > bd) continue;
 #pragma unroll 1
             for (int s = g * kFan; s < g * kFan + kFan; ++s) {
-                if (node_lbf<SMEM>(ix, boxes, sbase + s, qx, qy, qz) > bd) continue;
+                if (lbf(sbase + s, qx, qy, qz) > bd) continue;
 #pragma unroll 1
                 for (int c = s * kFan; c < s * kFan + kFan; ++c) {
                     if (c == seeded) continue;
-                    if (node_lbf<SMEM>(ix, boxes, cbase + c, qx, qy, qz) > bd) continue;
+                    if (lbf(cbase + c, qx, qy, qz) > bd) continue;
                     visit(c);
                 }
             }
@@ -436,10 +452,11 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
     if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
         // one thread per query: enough queries to fill the machine with 256-thread CTAs
         long blocks = (total + 255) / 256;
-        const long cap = (long)PSI_NUM_SMS * 3;
+        const long cap = (long)PSI_NUM_SMS * 8;
         if (blocks > cap) blocks = cap;
-        if (smem)
-            nn_index_thread_kernel<true><<<(unsigned)blocks, 256, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+        const size_t top_bytes = (size_t)2 * (ix->mpad + ix->num_supers) * sizeof(float4);
+        if (top_bytes <= 24 * 1024)
+            nn_index_thread_kernel<true><<<(unsigned)blocks, 256, top_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
         else
             nn_index_thread_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     } else {
