@@ -596,6 +596,6 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
     return psi_fit_end(c, xhr_out, losses_out, stream);
 }
 
-int psi_fit_launches_per_iteration(void) { return 12; }
+int psi_fit_launches_per_iteration(void) { return 13; }
 
 }  // extern "C"

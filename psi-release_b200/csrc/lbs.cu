@@ -276,14 +276,6 @@ __global__ void __launch_bounds__(kVfWarps * 32, 3) lbs_vertex_fwd_kernel(const 
     const int v = tile * 32 + lane;
     if (v >= p.V) return;
     const float t0 = p.v_template[3 * v], t1 = p.v_template[3 * v + 1], t2 = p.v_template[3 * v + 2];
-    int sj[8];
-    float sw[8];
-    const int kw = p.KW;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        sj[k] = (k < kw) ? p.skin_j[(size_t)v * kw + k] : 0;
-        sw[k] = (k < kw) ? p.skin_w[(size_t)v * kw + k] : 0.f;
-    }
     // phase A (unrolled, compile-time accumulator indices): v_posed = blend + template, stored once
     // (the backward needs it anyway); phase B (rolled): skinning reads it back, so the 24
     // accumulators are dead before the register-hungry part starts
@@ -296,48 +288,48 @@ __global__ void __launch_bounds__(kVfWarps * 32, 3) lbs_vertex_fwd_kernel(const 
         vp[1] = acc[i][1] + t1;
         vp[2] = acc[i][2] + t2;
     }
-#pragma unroll 1
-    for (int i = 0; i < kBPT; ++i) {
-        const int b = bg * kBG + w * kBPT + i;
-        if (b >= p.B) break;
-        const float *vp = p.vp_out + ((size_t)b * p.V + v) * 3;
-        const float x = vp[0], y = vp[1], z = vp[2];
-        float T[12];
+}
+
+// skinning + translation + camera transform, one thread per (body, vertex): a streaming pass over
+// v_posed with gathers from the [B,J,12] transform table (169 kB at B=64, cache resident).
+// (lbs.py:108-116, body_model.py:246-247, cvae.py:141-149)
+__global__ void __launch_bounds__(256)
+lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const float *__restrict__ skin_w,
+                    const float *__restrict__ A, const float *__restrict__ vp_in,
+                    const float *__restrict__ transl, const float *__restrict__ cam, long cam_bstride,
+                    float *__restrict__ verts) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (v >= V) return;
+    const float *vp = vp_in + ((size_t)b * V + v) * 3;
+    const float x = vp[0], y = vp[1], z = vp[2];
+    float T[12];
 #pragma unroll
-        for (int e = 0; e < 12; ++e) T[e] = 0.f;
-        const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(p.A + (size_t)b * p.J * 12);
-#define PSI_SKIN_ACC(j, wt)                                                                        \
-    {                                                                                              \
-        const float4 r0 = __ldg(Ab + (j) * 3), r1 = __ldg(Ab + (j) * 3 + 1), r2 = __ldg(Ab + (j) * 3 + 2); \
-        T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]); T[3] = fmaf(wt, r0.w, T[3]); \
-        T[4] = fmaf(wt, r1.x, T[4]); T[5] = fmaf(wt, r1.y, T[5]); T[6] = fmaf(wt, r1.z, T[6]); T[7] = fmaf(wt, r1.w, T[7]); \
-        T[8] = fmaf(wt, r2.x, T[8]); T[9] = fmaf(wt, r2.y, T[9]); T[10] = fmaf(wt, r2.z, T[10]); T[11] = fmaf(wt, r2.w, T[11]); \
+    for (int e = 0; e < 12; ++e) T[e] = 0.f;
+    const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
+    for (int k = 0; k < KW; ++k) {
+        const int j = skin_j[(size_t)v * KW + k];
+        const float wt = skin_w[(size_t)v * KW + k];
+        const float4 r0 = __ldg(Ab + j * 3), r1 = __ldg(Ab + j * 3 + 1), r2 = __ldg(Ab + j * 3 + 2);
+        T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]); T[3] = fmaf(wt, r0.w, T[3]);
+        T[4] = fmaf(wt, r1.x, T[4]); T[5] = fmaf(wt, r1.y, T[5]); T[6] = fmaf(wt, r1.z, T[6]); T[7] = fmaf(wt, r1.w, T[7]);
+        T[8] = fmaf(wt, r2.x, T[8]); T[9] = fmaf(wt, r2.y, T[9]); T[10] = fmaf(wt, r2.z, T[10]); T[11] = fmaf(wt, r2.w, T[11]);
     }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < kw) PSI_SKIN_ACC(sj[k], sw[k]);
-        for (int k = 8; k < kw; ++k) {
-            const int j = p.skin_j[(size_t)v * kw + k];
-            const float wt = p.skin_w[(size_t)v * kw + k];
-            PSI_SKIN_ACC(j, wt);
-        }
-#undef PSI_SKIN_ACC
-        float ox = T[0] * x + T[1] * y + T[2] * z + T[3];
-        float oy = T[4] * x + T[5] * y + T[6] * z + T[7];
-        float oz = T[8] * x + T[9] * y + T[10] * z + T[11];
-        if (p.transl) {
-            ox += p.transl[(size_t)b * 3]; oy += p.transl[(size_t)b * 3 + 1]; oz += p.transl[(size_t)b * 3 + 2];
-        }
-        if (p.cam) {
-            const float *C = p.cam + (size_t)b * p.cam_bstride;
-            const float cx = C[0] * ox + C[1] * oy + C[2] * oz + C[3];
-            const float cy = C[4] * ox + C[5] * oy + C[6] * oz + C[7];
-            const float cz = C[8] * ox + C[9] * oy + C[10] * oz + C[11];
-            ox = cx; oy = cy; oz = cz;
-        }
-        float *o = p.verts + ((size_t)b * p.V + v) * 3;
-        o[0] = ox; o[1] = oy; o[2] = oz;
+    float ox = T[0] * x + T[1] * y + T[2] * z + T[3];
+    float oy = T[4] * x + T[5] * y + T[6] * z + T[7];
+    float oz = T[8] * x + T[9] * y + T[10] * z + T[11];
+    if (transl) {
+        ox += transl[(size_t)b * 3]; oy += transl[(size_t)b * 3 + 1]; oz += transl[(size_t)b * 3 + 2];
     }
+    if (cam) {
+        const float *C = cam + (size_t)b * cam_bstride;
+        const float cx = C[0] * ox + C[1] * oy + C[2] * oz + C[3];
+        const float cy = C[4] * ox + C[5] * oy + C[6] * oz + C[7];
+        const float cz = C[8] * ox + C[9] * oy + C[10] * oz + C[11];
+        ox = cx; oy = cy; oz = cz;
+    }
+    float *o = verts + ((size_t)b * V + v) * 3;
+    o[0] = ox; o[1] = oy; o[2] = oz;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -865,6 +857,7 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
     if (B == 0) return PSI_OK;
     if (!betas || !pose || !verts || !saved) return PSI_ERR_BAD_ARG;
     if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !rot_in)) return PSI_ERR_BAD_ARG;
+    if (B > 65535) return PSI_ERR_UNSUPPORTED;
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
@@ -889,6 +882,12 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
     dim3 grid((unsigned)(m->Npad / kTileN), (unsigned)((B + kBG - 1) / kBG));
     lbs_vertex_fwd_kernel<<<grid, kVfWarps * 32, smem, st>>>(p);
     PSI_LAUNCHED();
+    {
+        dim3 sgrid((unsigned)((m->V + 255) / 256), (unsigned)B);
+        lbs_skin_fwd_kernel<<<sgrid, 256, 0, st>>>(m->V, m->J, m->KW, m->skin_j, m->skin_w, saved + L.A, saved + L.vp,
+                                                   transl, cam, cam_bstride, verts);
+        PSI_LAUNCHED();
+    }
     return PSI_OK;
 }
 
