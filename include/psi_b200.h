@@ -195,6 +195,16 @@ PSI_API int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const
                 float *grad_rot, int num_rot,
                 void *workspace, size_t workspace_bytes, psi_stream_t stream);
 
+/* psi_lbs_bwd with an optional side stream (cudaStream_t) and two cudaEvent_t (fork, join): the
+ * per-joint gather-reduce runs on the side stream next to the d-coefficient GEMM.  NULL = serial. */
+PSI_API int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                 const float *cam, long cam_bstride, const float *saved,
+                 const float *grad_verts, const float *grad_joints,
+                 float *grad_betas, float *grad_pose, float *grad_transl,
+                 float *grad_rot, int num_rot,
+                 void *workspace, size_t workspace_bytes, psi_stream_t stream,
+                 psi_stream_t side_stream, void *ev_fork, void *ev_join);
+
 /* ------------------------------------------------------------------------------------------
  * The fused fitting loop.
  * Replaces: FittingOP.cal_loss + loss.backward + optimizer.step, i.e. the body of the loop at

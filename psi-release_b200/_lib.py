@@ -70,6 +70,8 @@ def lib():
         "psi_lbs_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _l, _vp, _i, _vp, _vp, _vp, _vp]),
         "psi_lbs_bwd_workspace_bytes": (_sz, [_vp, _i]),
         "psi_lbs_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+        "psi_lbs_bwd2": (_i, [_vp, _i, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp,
+                              _vp, _vp, _vp]),
         "psi_fit_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i,
                                 ctypes.POINTER(FitConfig), _vp]),
@@ -93,7 +95,7 @@ EXPORTS = ["psi_abi_version", "psi_error_string", "psi_launch_count", "psi_nn_wo
            "psi_chamfer_fwd", "psi_nn_bwd", "psi_chamfer_bwd", "psi_nn_index_create", "psi_nn_index_destroy",
            "psi_nn_index_bytes", "psi_nn_index_query", "psi_nn_index_query_hint", "psi_nn_index_query_mode", "psi_sdf_num_partials", "psi_sdf_fwd",
            "psi_sdf_bwd", "psi_lbs_model_create", "psi_lbs_model_destroy", "psi_lbs_model_bytes",
-           "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd",
+           "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd", "psi_lbs_bwd2",
            "psi_fit_create", "psi_fit_destroy", "psi_fit_run", "psi_fit_begin", "psi_fit_end",
            "psi_fit_launches_per_iteration"]
 

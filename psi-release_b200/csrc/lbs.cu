@@ -891,18 +891,26 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
     return PSI_OK;
 }
 
+int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
+                const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
+                float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
+                psi_stream_t stream);
+
 size_t psi_lbs_bwd_workspace_bytes(const psi_lbs_model *m, int B) {
     if (!m || B <= 0) return 0;
     return psi::bwd_layout(m, B).total * sizeof(float);
 }
 
-int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
-                const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
-                const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
-                float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
-                psi_stream_t stream) {
+int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                 const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
+                 const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
+                 float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
+                 psi_stream_t stream, psi_stream_t side_stream, void *ev_fork, void *ev_join) {
     using namespace psi;
     (void)betas;
+    // optional side stream: lbs_dA runs next to lbs_dcoef (both only depend on lbs_vertex_bwd)
+    cudaStream_t side = (side_stream && ev_fork && ev_join) ? (cudaStream_t)side_stream : nullptr;
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!pose || !saved || !grad_verts || !grad_betas || !grad_pose || !workspace) return PSI_ERR_BAD_ARG;
@@ -922,10 +930,18 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
         PSI_LAUNCHED();
     }
     {
+        cudaStream_t sa = st;
+        if (side) {
+            if (cudaEventRecord((cudaEvent_t)ev_fork, st) != cudaSuccess ||
+                cudaStreamWaitEvent(side, (cudaEvent_t)ev_fork, 0) != cudaSuccess)
+                return PSI_ERR_BAD_ARG;
+            sa = side;
+        }
         dim3 grid((unsigned)(m->J + 1), (unsigned)B);
-        lbs_dA_kernel<<<grid, 128, 0, st>>>(m->V, m->J, m->jl_start, m->jl_vert, m->jl_w,
+        lbs_dA_kernel<<<grid, 128, 0, sa>>>(m->V, m->J, m->jl_start, m->jl_vert, m->jl_w,
                                             ws + W.gw, saved + L.vp, ws + W.dA, ws + W.dtr);
         PSI_LAUNCHED();
+        if (side && cudaEventRecord((cudaEvent_t)ev_join, side) != cudaSuccess) return PSI_ERR_BAD_ARG;
     }
     {
         const int total_chunks = m->Npad / 32;
@@ -938,12 +954,23 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
         lbs_dcoef_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(ws + W.part, kNSplit, per_split, ws + W.dsum);
         PSI_LAUNCHED();
     }
+    if (side && cudaStreamWaitEvent(st, (cudaEvent_t)ev_join, 0) != cudaSuccess) return PSI_ERR_BAD_ARG;
     lbs_pose_bwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
                                           m->parents, pose, saved, L, ws + W.dA, ws + W.dtr,
                                           ws + W.dsum, grad_joints, grad_betas, grad_pose,
                                           grad_transl, grad_rot, num_rot, m->tree);
     PSI_LAUNCHED();
     return PSI_OK;
+}
+
+int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
+                const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
+                float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
+                psi_stream_t stream) {
+    return psi_lbs_bwd2(m, B, betas, pose, cam, cam_bstride, saved, grad_verts, grad_joints, grad_betas,
+                        grad_pose, grad_transl, grad_rot, num_rot, workspace, workspace_bytes, stream,
+                        nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"
