@@ -38,8 +38,8 @@ struct psi_fit_ctx {
     size_t lbs_ws_bytes;
     cudaGraphExec_t exec;
     int pending_join;
-    cudaStream_t gstream, side;    // graphs cannot be captured on the legacy default stream
-    cudaEvent_t ev_in, ev_out, ev_f1, ev_j1, ev_f2, ev_j2;
+    cudaStream_t gstream;          // graphs cannot be captured on the legacy default stream
+    cudaEvent_t ev_in, ev_out;
     std::vector<void *> owned;
 };
 
@@ -368,17 +368,12 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     int rc = psi_lbs_fwd(c->model, c->B, c->shape, c->pose, c->transl, c->cam, 12, c->rot, c->num_rot,
                          c->verts, nullptr, c->saved, st);
     if (rc) return rc;
-    // the SDF lookup only needs the vertices: it runs on the side stream next to the NN query
-    if (cudaEventRecord(c->ev_f1, st) != cudaSuccess || cudaStreamWaitEvent(c->side, c->ev_f1, 0) != cudaSuccess)
-        return PSI_ERR_BAD_ARG;
-    rc = psi_sdf_fwd(c->sdf, 1, c->D, c->gmin, c->gmax, c->verts, c->B, c->V, nullptr, c->sdfv, c->sdfg,
-                     c->partial, c->side);
-    if (rc) return rc;
-    if (cudaEventRecord(c->ev_j1, c->side) != cudaSuccess) return PSI_ERR_BAD_ARG;
     rc = psi_nn_index_query_hint(c->index, c->verts, (long)c->V * 3, c->B, c->nu, c->csel, c->nnd, c->nni,
                                  c->nnhint, st);
     if (rc) return rc;
-    if (cudaStreamWaitEvent(st, c->ev_j1, 0) != cudaSuccess) return PSI_ERR_BAD_ARG;
+    rc = psi_sdf_fwd(c->sdf, 1, c->D, c->gmin, c->gmax, c->verts, c->B, c->V, nullptr, c->sdfv, c->sdfg,
+                     c->partial, st);
+    if (rc) return rc;
     {
         dim3 grid((unsigned)c->nchunk, (unsigned)c->B);
         fit_vertex_grad_kernel<<<grid, 256, 0, st>>>(c->V, c->nu, c->np_sdf, c->num_contact, c->verts,
@@ -387,9 +382,8 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
                                                      c->cfg.w_collision, c->cfg.robust_c, c->gverts, c->cpart);
         PSI_LAUNCHED();
     }
-    rc = psi_lbs_bwd2(c->model, c->B, c->shape, c->pose, c->cam, 12, c->saved, c->gverts, nullptr, c->gshape,
-                      c->gpose, c->gtransl, c->grot, c->num_rot, c->lbs_ws, c->lbs_ws_bytes, st, c->side,
-                      c->ev_f2, c->ev_j2);
+    rc = psi_lbs_bwd(c->model, c->B, c->shape, c->pose, c->cam, 12, c->saved, c->gverts, nullptr, c->gshape,
+                     c->gpose, c->gtransl, c->grot, c->num_rot, c->lbs_ws, c->lbs_ws_bytes, st);
     if (rc) return rc;
     fit_epilogue2_kernel<<<c->B, kMlpThreads, sizeof(MlpSmem), st>>>(d, c->cfg, c->np_sdf, c->nchunk, c->num_contact, c->x0, c->x,
                                               c->am, c->av, c->step, c->W1, c->W2, c->W3, c->hand_l,
@@ -407,11 +401,6 @@ void psi_fit_destroy(psi_fit_ctx *c) {
     if (!c) return;
     if (c->exec) cudaGraphExecDestroy(c->exec);
     if (c->gstream) cudaStreamDestroy(c->gstream);
-    if (c->side) cudaStreamDestroy(c->side);
-    if (c->ev_f1) cudaEventDestroy(c->ev_f1);
-    if (c->ev_j1) cudaEventDestroy(c->ev_j1);
-    if (c->ev_f2) cudaEventDestroy(c->ev_f2);
-    if (c->ev_j2) cudaEventDestroy(c->ev_j2);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     for (void *p : c->owned) cudaFree(p);
@@ -440,13 +429,8 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->model = model; c->index = index; c->cfg = *cfg;
     c->B = cfg->B; c->V = V; c->J = J; c->NB = NB; c->latent = latent; c->hidden = hidden; c->nbody = nbody;
     c->ncomp = ncomp; c->num_rot = nbody + 1; c->D = D; c->sdf = sdf; c->scene_pts = scene_points;
-    c->num_contact = num_contact; c->exec = nullptr; c->pending_join = 0; c->gstream = nullptr; c->side = nullptr; c->ev_in = c->ev_out = c->ev_f1 = c->ev_j1 = c->ev_f2 = c->ev_j2 = nullptr;
+    c->num_contact = num_contact; c->exec = nullptr; c->pending_join = 0; c->gstream = nullptr; c->ev_in = c->ev_out = nullptr;
     if (cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_f1, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_j1, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_f2, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_j2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
         psi_fit_destroy(c);
