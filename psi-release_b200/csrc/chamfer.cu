@@ -28,6 +28,17 @@ __device__ __forceinline__ float ref_dist(float sx, float sy, float sz, float qx
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// two queries per instruction: Blackwell's packed FP32 ops (SASS FADD2 / FMUL2 / FFMA2; the scene
+// coordinate enters as a broadcast scalar operand).  Each lane of a packed op is an independent
+// IEEE round-to-nearest operation, so the bits equal the scalar form above.
+__device__ __forceinline__ float2 ref_dist2(float sx, float sy, float sz, float2 nqx, float2 nqy,
+                                            float2 nqz) {
+    const float2 dx = __fadd2_rn(make_float2(sx, sx), nqx);   // s - q, with -q precomputed (exact)
+    const float2 dy = __fadd2_rn(make_float2(sy, sy), nqy);
+    const float2 dz = __fadd2_rn(make_float2(sz, sz), nqz);
+    return __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+}
+
 struct NNParams {
     const float *q;
     long q_bstride;
@@ -47,7 +58,7 @@ struct NNParams {
 
 template <int Q, int G, int THREADS, int TP, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) nn_fwd_kernel(const NNParams p) {
-    static_assert(G % 4 == 0 && TP % G == 0, "tile/group sizes");
+    static_assert(G % 4 == 0 && TP % G == 0 && Q % 2 == 0, "tile/group sizes");
     constexpr int NS = 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw);  // NS x TP x 3 floats
@@ -81,6 +92,13 @@ __global__ void __launch_bounds__(THREADS, MINB) nn_fwd_kernel(const NNParams p)
         }
         best[i] = CUDART_INF_F;
         bgrp[i] = k_begin / G;
+    }
+    float2 nqx[Q / 2], nqy[Q / 2], nqz[Q / 2];          // negated query pairs for the packed ops
+#pragma unroll
+    for (int i = 0; i < Q / 2; ++i) {
+        nqx[i] = make_float2(-qx[2 * i], -qx[2 * i + 1]);
+        nqy[i] = make_float2(-qy[2 * i], -qy[2 * i + 1]);
+        nqz[i] = make_float2(-qz[2 * i], -qz[2 * i + 1]);
     }
 
     if (p.tma_ok && tid == 0) {
@@ -130,15 +148,17 @@ __global__ void __launch_bounds__(THREADS, MINB) nn_fwd_kernel(const NNParams p)
                 const float4 b = t4[(g * (G / 4) + u) * 3 + 1];
                 const float4 c = t4[(g * (G / 4) + u) * 3 + 2];
 #pragma unroll
-                for (int i2 = 0; i2 < Q; ++i2) {
-                    const float d0 = ref_dist(a.x, a.y, a.z, qx[i2], qy[i2], qz[i2]);
-                    const float d1 = ref_dist(a.w, b.x, b.y, qx[i2], qy[i2], qz[i2]);
-                    const float d2 = ref_dist(b.z, b.w, c.x, qx[i2], qy[i2], qz[i2]);
-                    const float d3 = ref_dist(c.y, c.z, c.w, qx[i2], qy[i2], qz[i2]);
-                    float mn = (u == 0) ? d0 : fminf(gm[i2], d0);
-                    mn = fminf(mn, d1);
-                    mn = fminf(mn, d2);
-                    gm[i2] = fminf(mn, d3);
+                for (int i2 = 0; i2 < Q / 2; ++i2) {
+                    const float2 d0 = ref_dist2(a.x, a.y, a.z, nqx[i2], nqy[i2], nqz[i2]);
+                    const float2 d1 = ref_dist2(a.w, b.x, b.y, nqx[i2], nqy[i2], nqz[i2]);
+                    const float2 d2 = ref_dist2(b.z, b.w, c.x, nqx[i2], nqy[i2], nqz[i2]);
+                    const float2 d3 = ref_dist2(c.y, c.z, c.w, nqx[i2], nqy[i2], nqz[i2]);
+                    float m0 = (u == 0) ? d0.x : fminf(gm[2 * i2], d0.x);
+                    float m1 = (u == 0) ? d0.y : fminf(gm[2 * i2 + 1], d0.y);
+                    m0 = fminf(m0, d1.x); m1 = fminf(m1, d1.y);
+                    m0 = fminf(m0, d2.x); m1 = fminf(m1, d2.y);
+                    gm[2 * i2] = fminf(m0, d3.x);
+                    gm[2 * i2 + 1] = fminf(m1, d3.y);
                 }
             }
 #pragma unroll

@@ -172,3 +172,43 @@ def test_multi_scene_fit_equals_per_scene_fits(small_model):
     assert out.shape == (5, 72)
     ref = torch.cat([make(s, xhs[s].shape[0]).fit(xhs[s].cuda(), cams[s].cuda()) for s in range(2)])
     assert torch.equal(out, ref)
+
+
+def test_training_geometry_block_matches_train_s2_definition(small_model):
+    """training.SceneLossBlock vs train_s2.py:136-202 restated on the CPU: two scenes in one batch,
+    gradients reach an upstream (stock torch) layer, and the block is gated by the epoch."""
+    from psi_release_b200 import body_model, synthetic, training
+    from psi_release_b200.geometry import VPoserDecoder
+    B = 5
+    scenes = [synthetic.make_scene(seed=s, dim=24, num_points=1200) for s in (7, 8)]
+    scene_ids = [0, 1, 1, 0, 1]
+    xh = np.concatenate([synthetic.make_body_params(scenes[s], 1, seed=30 + i) for i, s in enumerate(scene_ids)])
+    cams = torch.stack([torch.tensor(scenes[s].cam_ext) for s in scene_ids])
+    cid = synthetic.make_contact_ids(431, "parts")
+    vw = synthetic.make_vposer_weights()
+    blk = training.SceneLossBlock(body_model.create(model_data=small_model, num_pca_comps=12, batch_size=B),
+                                  VPoserDecoder.from_weights(vw), scenes, cid, 0.001, 0.01, 0.1)
+    lin = torch.nn.Linear(72, 72).cuda()                       # stand-in for the CVAE decoder head
+    with torch.no_grad():
+        lin.weight.copy_(torch.eye(72)); lin.bias.zero_()
+    x = torch.tensor(xh).cuda()
+    lc, lv, lp = blk(lin(x), cams.cuda(), scene_ids, ep=29, epochs=30)
+    (lc + lv + lp).backward()
+    assert lin.weight.grad is not None and float(lin.weight.grad.abs().sum()) > 0
+    # CPU restatement
+    so = oracle.SMPLXOracle(small_model); vp = oracle.VPoserDecoderOracle(vw)
+    cx = torch.tensor(xh)
+    v, _ = so(body_pose=vp.decode(cx[:, 16:48]), transl=cx[:, :3], global_orient=cx[:, 3:6], betas=cx[:, 6:16],
+              left_hand_pose=cx[:, 48:60], right_hand_pose=cx[:, 60:])
+    v = oracle.verts_transform(v, cams)
+    d = np.stack([oracle.nn_fwd(v[b:b + 1, cid].numpy(), scenes[s].points)[0][0] for b, s in enumerate(scene_ids)])
+    sq = np.sqrt(d + 1e-4)
+    ref_c = 0.01 * np.mean(sq / (sq + 1.0))
+    sdf = torch.cat([oracle.sdf_lookup_torch(torch.tensor(scenes[s].sdf), torch.tensor(scenes[s].grid_min),
+                                             torch.tensor(scenes[s].grid_max), v[b:b + 1]) for b, s in enumerate(scene_ids)])
+    ref_p = 0.1 * float(sdf[sdf < 0].abs().mean()) if int((sdf < 0).sum()) else 0.0
+    assert abs(float(lc) - ref_c) < 1e-5 and abs(float(lp) - ref_p) < 1e-5
+    assert abs(float(lv) - 0.001 * float((cx[:, 16:48] ** 2).mean())) < 1e-7
+    # before 75 % of the epochs the block is skipped (the reference multiplies it by 0.0)
+    lc0, lv0, lp0 = blk(x, cams.cuda(), scene_ids, ep=3, epochs=30)
+    assert float(lc0) == 0.0 and float(lp0) == 0.0 and float(lv0) > 0
