@@ -30,27 +30,18 @@ __device__ __forceinline__ void matvec_stream(const float *__restrict__ W, int K
     const int R = kMvTileFloats / N;                 // rows per tile
     const int ntiles = (K + R - 1) / R;
     const int groups = kMlpThreads / N, g = tid / N, col = tid - g * N;
-    // a tile goes out as up to 4 concurrent bulk copies (lanes 0..3 of warp 0): more requests in
-    // flight per SM than one 32 kB copy
-    auto issue = [&](int t) {     // called by warp 0
+    auto issue = [&](int t) {
         const uint32_t slot = (st.tiles + t) % kMvStages;
         const int rows = min(R, K - t * R);
         const uint32_t bytes = (uint32_t)rows * N * 4u;
-        if (tid == 0) mbar_arrive_expect_tx(&st.bars[slot], bytes);
-        __syncwarp();
-        const uint32_t part = ((bytes / 4u) + 15u) & ~15u;            // 16-byte multiples
-        const uint32_t off = (uint32_t)tid * part;
-        if (tid < 4 && off < bytes) {
-            const uint32_t nb = min(part, bytes - off);
-            tma_load_1d(reinterpret_cast<unsigned char *>(st.ring + (size_t)slot * kMvTileFloats) + off,
-                        reinterpret_cast<const unsigned char *>(W + (size_t)t * R * N) + off, nb, &st.bars[slot]);
-        }
+        mbar_arrive_expect_tx(&st.bars[slot], bytes);
+        tma_load_1d(st.ring + (size_t)slot * kMvTileFloats, W + (size_t)t * R * N, bytes, &st.bars[slot]);
     };
-    if (tid < 32)
+    if (tid == 0)
         for (int t = 0; t < kMvStages - 1 && t < ntiles; ++t) issue(t);
     float acc = 0.f;
     for (int t = 0; t < ntiles; ++t) {
-        if (tid < 32 && t + kMvStages - 1 < ntiles) issue(t + kMvStages - 1);
+        if (tid == 0 && t + kMvStages - 1 < ntiles) issue(t + kMvStages - 1);
         const uint32_t seq = st.tiles + t, slot = seq % kMvStages;
         mbar_wait(&st.bars[slot], (seq / kMvStages) & 1u);
         const float *tile = st.ring + (size_t)slot * kMvTileFloats;

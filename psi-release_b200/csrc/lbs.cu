@@ -338,8 +338,7 @@ __global__ void __launch_bounds__(256)
 lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restrict__ skin_j,
                       const float *__restrict__ skin_w, const float *__restrict__ A,
                       const float *__restrict__ cam, long cam_bstride,
-                      const float *__restrict__ gverts, const float *__restrict__ vp_in,
-                      float *__restrict__ gw_out,
+                      const float *__restrict__ gverts, float *__restrict__ gw_out,
                       float *__restrict__ gvp_out) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -358,12 +357,8 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         const float z = C[2] * gx + C[6] * gy + C[10] * gz;
         gx = x; gy = y; gz = z;
     }
-    // one 32-byte record per (body, vertex) for the per-joint gather-reduce: a single sector
-    // instead of two or three partial ones
-    const float *vpv = vp_in + ((size_t)b * V + v) * 3;
-    float4 *rec = reinterpret_cast<float4 *>(gw_out) + ((size_t)b * V + v) * 2;
-    rec[0] = make_float4(gx, gy, gz, 0.f);
-    rec[1] = make_float4(vpv[0], vpv[1], vpv[2], 0.f);
+    float *gw = gw_out + ((size_t)b * V + v) * 3;
+    gw[0] = gx; gw[1] = gy; gw[2] = gz;
     float T[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) T[e] = 0.f;
@@ -390,24 +385,21 @@ lbs_dA_kernel(int V, int J, const int *__restrict__ jl_start, const int *__restr
     float acc[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) acc[e] = 0.f;
-    (void)vp;
-    const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(gw) + (size_t)b * V * 2;
+    const float *gwb = gw + (size_t)b * V * 3, *vpb = vp + (size_t)b * V * 3;
     if (j < J) {
         const int s = jl_start[j], e_end = jl_start[j + 1];
         for (int e = s + tid; e < e_end; e += blockDim.x) {
             const int v = jl_vert[e];
             const float w = jl_w[e];
-            const float4 g4 = __ldg(rec + (size_t)v * 2), p4 = __ldg(rec + (size_t)v * 2 + 1);
-            const float g0 = w * g4.x, g1 = w * g4.y, g2 = w * g4.z;
-            const float x = p4.x, y = p4.y, z = p4.z;
+            const float g0 = w * gwb[v * 3], g1 = w * gwb[v * 3 + 1], g2 = w * gwb[v * 3 + 2];
+            const float x = vpb[v * 3], y = vpb[v * 3 + 1], z = vpb[v * 3 + 2];
             acc[0] = fmaf(g0, x, acc[0]); acc[1] = fmaf(g0, y, acc[1]); acc[2] = fmaf(g0, z, acc[2]); acc[3] += g0;
             acc[4] = fmaf(g1, x, acc[4]); acc[5] = fmaf(g1, y, acc[5]); acc[6] = fmaf(g1, z, acc[6]); acc[7] += g1;
             acc[8] = fmaf(g2, x, acc[8]); acc[9] = fmaf(g2, y, acc[9]); acc[10] = fmaf(g2, z, acc[10]); acc[11] += g2;
         }
     } else {
         for (int v = tid; v < V; v += blockDim.x) {
-            const float4 g4 = __ldg(rec + (size_t)v * 2);
-            acc[0] += g4.x; acc[1] += g4.y; acc[2] += g4.z;
+            acc[0] += gwb[v * 3]; acc[1] += gwb[v * 3 + 1]; acc[2] += gwb[v * 3 + 2];
         }
     }
     __shared__ float red[4][12];
@@ -674,7 +666,8 @@ static BwdLayout bwd_layout(const psi_lbs_model *m, int B) {
     BwdLayout l;
     l.Bpad = ((B + 31) / 32) * 32;
     size_t o = 0;
-    l.gw = o;   o += (size_t)B * m->V * 8;          // packed {gw, v_posed} records, 32 B each
+    l.gw = o;   o += (size_t)B * m->V * 3;
+    o = (o + 3) & ~(size_t)3;
     l.gvp = o;  o += (size_t)l.Bpad * m->Npad;
     l.dA = o;   o += (size_t)B * m->J * 12;
     l.dtr = o;  o += (size_t)B * 3;
@@ -933,7 +926,7 @@ int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float 
         dim3 grid((unsigned)((m->Npad / 3 + 255) / 256), (unsigned)B);
         lbs_vertex_bwd_kernel<<<grid, 256, 0, st>>>(m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                                                     m->skin_w, saved + L.A, cam, cam_bstride,
-                                                    grad_verts, saved + L.vp, ws + W.gw, ws + W.gvp);
+                                                    grad_verts, ws + W.gw, ws + W.gvp);
         PSI_LAUNCHED();
     }
     {
