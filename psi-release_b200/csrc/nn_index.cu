@@ -44,6 +44,9 @@ struct psi_nn_index {
     float4 *pts;    // [num_clusters*32] (x,y,z,orig index bits); pads = +inf / INT_MAX
     float4 *boxes;  // SoA: [lo: mega(mpad) | super | cluster][hi: same]; empty nodes lo=hi=+inf
     int *pos_of;    // sorted position of every original point (index -> cluster, for the hint)
+    float4 *pts2;   // thread kernel: point PAIRS {x0,x1,y0,y1},{z0,z1,idx0,idx1}  [num_clusters*16][2]
+    float4 *box2;   // thread kernel: node PAIRS {lo.x0,lo.x1,lo.y0,lo.y1},{lo.z0,lo.z1,-hi.x0,-hi.x1},
+                    //                {-hi.y0,-hi.y1,-hi.z0,-hi.z1}   [nbox/2][3]  (levels start at even nodes)
     int nbox;       // mpad + num_supers + num_clusters
     size_t bytes;
 };
@@ -223,54 +226,76 @@ __device__ __forceinline__ float node_lbf(const psi_nn_index &ix, const float4 *
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, long q_bstride, int n,
                        const int *__restrict__ qsel, long total, float *__restrict__ dist,
                        int *__restrict__ idx, int *__restrict__ hint) {
-    // Only the mega + super boxes (7 kB at 50 000 points) are staged in shared memory: 8 CTAs stay
-    // resident per SM (64 warps) -- this walk is latency bound; the cluster boxes (50 kB) come
-    // through L1, where the coherent warps hit.
+    // Packed FP32 (FADD2 / FMUL2 / FFMA2): two boxes or two points per instruction, from the
+    // pair-interleaved copies box2 / pts2.  Only the mega + super pairs (5.6 kB at 50 000 points)
+    // are staged in shared memory so that 8 CTAs stay resident per SM (the walk is latency
+    // bound); the cluster pairs come through L1, where the coherent warps hit.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ntop = ix.mpad + ix.num_supers;
+    const int ntop2 = (ix.mpad + ix.num_supers) / 2;           // node pairs of the two top levels
     float4 *s4 = reinterpret_cast<float4 *>(smem_raw);
     if (SMEM) {
-        for (int i = threadIdx.x; i < ntop; i += blockDim.x) {
-            s4[i] = __ldg(ix.boxes + i);
-            s4[ntop + i] = __ldg(ix.boxes + ix.nbox + i);
-        }
+        for (int i = threadIdx.x; i < ntop2 * 3; i += blockDim.x) s4[i] = __ldg(ix.box2 + i);
         __syncthreads();
     }
-    auto lbf = [&](int node, float qx, float qy, float qz) -> float {
-        float4 lo, hi;
-        if (SMEM && node < ntop) {
-            lo = s4[node];
-            hi = s4[ntop + node];
-        } else {
-            lo = __ldg(ix.boxes + node);
-            hi = __ldg(ix.boxes + ix.nbox + node);
-        }
-        return __uint_as_float(box_lb(lo, hi, qx, qy, qz));
-    };
     const int sbase = ix.mpad, cbase = ix.mpad + ix.num_supers;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
         const long b = t / n;
         const long j = t - b * n;
         const float *qp = q_in + b * q_bstride + (qsel ? (long)__ldg(qsel + j) : j) * 3;
         const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        const float2 q2x = make_float2(qx, qx), q2y = make_float2(qy, qy), q2z = make_float2(qz, qz);
+        const float2 n2x = make_float2(-qx, -qx), n2y = make_float2(-qy, -qy), n2z = make_float2(-qz, -qz);
         float bd = CUDART_INF_F;
         int bi = 0x7fffffff;
+        // bounds of the node pair (2p, 2p+1)
+        auto lb2 = [&](int pair) -> float2 {
+            float4 A, Bq, C;
+            if (SMEM && pair < ntop2) {
+                A = s4[pair * 3]; Bq = s4[pair * 3 + 1]; C = s4[pair * 3 + 2];
+            } else {
+                A = __ldg(ix.box2 + (size_t)pair * 3); Bq = __ldg(ix.box2 + (size_t)pair * 3 + 1);
+                C = __ldg(ix.box2 + (size_t)pair * 3 + 2);
+            }
+            const float2 lx = __fadd2_rn(make_float2(A.x, A.y), n2x), hx = __fadd2_rn(make_float2(Bq.z, Bq.w), q2x);
+            const float2 ly = __fadd2_rn(make_float2(A.z, A.w), n2y), hy = __fadd2_rn(make_float2(C.x, C.y), q2y);
+            const float2 lz = __fadd2_rn(make_float2(Bq.x, Bq.y), n2z), hz = __fadd2_rn(make_float2(C.z, C.w), q2z);
+            const float2 gx = make_float2(fmaxf(fmaxf(lx.x, hx.x), 0.f), fmaxf(fmaxf(lx.y, hx.y), 0.f));
+            const float2 gy = make_float2(fmaxf(fmaxf(ly.x, hy.x), 0.f), fmaxf(fmaxf(ly.y, hy.y), 0.f));
+            const float2 gz = make_float2(fmaxf(fmaxf(lz.x, hz.x), 0.f), fmaxf(fmaxf(lz.y, hz.y), 0.f));
+            return __ffma2_rn(gz, gz, __ffma2_rn(gx, gx, __fmul2_rn(gy, gy)));
+        };
+        // leaf c: pass 1 keeps only the minimum distance (one FMNMX3 per point pair); the index is
+        // recovered by a second pass only when the leaf improves or ties the best so far
         auto visit = [&](int c) {
-            const float4 *p = ix.pts + (size_t)c * kLeaf;
+            const float4 *p = ix.pts2 + (size_t)c * kLeaf;          // 16 pairs x 2 float4
+            float lm = CUDART_INF_F;
 #pragma unroll 8
-            for (int i = 0; i < kLeaf; ++i) {
-                const float4 pt = __ldg(p + i);
-                const float dx = __fsub_rn(pt.x, qx), dy = __fsub_rn(pt.y, qy), dz = __fsub_rn(pt.z, qz);
-                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                const int oi = __float_as_int(pt.w);
-                if (d < bd || (d == bd && oi < bi)) {
-                    bd = d;
-                    bi = oi;
+            for (int i = 0; i < kLeaf / 2; ++i) {
+                const float4 u = __ldg(p + 2 * i), w = __ldg(p + 2 * i + 1);
+                const float2 dx = __fadd2_rn(make_float2(u.x, u.y), n2x);
+                const float2 dy = __fadd2_rn(make_float2(u.z, u.w), n2y);
+                const float2 dz = __fadd2_rn(make_float2(w.x, w.y), n2z);
+                const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+                lm = fminf(lm, fminf(d.x, d.y));
+            }
+            if (lm <= bd) {
+                int li = 0x7fffffff;
+#pragma unroll 4
+                for (int i = 0; i < kLeaf / 2; ++i) {
+                    const float4 u = __ldg(p + 2 * i), w = __ldg(p + 2 * i + 1);
+                    const float2 dx = __fadd2_rn(make_float2(u.x, u.y), n2x);
+                    const float2 dy = __fadd2_rn(make_float2(u.z, u.w), n2y);
+                    const float2 dz = __fadd2_rn(make_float2(w.x, w.y), n2z);
+                    const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+                    if (d.x == lm) li = min(li, __float_as_int(w.z));
+                    if (d.y == lm) li = min(li, __float_as_int(w.w));
                 }
+                if (lm < bd || li < bi) bi = li;       // lm == bd: lowest original index wins
+                bd = lm;
             }
         };
         // seed: hinted leaf, else greedy descent (nearest mega -> super -> cluster)
@@ -278,36 +303,50 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
         if (seeded < 0 || seeded >= ix.num_clusters) {
             float best = CUDART_INF_F;
             int m0 = 0;
-            for (int g = 0; g < ix.num_megas; ++g) {
-                const float lb = lbf(g, qx, qy, qz);
-                if (lb < best) { best = lb; m0 = g; }
+            for (int g = 0; g < ix.mpad / 2; ++g) {
+                const float2 lb = lb2(g);
+                if (lb.x < best) { best = lb.x; m0 = 2 * g; }
+                if (lb.y < best) { best = lb.y; m0 = 2 * g + 1; }
             }
             best = CUDART_INF_F;
             int s0 = m0 * kFan;
-            for (int s = m0 * kFan; s < m0 * kFan + kFan; ++s) {
-                const float lb = lbf(sbase + s, qx, qy, qz);
-                if (lb < best) { best = lb; s0 = s; }
+            for (int pr = 0; pr < kFan / 2; ++pr) {
+                const float2 lb = lb2((sbase + m0 * kFan) / 2 + pr);
+                if (lb.x < best) { best = lb.x; s0 = m0 * kFan + 2 * pr; }
+                if (lb.y < best) { best = lb.y; s0 = m0 * kFan + 2 * pr + 1; }
             }
             best = CUDART_INF_F;
             seeded = s0 * kFan;
-            for (int c = s0 * kFan; c < s0 * kFan + kFan; ++c) {
-                const float lb = lbf(cbase + c, qx, qy, qz);
-                if (lb < best) { best = lb; seeded = c; }
+            for (int pr = 0; pr < kFan / 2; ++pr) {
+                const float2 lb = lb2((cbase + s0 * kFan) / 2 + pr);
+                if (lb.x < best) { best = lb.x; seeded = s0 * kFan + 2 * pr; }
+                if (lb.y < best) { best = lb.y; seeded = s0 * kFan + 2 * pr + 1; }
             }
         }
         visit(seeded);
         // ordered sweep with pruning against this query's best distance so far
 #pragma unroll 1
-        for (int g = 0; g < ix.num_megas; ++g) {
-            if (lbf(g, qx, qy, qz) > bd) continue;
+        for (int g2 = 0; g2 < (ix.num_megas + 1) / 2; ++g2) {
+            const float2 ml = lb2(g2);
 #pragma unroll 1
-            for (int s = g * kFan; s < g * kFan + kFan; ++s) {
-                if (lbf(sbase + s, qx, qy, qz) > bd) continue;
+            for (int gh = 0; gh < 2; ++gh) {
+                const int g = 2 * g2 + gh;
+                if ((gh ? ml.y : ml.x) > bd || g >= ix.num_megas) continue;
 #pragma unroll 1
-                for (int c = s * kFan; c < s * kFan + kFan; ++c) {
-                    if (c == seeded) continue;
-                    if (lbf(cbase + c, qx, qy, qz) > bd) continue;
-                    visit(c);
+                for (int sp = 0; sp < kFan / 2; ++sp) {
+                    const float2 sl = lb2((sbase + g * kFan) / 2 + sp);
+#pragma unroll 1
+                    for (int sh = 0; sh < 2; ++sh) {
+                        const int sidx = g * kFan + 2 * sp + sh;
+                        if ((sh ? sl.y : sl.x) > bd) continue;
+#pragma unroll 1
+                        for (int cp = 0; cp < kFan / 2; ++cp) {
+                            const float2 cl = lb2((cbase + sidx * kFan) / 2 + cp);
+                            const int c0 = sidx * kFan + 2 * cp;
+                            if (cl.x <= bd && c0 != seeded) visit(c0);
+                            if (cl.y <= bd && c0 + 1 != seeded) visit(c0 + 1);
+                        }
+                    }
                 }
             }
         }
@@ -348,6 +387,8 @@ void psi_nn_index_destroy(psi_nn_index *ix) {
     cudaFree(ix->pts);
     cudaFree(ix->boxes);
     cudaFree(ix->pos_of);
+    cudaFree(ix->pts2);
+    cudaFree(ix->box2);
     delete ix;
 }
 
@@ -370,7 +411,7 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
     for (int b = 0; b < m; b += super_pts) kd_order(h_points, ids.data() + b, std::min(super_pts, m - b), kLeaf);
     psi_nn_index *ix = new (std::nothrow) psi_nn_index();
     if (!ix) return PSI_ERR_ALLOC;
-    ix->pts = nullptr; ix->boxes = nullptr; ix->pos_of = nullptr;
+    ix->pts = nullptr; ix->boxes = nullptr; ix->pos_of = nullptr; ix->pts2 = nullptr; ix->box2 = nullptr;
     ix->m = m;
     ix->num_megas = num_megas;
     ix->rounds = rounds;
@@ -419,6 +460,24 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
     up((void **)&ix->pts, pts.data(), pts.size() * sizeof(float4));
     up((void **)&ix->boxes, boxes.data(), boxes.size() * sizeof(float4));
     up((void **)&ix->pos_of, pos_of.data(), pos_of.size() * sizeof(int));
+    {   // pair-interleaved copies for the packed (f32x2) thread-per-query kernel
+        std::vector<float4> pts2(pts.size()), box2((size_t)(ix->nbox / 2) * 3);
+        for (size_t p = 0; p < pts.size() / 2; ++p) {
+            const float4 a = pts[2 * p], b = pts[2 * p + 1];
+            pts2[2 * p] = make_float4(a.x, b.x, a.y, b.y);
+            pts2[2 * p + 1] = make_float4(a.z, b.z, a.w, b.w);
+        }
+        for (int p = 0; p < ix->nbox / 2; ++p) {
+            const float4 l0 = boxes[2 * p], l1 = boxes[2 * p + 1];
+            const float4 h0 = boxes[(size_t)ix->nbox + 2 * p], h1 = boxes[(size_t)ix->nbox + 2 * p + 1];
+            box2[(size_t)p * 3] = make_float4(l0.x, l1.x, l0.y, l1.y);
+            box2[(size_t)p * 3 + 1] = make_float4(l0.z, l1.z, -h0.x, -h1.x);
+            box2[(size_t)p * 3 + 2] = make_float4(-h0.y, -h1.y, -h0.z, -h1.z);
+        }
+        up((void **)&ix->pts2, pts2.data(), pts2.size() * sizeof(float4));
+        up((void **)&ix->box2, box2.data(), box2.size() * sizeof(float4));
+        if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;   // vectors die here
+    }
     if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;
     if (rc != PSI_OK) {
         psi_nn_index_destroy(ix);
@@ -446,7 +505,6 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
-        cudaFuncSetAttribute(nn_index_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
         attr = true;
     }
     if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
@@ -454,7 +512,8 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         long blocks = (total + 255) / 256;
         const long cap = (long)PSI_NUM_SMS * 8;
         if (blocks > cap) blocks = cap;
-        const size_t top_bytes = (size_t)2 * (ix->mpad + ix->num_supers) * sizeof(float4);
+        const size_t top_bytes = (size_t)3 * ((ix->mpad + ix->num_supers) / 2) * sizeof(float4);
+        // 64 registers (no spills with the packed pairs), 4 CTAs/SM; measured best of 3/4/5/6/8
         if (top_bytes <= 24 * 1024)
             nn_index_thread_kernel<true><<<(unsigned)blocks, 256, top_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
         else
