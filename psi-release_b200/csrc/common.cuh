@@ -66,6 +66,38 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
         : "memory");
 }
 
+// ---- tensor-core helpers: legacy mma.sync path (HMMA.1688.F32.TF32), FP32 accumulate ----
+// ldmatrix moves 8x8 b16 matrices = 8 rows x 16 bytes; with 32-bit elements a matrix is 8 rows x 4
+// words and lane l receives word (l % 4) of row (l / 4): exactly the m16n8k8 TF32 fragments when
+// both operands are stored with the reduction index contiguous.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(saddr) : "memory");
+}
+// x = hi + lo exactly: hi keeps the TF32 bits of x (sign, exponent, 10 mantissa bits), lo the 13
+// bits below (the tensor core reads the top 11 of them).  One LOP3 + one FADD per element;
+// cvt.rna.tf32 would cost five instructions (it is emulated, with NaN/Inf handling).
+// 3xTF32: a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b, relative error < 2^-19, FP32 accumulate.
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t &hi, uint32_t &lo) {
+    hi = x & 0xffffe000u;
+    lo = __float_as_uint(__uint_as_float(x) - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    mma_tf32(d, al, bh0, bh1);      // small terms first
+    mma_tf32(d, ah, bl0, bl1);
+    mma_tf32(d, ah, bh0, bh1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

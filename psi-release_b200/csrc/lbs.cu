@@ -35,11 +35,18 @@
 namespace psi {
 
 constexpr int kMaxJ = 64;
-constexpr int kKT = 16;         // basis rows per pipeline stage
-constexpr int kTileN = 96;      // basis columns per CTA = 32 vertices
-constexpr int kBG = 64;         // bodies per CTA (4 warps x 16)
-constexpr int kStages = 6;        // 6 x 10 kB ring: 5 stages of prefetch cover the L2->smem latency
-constexpr int kNSplit = 74;     // dcoef split of the N reduction: 4 k-tiles x 74 x (B/32) CTAs = 4 per SM at B=64
+constexpr int kBG = 64;         // bodies per CTA = M (forward) of the tensor-core tiles
+constexpr int kKC = 32;         // reduction elements per pipeline stage: one 128-byte row per operand row
+constexpr int kFT = 72;         // forward tile: 72 vertex coordinates (9 n8 tiles); 3V/72 = 437 tiles at
+                                // V = 10475 = 2.95 per SM -> one balanced wave at 3 CTAs per SM
+constexpr int kFStages = 4;     // forward ring: 4 x 17 kB
+constexpr int kDK = 128;        // dcoef tile: 128 coefficients x 64 bodies per CTA
+constexpr int kDStages = 4;     // dcoef ring: 4 x 24 kB, 2 CTAs per SM
+constexpr int kNSplit = 74;     // dcoef split of the coordinate reduction: 4 k-tiles x 74 = 2 CTAs per SM
+
+// Operand rows are 32 floats = 8 chunks of 16 bytes; chunk c of row r is stored at chunk
+// c ^ (r & 7), so the 8 rows of one ldmatrix 8x4 block fall into 8 different bank groups.
+__host__ __device__ inline int swz(int row, int col) { return ((((col >> 2) ^ row) & 7) << 2) | (col & 3); }
 
 }  // namespace psi
 
@@ -51,9 +58,9 @@ struct psi_lbs_tree {          // kinematic tree by levels (root = level 0) + ch
 struct psi_lbs_model {
     psi_lbs_tree tree;
     int *tree_buf;
-    int V, J, NB, P, K, Kpad, Npad, KW;
+    int V, J, NB, P, K, Kpad, Npad, KW, NC, NT;   // NC coordinate chunks of 32 (Npad = 32 NC), NT forward tiles of 72
     long nnz;
-    float *basis, *v_template, *Jt, *Jdirs, *skin_w, *jl_w;
+    float *basis_fwd, *basis_bwd, *v_template, *Jt, *Jdirs, *skin_w, *jl_w;
     int *skin_j, *parents, *jl_start, *jl_vert;
     size_t bytes;
 };
@@ -172,8 +179,8 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     sGt[j * 3 + r] + (transl ? transl[(size_t)b * 3 + r] : 0.f);
         }
     }
-    // blend coefficients, layout [body group][Kpad][32]
-    float *coef = saved + L.coef + (size_t)(b / kBG) * Kpad * kBG + (b % kBG);
+    // blend coefficients = the A operand of the blend GEMM: [body group][k chunk][64 bodies][32 k, swizzled]
+    float *coef = saved + L.coef + (size_t)(b / kBG) * Kpad * kBG + (size_t)(b % kBG) * kKC;
     for (int k = tid; k < Kpad; k += blockDim.x) {
         float v = 0.f;
         if (k < P) {
@@ -182,7 +189,7 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
         } else if (k < P + NB) {
             v = betas[(size_t)b * NB + (k - P)];
         }
-        coef[(size_t)k * kBG] = v;
+        coef[(size_t)(k / kKC) * (kBG * kKC) + swz(b % kBG, k % kKC)] = v;
     }
 }
 
@@ -193,100 +200,107 @@ __global__ void lbs_zero_coef_pad_kernel(float *coef, int B, int Kpad) {
     if (first == 0) return;
     float *base = coef + (size_t)(nbg - 1) * Kpad * kBG;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Kpad * kBG; i += gridDim.x * blockDim.x)
-        if ((i % kBG) >= first) base[i] = 0.f;
+        if (((i / kKC) % kBG) >= first) base[i] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
-struct VertexFwdParams {
-    const float *basis, *v_template, *skin_w, *A, *coef, *transl, *cam;
-    const int *skin_j;
-    long cam_bstride;
-    float *verts, *vp_out;
-    int V, J, Kpad, Npad, KW, B;
+struct BlendFwdParams {
+    const float *basis_fwd, *v_template, *coef;
+    float *vp_out;
+    int V, Kpad, B;
 };
 
-constexpr int kBPT = 8;                   // bodies per thread (24 accumulators); kBG / kBPT warps per CTA
-constexpr int kVfWarps = kBG / kBPT;      // 8 warps = 256 threads, 3 CTAs per SM: 17.7 warps/SM at B=64
+constexpr int kFStageBytes = (kFT + kBG) * kKC * 4;
 
-__global__ void __launch_bounds__(kVfWarps * 32, 3) lbs_vertex_fwd_kernel(const VertexFwdParams p) {
-    // 4 warps (16 bodies each, lane = vertex).  full[st]: bytes landed; empty[st]: all 4 warps
-    // released the stage.  Lane 0 of warp 0 refills a stage kStages-2 chunks ahead, so there is no
-    // block-wide barrier inside the K loop: warps may drift a chunk apart.
+// v_posed[b][n] = v_template[n] + sum_k coef[b][k] * basis[k][n]      (lbs.py:88-106)
+// as a [64 bodies x 72 coordinates x Kpad] GEMM per CTA on the tensor cores: 4 warps, warp w owns
+// bodies 16w..16w+15 (one m16 tile) x 9 n8 tiles; FP32 operands are split on the fly (3xTF32).
+// Thread 0 feeds a full/empty mbarrier ring with bulk copies (one 9 kB + one 8 kB block a stage).
+__global__ void __launch_bounds__(128, 3) lbs_blend_fwd_kernel(const BlendFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *sm = reinterpret_cast<float *>(smem_raw);
-    constexpr int kStageFloats = kKT * kTileN + kKT * kBG;  // 2560 floats = 10 kB
-    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
-
+    __shared__ __align__(8) uint64_t full[kFStages], empty[kFStages];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int tile = blockIdx.x, bg = blockIdx.y;
-    const int nchunks = p.Kpad / kKT;
-    // the basis is stored tile-major [tile][Kpad][96]: a stage is ONE contiguous 6 kB block
-    const float *__restrict__ basis_t = p.basis + (size_t)tile * p.Kpad * kTileN;
-    const float *__restrict__ coef_g = p.coef + (size_t)bg * p.Kpad * kBG;
+    const int nchunks = p.Kpad / kKC;
+    const float *__restrict__ basis_t = p.basis_fwd + (size_t)tile * p.Kpad * kFT;   // [chunk][72][32]
+    const float *__restrict__ coef_g = p.coef + (size_t)bg * p.Kpad * kBG;           // [chunk][64][32]
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kVfWarps); }
+        for (int i = 0; i < kFStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
         mbar_fence_init();
     }
     __syncthreads();
-
-    auto issue = [&](int c) {   // warp 0, lane 0 only
-        const int st = c % kStages;
-        mbar_wait(&empty[st], (uint32_t)(((c / kStages) & 1) ^ 1));   // first use: passes at once
-        float *dstB = sm + st * kStageFloats;
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageFloats * 4));
-        tma_load_1d(dstB, basis_t + (size_t)c * kKT * kTileN, kKT * kTileN * 4, &full[st]);
-        tma_load_1d(dstB + kKT * kTileN, coef_g + (size_t)c * kKT * kBG, kKT * kBG * 4, &full[st]);
+    auto issue = [&](int c) {   // thread 0 only
+        const int st = c % kFStages;
+        mbar_wait(&empty[st], (uint32_t)(((c / kFStages) & 1) ^ 1));   // first use: passes at once
+        unsigned char *dst = smem_raw + st * kFStageBytes;
+        mbar_arrive_expect_tx(&full[st], (uint32_t)kFStageBytes);
+        tma_load_1d(dst, basis_t + (size_t)c * kFT * kKC, kFT * kKC * 4, &full[st]);
+        tma_load_1d(dst + kFT * kKC * 4, coef_g + (size_t)c * kBG * kKC, kBG * kKC * 4, &full[st]);
     };
     if (tid == 0)
-        for (int c = 0; c < kStages - 2 && c < nchunks; ++c) issue(c);
+        for (int c = 0; c < kFStages - 1 && c < nchunks; ++c) issue(c);
 
-    float acc[kBPT][3];
+    float acc[9][4];
 #pragma unroll
-    for (int i = 0; i < kBPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+    for (int i = 0; i < 9; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+    // ldmatrix lane roles (row = lane & 7 inside an 8-row block, so the swizzle key is lane & 7)
+    const int l7 = lane & 7;
+    const uint32_t offA = (uint32_t)(kFT * kKC * 4 + (w * 16 + l7 + ((lane >> 3) & 1) * 8) * 128);   // coef rows
+    const int kcA = lane >> 4;
+    const uint32_t offB = (uint32_t)((l7 + ((lane >> 4) & 1) * 8) * 128);                             // basis rows
+    const int kcB = (lane >> 3) & 1;
+    const uint32_t offB8 = (uint32_t)((64 + l7) * 128);                                                // 9th n tile
+    const uint32_t smem0 = smem_u32(smem_raw);
 
     for (int c = 0; c < nchunks; ++c) {
-        if (tid == 0 && c + kStages - 2 < nchunks) issue(c + kStages - 2);
+        if (tid == 0 && c + kFStages - 1 < nchunks) issue(c + kFStages - 1);
         __syncwarp();
-        const int st = c % kStages;
-        mbar_wait(&full[st], (uint32_t)((c / kStages) & 1));
-        const float *bs = sm + st * kStageFloats + 3 * lane;
-        const float4 *cs = reinterpret_cast<const float4 *>(sm + st * kStageFloats + kKT * kTileN) + (kBPT / 4) * w;  // [kk][64 bodies]
-#pragma unroll 4
-        for (int kk = 0; kk < kKT; ++kk) {
-            const float b0 = bs[kk * kTileN], b1 = bs[kk * kTileN + 1], b2 = bs[kk * kTileN + 2];
-            float cf[kBPT];
+        const int st = c % kFStages;
+        mbar_wait(&full[st], (uint32_t)((c / kFStages) & 1));
+        const uint32_t sb = smem0 + st * kFStageBytes;
 #pragma unroll
-            for (int u = 0; u < kBPT / 4; ++u) {
-                const float4 cc = cs[kk * (kBG / 4) + u];
-                cf[4 * u] = cc.x; cf[4 * u + 1] = cc.y; cf[4 * u + 2] = cc.z; cf[4 * u + 3] = cc.w;
-            }
+        for (int s = 0; s < kKC / 8; ++s) {
+            const uint32_t ca = (uint32_t)(((2 * s + kcA) ^ l7) << 4), cb = (uint32_t)(((2 * s + kcB) ^ l7) << 4);
+            uint32_t a[4], ah[4], al[4];
+            ldsm_x4(a, sb + offA + ca);
 #pragma unroll
-            for (int i = 0; i < kBPT; ++i) {
-                acc[i][0] = fmaf(cf[i], b0, acc[i][0]);
-                acc[i][1] = fmaf(cf[i], b1, acc[i][1]);
-                acc[i][2] = fmaf(cf[i], b2, acc[i][2]);
+            for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bb[4], bh[4], bl[4];
+                ldsm_x4(bb, sb + offB + np * (16 * 128) + cb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32(bb[i], bh[i], bl[i]);
+                mma_3xtf32(acc[2 * np], ah, al, bh[0], bh[1], bl[0], bl[1]);
+                mma_3xtf32(acc[2 * np + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
             }
+            uint32_t b2[2], bh0, bh1, bl0, bl1;
+            ldsm_x2(b2, sb + offB8 + cb);
+            split_tf32(b2[0], bh0, bl0);
+            split_tf32(b2[1], bh1, bl1);
+            mma_3xtf32(acc[8], ah, al, bh0, bh1, bl0, bl1);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);   // this warp is done with stage st
     }
 
-    const int v = tile * 32 + lane;
-    if (v >= p.V) return;
-    const float t0 = p.v_template[3 * v], t1 = p.v_template[3 * v + 1], t2 = p.v_template[3 * v + 2];
-    // phase A (unrolled, compile-time accumulator indices): v_posed = blend + template, stored once
-    // (the backward needs it anyway); phase B (rolled): skinning reads it back, so the 24
-    // accumulators are dead before the register-hungry part starts
+    // accumulator fragment: rows g, g+8 (bodies), columns 2t, 2t+1 (coordinates) of each n8 tile
+    const int g = lane >> 2, t = lane & 3;
+    const int N = 3 * p.V;
 #pragma unroll
-    for (int i = 0; i < kBPT; ++i) {
-        const int b = bg * kBG + w * kBPT + i;
+    for (int h = 0; h < 2; ++h) {
+        const int b = bg * kBG + w * 16 + g + 8 * h;
         if (b >= p.B) continue;
-        float *vp = p.vp_out + ((size_t)b * p.V + v) * 3;
-        vp[0] = acc[i][0] + t0;
-        vp[1] = acc[i][1] + t1;
-        vp[2] = acc[i][2] + t2;
+        float *vp = p.vp_out + (size_t)b * N;
+#pragma unroll
+        for (int nt = 0; nt < 9; ++nt) {
+            const int n = tile * kFT + nt * 8 + 2 * t;
+            if (n < N) vp[n] = acc[nt][2 * h] + p.v_template[n];
+            if (n + 1 < N) vp[n + 1] = acc[nt][2 * h + 1] + p.v_template[n + 1];
+        }
     }
 }
 
@@ -333,7 +347,8 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, vertex side: gw = Rc^T g ; gvp = Tr^T gw
+// backward, vertex side: gw = Rc^T g ; gvp = Tr^T gw.  gvp is the A operand of the dcoef GEMM:
+// [body group][coordinate chunk][64 bodies][32 coordinates, swizzled]; rows of bodies >= B are zero.
 __global__ void __launch_bounds__(256)
 lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restrict__ skin_j,
                       const float *__restrict__ skin_w, const float *__restrict__ A,
@@ -343,9 +358,12 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (v * 3 >= Npad) return;
-    float *gvp = gvp_out + (size_t)b * Npad + (size_t)v * 3;
-    if (v >= V) {
-        gvp[0] = gvp[1] = gvp[2] = 0.f;
+    float *gvp_g = gvp_out + (size_t)(b / kBG) * Npad * kBG + (size_t)(b % kBG) * kKC;
+    auto put = [&](int n, float x) {
+        if (n < Npad) gvp_g[(size_t)(n / kKC) * (kBG * kKC) + swz(b % kBG, n % kKC)] = x;
+    };
+    if (v >= V || b >= B) {
+        put(3 * v, 0.f); put(3 * v + 1, 0.f); put(3 * v + 2, 0.f);
         return;
     }
     const float *g = gverts + ((size_t)b * V + v) * 3;
@@ -371,9 +389,9 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         T[3] = fmaf(wt, r1.x, T[3]); T[4] = fmaf(wt, r1.y, T[4]); T[5] = fmaf(wt, r1.z, T[5]);
         T[6] = fmaf(wt, r2.x, T[6]); T[7] = fmaf(wt, r2.y, T[7]); T[8] = fmaf(wt, r2.z, T[8]);
     }
-    gvp[0] = T[0] * gx + T[3] * gy + T[6] * gz;
-    gvp[1] = T[1] * gx + T[4] * gy + T[7] * gz;
-    gvp[2] = T[2] * gx + T[5] * gy + T[8] * gz;
+    put(3 * v, T[0] * gx + T[3] * gy + T[6] * gz);
+    put(3 * v + 1, T[1] * gx + T[4] * gy + T[7] * gz);
+    put(3 * v + 2, T[2] * gx + T[5] * gy + T[8] * gz);
 }
 
 // dA[b,j,:] = sum over the vertices skinned to j of w * [gw (x) vp | gw]; block (J, b) sums gw.
@@ -417,81 +435,98 @@ lbs_dA_kernel(int V, int J, const int *__restrict__ jl_start, const int *__restr
     }
 }
 
-// d coef partials: part[ns][b][k] = sum_{n in split ns} gvp[b][n] * basis[k][n]
-// CTA: 128 k x 32 bodies, 128 threads, register tile 8 k x 4 bodies, n in chunks of 32.
-__global__ void __launch_bounds__(128)
-lbs_dcoef_kernel(int Kpad, int Npad, int B, int Bpad, const float *__restrict__ basis,
-                 const float *__restrict__ gvp, float *__restrict__ part, int chunks_per_split) {
-    __shared__ __align__(16) float BsT[32][132];
-    __shared__ __align__(16) float GT[32][36];
-    const int tid = threadIdx.x, tk = tid & 15, tb = tid >> 4;
-    const int kbase = blockIdx.x * 128, ns = blockIdx.y, bbase = blockIdx.z * 32;
-    float acc[8][4];
+// d coef partials: part[ns][b][k] = sum_{n in split ns} gvp[b][n] * basis[k][n]   (backward of the blend GEMM)
+// CTA = 64 bodies x 128 coefficients over a range of coordinate chunks, on the tensor cores
+// (3xTF32): 8 warps, warp (wm, wn) owns 32 bodies x 32 coefficients = 2 m16 x 4 n8 tiles.
+constexpr int kDStageBytes = (kDK + kBG) * kKC * 4;
+
+__global__ void __launch_bounds__(256, 2)
+lbs_dcoef_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd,
+                 const float *__restrict__ gvp, float *__restrict__ part, int nsplit) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kDStages], empty[kDStages];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, wm = w & 1, wn = w >> 1;
+    const int kt = blockIdx.x, ns = blockIdx.y, bg = blockIdx.z;
+    const int c_begin = (int)((long)ns * NC / nsplit), c_end = (int)((long)(ns + 1) * NC / nsplit);
+    const int nchunks = c_end - c_begin;
+    const float *__restrict__ gvp_g = gvp + (size_t)bg * NC * (kBG * kKC);      // [chunk][64][32]
+    const float *__restrict__ basis_k = basis_bwd + (size_t)kt * kDK * kKC;     // [chunk][Kpad][32]
+
+    if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    const int total_chunks = Npad / 32;
-    const int c_begin = (int)((long)ns * total_chunks / chunks_per_split);           // balanced partition (chunks_per_split = number of splits)
-    const int c_end = (int)((long)(ns + 1) * total_chunks / chunks_per_split);
-    // software pipeline: the next chunk's global loads are in flight while this one is computed.
-    // store mapping: lanes run over 16 rows (k or body) x 2 column groups -> conflict-free
-    // transposed stores ((4n + row) % 32 covers all banks).
-    const int lrow = tid & 15, col4 = tid >> 4;
-    float4 pb[8], pg[2];
-    auto fetch = [&](int c) {
-        const int n0 = c * 32;
-        const float *bt = basis + (size_t)(n0 / kTileN) * Kpad * kTileN + (n0 % kTileN) + col4 * 4;
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            pb[r] = __ldg(reinterpret_cast<const float4 *>(bt + (size_t)(kbase + r * 16 + lrow) * kTileN));
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int row = r * 16 + lrow;
-            pg[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bbase + row < B)
-                pg[r] = __ldg(reinterpret_cast<const float4 *>(gvp + (size_t)(bbase + row) * Npad + n0 + col4 * 4));
-        }
+        for (int i = 0; i < kDStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int c) {   // thread 0 only; c counts from 0 inside this split
+        const int st = c % kDStages;
+        mbar_wait(&empty[st], (uint32_t)(((c / kDStages) & 1) ^ 1));
+        unsigned char *dst = smem_raw + st * kDStageBytes;
+        mbar_arrive_expect_tx(&full[st], (uint32_t)kDStageBytes);
+        tma_load_1d(dst, basis_k + (size_t)(c_begin + c) * Kpad * kKC, kDK * kKC * 4, &full[st]);
+        tma_load_1d(dst + kDK * kKC * 4, gvp_g + (size_t)(c_begin + c) * (kBG * kKC), kBG * kKC * 4, &full[st]);
     };
-    if (c_begin < c_end) fetch(c_begin);
-    for (int c = c_begin; c < c_end; ++c) {
-        __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < kDStages - 1 && c < nchunks; ++c) issue(c);
+
+    float acc[2][4][4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int row = r * 16 + lrow;
-            BsT[col4 * 4 + 0][row] = pb[r].x; BsT[col4 * 4 + 1][row] = pb[r].y;
-            BsT[col4 * 4 + 2][row] = pb[r].z; BsT[col4 * 4 + 3][row] = pb[r].w;
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+
+    const int l7 = lane & 7;
+    const uint32_t offA = (uint32_t)(kDK * kKC * 4 + (wm * 32 + l7 + ((lane >> 3) & 1) * 8) * 128);   // gvp rows (bodies)
+    const int kcA = lane >> 4;
+    const uint32_t offB = (uint32_t)((wn * 32 + l7 + ((lane >> 4) & 1) * 8) * 128);                    // basis rows (k)
+    const int kcB = (lane >> 3) & 1;
+    const uint32_t smem0 = smem_u32(smem_raw);
+
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0 && c + kDStages - 1 < nchunks) issue(c + kDStages - 1);
+        __syncwarp();
+        const int st = c % kDStages;
+        mbar_wait(&full[st], (uint32_t)((c / kDStages) & 1));
+        const uint32_t sb = smem0 + st * kDStageBytes;
+#pragma unroll
+        for (int s = 0; s < kKC / 8; ++s) {
+            const uint32_t ca = (uint32_t)(((2 * s + kcA) ^ l7) << 4), cb = (uint32_t)(((2 * s + kcB) ^ l7) << 4);
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t a[4];
+                ldsm_x4(a, sb + offA + mt * (16 * 128) + ca);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[mt][i], al[mt][i]);
+            }
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                uint32_t bb[4], bh[4], bl[4];
+                ldsm_x4(bb, sb + offB + np * (16 * 128) + cb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32(bb[i], bh[i], bl[i]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_3xtf32(acc[mt][2 * np], ah[mt], al[mt], bh[0], bh[1], bl[0], bl[1]);
+                    mma_3xtf32(acc[mt][2 * np + 1], ah[mt], al[mt], bh[2], bh[3], bl[2], bl[3]);
+                }
+            }
         }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int row = r * 16 + lrow;
-            GT[col4 * 4 + 0][row] = pg[r].x; GT[col4 * 4 + 1][row] = pg[r].y;
-            GT[col4 * 4 + 2][row] = pg[r].z; GT[col4 * 4 + 3][row] = pg[r].w;
-        }
-        __syncthreads();
-        if (c + 1 < c_end) fetch(c + 1);
-#pragma unroll 8
-        for (int n = 0; n < 32; ++n) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(&BsT[n][4 * tk]);
-            const float4 a1 = *reinterpret_cast<const float4 *>(&BsT[n][64 + 4 * tk]);
-            const float4 g = *reinterpret_cast<const float4 *>(&GT[n][4 * tb]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i], gg[jj], acc[i][jj]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
     }
+
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        const int b = bbase + tb * 4 + jj;
-        if (b >= Bpad) continue;
-        float *o = part + ((size_t)ns * Bpad + b) * Kpad + kbase;
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            o[4 * tk + i] = acc[i][jj];
-            o[64 + 4 * tk + i] = acc[4 + i][jj];
+        for (int h = 0; h < 2; ++h) {
+            const int b = bg * kBG + wm * 32 + mt * 16 + g + 8 * h;
+            float *o = part + ((size_t)ns * Bpad + b) * Kpad + kt * kDK + wn * 32 + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                *reinterpret_cast<float2 *>(o + nt * 8) = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
         }
-    }
 }
 
 // dsum[b][k] = sum over the N-splits, in a fixed order (4 interleaved partial sums)
@@ -664,10 +699,10 @@ struct BwdLayout {
 };
 static BwdLayout bwd_layout(const psi_lbs_model *m, int B) {
     BwdLayout l;
-    l.Bpad = ((B + 31) / 32) * 32;
+    l.Bpad = ((B + kBG - 1) / kBG) * kBG;
     size_t o = 0;
     l.gw = o;   o += (size_t)B * m->V * 3;
-    o = (o + 3) & ~(size_t)3;
+    o = (o + 31) & ~(size_t)31;
     l.gvp = o;  o += (size_t)l.Bpad * m->Npad;
     l.dA = o;   o += (size_t)B * m->J * 12;
     l.dtr = o;  o += (size_t)B * 3;
@@ -697,7 +732,7 @@ extern "C" {
 
 void psi_lbs_model_destroy(psi_lbs_model *m) {
     if (!m) return;
-    cudaFree(m->basis); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
+    cudaFree(m->basis_fwd); cudaFree(m->basis_bwd); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
     cudaFree(m->skin_w); cudaFree(m->jl_w); cudaFree(m->skin_j); cudaFree(m->parents);
     cudaFree(m->jl_start); cudaFree(m->jl_vert); cudaFree(m->tree_buf);
     delete m;
@@ -718,21 +753,31 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     psi_lbs_model *m = new (std::nothrow) psi_lbs_model();
     if (!m) return PSI_ERR_ALLOC;
     m->V = V; m->J = J; m->NB = NB; m->P = (J - 1) * 9; m->K = m->P + NB;
-    m->Kpad = ((m->K + 127) / 128) * 128;   // multiple of the dcoef k tile (and of kKT)
-    m->Npad = ((3 * V + kTileN - 1) / kTileN) * kTileN;
+    m->Kpad = ((m->K + kDK - 1) / kDK) * kDK;   // multiple of the dcoef k tile (and of kKC)
+    m->NC = (3 * V + kKC - 1) / kKC;
+    m->Npad = m->NC * kKC;
+    m->NT = (3 * V + kFT - 1) / kFT;
     m->bytes = 0;
     const int P = m->P, Kpad = m->Kpad, Npad = m->Npad;
     const size_t N = (size_t)3 * V;
 
-    // tile-major: element (k, n) lives at [n / 96][k][n % 96]
-    std::vector<float> basis((size_t)Kpad * Npad, 0.f);
-    auto bidx = [&](int k, size_t n) { return (n / kTileN) * (size_t)Kpad * kTileN + (size_t)k * kTileN + (n % kTileN); };
+    // The blend basis (posedirs rows, then shapedirs columns) twice, each as the B operand of its
+    // GEMM with the reduction index contiguous in swizzled 128-byte rows:
+    //   forward  [tile n/72][chunk k/32][row n%72][32 k]     (reduction over k)
+    //   backward [chunk n/32][row k][32 n]                    (reduction over n)
+    std::vector<float> bf((size_t)m->NT * Kpad * kFT, 0.f), bb((size_t)m->NC * Kpad * kKC, 0.f);
+    auto put = [&](int k, size_t n, float x) {
+        const int r = (int)(n % kFT);
+        bf[(n / kFT) * (size_t)Kpad * kFT + (size_t)(k / kKC) * (kFT * kKC) + (size_t)r * kKC + swz(r, k % kKC)] = x;
+        bb[(n / kKC) * (size_t)Kpad * kKC + (size_t)k * kKC + swz(k, (int)(n % kKC))] = x;
+    };
     for (int k = 0; k < P; ++k)
-        for (size_t n = 0; n < N; ++n) basis[bidx(k, n)] = h_posedirs[(size_t)k * N + n];
+        for (size_t n = 0; n < N; ++n) put(k, n, h_posedirs[(size_t)k * N + n]);
     for (int l = 0; l < NB; ++l)
-        for (size_t n = 0; n < N; ++n) basis[bidx(P + l, n)] = h_shapedirs[n * NB + l];
-    std::vector<float> vt((size_t)Npad, 0.f);
+        for (size_t n = 0; n < N; ++n) put(P + l, n, h_shapedirs[n * NB + l]);
+    std::vector<float> vt((size_t)m->NT * kFT, 0.f);
     for (size_t n = 0; n < N; ++n) vt[n] = h_v_template[n];
+    (void)Npad;
 
     // fold the joint regressor: Jt = Jreg * v_template, Jdirs = Jreg * shapedirs (double accum)
     std::vector<float> Jt((size_t)J * 3), Jdirs((size_t)J * 3 * NB);
@@ -812,7 +857,8 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     }
 
     int rc = PSI_OK;
-    if (rc == PSI_OK) rc = upload(&m->basis, basis, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->basis_fwd, bf, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->basis_bwd, bb, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->v_template, vt, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->Jt, Jt, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->Jdirs, Jdirs, st, &m->bytes);
@@ -868,19 +914,17 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
         lbs_zero_coef_pad_kernel<<<8, 256, 0, st>>>(saved + L.coef, B, m->Kpad);
         PSI_LAUNCHED();
     }
-    VertexFwdParams p;
-    p.basis = m->basis; p.v_template = m->v_template; p.skin_w = m->skin_w; p.skin_j = m->skin_j;
-    p.A = saved + L.A; p.coef = saved + L.coef; p.transl = transl; p.cam = cam;
-    p.cam_bstride = cam_bstride; p.verts = verts; p.vp_out = saved + L.vp;
-    p.V = m->V; p.J = m->J; p.Kpad = m->Kpad; p.Npad = m->Npad; p.KW = m->KW; p.B = B;
-    const size_t smem = (size_t)kStages * (kKT * kTileN + kKT * kBG) * sizeof(float);
+    BlendFwdParams p;
+    p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef = saved + L.coef;
+    p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B;
+    const size_t smem = (size_t)kFStages * kFStageBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(lbs_vertex_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(lbs_blend_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    dim3 grid((unsigned)(m->Npad / kTileN), (unsigned)((B + kBG - 1) / kBG));
-    lbs_vertex_fwd_kernel<<<grid, kVfWarps * 32, smem, st>>>(p);
+    dim3 grid((unsigned)m->NT, (unsigned)((B + kBG - 1) / kBG));
+    lbs_blend_fwd_kernel<<<grid, 128, smem, st>>>(p);
     PSI_LAUNCHED();
     {
         dim3 sgrid((unsigned)((m->V + 255) / 256), (unsigned)B);
@@ -923,7 +967,7 @@ int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float 
     float *ws = reinterpret_cast<float *>(workspace);
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     {
-        dim3 grid((unsigned)((m->Npad / 3 + 255) / 256), (unsigned)B);
+        dim3 grid((unsigned)(((m->Npad + 2) / 3 + 255) / 256), (unsigned)W.Bpad);
         lbs_vertex_bwd_kernel<<<grid, 256, 0, st>>>(m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                                                     m->skin_w, saved + L.A, cam, cam_bstride,
                                                     grad_verts, ws + W.gw, ws + W.gvp);
@@ -944,11 +988,14 @@ int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float 
         if (side && cudaEventRecord((cudaEvent_t)ev_join, side) != cudaSuccess) return PSI_ERR_BAD_ARG;
     }
     {
-        const int total_chunks = m->Npad / 32;
-        const int cps = kNSplit;
-        dim3 grid((unsigned)(m->Kpad / 128), (unsigned)kNSplit, (unsigned)(W.Bpad / 32));
-        lbs_dcoef_kernel<<<grid, 128, 0, st>>>(m->Kpad, m->Npad, B, W.Bpad, m->basis, ws + W.gvp,
-                                               ws + W.part, cps);
+        const size_t smem = (size_t)kDStages * kDStageBytes;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(lbs_dcoef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        dim3 grid((unsigned)(m->Kpad / kDK), (unsigned)kNSplit, (unsigned)(W.Bpad / kBG));
+        lbs_dcoef_kernel<<<grid, 256, smem, st>>>(m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp, ws + W.part, kNSplit);
         PSI_LAUNCHED();
         const long per_split = (long)W.Bpad * m->Kpad;
         lbs_dcoef_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(ws + W.part, kNSplit, per_split, ws + W.dsum);
