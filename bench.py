@@ -229,14 +229,16 @@ def run_ours(args):
         # the loop's own configuration: contact queries in Morton order of the template + last
         # iteration's hints (psi_fit_run keeps them); one call outside the timing warms the hints
         from psi_release_b200.fused import _spatial_order
-        sel = torch.tensor(_spatial_order(np.arange(NUM_VERTS), model["v_template"]), device=dev)
+        sel = torch.tensor(_spatial_order(np.arange(NUM_VERTS), model["v_template"], model["weights"],
+                                          model["kintree_table"][0]), device=dev)
         nnd = torch.empty(args.batch, NUM_VERTS, device=dev)
         nni = torch.empty(args.batch, NUM_VERTS, dtype=torch.int32, device=dev)
         nnh = torch.full((args.batch, NUM_VERTS), -1, dtype=torch.int32, device=dev)
 
         def nn_call():
-            rc = L.psi_nn_index_query_hint(op.s_index.h, _lib.ptr(verts), NUM_VERTS * 3, args.batch, NUM_VERTS,
-                                           _lib.ptr(sel), _lib.ptr(nnd), _lib.ptr(nni), _lib.ptr(nnh), _lib.stream_ptr())
+            rc = L.psi_nn_index_query_mode(op.s_index.h, _lib.ptr(verts), NUM_VERTS * 3, args.batch, NUM_VERTS,
+                                           _lib.ptr(sel), _lib.ptr(nnd), _lib.ptr(nni), _lib.ptr(nnh),
+                                           int(os.environ.get("PSI_FIT_NN_MODE", "3")), _lib.stream_ptr())
             assert rc == 0
     else:
         def nn_call():

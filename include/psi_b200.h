@@ -115,8 +115,9 @@ PSI_API int psi_nn_index_query(const psi_nn_index *ix, const float *q, long q_bs
 PSI_API int psi_nn_index_query_hint(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
                             const int *qsel, float *dist, int *idx, int *hint, psi_stream_t stream);
 /* Same, choosing the schedule: mode 0 = by query count (the two above), 1 = one warp per query,
- * 2 = one thread per query (fast when consecutive queries are spatial neighbours).  All modes
- * return identical bits. */
+ * 2 = one thread per query, 3 = one warp per GROUP of 32 consecutive queries of a body sharing one
+ * tree walk (2 and 3 are fast when consecutive queries are spatial neighbours; 3 is what the
+ * fitting loop uses).  All modes return identical bits. */
 PSI_API int psi_nn_index_query_mode(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
                             const int *qsel, float *dist, int *idx, int *hint, int mode,
                             psi_stream_t stream);
@@ -218,6 +219,7 @@ typedef struct psi_fit_config {
     float w_rec, w_vposer, w_contact, w_collision;   /* lossconfig, fitting_habitat.py:261-266 */
     float robust_c;       /* 1.0 (fitting_habitat.py:141) or 0.01 (fitting_proxe.py:139) */
     float lr, beta1, beta2, eps;                     /* torch.optim.Adam: init_lr_h, .9, .999, 1e-8 */
+    int nn_mode;          /* schedule of the in-loop NN query (psi_nn_index_query_mode); 0 = default (3) */
 } psi_fit_config;
 
 typedef struct psi_fit_ctx psi_fit_ctx;

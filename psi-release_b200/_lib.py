@@ -22,7 +22,7 @@ _f = ctypes.c_float
 class FitConfig(ctypes.Structure):
     """struct psi_fit_config (include/psi_b200.h)."""
     _fields_ = [("B", _i), ("use_graph", _i), ("w_rec", _f), ("w_vposer", _f), ("w_contact", _f),
-                ("w_collision", _f), ("robust_c", _f), ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f)]
+                ("w_collision", _f), ("robust_c", _f), ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("nn_mode", _i)]
 
 
 class PsiError(RuntimeError):

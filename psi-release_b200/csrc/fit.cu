@@ -368,8 +368,10 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     int rc = psi_lbs_fwd(c->model, c->B, c->shape, c->pose, c->transl, c->cam, 12, c->rot, c->num_rot,
                          c->verts, nullptr, c->saved, st);
     if (rc) return rc;
-    rc = psi_nn_index_query_hint(c->index, c->verts, (long)c->V * 3, c->B, c->nu, c->csel, c->nnd, c->nni,
-                                 c->nnhint, st);
+    // contact ids are ordered along a Morton curve of the template (fused.py): 32 consecutive
+    // queries are neighbours on the body -> the group schedule walks the index once per warp
+    rc = psi_nn_index_query_mode(c->index, c->verts, (long)c->V * 3, c->B, c->nu, c->csel, c->nnd, c->nni,
+                                 c->nnhint, c->cfg.nn_mode > 0 ? c->cfg.nn_mode : 3, st);
     if (rc) return rc;
     rc = psi_sdf_fwd(c->sdf, 1, c->D, c->gmin, c->gmax, c->verts, c->B, c->V, nullptr, c->sdfv, c->sdfg,
                      c->partial, st);

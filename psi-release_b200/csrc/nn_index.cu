@@ -158,7 +158,7 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         // seed the bound
         int seeded;
         const int h = hint ? hint[t] : -1;
-        if (h >= 0 && h < ix.num_clusters) {
+        if (h >= 0 && (long)h * kLeaf < ix.m) {
             seeded = h;                                             // last iteration's winning cluster
         } else {                                                    // best-first descent
             unsigned best = 0xffffffffu;
@@ -186,7 +186,7 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
 #pragma unroll
         for (int r = 0; r < kMaxMegaRounds; ++r) {
             if (r < ix.rounds) {
-                unsigned mmask = __ballot_sync(0xffffffffu, mlb[r] <= q.ub);
+                unsigned mmask = __ballot_sync(0xffffffffu, mlb[r] <= q.ub && r * 32 + lane < ix.num_megas);
                 while (mmask) {
                     const int src = take4(mmask, lane);
                     const int my_super = (r * 32 + (src < 0 ? 0 : src)) * kFan + (lane & 7);
@@ -300,7 +300,7 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
         };
         // seed: hinted leaf, else greedy descent (nearest mega -> super -> cluster)
         int seeded = hint ? hint[t] : -1;
-        if (seeded < 0 || seeded >= ix.num_clusters) {
+        if (seeded < 0 || (long)seeded * kLeaf >= ix.m) {
             float best = CUDART_INF_F;
             int m0 = 0;
             for (int g = 0; g < ix.mpad / 2; ++g) {
@@ -353,6 +353,233 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
         dist[t] = bd;
         if (idx) idx[t] = bi;
         if (hint) hint[t] = ((unsigned)bi < (unsigned)ix.m) ? __ldg(ix.pos_of + bi) / kLeaf : -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GROUP schedule: one warp owns 32 CONSECUTIVE queries of one body and walks the tree ONCE for
+// all of them.  (The thread-per-query kernel pays for the union of its 32 lanes' walks anyway --
+// divergent lanes wait -- and measured ~7000 warp instructions per 32 queries, most of them box
+// tests and loop control.)  Here the walk is warp-uniform:
+//   * nodes are tested lane-parallel (lane = node) against the group's query box [qlo,qhi] and the
+//     group bound ub = max over lanes of the lane's best distance so far;
+//   * an admitted leaf is tested once more against every lane's own query/bound, and if any lane
+//     still needs it ALL lanes evaluate its 32 points (packed f32x2, broadcast loads);
+//   * only the minimum distance and the leaf that produced it are tracked; the original index is
+//     recovered at the end by one scan of the winning leaf per lane (ties between leaves are
+//     resolved on the spot: lowest original index, as everywhere else).
+// Exactness.  For a lane with qlo <= q <= qhi (per axis), fl(lo-qhi) <= fl(lo-q) and
+// fl(qlo-hi) <= fl(q-hi) (rounding is monotone), hence lb_group(node) <= lb_lane(node) <= d(q,s) for
+// every point s of the node, all in floating point.  A node is skipped only if lb_group > ub >=
+// the lane's current best, a leaf only if lb_lane > the lane's best for EVERY lane; lanes that
+// evaluate extra leaves only see more real points.  Same bits as every other schedule.
+__device__ __forceinline__ unsigned fkey(float f) {          // order-preserving float -> uint
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+__device__ __forceinline__ unsigned box_lb_group(const float4 lo, const float4 hi, float lx, float ly, float lz,
+                                                 float hx, float hy, float hz) {
+    const float gx = fmaxf(fmaxf(__fsub_rn(lo.x, hx), __fsub_rn(lx, hi.x)), 0.f);
+    const float gy = fmaxf(fmaxf(__fsub_rn(lo.y, hy), __fsub_rn(ly, hi.y)), 0.f);
+    const float gz = fmaxf(fmaxf(__fsub_rn(lo.z, hz), __fsub_rn(lz, hi.z)), 0.f);
+    return __float_as_uint(__fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy))));
+}
+
+// minimum distance from (qx,qy,qz) (given negated, duplicated) to the 32 points of leaf c
+__device__ __forceinline__ float leaf_min(const float4 *__restrict__ pts2, int c, float2 n2x, float2 n2y, float2 n2z) {
+    const float4 *p = pts2 + (size_t)c * kLeaf;                 // 16 pairs x 2 float4
+    float lm = CUDART_INF_F;
+#pragma unroll 8
+    for (int i = 0; i < kLeaf / 2; ++i) {
+        const float4 u = __ldg(p + 2 * i), w = __ldg(p + 2 * i + 1);
+        const float2 dx = __fadd2_rn(make_float2(u.x, u.y), n2x);
+        const float2 dy = __fadd2_rn(make_float2(u.z, u.w), n2y);
+        const float2 dz = __fadd2_rn(make_float2(w.x, w.y), n2z);
+        const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+        lm = fminf(lm, fminf(d.x, d.y));
+    }
+    return lm;
+}
+// lowest original index among the points of leaf c at distance exactly lm
+__device__ __noinline__ int leaf_arg(const float4 *__restrict__ pts2, int c, float lm, float qx, float qy, float qz) {
+    const float4 *p = pts2 + (size_t)c * kLeaf;
+    const float2 n2x = make_float2(-qx, -qx), n2y = make_float2(-qy, -qy), n2z = make_float2(-qz, -qz);
+    int li = 0x7fffffff;
+#pragma unroll 4
+    for (int i = 0; i < kLeaf / 2; ++i) {
+        const float4 u = __ldg(p + 2 * i), w = __ldg(p + 2 * i + 1);
+        const float2 dx = __fadd2_rn(make_float2(u.x, u.y), n2x);
+        const float2 dy = __fadd2_rn(make_float2(u.z, u.w), n2y);
+        const float2 dz = __fadd2_rn(make_float2(w.x, w.y), n2z);
+        const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+        if (d.x == lm) li = min(li, __float_as_int(w.z));
+        if (d.y == lm) li = min(li, __float_as_int(w.w));
+    }
+    return li;
+}
+
+constexpr int kGrpThreads = 256;
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kGrpThreads, 4)
+nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, long q_bstride, int n,
+                      const int *__restrict__ qsel, int B, float *__restrict__ dist,
+                      int *__restrict__ idx, int *__restrict__ hint) {
+    // mega + super boxes (lo | hi, SoA) in shared memory; cluster boxes come through L1
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float4 s_sub[kGrpThreads / 32][4][2];            // per warp: 4 sub-group query boxes {lo, ub bits | hi}
+    const int ntop = ix.mpad + ix.num_supers;
+    const float4 *top_lo = ix.boxes, *top_hi = ix.boxes + ix.nbox;
+    if (SMEM) {
+        float4 *s4 = reinterpret_cast<float4 *>(smem_raw);
+        for (int i = threadIdx.x; i < ntop; i += blockDim.x) {
+            s4[i] = __ldg(ix.boxes + i);
+            s4[ntop + i] = __ldg(ix.boxes + ix.nbox + i);
+        }
+        __syncthreads();
+        top_lo = s4;
+        top_hi = s4 + ntop;
+    }
+    const float4 *__restrict__ c_lo = ix.boxes + ntop, *__restrict__ c_hi = ix.boxes + ix.nbox + ntop;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned submask = 0xffu << (lane & 24);               // my sub-group: 8 consecutive queries
+    float4(*sub)[2] = s_sub[threadIdx.x >> 5];
+    const int wpb = (n + 31) / 32;                               // warps (groups) per body
+    const long ngroups = (long)B * wpb;
+    const long nwarps = (long)gridDim.x * (kGrpThreads / 32);
+    for (long gw = (long)blockIdx.x * (kGrpThreads / 32) + (threadIdx.x >> 5); gw < ngroups; gw += nwarps) {
+        const long b = gw / wpb;
+        const int j = (int)(gw - b * wpb) * 32 + lane;
+        const int jj = min(j, n - 1);                            // lanes past the end duplicate the last query
+        const long t = b * n + jj;
+        const float *qp = q_in + b * q_bstride + (qsel ? (long)__ldg(qsel + jj) : (long)jj) * 3;
+        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        const float2 n2x = make_float2(-qx, -qx), n2y = make_float2(-qy, -qy), n2z = make_float2(-qz, -qz);
+        // query boxes: the 4 sub-groups (shared memory) and the whole group (registers)
+        float lx, ly, lz, hx, hy, hz;
+        {
+            const unsigned kx = fkey(qx), ky = fkey(qy), kz = fkey(qz);
+            const unsigned ax = __reduce_min_sync(submask, kx), bx = __reduce_max_sync(submask, kx);
+            const unsigned ay = __reduce_min_sync(submask, ky), by = __reduce_max_sync(submask, ky);
+            const unsigned az = __reduce_min_sync(submask, kz), bz = __reduce_max_sync(submask, kz);
+            __syncwarp();
+            if ((lane & 7) == 0) {
+                sub[lane >> 3][0] = make_float4(fkey_inv(ax), fkey_inv(ay), fkey_inv(az), CUDART_INF_F);
+                sub[lane >> 3][1] = make_float4(fkey_inv(bx), fkey_inv(by), fkey_inv(bz), 0.f);
+            }
+            lx = fkey_inv(__reduce_min_sync(full, ax)); hx = fkey_inv(__reduce_max_sync(full, bx));
+            ly = fkey_inv(__reduce_min_sync(full, ay)); hy = fkey_inv(__reduce_max_sync(full, by));
+            lz = fkey_inv(__reduce_min_sync(full, az)); hz = fkey_inv(__reduce_max_sync(full, bz));
+        }
+        float bd = CUDART_INF_F;     // this lane's best distance so far ...
+        int bleaf = -1;              // ... the leaf it was found in ...
+        int bi = -1;                 // ... and its original index once known (-1: not recovered yet)
+        auto visit = [&](int c) {    // all lanes, warp-uniform c
+            const float lm = leaf_min(ix.pts2, c, n2x, n2y, n2z);
+            if (lm < bd) {
+                bd = lm; bleaf = c; bi = -1;
+            } else if (lm == bd && c != bleaf && bleaf >= 0) {   // exact tie between two leaves
+                if (bi < 0) bi = leaf_arg(ix.pts2, bleaf, bd, qx, qy, qz);
+                bi = min(bi, leaf_arg(ix.pts2, c, lm, qx, qy, qz));
+            }
+        };
+        // bounds: ub = max over the group, sub[g][0].w = max over sub-group g (bits of distances already seen)
+        unsigned ub;
+        auto publish_bounds = [&]() {
+            const unsigned mine = __reduce_max_sync(submask, __float_as_uint(bd));
+            ub = __reduce_max_sync(full, mine);
+            if ((lane & 7) == 0) sub[lane >> 3][0].w = __uint_as_float(mine);
+            __syncwarp();
+        };
+        // ---- seeds: last iteration's winning leaves, or a greedy descent for the lanes without one
+        int h = hint ? hint[t] : -1;
+        const bool need = h < 0 || (long)h * kLeaf >= ix.m;         // no hint, or not a leaf that holds points
+        const unsigned needm = __ballot_sync(full, need);
+        if (needm) {
+            const int src = __ffs(needm) - 1;
+            const float cx = __shfl_sync(full, qx, src), cy = __shfl_sync(full, qy, src), cz = __shfl_sync(full, qz, src);
+            unsigned best = 0xffffffffu;
+            int m0 = 0;
+            for (int r = 0; r < ix.rounds; ++r) {
+                const unsigned lb = box_lb(top_lo[r * 32 + lane], top_hi[r * 32 + lane], cx, cy, cz);
+                const unsigned mn = __reduce_min_sync(full, lb);
+                if (mn < best) { best = mn; m0 = r * 32 + __ffs(__ballot_sync(full, lb == mn)) - 1; }
+            }
+            unsigned lb8 = 0x7f800000u;
+            if (lane < kFan) lb8 = box_lb(top_lo[ix.mpad + m0 * kFan + lane], top_hi[ix.mpad + m0 * kFan + lane], cx, cy, cz);
+            unsigned mn = __reduce_min_sync(full, lb8);
+            const int s0 = m0 * kFan + __ffs(__ballot_sync(full, lb8 == mn)) - 1;
+            lb8 = 0x7f800000u;
+            if (lane < kFan) lb8 = box_lb(__ldg(c_lo + s0 * kFan + lane), __ldg(c_hi + s0 * kFan + lane), cx, cy, cz);
+            mn = __reduce_min_sync(full, lb8);
+            const int c0 = s0 * kFan + __ffs(__ballot_sync(full, lb8 == mn)) - 1;
+            if (need) h = c0;
+        }
+        int myvis = -1, nvis = 0;    // lane k remembers the k-th seed leaf (at most 32 distinct seeds)
+        {
+            unsigned todo = full;
+            while (todo) {
+                const int c = __shfl_sync(full, h, __ffs(todo) - 1);
+                visit(c);
+                if (lane == nvis) myvis = c;
+                ++nvis;
+                todo &= ~__ballot_sync(full, h == c);
+            }
+        }
+        publish_bounds();
+        // ---- sweep: megas -> supers -> clusters, 32 nodes per round, all warp-uniform
+        for (int r = 0; r < ix.rounds; ++r) {
+            const unsigned lbm = box_lb_group(top_lo[r * 32 + lane], top_hi[r * 32 + lane], lx, ly, lz, hx, hy, hz);
+            // (pad megas never enter: with ub = +inf -- NaN queries -- their children would be out of range)
+            unsigned mmask = __ballot_sync(full, lbm <= ub && r * 32 + lane < ix.num_megas);
+            while (mmask) {
+                const int src = take4(mmask, lane);
+                const int my_super = (r * 32 + (src < 0 ? 0 : src)) * kFan + (lane & 7);
+                unsigned slb = 0x7f800000u;
+                if (src >= 0) slb = box_lb_group(top_lo[ix.mpad + my_super], top_hi[ix.mpad + my_super], lx, ly, lz, hx, hy, hz);
+                unsigned smask = __ballot_sync(full, src >= 0 && slb <= ub);
+                while (smask) {
+                    const int src2 = take4(smask, lane);
+                    const int cid = __shfl_sync(full, my_super, src2 < 0 ? 0 : src2) * kFan + (lane & 7);
+                    // lane = cluster: admitted if any of the 4 sub-groups (tighter boxes, tighter bounds) may need it
+                    bool adm = false;
+                    if (src2 >= 0) {
+                        const float4 clo = __ldg(c_lo + cid), chi = __ldg(c_hi + cid);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sl = sub[g][0], sh = sub[g][1];
+                            adm |= box_lb_group(clo, chi, sl.x, sl.y, sl.z, sh.x, sh.y, sh.z) <= __float_as_uint(sl.w);
+                        }
+                    }
+                    unsigned cmask = __ballot_sync(full, adm);
+                    for (int k = 0; k < nvis && cmask; ++k)                     // the seeds were evaluated already
+                        cmask &= ~__ballot_sync(full, cid == __shfl_sync(full, myvis, k));
+                    while (cmask) {
+                        const int cl = __ffs(cmask) - 1;
+                        cmask &= cmask - 1;
+                        const int c = __shfl_sync(full, cid, cl);
+                        // lane = query: does any lane still need leaf c?
+                        const float lbl = __uint_as_float(box_lb(__ldg(c_lo + c), __ldg(c_hi + c), qx, qy, qz));
+                        if (__any_sync(full, lbl <= bd)) {
+                            visit(c);
+                            publish_bounds();
+                        }
+                    }
+                    smask &= __ballot_sync(full, slb <= ub);
+                }
+                mmask &= __ballot_sync(full, lbm <= ub);
+            }
+        }
+        if (bi < 0) bi = bleaf >= 0 ? leaf_arg(ix.pts2, bleaf, bd, qx, qy, qz) : 0x7fffffff;
+        if (j < n) {
+            dist[t] = bd;
+            if (idx) idx[t] = bi;
+            if (hint) hint[t] = bleaf;
+        }
     }
 }
 
@@ -507,7 +734,18 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
         attr = true;
     }
-    if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
+    if (mode == 3) {
+        // one warp per 32 consecutive queries of a body (coherent query order: the fitting loop)
+        const long ngroups = (long)B * ((n + 31) / 32);
+        long blocks = (ngroups + kGrpThreads / 32 - 1) / (kGrpThreads / 32);
+        const long cap = (long)PSI_NUM_SMS * 16;
+        if (blocks > cap) blocks = cap;
+        const size_t top_bytes = (size_t)2 * (ix->mpad + ix->num_supers) * sizeof(float4);
+        if (top_bytes <= 24 * 1024)
+            nn_index_group_kernel<true><<<(unsigned)blocks, kGrpThreads, top_bytes, st>>>(*ix, q, q_bstride, n, qsel, B, dist, idx, hint);
+        else
+            nn_index_group_kernel<false><<<(unsigned)blocks, kGrpThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, B, dist, idx, hint);
+    } else if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
         // one thread per query: enough queries to fill the machine with 256-thread CTAs
         long blocks = (total + 255) / 256;
         const long cap = (long)PSI_NUM_SMS * 8;

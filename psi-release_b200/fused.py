@@ -10,6 +10,7 @@ deterministic).
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -17,21 +18,51 @@ import torch
 from . import _lib
 
 
-def _spatial_order(ids, v_template):
-    """Sort vertex ids along a Morton curve of the template mesh (duplicates stay adjacent)."""
+def _kd_runs(pts, ids, leaf=32):
+    """Order `ids` so that aligned runs of `leaf` are compact kd cells (median split of the longest
+    axis, left part a multiple of `leaf`) -- the same construction as the scene index."""
+    out = []
+    stack = [np.asarray(ids, dtype=np.int64)]
+    while stack:
+        cur = stack.pop()
+        if len(cur) <= leaf:
+            out.append(cur)
+            continue
+        p = pts[cur]
+        ax = int(np.argmax(p.max(0) - p.min(0)))
+        nl = ((len(cur) // leaf + 1) // 2) * leaf
+        o = np.argsort(p[:, ax], kind="stable")
+        stack.append(cur[o[nl:]])          # popped after the left part: keeps left-to-right order
+        stack.append(cur[o[:nl]])
+    return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+
+def _spatial_order(ids, v_template, weights=None, parents=None):
+    """Order the contact vertex ids so that 32 consecutive ids stay neighbours on the POSED body:
+    vertices are grouped by the joint that dominates their skinning weights (they move together),
+    joints are laid out depth-first along the kinematic tree (parent and child bones touch), and
+    inside a joint the vertices follow a kd order of the template.  Duplicate ids stay adjacent.
+    The NN result does not depend on the order; the group schedule's speed does."""
     vt = np.asarray(v_template, dtype=np.float64)
-    cell = ((vt - vt.min(0)) / np.maximum(vt.max(0) - vt.min(0), 1e-12) * 1023.0 + 0.5).astype(np.int64)
-
-    def spread(v):
-        v = v & 0x3FF
-        v = (v | (v << 16)) & 0x030000FF
-        v = (v | (v << 8)) & 0x0300F00F
-        v = (v | (v << 4)) & 0x030C30C3
-        return (v | (v << 2)) & 0x09249249
-
-    rank = spread(cell[:, 0]) | (spread(cell[:, 1]) << 1) | (spread(cell[:, 2]) << 2)
     ids = np.asarray(ids, dtype=np.int64)
-    return np.ascontiguousarray(ids[np.argsort(rank[ids], kind="stable")].astype(np.int32))
+    uniq, counts = np.unique(ids, return_counts=True)
+    if weights is None or parents is None:
+        order = _kd_runs(vt, uniq)
+    else:
+        owner = np.asarray(weights)[uniq].argmax(1)
+        parents = np.asarray(parents, dtype=np.int64)
+        nj = len(parents)
+        kids = [[] for _ in range(nj)]
+        for j in range(1, nj):
+            kids[int(parents[j])].append(j)
+        dfs, stack = [], [0]
+        while stack:
+            j = stack.pop()
+            dfs.append(j)
+            stack.extend(reversed(kids[j]))
+        order = np.concatenate([_kd_runs(vt, uniq[owner == j]) for j in dfs] + [np.zeros(0, np.int64)])
+    mult = dict(zip(uniq.tolist(), counts.tolist()))
+    return np.ascontiguousarray(np.repeat(order, [mult[int(v)] for v in order]).astype(np.int32))
 
 
 class FusedFit:
@@ -54,7 +85,8 @@ class FusedFit:
         # Query order = order of first appearance in the id list: spatially sorted ids make the 32
         # queries of a warp neighbours on the body (needed by the thread-per-query NN schedule);
         # the result does not depend on the order.
-        cid = _spatial_order(contact_ids, body_model._model_data["v_template"])
+        md = body_model._model_data
+        cid = _spatial_order(contact_ids, md["v_template"], md["weights"], np.asarray(md["kintree_table"])[0])
         if num_streams is None:
             num_streams = 1     # measured: two half-batch contexts are not faster (kernels do not shrink with B)
         num_streams = max(1, min(int(num_streams), self.B))
@@ -68,7 +100,8 @@ class FusedFit:
             cfg = _lib.FitConfig(B=nb, use_graph=1 if use_graph else 0,
                                  w_rec=float(weights["weight_loss_rec"]), w_vposer=float(weights["weight_loss_vposer"]),
                                  w_contact=float(weights["weight_contact"]), w_collision=float(weights["weight_collision"]),
-                                 robust_c=float(robust_c), lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8)
+                                 robust_c=float(robust_c), lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8,
+                                 nn_mode=int(os.environ.get("PSI_FIT_NN_MODE", "0")))
             h = ctypes.c_void_p()
             with torch.cuda.device(self.device):
                 rc = _lib.lib().psi_fit_create(

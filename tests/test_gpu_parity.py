@@ -360,7 +360,8 @@ def test_nn_index_hints_never_change_results_and_multi_round_megas():
 
 
 def test_nn_index_schedules_agree_bit_for_bit():
-    """Warp-per-query and thread-per-query walks of the index return the same bits (and the oracle's)."""
+    """Warp-per-query, thread-per-query and 32-query-group walks of the index return the same bits
+    (and the oracle's)."""
     from psi_release_b200 import chamfer, _lib
     rng = np.random.default_rng(31)
     m, B, n = 30000, 3, 2000
@@ -373,7 +374,7 @@ def test_nn_index_schedules_agree_bit_for_bit():
     d_o, i_o = oracle.nn_fwd(q, s)
     L = _lib.lib()
     tq = _cuda(q)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         for use_hint in (False, True):
             dist = torch.empty(B, n, device="cuda"); idx = torch.empty(B, n, dtype=torch.int32, device="cuda")
             hint = torch.randint(-3, m // 32 + 5, (B, n), dtype=torch.int32, device="cuda") if use_hint else None
@@ -383,3 +384,47 @@ def test_nn_index_schedules_agree_bit_for_bit():
                 assert rc == 0
                 assert np.array_equal(idx.cpu().numpy(), i_o), (mode, use_hint)
                 assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o)), (mode, use_hint)
+
+
+@pytest.mark.parametrize("n,m", [(1, 40), (33, 700), (1000, 729), (2051, 20000)])
+def test_nn_index_group_schedule_coherent_queries_ties_and_qsel(n, m):
+    """The group schedule (one warp = 32 consecutive queries, one shared tree walk) on what it is
+    built for -- spatially coherent query runs -- plus lattice scenes (exact ties between leaves),
+    a ragged last group (n % 32 != 0), row selection and stale / garbage hints."""
+    from psi_release_b200 import chamfer, _lib
+    rng = np.random.default_rng(n * 13 + m)
+    if m == 729:
+        g = np.arange(-4, 5, dtype=np.float32) * 0.25
+        s = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+        s = s[rng.permutation(len(s))].copy()
+    else:
+        s = rng.uniform(-2, 2, (m, 3)).astype(np.float32)
+        s[: m // 2, 2] = -1.5
+        s[m // 3] = s[7]; s[m - 2] = s[7]
+    B, rows = 3, n + 5
+    # a smooth curve through the scene: consecutive queries are neighbours
+    tt = np.linspace(0, 1, rows, dtype=np.float32)
+    base = np.stack([np.cos(6 * tt) * 1.5, np.sin(4 * tt) * 1.5, tt * 3 - 1.5], -1)
+    allq = (base[None] + rng.normal(0, 0.02, (B, rows, 3))).astype(np.float32)
+    if m == 729:
+        allq = (np.round(allq * 4) / 4 + np.float32(0.125)).astype(np.float32)   # cell centres: 8-way ties
+    allq[:, 0] = s[7]
+    sel_np = np.sort(rng.choice(rows, n, replace=False)).astype(np.int32)
+    q = allq[:, sel_np]
+    d_o, i_o = oracle.nn_fwd(q, s)
+    ix = chamfer.SceneIndex(_cuda(s))
+    L = _lib.lib()
+    tq, sel = _cuda(allq), torch.tensor(sel_np, device="cuda")
+    hint = torch.randint(-3, m // 32 + 5, (B, n), dtype=torch.int32, device="cuda")
+    for rep in range(3):     # garbage hints, then the hints each call wrote
+        dist = torch.empty(B, n, device="cuda"); idx = torch.empty(B, n, dtype=torch.int32, device="cuda")
+        rc = L.psi_nn_index_query_mode(ix.h, _lib.ptr(tq), rows * 3, B, n, _lib.ptr(sel), _lib.ptr(dist), _lib.ptr(idx),
+                                       _lib.ptr(hint) if rep else None, 3, _lib.stream_ptr())
+        assert rc == 0
+        assert np.array_equal(idx.cpu().numpy(), i_o), rep
+        assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o)), rep
+    # distances only (idx == NULL)
+    dist = torch.empty(B, n, device="cuda")
+    assert L.psi_nn_index_query_mode(ix.h, _lib.ptr(tq), rows * 3, B, n, _lib.ptr(sel), _lib.ptr(dist), None,
+                                     None, 3, _lib.stream_ptr()) == 0
+    assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o))

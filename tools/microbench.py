@@ -80,16 +80,20 @@ def main():
         return (v | (v << 2)) & 0x09249249
     rank = spread(cell[:, 0]) | (spread(cell[:, 1]) << 1) | (spread(cell[:, 2]) << 2)
     sel_sorted = torch.tensor(np.argsort(rank, kind="stable").astype(np.int32), device=dev)
+    from psi_release_b200.fused import _spatial_order
+    sel_jkd = torch.tensor(_spatial_order(np.arange(V), model["v_template"], model["weights"], model["kintree_table"][0]), device=dev)
     dq = torch.empty(B, V, device=dev); iq = torch.empty(B, V, dtype=torch.int32, device=dev)
     hint = torch.full((B, V), -1, dtype=torch.int32, device=dev)
     def run(mode, sel, hnt):
         rc = L.psi_nn_index_query_mode(ix.h, _lib.ptr(verts), V * 3, B, V, _lib.ptr(sel), _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(hnt), mode, _lib.stream_ptr())
         assert rc == 0
-    for mode in (1, 2):
-        for name, sel in (("natural", None), ("sorted", sel_sorted)):
+    for mode in (1, 2, 3):
+        for name, sel in (("natural", None), ("sorted", sel_sorted), ("jointkd", sel_jkd)):
             out["nn_mode%d_%s_nohint_ms" % (mode, name)] = timeit(lambda: run(mode, sel, None), flush=flush)[0]
             hint.fill_(-1); run(mode, sel, hint)
             out["nn_mode%d_%s_hint_ms" % (mode, name)] = timeit(lambda: run(mode, sel, hint), flush=flush)[0]
+    run(3, sel_sorted, hint)
+    out["nn_mode3_equal_bruteforce"] = bool(torch.equal(iq, ib[:, sel_sorted.long()]) and torch.equal(dq.view(torch.int32), db[:, sel_sorted.long()].view(torch.int32)))
     run(2, None, None)
     out["nn_mode2_equal_bruteforce"] = bool(torch.equal(iq, ib) and torch.equal(dq.view(torch.int32), db.view(torch.int32)))
 
