@@ -124,6 +124,192 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ------------------------------------------------------------------------------- rooflines
+def _latest_traffic():
+    """dram bytes per launch from the newest committed `ncu --set full` summary (profiles/*_traffic.json)."""
+    d = os.path.join(ROOT, "profiles")
+    files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json")) if os.path.isdir(d) else []
+    if not files:
+        return {}, None
+    with open(os.path.join(d, files[-1])) as f:
+        return json.load(f)["kernels"], "profiles/" + files[-1]
+
+
+def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clocks, rank):
+    """Every kernel of one fitting iteration timed LIVE: psi_fit_profile replays the iteration
+    eagerly with a CUDA event behind each launch on the launching stream (100 iterations after 30
+    warm ones, data in the state the loop leaves it in).  `roofline` = the kernel with the largest
+    share of the iteration; algorithmic bytes per launch follow SURVEY.md 8(d) / DESIGN.md section 3."""
+    prof = op.profile_iteration(xh_dev, cam_dev, warm_iters=30, timed_iters=100)
+    if rank != 0:
+        return None
+    B, V, M = args.batch, NUM_VERTS, NUM_POINTS
+    basis = (486 + 20) * 3 * V * 4 + 3 * V * 4          # posedirs + shapedirs + v_template
+    hid = 512
+    alg = {   # algorithmic bytes of ONE launch
+        "nn_index_group": B * V * 12 + B * V * 8 + M * 12,
+        "nn_index_query": B * V * 12 + B * V * 8 + M * 12,
+        "lbs_blend_fwd": basis + B * 506 * 4 + B * V * 12,
+        "lbs_dcoef": basis + B * V * 12 + B * 506 * 4,
+        "lbs_skin_fwd": 2 * B * V * 12 + V * 55 * 4 + B * 55 * 48,
+        "lbs_vertex_bwd": 3 * B * V * 12 + V * 55 * 4 + B * 55 * 48,
+        "lbs_dA": 2 * B * V * 12 + V * 55 * 4 + B * 55 * 48,
+        "lbs_dcoef_reduce": 75 * B * 512 * 4,
+        "lbs_pose_fwd": B * (740 + 55 * 48 + 506 * 4) + 55 * 3 * 21 * 4,
+        "lbs_pose_bwd": B * (55 * 48 + 506 * 4 + 740) + 55 * 3 * 21 * 4,
+        "sdf_fwd": B * V * (32 + 12 + 4 + 12),
+        "fit_vertex_grad": B * V * (12 + 4 + 12 + 8 + 12 + 12),
+        "fit_linear": hid * hid * 4 + 2 * B * hid * 4,
+        "fit_pre": B * 75 * 8, "fit_post": B * 75 * 24,
+    }
+    agg = {}
+    for name, ms in prof:
+        a = agg.setdefault(name, [0.0, 0])
+        a[0] += ms
+        a[1] += 1
+    it_ms = sum(a[0] for a in agg.values())
+    traffic, tsrc = _latest_traffic()
+
+    def entry(name):
+        tot, n = agg[name]
+        per = tot / n
+        ach = alg.get(name, 0) / (per * 1e-3) / 1e9
+        tr = next((v for k, v in traffic.items() if name in k), None)
+        return {"kernel": "psi::" + name + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "peak_source": peak_src,
+                "traffic": None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"]),
+                "traffic_source": tsrc if tr is not None else None, "launch_ms": per, "launches_per_iteration": n,
+                "algorithmic_bytes_per_launch": alg.get(name, 0), "share_of_iteration": tot / it_ms}
+
+    top = max(agg, key=lambda k: agg[k][0])
+    roofline = entry(top)
+    roofline["timed"] = ("live: CUDA events around every launch of 100 eager iterations on the launching stream "
+                         "(psi_fit_profile), inputs as the loop leaves them")
+    roofline["iteration_ms_eager_sum"] = it_ms
+    roofline["iteration_ms_graph"] = step_ms / args.iters
+    roofline["others"] = {k: entry(k) for k in sorted(agg, key=lambda k: -agg[k][0]) if k != top}
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    nn_name = next((k for k in agg if k.startswith("nn_")), None)
+    gemm = 2.0 * B * 512 * 3 * V
+    roofline["note"] = ("the exact box-tree NN evaluates a few of the 1563 leaf clusters per query: an instruction/"
+                        "latency-bound tree walk over L2-resident data, neither HBM- nor tensor-bound; "
+                        "brute-force-equivalent rate = %.3g pair/s.  LBS blend GEMMs (3xTF32 mma.sync): forward %.1f, "
+                        "dcoef %.1f TFLOP/s FP32-equivalent (nominal FP32 CUDA-core peak %.1f)"
+                        % (B * V * M / (agg[nn_name][0] / agg[nn_name][1] * 1e-3) if nn_name else 0.0,
+                           gemm / (agg["lbs_blend_fwd"][0] * 1e-3) / 1e12, gemm / (agg["lbs_dcoef"][0] * 1e-3) / 1e12,
+                           fp32_peak))
+    return roofline
+
+
+def roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak, peak_src, step_ms, clocks, rank):
+    """Autograd engine (the generic drop-in path): the psi ops of one iteration, each timed ALONE
+    with CUDA events on its launching stream (10 launches, L2 flushed in between); the slowest one
+    carries `roofline`."""
+    from psi_release_b200 import _lib, chamfer
+    L = _lib.lib()
+    from psi_release_b200 import body_model as bm, sdf as sdf_mod
+    verts = op.body_verts(xh_dev, cam_dev).detach().contiguous()
+    h = op.body_mesh_model.handle(dev)
+    rng = np.random.default_rng(0)
+    betas = torch.tensor(rng.standard_normal((args.batch, 20)).astype(np.float32), device=dev)
+    pose = torch.tensor((rng.standard_normal((args.batch, 165)) * 0.3).astype(np.float32), device=dev)
+    bq, pq = betas.clone().requires_grad_(True), pose.clone().requires_grad_(True)
+    vq, _ = bm.lbs(bq, pq, h, cam=cam_dev)
+    gq = torch.randn_like(vq)
+
+    def alone(fn):
+        for _ in range(3):
+            fn()
+        ks = []
+        for _ in range(10):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ks.append(e0.elapsed_time(e1))
+        return float(np.mean(ks))
+
+    nn_target = op.s_index if op.s_index is not None else op.s_verts
+    if op.s_index is not None:
+        # the loop's own configuration: contact queries in Morton order of the template + last
+        # iteration's hints (psi_fit_run keeps them); one call outside the timing warms the hints
+        from psi_release_b200.fused import _spatial_order
+        sel = torch.tensor(_spatial_order(np.arange(NUM_VERTS), model["v_template"], model["weights"],
+                                          model["kintree_table"][0]), device=dev)
+        nnd = torch.empty(args.batch, NUM_VERTS, device=dev)
+        nni = torch.empty(args.batch, NUM_VERTS, dtype=torch.int32, device=dev)
+        nnh = torch.full((args.batch, NUM_VERTS), -1, dtype=torch.int32, device=dev)
+
+        def nn_call():
+            rc = L.psi_nn_index_query_mode(op.s_index.h, _lib.ptr(verts), NUM_VERTS * 3, args.batch, NUM_VERTS,
+                                           _lib.ptr(sel), _lib.ptr(nnd), _lib.ptr(nni), _lib.ptr(nnh),
+                                           int(os.environ.get("PSI_FIT_NN_MODE", "3")), _lib.stream_ptr())
+            assert rc == 0
+    else:
+        def nn_call():
+            chamfer.nn_forward(verts, nn_target)
+    kernel_ms = {
+        "nn": alone(nn_call),
+        "lbs_fwd": alone(lambda: bm.lbs(betas, pose, h, cam=cam_dev)),
+        "lbs_bwd": alone(lambda: torch.autograd.grad(vq, (bq, pq), gq, retain_graph=True)),
+        "sdf": alone(lambda: sdf_mod.sdf_forward(op.scene_sdf, verts, want_grad=True, want_partials=True)),
+    }
+
+    if rank != 0:
+        return None
+    B = args.batch
+    pairs = B * NUM_VERTS * NUM_POINTS
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    model_bytes = h.nbytes()
+    # algorithmic bytes per launch (DESIGN.md section 3; SURVEY.md 8(d) per-body figures x B)
+    alg = {
+        "nn": (B * NUM_VERTS * 12 + B * NUM_VERTS * 8 + NUM_POINTS * 12),
+        "lbs_fwd": model_bytes + B * (740 + NUM_VERTS * 12),
+        "lbs_bwd": model_bytes + B * (NUM_VERTS * 24 + 740),
+        "sdf": B * NUM_VERTS * (32 + 12 + 4 + 12),
+    }
+    names = {"nn": ("psi::nn_index_thread_kernel<true> (exact box-tree NN, Morton-ordered queries + hints)" if op.s_index is not None
+                    else "psi::nn_fwd_kernel<8,16,256,1024,2> (brute-force NN)"),
+             "lbs_fwd": "psi::lbs_pose_fwd_kernel + psi::lbs_blend_fwd_kernel + psi::lbs_skin_fwd_kernel",
+             "lbs_bwd": "psi::lbs_vertex_bwd/dA/dcoef/pose_bwd kernels", "sdf": "psi::sdf_fwd_kernel"}
+    top = max(kernel_ms, key=kernel_ms.get)
+
+    traffic = {}
+
+    def roof(k):
+        ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
+        tr = traffic.get(k)
+        tr = None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+        return {"kernel": names[k], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "peak_source": peak_src, "traffic": tr,
+                "traffic_source": None,
+                "launch_ms": kernel_ms[k],
+                "algorithmic_bytes_per_launch": alg[k],
+                "share_of_step": kernel_ms[k] * args.iters / step_ms}
+
+    roofline = roof(top)
+    roofline["timed"] = "alone, 10 launches, CUDA events on the launching stream, L2 flushed"
+    roofline["others"] = {k: roof(k) for k in kernel_ms if k != top}
+    if op.s_index is None:
+        roofline["fp32"] = {"bound": "fp32 issue", "achieved": pairs * 8 / (kernel_ms["nn"] * 1e-3) / 1e12,
+                            "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": pairs * 8 / (kernel_ms["nn"] * 1e-3) / 1e12 / fp32_peak,
+                            "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm (no measured FP32 peak)",
+                            "pairs_per_s": pairs / (kernel_ms["nn"] * 1e-3)}
+    else:
+        roofline["note"] = ("the index evaluates ~3 of 1563 leaf clusters per query (plus ~80 box bounds): an "
+                            "instruction/latency-bound tree walk over L2-resident data, neither HBM- nor "
+                            "tensor-bound; brute-force-equivalent rate = %.3g pair/s"
+                            % (pairs / (kernel_ms["nn"] * 1e-3)))
+    roofline["lbs_fwd_fp32_frac"] = 49.3e6 * B / (kernel_ms["lbs_fwd"] * 1e-3) / 1e12 / fp32_peak
+    return roofline
+
+
 # ----------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch.distributed as dist
@@ -197,59 +383,13 @@ def run_ours(args):
     all_fitted = gather_rows(fitted, args.batch * world) if world > 1 else fitted
     assert all_fitted.shape == (args.batch * world, 72) and torch.isfinite(all_fitted).all()
 
-    # the psi kernels of one iteration, each timed ALONE with CUDA events on its launching stream
-    # (10 launches, L2 flushed in between); the slowest one carries `roofline`
-    from psi_release_b200 import body_model as bm, sdf as sdf_mod
-    verts = op.body_verts(xh_dev, cam_dev).detach().contiguous()
-    h = op.body_mesh_model.handle(dev)
-    rng = np.random.default_rng(0)
-    betas = torch.tensor(rng.standard_normal((args.batch, 20)).astype(np.float32), device=dev)
-    pose = torch.tensor((rng.standard_normal((args.batch, 165)) * 0.3).astype(np.float32), device=dev)
-    bq, pq = betas.clone().requires_grad_(True), pose.clone().requires_grad_(True)
-    vq, _ = bm.lbs(bq, pq, h, cam=cam_dev)
-    gq = torch.randn_like(vq)
-
-    def alone(fn):
-        for _ in range(3):
-            fn()
-        ks = []
-        for _ in range(10):
-            flush.zero_()
-            torch.cuda.synchronize(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize(dev)
-            ks.append(e0.elapsed_time(e1))
-        return float(np.mean(ks))
-
-    nn_target = op.s_index if op.s_index is not None else op.s_verts
-    if op.s_index is not None:
-        # the loop's own configuration: contact queries in Morton order of the template + last
-        # iteration's hints (psi_fit_run keeps them); one call outside the timing warms the hints
-        from psi_release_b200.fused import _spatial_order
-        sel = torch.tensor(_spatial_order(np.arange(NUM_VERTS), model["v_template"], model["weights"],
-                                          model["kintree_table"][0]), device=dev)
-        nnd = torch.empty(args.batch, NUM_VERTS, device=dev)
-        nni = torch.empty(args.batch, NUM_VERTS, dtype=torch.int32, device=dev)
-        nnh = torch.full((args.batch, NUM_VERTS), -1, dtype=torch.int32, device=dev)
-
-        def nn_call():
-            rc = L.psi_nn_index_query_mode(op.s_index.h, _lib.ptr(verts), NUM_VERTS * 3, args.batch, NUM_VERTS,
-                                           _lib.ptr(sel), _lib.ptr(nnd), _lib.ptr(nni), _lib.ptr(nnh),
-                                           int(os.environ.get("PSI_FIT_NN_MODE", "3")), _lib.stream_ptr())
-            assert rc == 0
+    hbm_peak, peak_src = peaks()
+    step_ms = ms_dev / args.steps
+    if op.engine == "fused":
+        roofline = roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clocks, rank)
     else:
-        def nn_call():
-            chamfer.nn_forward(verts, nn_target)
-    kernel_ms = {
-        "nn": alone(nn_call),
-        "lbs_fwd": alone(lambda: bm.lbs(betas, pose, h, cam=cam_dev)),
-        "lbs_bwd": alone(lambda: torch.autograd.grad(vq, (bq, pq), gq, retain_graph=True)),
-        "sdf": alone(lambda: sdf_mod.sdf_forward(op.scene_sdf, verts, want_grad=True, want_partials=True)),
-    }
-
+        roofline = roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak, peak_src,
+                                  step_ms, clocks, rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -257,59 +397,6 @@ def run_ours(args):
     bodies = args.batch * world * args.steps
     value = bodies / (ms_dev * 1e-3)
     e2e = bodies / (ms_e2e * 1e-3)
-    hbm_peak, peak_src = peaks()
-    B = args.batch
-    pairs = B * NUM_VERTS * NUM_POINTS
-    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
-    model_bytes = h.nbytes()
-    # algorithmic bytes per launch (SURVEY.md 8(d) per-body figures x B)
-    alg = {
-        "nn": (B * NUM_VERTS * 12 + B * NUM_VERTS * 8 + NUM_POINTS * 12),
-        "lbs_fwd": model_bytes + B * (740 + NUM_VERTS * 12),
-        "lbs_bwd": model_bytes + B * (NUM_VERTS * 24 + 740),
-        "sdf": B * NUM_VERTS * (32 + 12 + 4 + 12),
-    }
-    names = {"nn": ("psi::nn_index_thread_kernel<true> (exact box-tree NN, Morton-ordered queries + hints)" if op.s_index is not None
-                    else "psi::nn_fwd_kernel<8,16,256,1024,2> (brute-force NN)"),
-             "lbs_fwd": "psi::lbs_pose_fwd_kernel + psi::lbs_vertex_fwd_kernel",
-             "lbs_bwd": "psi::lbs_vertex_bwd/dA/dcoef/pose_bwd kernels", "sdf": "psi::sdf_fwd_kernel"}
-    top = max(kernel_ms, key=kernel_ms.get)
-    step_ms = ms_dev / args.steps
-
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01k_traffic.json")
-    if os.path.exists(tpath) and op.s_index is not None and B == 64:
-        with open(tpath) as f:
-            tk = json.load(f)["kernels"]
-        traffic = {"nn": tk["nn"], "sdf": tk["sdf"], "lbs_fwd": tk["lbs_vertex_fwd"], "lbs_bwd": tk["lbs_dcoef"]}
-
-    def roof(k):
-        ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
-        tr = traffic.get(k)
-        tr = None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
-        return {"kernel": names[k], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "peak_source": peak_src, "traffic": tr,
-                "traffic_source": "profiles/r01k_traffic.json (ncu --set full, dominant kernel of the group)" if tr else None,
-                "launch_ms": kernel_ms[k],
-                "algorithmic_bytes_per_launch": alg[k],
-                "share_of_step": kernel_ms[k] * args.iters / step_ms}
-
-    roofline = roof(top)
-    roofline["timed"] = "alone, 10 launches, CUDA events on the launching stream, L2 flushed"
-    roofline["others"] = {k: roof(k) for k in kernel_ms if k != top}
-    if op.s_index is None:
-        roofline["fp32"] = {"bound": "fp32 issue", "achieved": pairs * 8 / (kernel_ms["nn"] * 1e-3) / 1e12,
-                            "peak": fp32_peak, "unit": "TFLOP/s",
-                            "frac": pairs * 8 / (kernel_ms["nn"] * 1e-3) / 1e12 / fp32_peak,
-                            "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm (no measured FP32 peak)",
-                            "pairs_per_s": pairs / (kernel_ms["nn"] * 1e-3)}
-    else:
-        roofline["note"] = ("the index evaluates ~3 of 1563 leaf clusters per query (plus ~80 box bounds): an "
-                            "instruction/latency-bound tree walk over L2-resident data, neither HBM- nor "
-                            "tensor-bound; brute-force-equivalent rate = %.3g pair/s"
-                            % (pairs / (kernel_ms["nn"] * 1e-3)))
-    roofline["lbs_fwd_fp32_frac"] = 49.3e6 * B / (kernel_ms["lbs_fwd"] * 1e-3) / 1e12 / fp32_peak
     out = {
         "metric": METRIC, "value": value, "unit": "bodies/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,

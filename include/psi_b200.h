@@ -252,6 +252,13 @@ PSI_API int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *ca
                   int num_iter, psi_stream_t stream);
 PSI_API int psi_fit_end(psi_fit_ctx *c, float *xhr_out, float *losses_out, psi_stream_t stream);
 PSI_API int psi_fit_launches_per_iteration(void);
+/* Measurement aid (bench.py `roofline`): runs warm_iters + timed_iters iterations EAGERLY on
+ * `stream` with a CUDA event recorded behind every kernel launch and returns the launch count n
+ * of one iteration (< 0 on error); h_ms[i] (host) = average duration of launch i over the timed
+ * iterations, h_names[i] = its kernel's name (static strings).  Synchronises the stream. */
+PSI_API int psi_fit_profile(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride,
+                    int warm_iters, int timed_iters, float *h_ms, const char **h_names, int max_launches,
+                    psi_stream_t stream);
 
 #ifdef __cplusplus
 }

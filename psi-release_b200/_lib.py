@@ -80,6 +80,7 @@ def lib():
         "psi_fit_begin": (_i, [_vp, _vp, _vp, _l, _i, _vp]),
         "psi_fit_end": (_i, [_vp, _vp, _vp, _vp]),
         "psi_fit_launches_per_iteration": (_i, []),
+        "psi_fit_profile": (_i, [_vp, _vp, _vp, _l, _i, _i, _vp, _vp, _i, _vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)      # AttributeError here = header / library mismatch
@@ -95,7 +96,7 @@ EXPORTS = ["psi_abi_version", "psi_error_string", "psi_launch_count", "psi_nn_wo
            "psi_chamfer_fwd", "psi_nn_bwd", "psi_chamfer_bwd", "psi_nn_index_create", "psi_nn_index_destroy",
            "psi_nn_index_bytes", "psi_nn_index_query", "psi_nn_index_query_hint", "psi_nn_index_query_mode", "psi_sdf_num_partials", "psi_sdf_fwd",
            "psi_sdf_bwd", "psi_lbs_model_create", "psi_lbs_model_destroy", "psi_lbs_model_bytes",
-           "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd", "psi_lbs_bwd2",
+           "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd", "psi_lbs_bwd2", "psi_fit_profile",
            "psi_fit_create", "psi_fit_destroy", "psi_fit_run", "psi_fit_begin", "psi_fit_end",
            "psi_fit_launches_per_iteration"]
 

@@ -26,8 +26,8 @@ def _nvcc() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     out = lib_path()
     srcs = [os.path.join(HERE, "csrc", s) for s in SOURCES]
-    deps = srcs + [os.path.join(HERE, "csrc", "common.cuh"),
-                   os.path.join(os.path.dirname(HERE), "include", "psi_b200.h")]
+    deps = srcs + [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "psi_b200.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)

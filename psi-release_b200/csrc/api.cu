@@ -4,7 +4,17 @@
 
 namespace psi {
 static std::atomic<unsigned long long> g_launches{0};
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local LaunchRecorder *g_rec = nullptr;
+void recorder_set(LaunchRecorder *r) { g_rec = r; }
+void count_launch(const char *name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LaunchRecorder *r = g_rec;
+    if (r && r->n < 64) {
+        r->names[r->n] = name;
+        cudaEventRecord(r->ev[r->n + 1], r->st);
+        ++r->n;
+    }
+}
 }  // namespace psi
 
 extern "C" {

@@ -10,18 +10,53 @@
         if (e__ != cudaSuccess) return (int)e__;       \
     } while (0)
 
-// counts the launch, then reports a launch-time error
-#define PSI_LAUNCHED()                                 \
+// counts the launch (and, under psi_fit_profile, records an event behind it), then reports a
+// launch-time error
+#define PSI_LAUNCHED_K(name)                           \
     do {                                               \
-        psi::count_launch();                           \
+        psi::count_launch(name);                       \
         PSI_RETURN_IF_LAUNCH_FAILED();                 \
     } while (0)
+#define PSI_LAUNCHED() PSI_LAUNCHED_K("kernel")
 
 #define PSI_NUM_SMS 148  // B200: 2 dies x 74 SMs
 
+struct psi_lbs_model;
+
 namespace psi {
 
-void count_launch();   // api.cu
+void count_launch(const char *name);   // api.cu
+// per-launch timing for psi_fit_profile: while a recorder is active on this thread, every counted
+// launch is followed by an event on `st`
+struct LaunchRecorder {
+    cudaStream_t st;
+    const char *names[64];
+    cudaEvent_t ev[65];
+    int n;
+};
+void recorder_set(LaunchRecorder *r);
+
+// ---- operand layout shared by the tensor-core GEMMs (LBS blend, VPoser decoder) --------------
+constexpr int kBG = 64;         // bodies per CTA = M of the tensor-core tiles
+constexpr int kKC = 32;         // reduction elements per pipeline stage: one 128-byte row per operand row
+// Operand rows are 32 floats = 8 chunks of 16 bytes; chunk c of row r is stored at chunk
+// c ^ (r & 7), so the 8 rows of one ldmatrix 8x4 block fall into 8 different bank groups.
+__host__ __device__ inline int swz(int row, int col) { return ((((col >> 2) ^ row) & 7) << 2) | (col & 3); }
+// element (body b, reduction index k) of an A operand [body group][chunk k/32][64 bodies][32 k]
+__host__ __device__ inline size_t a_index(int b, int k, int kpad) {
+    return (size_t)(b / kBG) * kpad * kBG + (size_t)(k / kKC) * (kBG * kKC) + (size_t)(b % kBG) * kKC +
+           swz(b % kBG, k % kKC);
+}
+
+// lbs.cu, used by the fused fitting loop (fit.cu)
+int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float *pose, const float *transl,
+                 const float *cam, long cam_bstride, const float *rot_in, const float *rot6d, int num_rot,
+                 float *verts, float *joints, float *saved, cudaStream_t st);
+int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *cam, long cam_bstride,
+                 const float *saved, const float *grad_verts, const float *grad_joints, float *grad_betas,
+                 float *grad_pose, float *grad_transl, float *grad_rot, int num_rot, const float *rot6d,
+                 float *g6_root, float *g6A, int g6_kpad, void *workspace, size_t workspace_bytes,
+                 psi_stream_t stream, psi_stream_t side_stream, void *ev_fork, void *ev_join);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -17,6 +17,7 @@
 // body is optimised exactly as the shipped batch_size-1 scripts do, bodies never interact.
 // All reductions have a fixed order: results are bit-reproducible and independent of B.
 #include "common.cuh"
+#include "rot6d.cuh"
 #include <math.h>
 #include <new>
 #include <vector>
@@ -26,14 +27,16 @@ struct psi_fit_ctx {
     const psi_nn_index *index;
     psi_fit_config cfg;
     int B, V, J, NB, latent, hidden, nbody, ncomp, num_rot, nu, num_contact, D, np_sdf, nchunk;
-    // constants
-    float *W1, *W1T, *b1, *W2, *W2T, *b2, *W3, *W3T, *W3Tp, *b3, *hand_l, *hand_r, *pose_mean, *cweight;
+    // constants: decoder weights as GEMM tiles (forward: W[out][in]; backward: W^T), biases, hands
+    float *Wf1, *Wf2, *Wf3, *Wb3, *Wb2, *Wb1, *b1, *b2, *b3, *hand_l, *hand_r, *pose_mean, *cweight;
+    int no_pad;                    // decoder outputs (nbody*6) padded to the GEMM's N / K granularity
     int *csel, *cslot;
     const float *sdf, *scene_pts;
     float gmin[3], gmax[3];
-    // state + scratch
-    float *x0, *x, *am, *av, *cam, *rot, *pose, *shape, *transl, *h1pre, *h2pre, *o6, *verts, *saved,
-        *sdfv, *sdfg, *partial, *nnd, *gverts, *cpart, *gshape, *gpose, *grot, *gtransl, *lbs_ws, *losses;
+    // state + scratch.  *A buffers are GEMM A operands ([body group][K/32][64][32], rows >= B zero)
+    float *x0, *x, *am, *av, *cam, *rot6d, *pose, *shape, *transl, *zA, *h1pre, *h1A, *h2pre, *h2A,
+        *g6_root, *g6A, *dh2A, *dh1A, *dz, *verts, *saved, *sdfv, *sdfg, *partial, *nnd, *gverts, *cpart,
+        *gshape, *gpose, *gtransl, *lbs_ws, *losses;
     int *nni, *step, *nnhint;
     size_t lbs_ws_bytes;
     cudaGraphExec_t exec;
@@ -48,120 +51,32 @@ namespace psi {
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.2f * v; }
 __device__ __forceinline__ float lrelu_grad(float pre) { return pre > 0.f ? 1.0f : 0.2f; }
 
-// cvae.py:46-55: x6 viewed [3,2]; columns a1 = (x0,x2,x4), a2 = (x1,x3,x5)
-__device__ void gs_fwd(const float *x6, float *R) {
-    const float a1[3] = {x6[0], x6[2], x6[4]}, a2[3] = {x6[1], x6[3], x6[5]};
-    const float n1 = fmaxf(sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12f);
-    const float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
-    const float s = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
-    const float u[3] = {a2[0] - s * b1[0], a2[1] - s * b1[1], a2[2] - s * b1[2]};
-    const float n2 = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
-    const float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
-    const float b3[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        R[r * 3 + 0] = b1[r];
-        R[r * 3 + 1] = b2[r];
-        R[r * 3 + 2] = b3[r];
-    }
-}
-
-__device__ void gs_bwd(const float *x6, const float *dR, float *dx6) {
-    const float a1[3] = {x6[0], x6[2], x6[4]}, a2[3] = {x6[1], x6[3], x6[5]};
-    const float n1 = fmaxf(sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12f);
-    const float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
-    const float s = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
-    const float u[3] = {a2[0] - s * b1[0], a2[1] - s * b1[1], a2[2] - s * b1[2]};
-    const float n2 = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
-    const float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
-    float db1[3] = {dR[0], dR[3], dR[6]}, db2[3] = {dR[1], dR[4], dR[7]};
-    const float db3[3] = {dR[2], dR[5], dR[8]};
-    // b3 = b1 x b2
-    db1[0] += b2[1] * db3[2] - b2[2] * db3[1];
-    db1[1] += b2[2] * db3[0] - b2[0] * db3[2];
-    db1[2] += b2[0] * db3[1] - b2[1] * db3[0];
-    db2[0] += db3[1] * b1[2] - db3[2] * b1[1];
-    db2[1] += db3[2] * b1[0] - db3[0] * b1[2];
-    db2[2] += db3[0] * b1[1] - db3[1] * b1[0];
-    // b2 = u / |u|
-    const float p2 = b2[0] * db2[0] + b2[1] * db2[1] + b2[2] * db2[2];
-    const float du[3] = {(db2[0] - p2 * b2[0]) / n2, (db2[1] - p2 * b2[1]) / n2, (db2[2] - p2 * b2[2]) / n2};
-    // u = a2 - (b1.a2) b1
-    const float dub1 = du[0] * b1[0] + du[1] * b1[1] + du[2] * b1[2];
-    const float da2[3] = {du[0] - dub1 * b1[0], du[1] - dub1 * b1[1], du[2] - dub1 * b1[2]};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) db1[r] += -s * du[r] - dub1 * a2[r];
-    // b1 = a1 / |a1|
-    const float p1 = b1[0] * db1[0] + b1[1] * db1[1] + b1[2] * db1[2];
-    const float da1[3] = {(db1[0] - p1 * b1[0]) / n1, (db1[1] - p1 * b1[1]) / n1, (db1[2] - p1 * b1[2]) / n1};
-    dx6[0] = da1[0]; dx6[2] = da1[1]; dx6[4] = da1[2];
-    dx6[1] = da2[0]; dx6[3] = da2[1]; dx6[5] = da2[2];
-}
-
 struct FitDims {
     int B, V, J, NB, latent, hidden, nbody, ncomp, num_rot;
 };
 
 }  // namespace psi
-#include "fit_mlp.cuh"
+#include "fit_linear.cuh"
 namespace psi {
 
 // x layout [75]: t3 | 6D | betas10 | z32 | lh12 | rh12   (cvae.py:28-33 after convert_to_6D_rot)
-__global__ void __launch_bounds__(256)
-fit_prologue_kernel(FitDims d, const float *__restrict__ x0, const float *__restrict__ x,
-                    const float *__restrict__ W1T, const float *__restrict__ b1,
-                    const float *__restrict__ W2T, const float *__restrict__ b2,
-                    const float *__restrict__ W3T, const float *__restrict__ b3,
-                    const float *__restrict__ hand_l, const float *__restrict__ hand_r,
-                    const float *__restrict__ pose_mean, float w_rec, float w_vp,
-                    float *__restrict__ rot, float *__restrict__ pose, float *__restrict__ shape,
-                    float *__restrict__ transl, float *__restrict__ h1pre, float *__restrict__ h2pre,
-                    float *__restrict__ o6, float *__restrict__ losses) {
-    __shared__ float sx[80], sh1[512], sh2[512], so[128];
+// Per body, before the decoder GEMMs: the latent z as the first layer's A operand, the global
+// orientation's 6D vector, betas, translation, hand PCA + pose_mean (smplx), L_rec and L_vposer.
+__global__ void __launch_bounds__(128)
+fit_pre_kernel(FitDims d, const float *__restrict__ x0, const float *__restrict__ x,
+               const float *__restrict__ hand_l, const float *__restrict__ hand_r,
+               const float *__restrict__ pose_mean, float w_rec, float w_vp, float *__restrict__ zA,
+               float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
+               float *__restrict__ transl, float *__restrict__ losses) {
+    __shared__ float sx[96];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int H = d.hidden, Lz = d.latent, NO = d.nbody * 6;
+    const int Lz = d.latent;
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;   // 75
     const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
     for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
     __syncthreads();
-    for (int j = tid; j < H; j += blockDim.x) {
-        float a = b1[j];
-        for (int i = 0; i < Lz; ++i) a = fmaf(W1T[(size_t)i * H + j], sx[zoff + i], a);
-        h1pre[(size_t)b * H + j] = a;
-        sh1[j] = lrelu(a);
-    }
-    __syncthreads();
-    for (int j = tid; j < H; j += blockDim.x) {
-        float a0 = b2[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int i = 0; i < H; i += 4) {
-            a0 = fmaf(W2T[(size_t)i * H + j], sh1[i], a0);
-            a1 = fmaf(W2T[(size_t)(i + 1) * H + j], sh1[i + 1], a1);
-            a2 = fmaf(W2T[(size_t)(i + 2) * H + j], sh1[i + 2], a2);
-            a3 = fmaf(W2T[(size_t)(i + 3) * H + j], sh1[i + 3], a3);
-        }
-        const float a = (a0 + a1) + (a2 + a3);
-        h2pre[(size_t)b * H + j] = a;
-        sh2[j] = lrelu(a);
-    }
-    __syncthreads();
-    for (int k = tid; k < NO; k += blockDim.x) {
-        float a0 = b3[k], a1 = 0.f;
-        for (int i = 0; i < H; i += 2) {
-            a0 = fmaf(W3T[(size_t)i * NO + k], sh2[i], a0);
-            a1 = fmaf(W3T[(size_t)(i + 1) * NO + k], sh2[i + 1], a1);
-        }
-        const float a = a0 + a1;
-        so[k] = a;
-        o6[(size_t)b * NO + k] = a;
-    }
-    __syncthreads();
-    // rotations of joints 0..nbody: global orientation from x[3:9], body joints from the decoder
-    if (tid <= d.nbody) {
-        float R[9];
-        gs_fwd(tid == 0 ? sx + 3 : so + (tid - 1) * 6, R);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) rot[((size_t)b * d.num_rot + tid) * 9 + e] = R[e];
-    }
+    if (tid < Lz) zA[a_index(b, tid, Lz)] = sx[zoff + tid];
+    if (tid < 6) rot6d[(size_t)b * d.num_rot * 6 + tid] = sx[3 + tid];
     // axis-angle pose vector [J*3]: only joints >= num_rot are read by the LBS kernels
     const int hl0 = (d.J - 30) * 3, hr0 = (d.J - 15) * 3;
     for (int e = tid; e < d.J * 3; e += blockDim.x) {
@@ -177,7 +92,7 @@ fit_prologue_kernel(FitDims d, const float *__restrict__ x0, const float *__rest
     }
     for (int e = tid; e < d.NB; e += blockDim.x) shape[(size_t)b * d.NB + e] = e < 10 ? sx[9 + e] : 0.f;
     if (tid < 3) transl[(size_t)b * 3 + tid] = sx[tid];
-    if (tid == 0) {
+    if (tid == 32) {
         float r = 0.f, zz = 0.f;
         for (int e = 0; e < xdim; ++e) r += fabsf(x0[(size_t)b * xdim + e] - sx[e]);
         for (int i = 0; i < Lz; ++i) zz = fmaf(sx[zoff + i], sx[zoff + i], zz);
@@ -243,41 +158,32 @@ fit_vertex_grad_kernel(int V, int nu, int np_sdf, int num_contact, const float *
     }
 }
 
-__global__ void __launch_bounds__(256)
-fit_epilogue_kernel(FitDims d, psi_fit_config cfg, int np_sdf, int nchunk, int num_contact,
-                    const float *__restrict__ x0, float *__restrict__ x, float *__restrict__ am,
-                    float *__restrict__ av, int *__restrict__ step, const float *__restrict__ W1,
-                    const float *__restrict__ W2, const float *__restrict__ W3,
-                    const float *__restrict__ hand_l, const float *__restrict__ hand_r,
-                    const float *__restrict__ h1pre, const float *__restrict__ h2pre,
-                    const float *__restrict__ o6, const float *__restrict__ grot,
-                    const float *__restrict__ gpose, const float *__restrict__ gshape,
-                    const float *__restrict__ gtransl, const float *__restrict__ partial,
-                    const float *__restrict__ cpart, float *__restrict__ losses) {
-    __shared__ float sx[80], g[80], dso[128], dh2[512], dh1[512], pz[8][32];
+// Per body, after the decoder's backward GEMMs: assemble dL/dx (translation, 6D global
+// orientation, betas, latent, hand PCA), add d L_rec, Adam step (torch.optim.Adam defaults,
+// fitting_habitat.py:76; bias corrections in double), loss values.
+__global__ void __launch_bounds__(128)
+fit_post_kernel(FitDims d, psi_fit_config cfg, int np_sdf, int nchunk, int num_contact,
+                const float *__restrict__ x0, float *__restrict__ x, float *__restrict__ am,
+                float *__restrict__ av, int *__restrict__ step, const float *__restrict__ hand_l,
+                const float *__restrict__ hand_r, const float *__restrict__ dz,
+                const float *__restrict__ g6_root, const float *__restrict__ gpose,
+                const float *__restrict__ gshape, const float *__restrict__ gtransl,
+                const float *__restrict__ partial, const float *__restrict__ cpart,
+                float *__restrict__ losses) {
+    __shared__ float sx[96], g[96];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int H = d.hidden, Lz = d.latent, NO = d.nbody * 6;
+    const int Lz = d.latent;
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;
     const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
-    for (int e = tid; e < xdim; e += blockDim.x) { sx[e] = x[(size_t)b * xdim + e]; g[e] = 0.f; }
+    for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
     __syncthreads();
-    // Gram-Schmidt backward: joint 0 -> x[3:9], joints 1..nbody -> decoder outputs
-    if (tid <= d.nbody) {
-        float dx6[6];
-        gs_bwd(tid == 0 ? sx + 3 : o6 + (size_t)b * NO + (tid - 1) * 6,
-               grot + ((size_t)b * d.num_rot + tid) * 9, dx6);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) {
-            if (tid == 0) g[3 + e] = dx6[e];
-            else dso[(tid - 1) * 6 + e] = dx6[e];
-        }
-    }
     if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
-    if (tid < 10) g[9 + tid] = gshape[(size_t)b * d.NB + tid];
-    // hand PCA backward
-    if (tid < 2 * d.ncomp) {
-        const int c = tid % d.ncomp;
-        const bool right = tid >= d.ncomp;
+    else if (tid < 9) g[tid] = g6_root[(size_t)b * 6 + tid - 3];
+    else if (tid < 19) g[tid] = gshape[(size_t)b * d.NB + tid - 9];
+    else if (tid < 19 + Lz) g[tid] = dz[(size_t)b * Lz + tid - zoff] + cfg.w_vposer * (2.0f * sx[tid] / (float)Lz);
+    else if (tid < xdim) {                       // hand PCA backward
+        const int u = tid - lhoff, c = u % d.ncomp;
+        const bool right = u >= d.ncomp;
         const float *comp = (right ? hand_r : hand_l) + c * 45;
         const float *gp = gpose + (size_t)b * d.J * 3 + (right ? (d.J - 15) * 3 : (d.J - 30) * 3);
         float a = 0.f;
@@ -285,39 +191,6 @@ fit_epilogue_kernel(FitDims d, psi_fit_config cfg, int np_sdf, int nchunk, int n
         g[(right ? rhoff : lhoff) + c] = a;
     }
     __syncthreads();
-    // MLP backward (W in the reference [out][in] layout -> coalesced over the input index)
-    for (int i = tid; i < H; i += blockDim.x) {
-        float a = 0.f;
-        for (int k = 0; k < NO; ++k) a = fmaf(W3[(size_t)k * H + i], dso[k], a);
-        dh2[i] = a * lrelu_grad(h2pre[(size_t)b * H + i]);
-    }
-    __syncthreads();
-    for (int i = tid; i < H; i += blockDim.x) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int o = 0; o < H; o += 4) {
-            a0 = fmaf(W2[(size_t)o * H + i], dh2[o], a0);
-            a1 = fmaf(W2[(size_t)(o + 1) * H + i], dh2[o + 1], a1);
-            a2 = fmaf(W2[(size_t)(o + 2) * H + i], dh2[o + 2], a2);
-            a3 = fmaf(W2[(size_t)(o + 3) * H + i], dh2[o + 3], a3);
-        }
-        dh1[i] = ((a0 + a1) + (a2 + a3)) * lrelu_grad(h1pre[(size_t)b * H + i]);
-    }
-    __syncthreads();
-    {   // dz[i] = sum_o W1[o][i] dh1[o] : 8 slices of the o range, reduced in fixed order
-        const int i = tid & 31, sl = tid >> 5;
-        float a = 0.f;
-        if (i < Lz)
-            for (int o = sl * (H / 8); o < (sl + 1) * (H / 8); ++o) a = fmaf(W1[(size_t)o * Lz + i], dh1[o], a);
-        pz[sl][i] = a;
-    }
-    __syncthreads();
-    if (tid < Lz) {
-        float a = 0.f;
-        for (int sl = 0; sl < 8; ++sl) a += pz[sl][tid];
-        g[zoff + tid] = a + cfg.w_vposer * (2.0f * sx[zoff + tid] / (float)Lz);
-    }
-    __syncthreads();
-    // + d L_rec, then Adam (torch.optim.Adam defaults; bias corrections in double)
     const int t = step[b] + 1;
     if (tid < xdim) {
         const float xe = sx[tid], diff = xe - x0[(size_t)b * xdim + tid];
@@ -334,8 +207,7 @@ fit_epilogue_kernel(FitDims d, psi_fit_config cfg, int np_sdf, int nchunk, int n
         const float denom = sqrtf(v) / (float)sqrt(bc2) + cfg.eps;
         x[o] = xe - (m / denom) * step_size;
     }
-    if (tid == 0) {
-        step[b] = t;
+    if (tid == 96) {
         float sn = 0.f, cn = 0.f, cs = 0.f;
         for (int i = 0; i < np_sdf; ++i) {
             sn += partial[((size_t)b * np_sdf + i) * 2];
@@ -345,6 +217,8 @@ fit_epilogue_kernel(FitDims d, psi_fit_config cfg, int np_sdf, int nchunk, int n
         losses[(size_t)b * 4 + 2] = cfg.w_contact * (cs / (float)num_contact);
         losses[(size_t)b * 4 + 3] = cfg.w_collision * (cn > 0.f ? sn / cn : 0.f);
     }
+    __syncthreads();
+    if (tid == 0) step[b] = t;
 }
 
 __global__ void fit_reset_kernel(float *am, float *av, int *step, long n, int B) {
@@ -358,40 +232,67 @@ __global__ void fit_cam_kernel(const float *cam, long stride, int B, float *out)
     if (i < B * 12) out[i] = cam[(size_t)(i / 12) * stride + (i % 12)];
 }
 
+static int launch_linear(cudaStream_t st, int B, const float *A, const float *W, int K, int N, const float *bias,
+                         const float *gate, float *pre_out, float *out_rm, int ld, int n_valid, float *outA,
+                         int outA_kpad, int act) {
+    LinearParams p;
+    p.A = A; p.W = W; p.bias = bias; p.gate = gate; p.pre_out = pre_out; p.out_rm = out_rm; p.outA = outA;
+    p.K = K; p.N = N; p.B = B; p.n_valid = n_valid; p.ld = ld; p.outA_kpad = outA_kpad; p.act = act;
+    dim3 grid((unsigned)(N / kLT), (unsigned)((B + kBG - 1) / kBG));
+    const int stages = K / kKC < kLStages ? K / kKC : kLStages;
+    fit_linear_kernel<<<grid, 128, (size_t)stages * kLStageBytes, st>>>(p);
+    PSI_LAUNCHED_K("fit_linear");
+    return PSI_OK;
+}
+
 static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     const FitDims d = {c->B, c->V, c->J, c->NB, c->latent, c->hidden, c->nbody, c->ncomp, c->num_rot};
-    fit_prologue2_kernel<<<c->B, kMlpThreads, sizeof(MlpSmem), st>>>(d, c->x0, c->x, c->W1T, c->b1, c->W2T, c->b2, c->W3Tp, c->b3,
-                                              c->hand_l, c->hand_r, c->pose_mean, c->cfg.w_rec,
-                                              c->cfg.w_vposer, c->rot, c->pose, c->shape, c->transl,
-                                              c->h1pre, c->h2pre, c->o6, c->losses);
-    PSI_LAUNCHED();
-    int rc = psi_lbs_fwd(c->model, c->B, c->shape, c->pose, c->transl, c->cam, 12, c->rot, c->num_rot,
-                         c->verts, nullptr, c->saved, st);
+    const int H = c->hidden, Lz = c->latent, NO = c->nbody * 6, NOp = c->no_pad, B = c->B;
+    fit_pre_kernel<<<B, 128, 0, st>>>(d, c->x0, c->x, c->hand_l, c->hand_r, c->pose_mean, c->cfg.w_rec,
+                                      c->cfg.w_vposer, c->zA, c->rot6d, c->pose, c->shape, c->transl, c->losses);
+    PSI_LAUNCHED_K("fit_pre");
+    // VPoser decode: 32 -> 512 -> 512 -> nbody*6 (the 6D vectors land behind the root's in rot6d)
+    int rc = launch_linear(st, B, c->zA, c->Wf1, Lz, H, c->b1, nullptr, c->h1pre, nullptr, 0, H, c->h1A, H, 1);
     if (rc) return rc;
-    // contact ids are ordered along a Morton curve of the template (fused.py): 32 consecutive
-    // queries are neighbours on the body -> the group schedule walks the index once per warp
-    rc = psi_nn_index_query_mode(c->index, c->verts, (long)c->V * 3, c->B, c->nu, c->csel, c->nnd, c->nni,
+    rc = launch_linear(st, B, c->h1A, c->Wf2, H, H, c->b2, nullptr, c->h2pre, nullptr, 0, H, c->h2A, H, 1);
+    if (rc) return rc;
+    rc = launch_linear(st, B, c->h2A, c->Wf3, H, NOp, c->b3, nullptr, nullptr, c->rot6d + 6, c->num_rot * 6, NO,
+                       nullptr, 0, 0);
+    if (rc) return rc;
+    rc = lbs_fwd_impl(c->model, B, c->shape, c->pose, c->transl, c->cam, 12, nullptr, c->rot6d, c->num_rot,
+                      c->verts, nullptr, c->saved, st);
+    if (rc) return rc;
+    // contact ids are ordered by dominant joint + kd cells of the template (fused.py): 32 consecutive
+    // queries are neighbours on the posed body -> the group schedule walks the index once per warp
+    rc = psi_nn_index_query_mode(c->index, c->verts, (long)c->V * 3, B, c->nu, c->csel, c->nnd, c->nni,
                                  c->nnhint, c->cfg.nn_mode > 0 ? c->cfg.nn_mode : 3, st);
     if (rc) return rc;
-    rc = psi_sdf_fwd(c->sdf, 1, c->D, c->gmin, c->gmax, c->verts, c->B, c->V, nullptr, c->sdfv, c->sdfg,
+    rc = psi_sdf_fwd(c->sdf, 1, c->D, c->gmin, c->gmax, c->verts, B, c->V, nullptr, c->sdfv, c->sdfg,
                      c->partial, st);
     if (rc) return rc;
     {
-        dim3 grid((unsigned)c->nchunk, (unsigned)c->B);
+        dim3 grid((unsigned)c->nchunk, (unsigned)B);
         fit_vertex_grad_kernel<<<grid, 256, 0, st>>>(c->V, c->nu, c->np_sdf, c->num_contact, c->verts,
                                                      c->scene_pts, c->sdfv, c->sdfg, c->partial, c->nnd,
                                                      c->nni, c->cslot, c->cweight, c->cfg.w_contact,
                                                      c->cfg.w_collision, c->cfg.robust_c, c->gverts, c->cpart);
-        PSI_LAUNCHED();
+        PSI_LAUNCHED_K("fit_vertex_grad");
     }
-    rc = psi_lbs_bwd(c->model, c->B, c->shape, c->pose, c->cam, 12, c->saved, c->gverts, nullptr, c->gshape,
-                     c->gpose, c->gtransl, c->grot, c->num_rot, c->lbs_ws, c->lbs_ws_bytes, st);
+    rc = lbs_bwd_impl(c->model, B, c->pose, c->cam, 12, c->saved, c->gverts, nullptr, c->gshape, c->gpose,
+                      c->gtransl, nullptr, c->num_rot, c->rot6d, c->g6_root, c->g6A, NOp, c->lbs_ws,
+                      c->lbs_ws_bytes, st, nullptr, nullptr, nullptr);
     if (rc) return rc;
-    fit_epilogue2_kernel<<<c->B, kMlpThreads, sizeof(MlpSmem), st>>>(d, c->cfg, c->np_sdf, c->nchunk, c->num_contact, c->x0, c->x,
-                                              c->am, c->av, c->step, c->W1, c->W2, c->W3, c->hand_l,
-                                              c->hand_r, c->h1pre, c->h2pre, c->o6, c->grot, c->gpose,
-                                              c->gshape, c->gtransl, c->partial, c->cpart, c->losses);
-    PSI_LAUNCHED();
+    // decoder backward: d h2 = (d o . W3) * lrelu', d h1 = (d h2 . W2) * lrelu', d z = d h1 . W1
+    rc = launch_linear(st, B, c->g6A, c->Wb3, NOp, H, nullptr, c->h2pre, nullptr, nullptr, 0, H, c->dh2A, H, 0);
+    if (rc) return rc;
+    rc = launch_linear(st, B, c->dh2A, c->Wb2, H, H, nullptr, c->h1pre, nullptr, nullptr, 0, H, c->dh1A, H, 0);
+    if (rc) return rc;
+    rc = launch_linear(st, B, c->dh1A, c->Wb1, H, Lz, nullptr, nullptr, nullptr, c->dz, Lz, Lz, nullptr, 0, 0);
+    if (rc) return rc;
+    fit_post_kernel<<<B, 128, 0, st>>>(d, c->cfg, c->np_sdf, c->nchunk, c->num_contact, c->x0, c->x, c->am, c->av,
+                                       c->step, c->hand_l, c->hand_r, c->dz, c->g6_root, c->gpose, c->gshape,
+                                       c->gtransl, c->partial, c->cpart, c->losses);
+    PSI_LAUNCHED_K("fit_post");
     return PSI_OK;
 }
 
@@ -439,6 +340,10 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         return PSI_ERR_ALLOC;
     }
     for (int a = 0; a < 3; ++a) { c->gmin[a] = h_grid_min[a]; c->gmax[a] = h_grid_max[a]; }
+    if (cudaFuncSetAttribute(fit_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLStages * kLStageBytes) != cudaSuccess) {
+        psi_fit_destroy(c);
+        return PSI_ERR_UNSUPPORTED;
+    }
     c->np_sdf = psi_sdf_num_partials(V);
     c->nchunk = (V + 255) / 256;
     int rc = PSI_OK;
@@ -460,11 +365,6 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         return p;
     };
     const int H = hidden, NO = nbody * 6;
-    std::vector<float> W1(h_W1, h_W1 + (size_t)H * latent), W2(h_W2, h_W2 + (size_t)H * H), W3(h_W3, h_W3 + (size_t)NO * H);
-    std::vector<float> W1T((size_t)latent * H), W2T((size_t)H * H), W3T((size_t)H * NO);
-    for (int o = 0; o < H; ++o) for (int i = 0; i < latent; ++i) W1T[(size_t)i * H + o] = W1[(size_t)o * latent + i];
-    for (int o = 0; o < H; ++o) for (int i = 0; i < H; ++i) W2T[(size_t)i * H + o] = W2[(size_t)o * H + i];
-    for (int o = 0; o < NO; ++o) for (int i = 0; i < H; ++i) W3T[(size_t)i * NO + o] = W3[(size_t)o * H + i];
     // contact vertices: unique ids + multiplicity (duplicates across parts are kept by the reference, cvae.py:105-112)
     std::vector<int> cslot((size_t)V, -1), csel;
     std::vector<float> cweight((size_t)V, 0.f);
@@ -475,36 +375,59 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         cweight[v] += 1.0f;
     }
     c->nu = (int)csel.size();
-    std::vector<float> keep_alive[8] = {std::vector<float>(h_b1, h_b1 + H), std::vector<float>(h_b2, h_b2 + H),
-                                        std::vector<float>(h_b3, h_b3 + NO),
-                                        std::vector<float>(h_hand_l, h_hand_l + (size_t)ncomp * 45),
-                                        std::vector<float>(h_hand_r, h_hand_r + (size_t)ncomp * 45),
-                                        std::vector<float>(h_pose_mean, h_pose_mean + (size_t)J * 3)};
-    c->W1 = upload_f(W1); c->W2 = upload_f(W2); c->W3 = upload_f(W3);
-    c->W1T = upload_f(W1T); c->W2T = upload_f(W2T); c->W3T = upload_f(W3T);
-    {   // output layer transposed and padded to 128 columns (16-byte aligned rows for the bulk copies)
-        std::vector<float> W3Tp((size_t)H * 128, 0.f);
-        for (int o = 0; o < NO; ++o) for (int i = 0; i < H; ++i) W3Tp[(size_t)i * 128 + o] = W3[(size_t)o * H + i];
-        c->W3Tp = upload_f(W3Tp);
-        if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;   // W3Tp dies here
+    {   // decoder weights as GEMM tiles: forward layers use W[out][in] as given, backward layers W^T
+        auto transpose = [](const float *M, int R, int C) {
+            std::vector<float> T((size_t)R * C);
+            for (int r = 0; r < R; ++r) for (int q = 0; q < C; ++q) T[(size_t)q * R + r] = M[(size_t)r * C + q];
+            return T;
+        };
+        int np = 0, kp = 0;
+        std::vector<float> t1 = linear_weight_tiles(h_W1, H, latent, &np, &kp);
+        c->Wf1 = upload_f(t1);
+        std::vector<float> t2 = linear_weight_tiles(h_W2, H, H, &np, &kp);
+        c->Wf2 = upload_f(t2);
+        std::vector<float> t3 = linear_weight_tiles(h_W3, NO, H, &np, &kp);
+        c->Wf3 = upload_f(t3);
+        c->no_pad = (np + kKC - 1) / kKC * kKC;                     // N of layer 3 = K of its backward: 126 -> 128
+        if (c->no_pad != np) rc = PSI_ERR_UNSUPPORTED;              // (nbody*6 rounded to 16 must also be a multiple of 32)
+        const std::vector<float> tr3 = transpose(h_W3, NO, H);      // [H][NO]
+        std::vector<float> tb3 = linear_weight_tiles(tr3.data(), H, NO, &np, &kp);
+        c->Wb3 = upload_f(tb3);
+        const std::vector<float> tr2 = transpose(h_W2, H, H);
+        std::vector<float> tb2 = linear_weight_tiles(tr2.data(), H, H, &np, &kp);
+        c->Wb2 = upload_f(tb2);
+        const std::vector<float> tr1 = transpose(h_W1, H, latent);  // [latent][H]
+        std::vector<float> tb1 = linear_weight_tiles(tr1.data(), latent, H, &np, &kp);
+        c->Wb1 = upload_f(tb1);
+        std::vector<float> v1(h_b1, h_b1 + H), v2(h_b2, h_b2 + H), v3(h_b3, h_b3 + NO),
+            hl(h_hand_l, h_hand_l + (size_t)ncomp * 45), hr(h_hand_r, h_hand_r + (size_t)ncomp * 45),
+            pm(h_pose_mean, h_pose_mean + (size_t)J * 3);
+        c->b1 = upload_f(v1); c->b2 = upload_f(v2); c->b3 = upload_f(v3);
+        c->hand_l = upload_f(hl); c->hand_r = upload_f(hr); c->pose_mean = upload_f(pm);
+        c->cweight = upload_f(cweight); c->csel = upload_i(csel); c->cslot = upload_i(cslot);
+        if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;   // host vectors die here
     }
-    if (cudaFuncSetAttribute(fit_prologue2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem)) != cudaSuccess ||
-        cudaFuncSetAttribute(fit_epilogue2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem)) != cudaSuccess)
-        rc = PSI_ERR_UNSUPPORTED;
-    c->b1 = upload_f(keep_alive[0]); c->b2 = upload_f(keep_alive[1]); c->b3 = upload_f(keep_alive[2]);
-    c->hand_l = upload_f(keep_alive[3]); c->hand_r = upload_f(keep_alive[4]); c->pose_mean = upload_f(keep_alive[5]);
-    c->cweight = upload_f(cweight); c->csel = upload_i(csel); c->cslot = upload_i(cslot);
     const size_t B = (size_t)c->B, xd = 9 + 10 + (size_t)latent + 2 * (size_t)ncomp;
     auto fbuf = [&](size_t n) { return (float *)dev_alloc(n * sizeof(float)); };
+    // GEMM A operands: zero-initialised once (rows of bodies >= B and padded k stay zero)
+    const size_t Bp = (B + kBG - 1) / kBG * kBG;
+    auto zbuf = [&](size_t n) {
+        float *p = fbuf(n);
+        if (p && cudaMemsetAsync(p, 0, n * sizeof(float), st) != cudaSuccess) rc = PSI_ERR_ALLOC;
+        return p;
+    };
     c->x0 = fbuf(B * xd); c->x = fbuf(B * xd); c->am = fbuf(B * xd); c->av = fbuf(B * xd);
-    c->cam = fbuf(B * 12); c->rot = fbuf(B * c->num_rot * 9); c->pose = fbuf(B * J * 3); c->shape = fbuf(B * NB);
-    c->transl = fbuf(B * 3); c->h1pre = fbuf(B * H); c->h2pre = fbuf(B * H); c->o6 = fbuf(B * NO);
+    c->cam = fbuf(B * 12); c->rot6d = fbuf(B * c->num_rot * 6); c->pose = fbuf(B * J * 3); c->shape = fbuf(B * NB);
+    c->transl = fbuf(B * 3); c->h1pre = fbuf(B * H); c->h2pre = fbuf(B * H);
+    c->zA = zbuf(Bp * latent); c->h1A = zbuf(Bp * H); c->h2A = zbuf(Bp * H);
+    c->g6A = zbuf(Bp * c->no_pad); c->dh2A = zbuf(Bp * H); c->dh1A = zbuf(Bp * H);
+    c->g6_root = fbuf(B * 6); c->dz = fbuf(B * latent);
     c->verts = fbuf(B * V * 3); c->saved = fbuf(psi_lbs_saved_floats(model, c->B) + 64);
     c->sdfv = fbuf(B * V); c->sdfg = fbuf(B * V * 3); c->partial = fbuf(B * c->np_sdf * 2);
     c->nnd = fbuf(B * c->nu); c->nni = (int *)dev_alloc(B * c->nu * sizeof(int));
     c->nnhint = (int *)dev_alloc(B * c->nu * sizeof(int)); c->gverts = fbuf(B * V * 3);
     c->cpart = fbuf(B * c->nchunk); c->gshape = fbuf(B * NB); c->gpose = fbuf(B * J * 3);
-    c->grot = fbuf(B * c->num_rot * 9); c->gtransl = fbuf(B * 3); c->losses = fbuf(B * 4);
+    c->gtransl = fbuf(B * 3); c->losses = fbuf(B * 4);
     c->step = (int *)dev_alloc(B * sizeof(int));
     c->lbs_ws_bytes = psi_lbs_bwd_workspace_bytes(model, c->B) + 64;
     c->lbs_ws = (float *)dev_alloc(c->lbs_ws_bytes);
@@ -598,6 +521,42 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
     return psi_fit_end(c, xhr_out, losses_out, stream);
 }
 
-int psi_fit_launches_per_iteration(void) { return 13; }
+int psi_fit_launches_per_iteration(void) { return 19; }
+
+int psi_fit_profile(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int warm_iters,
+                    int timed_iters, float *h_ms, const char **h_names, int max_launches, psi_stream_t stream) {
+    using namespace psi;
+    if (!c || !xhr_init || !cam || !h_ms || !h_names || warm_iters < 0 || timed_iters < 1 || max_launches < 1)
+        return PSI_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int graph = c->cfg.use_graph;
+    c->cfg.use_graph = 0;                                   // eager iterations on the caller's stream
+    int rc = psi_fit_begin(c, xhr_init, cam, cam_bstride, warm_iters, stream);
+    c->cfg.use_graph = graph;
+    if (rc) return rc;
+    LaunchRecorder rec;
+    rec.st = st;
+    for (int i = 0; i < 65; ++i)
+        if (cudaEventCreate(&rec.ev[i]) != cudaSuccess) return PSI_ERR_ALLOC;
+    int n = 0;
+    for (int i = 0; i < max_launches; ++i) h_ms[i] = 0.f;
+    for (int it = 0; it < timed_iters && rc == PSI_OK; ++it) {
+        rec.n = 0;
+        cudaEventRecord(rec.ev[0], st);
+        recorder_set(&rec);
+        rc = enqueue_iteration(c, st);
+        recorder_set(nullptr);
+        if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;
+        n = rec.n < max_launches ? rec.n : max_launches;
+        for (int i = 0; i < n && rc == PSI_OK; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, rec.ev[i], rec.ev[i + 1]);
+            h_ms[i] += ms / (float)timed_iters;
+            h_names[i] = rec.names[i];
+        }
+    }
+    for (int i = 0; i < 65; ++i) cudaEventDestroy(rec.ev[i]);
+    return rc == PSI_OK ? n : -rc - 1000;                   // >= 0: launches per iteration
+}
 
 }  // extern "C"

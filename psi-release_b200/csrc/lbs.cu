@@ -28,6 +28,7 @@
 //   lbs_pose_bwd     partial sums -> chain / Rodrigues backward -> d beta, d pose, d transl
 // All reductions use fixed orders: results are bit-reproducible run to run.
 #include "common.cuh"
+#include "rot6d.cuh"
 #include <math.h>
 #include <new>
 #include <vector>
@@ -35,18 +36,12 @@
 namespace psi {
 
 constexpr int kMaxJ = 64;
-constexpr int kBG = 64;         // bodies per CTA = M (forward) of the tensor-core tiles
-constexpr int kKC = 32;         // reduction elements per pipeline stage: one 128-byte row per operand row
 constexpr int kFT = 72;         // forward tile: 72 vertex coordinates (9 n8 tiles); 3V/72 = 437 tiles at
                                 // V = 10475 = 2.95 per SM -> one balanced wave at 3 CTAs per SM
 constexpr int kFStages = 4;     // forward ring: 4 x 17 kB
 constexpr int kDK = 128;        // dcoef tile: 128 coefficients x 64 bodies per CTA
 constexpr int kDStages = 4;     // dcoef ring: 4 x 24 kB, 2 CTAs per SM
 constexpr int kNSplit = 74;     // dcoef split of the coordinate reduction: 4 k-tiles x 74 = 2 CTAs per SM
-
-// Operand rows are 32 floats = 8 chunks of 16 bytes; chunk c of row r is stored at chunk
-// c ^ (r & 7), so the 8 rows of one ldmatrix 8x4 block fall into 8 different bank groups.
-__host__ __device__ inline int swz(int row, int col) { return ((((col >> 2) ^ row) & 7) << 2) | (col & 3); }
 
 }  // namespace psi
 
@@ -114,11 +109,16 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ betas, const float *__restrict__ pose,
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
                     float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
-                    const psi_lbs_tree tree) {
+                    const float *__restrict__ rot6d, const psi_lbs_tree tree) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int j = tid; j < J; j += blockDim.x) {
-        if (j < num_rot) {   // rotation matrices handed over directly (no axis-angle round trip)
+        if (j < num_rot && rot6d) {   // 6D representation -> R by Gram-Schmidt (cvae.py:46-55), fused here
+            float R[9];
+            gs_fwd(rot6d + ((size_t)b * num_rot + j) * 6, R);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) sR[j * 9 + e] = R[e];
+        } else if (j < num_rot) {     // rotation matrices handed over directly (no axis-angle round trip)
 #pragma unroll
             for (int e = 0; e < 9; ++e) sR[j * 9 + e] = rot_in[((size_t)b * num_rot + j) * 9 + e];
         } else {
@@ -555,7 +555,8 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     const float *__restrict__ part, const float *__restrict__ gjoints,
                     float *__restrict__ gbetas, float *__restrict__ gpose,
                     float *__restrict__ gtransl, float *__restrict__ grot, int num_rot,
-                    const psi_lbs_tree tree) {
+                    const float *__restrict__ rot6d, float *__restrict__ g6_root, float *__restrict__ g6A,
+                    int g6_kpad, const psi_lbs_tree tree) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], drel_s[kMaxJ * 3];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
     __shared__ float dbeta_direct[64];
@@ -639,6 +640,22 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     // Rodrigues backward (lbs.py:177-191); joints given as matrices export dR itself
     for (int j = tid; j < J; j += blockDim.x) {
         float *o = gpose + ((size_t)b * J + j) * 3;
+        if (j < num_rot && rot6d) {
+            // Gram-Schmidt backward fused here: joint 0 -> g6_root [B,6]; joints 1.. -> g6A, the
+            // A operand ([chunk][64 bodies][32 k, swizzled], k = (j-1)*6+e, zero up to g6_kpad) of the
+            // decoder's backward GEMM (fit.cu)
+            float dx6[6];
+            gs_bwd(rot6d + ((size_t)b * num_rot + j) * 6, dR + j * 9, dx6);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+                if (j == 0) g6_root[(size_t)b * 6 + e] = dx6[e];
+                else g6A[a_index(b, (j - 1) * 6 + e, g6_kpad)] = dx6[e];
+            }
+            if (j == num_rot - 1)
+                for (int k = (num_rot - 1) * 6; k < g6_kpad; ++k) g6A[a_index(b, k, g6_kpad)] = 0.f;
+            o[0] = o[1] = o[2] = 0.f;
+            continue;
+        }
         if (j < num_rot) {
 #pragma unroll
             for (int e = 0; e < 9; ++e) grot[((size_t)b * num_rot + j) * 9 + e] = dR[j * 9 + e];
@@ -895,24 +912,28 @@ size_t psi_lbs_saved_floats(const psi_lbs_model *m, int B) {
     return psi::saved_layout(B, m->J, m->V, m->Kpad).total;
 }
 
-int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
-                const float *transl, const float *cam, long cam_bstride, const float *rot_in,
-                int num_rot, float *verts, float *joints, float *saved, psi_stream_t stream) {
-    using namespace psi;
+}  // extern "C"
+
+namespace psi {
+// psi_lbs_fwd with the leading num_rot joints given either as matrices (rot_in) or in the 6D
+// representation (rot6d [B,num_rot,6], Gram-Schmidt fused into the pose kernel: the fitting loop)
+int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                 const float *transl, const float *cam, long cam_bstride, const float *rot_in,
+                 const float *rot6d, int num_rot, float *verts, float *joints, float *saved,
+                 cudaStream_t st) {
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!betas || !pose || !verts || !saved) return PSI_ERR_BAD_ARG;
-    if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !rot_in)) return PSI_ERR_BAD_ARG;
+    if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !rot_in && !rot6d)) return PSI_ERR_BAD_ARG;
     if (B > 65535) return PSI_ERR_UNSUPPORTED;
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     lbs_pose_fwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, m->tree);
-    PSI_LAUNCHED();
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, m->tree);
+    PSI_LAUNCHED_K("lbs_pose_fwd");
     if (B % kBG) {
         lbs_zero_coef_pad_kernel<<<8, 256, 0, st>>>(saved + L.coef, B, m->Kpad);
-        PSI_LAUNCHED();
+        PSI_LAUNCHED_K("lbs_zero_coef_pad");
     }
     BlendFwdParams p;
     p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef = saved + L.coef;
@@ -925,40 +946,49 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
     }
     dim3 grid((unsigned)m->NT, (unsigned)((B + kBG - 1) / kBG));
     lbs_blend_fwd_kernel<<<grid, 128, smem, st>>>(p);
-    PSI_LAUNCHED();
+    PSI_LAUNCHED_K("lbs_blend_fwd");
     {
         dim3 sgrid((unsigned)((m->V + 255) / 256), (unsigned)B);
         lbs_skin_fwd_kernel<<<sgrid, 256, 0, st>>>(m->V, m->J, m->KW, m->skin_j, m->skin_w, saved + L.A, saved + L.vp,
                                                    transl, cam, cam_bstride, verts);
-        PSI_LAUNCHED();
+        PSI_LAUNCHED_K("lbs_skin_fwd");
     }
     return PSI_OK;
 }
+}  // namespace psi
 
-int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
-                const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
-                const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
-                float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
-                psi_stream_t stream);
+extern "C" {
+
+int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                const float *transl, const float *cam, long cam_bstride, const float *rot_in,
+                int num_rot, float *verts, float *joints, float *saved, psi_stream_t stream) {
+    if (num_rot > 0 && !rot_in) return PSI_ERR_BAD_ARG;
+    return psi::lbs_fwd_impl(m, B, betas, pose, transl, cam, cam_bstride, rot_in, nullptr, num_rot, verts,
+                             joints, saved, (cudaStream_t)stream);
+}
 
 size_t psi_lbs_bwd_workspace_bytes(const psi_lbs_model *m, int B) {
     if (!m || B <= 0) return 0;
     return psi::bwd_layout(m, B).total * sizeof(float);
 }
 
-int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float *pose,
-                 const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
-                 const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
-                 float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
+}  // extern "C"
+
+namespace psi {
+// psi_lbs_bwd2 + the 6D variant: with rot6d the gradient of the leading joints is returned through
+// the Gram-Schmidt backward (g6_root [B,6], g6A = GEMM operand layout, see lbs_pose_bwd_kernel)
+int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *cam, long cam_bstride,
+                 const float *saved, const float *grad_verts, const float *grad_joints, float *grad_betas,
+                 float *grad_pose, float *grad_transl, float *grad_rot, int num_rot, const float *rot6d,
+                 float *g6_root, float *g6A, int g6_kpad, void *workspace, size_t workspace_bytes,
                  psi_stream_t stream, psi_stream_t side_stream, void *ev_fork, void *ev_join) {
-    using namespace psi;
-    (void)betas;
     // optional side stream: lbs_dA runs next to lbs_dcoef (both only depend on lbs_vertex_bwd)
     cudaStream_t side = (side_stream && ev_fork && ev_join) ? (cudaStream_t)side_stream : nullptr;
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!pose || !saved || !grad_verts || !grad_betas || !grad_pose || !workspace) return PSI_ERR_BAD_ARG;
-    if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !grad_rot)) return PSI_ERR_BAD_ARG;
+    if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !grad_rot && !rot6d)) return PSI_ERR_BAD_ARG;
+    if (rot6d && (!g6_root || !g6A || g6_kpad < (num_rot - 1) * 6)) return PSI_ERR_BAD_ARG;
     if (B > 65535) return PSI_ERR_UNSUPPORTED;
     const BwdLayout W = bwd_layout(m, B);
     if (workspace_bytes < W.total * sizeof(float)) return PSI_ERR_WORKSPACE;
@@ -971,7 +1001,7 @@ int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float 
         lbs_vertex_bwd_kernel<<<grid, 256, 0, st>>>(m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                                                     m->skin_w, saved + L.A, cam, cam_bstride,
                                                     grad_verts, ws + W.gw, ws + W.gvp);
-        PSI_LAUNCHED();
+        PSI_LAUNCHED_K("lbs_vertex_bwd");
     }
     {
         cudaStream_t sa = st;
@@ -984,7 +1014,7 @@ int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float 
         dim3 grid((unsigned)(m->J + 1), (unsigned)B);
         lbs_dA_kernel<<<grid, 128, 0, sa>>>(m->V, m->J, m->jl_start, m->jl_vert, m->jl_w,
                                             ws + W.gw, saved + L.vp, ws + W.dA, ws + W.dtr);
-        PSI_LAUNCHED();
+        PSI_LAUNCHED_K("lbs_dA");
         if (side && cudaEventRecord((cudaEvent_t)ev_join, side) != cudaSuccess) return PSI_ERR_BAD_ARG;
     }
     {
@@ -996,18 +1026,33 @@ int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float 
         }
         dim3 grid((unsigned)(m->Kpad / kDK), (unsigned)kNSplit, (unsigned)(W.Bpad / kBG));
         lbs_dcoef_kernel<<<grid, 256, smem, st>>>(m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp, ws + W.part, kNSplit);
-        PSI_LAUNCHED();
+        PSI_LAUNCHED_K("lbs_dcoef");
         const long per_split = (long)W.Bpad * m->Kpad;
         lbs_dcoef_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(ws + W.part, kNSplit, per_split, ws + W.dsum);
-        PSI_LAUNCHED();
+        PSI_LAUNCHED_K("lbs_dcoef_reduce");
     }
     if (side && cudaStreamWaitEvent(st, (cudaEvent_t)ev_join, 0) != cudaSuccess) return PSI_ERR_BAD_ARG;
     lbs_pose_bwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
                                           m->parents, pose, saved, L, ws + W.dA, ws + W.dtr,
                                           ws + W.dsum, grad_joints, grad_betas, grad_pose,
-                                          grad_transl, grad_rot, num_rot, m->tree);
-    PSI_LAUNCHED();
+                                          grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree);
+    PSI_LAUNCHED_K("lbs_pose_bwd");
     return PSI_OK;
+}
+}  // namespace psi
+
+extern "C" {
+
+int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float *pose,
+                 const float *cam, long cam_bstride, const float *saved, const float *grad_verts,
+                 const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
+                 float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
+                 psi_stream_t stream, psi_stream_t side_stream, void *ev_fork, void *ev_join) {
+    (void)betas;
+    if (num_rot > 0 && !grad_rot) return PSI_ERR_BAD_ARG;
+    return psi::lbs_bwd_impl(m, B, pose, cam, cam_bstride, saved, grad_verts, grad_joints, grad_betas, grad_pose,
+                             grad_transl, grad_rot, num_rot, nullptr, nullptr, nullptr, 0, workspace,
+                             workspace_bytes, stream, side_stream, ev_fork, ev_join);
 }
 
 int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,

@@ -765,7 +765,7 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         else
             nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     }
-    PSI_LAUNCHED();
+    PSI_LAUNCHED_K(mode == 3 ? "nn_index_group" : "nn_index_query");
     return PSI_OK;
 }
 

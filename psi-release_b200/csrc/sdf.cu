@@ -156,7 +156,7 @@ int psi_sdf_fwd(const float *sdf, int S, int D, const float *h_grid_min, const f
     dim3 grid((unsigned)np, (unsigned)B);
     psi::sdf_fwd_kernel<<<grid, psi::kSdfThreads, 0, (cudaStream_t)stream>>>(
         sdf, D, sc, verts, V, body_scene, out, grad, partial, np);
-    PSI_LAUNCHED();
+    PSI_LAUNCHED_K("sdf_fwd");
     return PSI_OK;
 }
 

@@ -31,6 +31,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from . import body_model as smplx_b200
 from . import chamfer, sdf as sdf_mod
 from .geometry import BodyParamParser, GeometryTransformer, VPoserDecoder
@@ -250,6 +251,14 @@ class FittingOP:
                         print("[INFO][fitting] iter={:d}, l_rec={:f}, l_vposer={:f}, l_contact={:f}, "
                               "l_collision={:f}".format(ii, *l))
             return GeometryTransformer.convert_to_3D_rot(self.xhr_rec.detach())
+
+    def profile_iteration(self, xh, cam_ext, warm_iters=20, timed_iters=50):
+        """Fused engine only: [(kernel name, mean ms per launch)] of one fitting iteration, each
+        launch bracketed by CUDA events on its own stream (psi_fit_profile)."""
+        if self._fused is None:
+            raise _lib.PsiError("profile_iteration needs engine='fused'")
+        with torch.cuda.device(self.device):
+            return self._fused.profile(GeometryTransformer.convert_to_6D_rot(xh), cam_ext, warm_iters, timed_iters)
 
     def fit_host(self, xh_host, cam_ext_host, num_iter=None):
         """End-to-end call with HOST buffers (pinned tensors recommended): H2D of the body

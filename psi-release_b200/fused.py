@@ -138,6 +138,24 @@ class FusedFit:
                 _lib.check(rc, "psi_fit_end")
         return out, losses
 
+    def profile(self, xhr, cam_ext, warm_iters=20, timed_iters=50):
+        """Per-kernel timing of one fitting iteration (psi_fit_profile: eager launches with a CUDA
+        event behind each, on the launching stream) -> list of (kernel name, mean ms per launch)."""
+        _lib.require_cuda(xhr, cam_ext)
+        xhr = xhr.contiguous().float()
+        cam = cam_ext.reshape(-1, 16)[:, :12].contiguous().float()
+        shared = cam.shape[0] == 1
+        s, nb, h = self.parts[0]
+        ms = (ctypes.c_float * 64)()
+        names = (ctypes.c_char_p * 64)()
+        with torch.cuda.device(self.device):
+            n = _lib.lib().psi_fit_profile(h, _lib.ptr(xhr[s:s + nb]), _lib.ptr(cam if shared else cam[s:s + nb]),
+                                           0 if shared else 12, int(warm_iters), int(timed_iters), ms, names, 64,
+                                           _lib.stream_ptr())
+        if n < 0:
+            _lib.check(-n - 1000, "psi_fit_profile")
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
     def __del__(self):
         try:
             for _, _, h in getattr(self, "parts", []):

@@ -89,7 +89,7 @@ def test_independent_mode_is_shard_invariant(small_model):
 
 
 def test_fused_engine_matches_autograd_engine_and_cpu_loop(small_model):
-    """psi_fit_run (11 launches/iteration) vs torch autograd over the psi ops vs the CPU restatement.
+    """psi_fit_run vs torch autograd over the psi ops vs the CPU restatement.
     The fused path hands rotation matrices to LBS instead of the reference's matrix -> axis-angle ->
     Rodrigues round trip (identity on SO(3) up to rounding), hence tolerances, not equality."""
     from psi_release_b200.fitting import FittingOP
@@ -101,7 +101,11 @@ def test_fused_engine_matches_autograd_engine_and_cpu_loop(small_model):
         # one iteration: the Adam step is lr*sign(g) -> any sign disagreement shows up as 0.2
         f1 = fused.fit(torch.tensor(xh).cuda(), cam.cuda(), num_iter=1)
         a1 = auto.fit(torch.tensor(xh).cuda(), cam.cuda(), num_iter=1)
-        assert float((f1 - a1).abs().max()) < 2e-3
+        # (components whose gradient is at Adam's eps scale, |g| ~ 1e-8, take a partial step that
+        # amplifies rounding noise: they get a looser band)
+        full_step = ((f1 - torch.tensor(xh).cuda()).abs() > 0.09) | ((a1 - torch.tensor(xh).cuda()).abs() > 0.09)
+        d1 = (f1 - a1).abs()
+        assert float(d1[full_step].max()) < 2e-3 and float(d1.max()) < 3e-2
         ff = fused.fit(torch.tensor(xh).cuda(), cam.cuda())
         aa = auto.fit(torch.tensor(xh).cuda(), cam.cuda())
         assert float((ff - aa).abs().max()) < 2e-2
