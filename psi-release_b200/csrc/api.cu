@@ -1,9 +1,16 @@
 // ABI version and error strings for libpsi_b200.
 #include "common.cuh"
 #include <atomic>
+#include <stdlib.h>
 
 namespace psi {
 static std::atomic<unsigned long long> g_launches{0};
+bool pdl_enabled() {
+    // opt-in: measured SLOWER on B200 for this chain (460 vs 535 bodies/s at r01p: the early-scheduled
+    // dependents do not shorten the chain, the graph's programmatic edges cost more than they save)
+    static const bool on = [] { const char *e = getenv("PSI_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
 static thread_local LaunchRecorder *g_rec = nullptr;
 void recorder_set(LaunchRecorder *r) { g_rec = r; }
 void count_launch(const char *name) {

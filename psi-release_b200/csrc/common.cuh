@@ -48,15 +48,47 @@ __host__ __device__ inline size_t a_index(int b, int k, int kpad) {
            swz(b % kBG, k % kKC);
 }
 
-// lbs.cu, used by the fused fitting loop (fit.cu)
+// lbs.cu, used by the fused fitting loop (fit.cu); SdfFuse / VGradFuse: fit_fuse.cuh
+struct SdfFuse;
+struct VGradFuse;
 int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float *pose, const float *transl,
                  const float *cam, long cam_bstride, const float *rot_in, const float *rot6d, int num_rot,
-                 float *verts, float *joints, float *saved, cudaStream_t st);
+                 float *verts, float *joints, float *saved, const SdfFuse *sdf, cudaStream_t st);
 int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *cam, long cam_bstride,
-                 const float *saved, const float *grad_verts, const float *grad_joints, float *grad_betas,
-                 float *grad_pose, float *grad_transl, float *grad_rot, int num_rot, const float *rot6d,
-                 float *g6_root, float *g6A, int g6_kpad, void *workspace, size_t workspace_bytes,
-                 psi_stream_t stream, psi_stream_t side_stream, void *ev_fork, void *ev_join);
+                 const float *saved, const float *grad_verts, const VGradFuse *vg, const float *grad_joints,
+                 float *grad_betas, float *grad_pose, float *grad_transl, float *grad_rot, int num_rot,
+                 const float *rot6d, float *g6_root, float *g6A, int g6_kpad, void *workspace,
+                 size_t workspace_bytes, cudaStream_t st);
+int lbs_vertex_chunks(const psi_lbs_model *m);   // 256-vertex chunks = rows of SdfFuse::partial / VGradFuse::cpart
+
+// ---- programmatic dependent launch -----------------------------------------------------------
+// The fitting iteration is a chain of ~16 short dependent kernels; with a plain stream (or graph)
+// dependency each one pays the full launch latency after its predecessor has drained.  Launched
+// with the programmatic-stream-serialization attribute, a kernel's CTAs are scheduled while the
+// predecessor is still finishing (it signals with pdl_launch_dependents at its top) and block in
+// pdl_wait until the predecessor has COMPLETED and its writes are visible -- so everything that
+// touches a predecessor's output (or overwrites its input) comes after pdl_wait; only barrier
+// initialisation and loads of constants precede it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // api.cu: true only when PSI_PDL=1 (measured slower, see api.cu)
+// launch `kernel`; it MUST call pdl_wait() before touching global memory other than constants
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

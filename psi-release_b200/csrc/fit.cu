@@ -18,6 +18,7 @@
 // All reductions have a fixed order: results are bit-reproducible and independent of B.
 #include "common.cuh"
 #include "rot6d.cuh"
+#include "fit_fuse.cuh"
 #include <math.h>
 #include <new>
 #include <vector>
@@ -35,7 +36,7 @@ struct psi_fit_ctx {
     float gmin[3], gmax[3];
     // state + scratch.  *A buffers are GEMM A operands ([body group][K/32][64][32], rows >= B zero)
     float *x0, *x, *am, *av, *cam, *rot6d, *pose, *shape, *transl, *zA, *h1pre, *h1A, *h2pre, *h2A,
-        *g6_root, *g6A, *dh2A, *dh1A, *dz, *verts, *saved, *sdfv, *sdfg, *partial, *nnd, *gverts, *cpart,
+        *g6_root, *g6A, *dh2A, *dh1A, *dz, *verts, *saved, *sdfv, *sdfg, *partial, *nnd, *cpart,
         *gshape, *gpose, *gtransl, *lbs_ws, *losses;
     int *nni, *step, *nnhint;
     size_t lbs_ws_bytes;
@@ -60,21 +61,92 @@ struct FitDims {
 namespace psi {
 
 // x layout [75]: t3 | 6D | betas10 | z32 | lh12 | rh12   (cvae.py:28-33 after convert_to_6D_rot)
-// Per body, before the decoder GEMMs: the latent z as the first layer's A operand, the global
-// orientation's 6D vector, betas, translation, hand PCA + pose_mean (smplx), L_rec and L_vposer.
+//
+// One per-body kernel closes an iteration and opens the next:
+//   do_post: assemble dL/dx (translation, 6D global orientation, betas, latent through the decoder's
+//            backward GEMMs, hand PCA), add d L_rec and d L_vposer, Adam step (torch.optim.Adam
+//            defaults, fitting_habitat.py:76; bias corrections in double), the four loss values of
+//            the iteration just evaluated;
+//   then, for the (updated) x: the latent z as the decoder's first A operand, the root's 6D vector,
+//            betas, translation, hand PCA + pose_mean (smplx) for the LBS kernels.
+// psi_fit_begin launches it once with do_post = 0.
 __global__ void __launch_bounds__(128)
-fit_pre_kernel(FitDims d, const float *__restrict__ x0, const float *__restrict__ x,
-               const float *__restrict__ hand_l, const float *__restrict__ hand_r,
-               const float *__restrict__ pose_mean, float w_rec, float w_vp, float *__restrict__ zA,
-               float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
-               float *__restrict__ transl, float *__restrict__ losses) {
-    __shared__ float sx[96];
+fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchunk, int num_contact,
+                const float *__restrict__ x0, float *__restrict__ x, float *__restrict__ am,
+                float *__restrict__ av, int *__restrict__ step, const float *__restrict__ hand_l,
+                const float *__restrict__ hand_r, const float *__restrict__ pose_mean,
+                const float *__restrict__ dz, const float *__restrict__ g6_root,
+                const float *__restrict__ gpose, const float *__restrict__ gshape,
+                const float *__restrict__ gtransl, const float *__restrict__ partial,
+                const float *__restrict__ cpart, float *__restrict__ losses, float *__restrict__ zA,
+                float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
+                float *__restrict__ transl) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float sx[96], g[96];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int Lz = d.latent;
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;   // 75
     const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
     for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
     __syncthreads();
+    if (do_post) {
+        if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
+        else if (tid < 9) g[tid] = g6_root[(size_t)b * 6 + tid - 3];
+        else if (tid < 19) g[tid] = gshape[(size_t)b * d.NB + tid - 9];
+        else if (tid < 19 + Lz) g[tid] = dz[(size_t)b * Lz + tid - zoff] + cfg.w_vposer * (2.0f * sx[tid] / (float)Lz);
+        else if (tid < xdim) {                       // hand PCA backward
+            const int u = tid - lhoff, c = u % d.ncomp;
+            const bool right = u >= d.ncomp;
+            const float *comp = (right ? hand_r : hand_l) + c * 45;
+            const float *gp = gpose + (size_t)b * d.J * 3 + (right ? (d.J - 15) * 3 : (d.J - 30) * 3);
+            float a = 0.f;
+            for (int k = 0; k < 45; ++k) a = fmaf(comp[k], gp[k], a);
+            g[(right ? rhoff : lhoff) + c] = a;
+        }
+        if (tid >= 96) {        // warp 3: loss values of the iteration just evaluated (x before the update)
+            const int ln = tid - 96;
+            float r = 0.f, zz = 0.f, sn = 0.f, cn = 0.f, cs = 0.f;
+            for (int e = ln; e < xdim; e += 32) r += fabsf(x0[(size_t)b * xdim + e] - sx[e]);
+            for (int i = ln; i < Lz; i += 32) zz = fmaf(sx[zoff + i], sx[zoff + i], zz);
+            for (int i = ln; i < np_sdf; i += 32) {
+                sn += partial[((size_t)b * np_sdf + i) * 2];
+                cn += partial[((size_t)b * np_sdf + i) * 2 + 1];
+            }
+            for (int i = ln; i < nchunk; i += 32) cs += cpart[(size_t)b * nchunk + i];
+            r = warp_sum(r); zz = warp_sum(zz); sn = warp_sum(sn); cn = warp_sum(cn); cs = warp_sum(cs);
+            if (ln == 0) {
+            losses[(size_t)b * 4 + 0] = cfg.w_rec * (r / (float)xdim);
+            losses[(size_t)b * 4 + 1] = cfg.w_vposer * (zz / (float)Lz);
+            losses[(size_t)b * 4 + 2] = cfg.w_contact * (cs / (float)num_contact);
+            losses[(size_t)b * 4 + 3] = cfg.w_collision * (cn > 0.f ? sn / cn : 0.f);
+            }
+        }
+        __syncthreads();
+        const int t = step[b] + 1;
+        float xn = 0.f;
+        if (tid < xdim) {
+            const float xe = sx[tid], diff = xe - x0[(size_t)b * xdim + tid];
+            const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+            const float ge = g[tid] + cfg.w_rec * sgn / (float)xdim;
+            const size_t o = (size_t)b * xdim + tid;
+            const float m = cfg.beta1 * am[o] + (1.0f - cfg.beta1) * ge;
+            const float v = cfg.beta2 * av[o] + (1.0f - cfg.beta2) * ge * ge;
+            am[o] = m;
+            av[o] = v;
+            const double bc1 = 1.0 - pow((double)cfg.beta1, (double)t);
+            const double bc2 = 1.0 - pow((double)cfg.beta2, (double)t);
+            const float step_size = (float)((double)cfg.lr / bc1);
+            const float denom = sqrtf(v) / (float)sqrt(bc2) + cfg.eps;
+            xn = xe - (m / denom) * step_size;
+            x[o] = xn;
+        }
+        __syncthreads();           // everyone has read sx / step[b]
+        if (tid < xdim) sx[tid] = xn;
+        if (tid == 0) step[b] = t;
+        __syncthreads();
+    }
+    // inputs of the next evaluation
     if (tid < Lz) zA[a_index(b, tid, Lz)] = sx[zoff + tid];
     if (tid < 6) rot6d[(size_t)b * d.num_rot * 6 + tid] = sx[3 + tid];
     // axis-angle pose vector [J*3]: only joints >= num_rot are read by the LBS kernels
@@ -92,133 +164,6 @@ fit_pre_kernel(FitDims d, const float *__restrict__ x0, const float *__restrict_
     }
     for (int e = tid; e < d.NB; e += blockDim.x) shape[(size_t)b * d.NB + e] = e < 10 ? sx[9 + e] : 0.f;
     if (tid < 3) transl[(size_t)b * 3 + tid] = sx[tid];
-    if (tid == 32) {
-        float r = 0.f, zz = 0.f;
-        for (int e = 0; e < xdim; ++e) r += fabsf(x0[(size_t)b * xdim + e] - sx[e]);
-        for (int i = 0; i < Lz; ++i) zz = fmaf(sx[zoff + i], sx[zoff + i], zz);
-        losses[(size_t)b * 4 + 0] = w_rec * (r / (float)xdim);
-        losses[(size_t)b * 4 + 1] = w_vp * (zz / (float)Lz);
-    }
-}
-
-// dL/dverts (scene frame) of the contact and collision terms of body b
-__global__ void __launch_bounds__(256)
-fit_vertex_grad_kernel(int V, int nu, int np_sdf, int num_contact, const float *__restrict__ verts,
-                       const float *__restrict__ scene, const float *__restrict__ sdfv,
-                       const float *__restrict__ sdfg, const float *__restrict__ partial,
-                       const float *__restrict__ nnd, const int *__restrict__ nni,
-                       const int *__restrict__ cslot, const float *__restrict__ cweight, float w_contact,
-                       float w_coll, float robust_c, float *__restrict__ gverts,
-                       float *__restrict__ cpart) {
-    __shared__ float s_cnt;
-    __shared__ float red[8];
-    const int b = blockIdx.y, v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) {
-        float c = 0.f;
-        for (int i = 0; i < np_sdf; ++i) c += partial[((size_t)b * np_sdf + i) * 2 + 1];
-        s_cnt = c;
-    }
-    __syncthreads();
-    float closs = 0.f;
-    if (v < V) {
-        const size_t o = (size_t)b * V + v;
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        if (sdfv[o] < 0.f) {   // d/dv [ w * sum(-sdf)/cnt ]
-            const float k = -w_coll / s_cnt;
-            gx = k * sdfg[o * 3];
-            gy = k * sdfg[o * 3 + 1];
-            gz = k * sdfg[o * 3 + 2];
-        }
-        const int slot = cslot[v];
-        if (slot >= 0) {
-            const float dd = nnd[(size_t)b * nu + slot];
-            const float s = sqrtf(dd + 1e-4f);
-            const float den = s + robust_c;
-            const float wgt = cweight[v];
-            closs = wgt * (s / den);
-            // d/dd [ s/(s+c) ] = c/(s+c)^2 * 1/(2s);   d dd/dp = 2 (p - q)   (chamfer.cu:165-168)
-            const float gd = (w_contact / (float)num_contact) * wgt * (robust_c / (den * den)) * (0.5f / s);
-            const float g2 = gd * 2.0f;
-            const float *q = scene + (size_t)nni[(size_t)b * nu + slot] * 3;
-            gx += g2 * (verts[o * 3] - q[0]);
-            gy += g2 * (verts[o * 3 + 1] - q[1]);
-            gz += g2 * (verts[o * 3 + 2] - q[2]);
-        }
-        gverts[o * 3] = gx;
-        gverts[o * 3 + 1] = gy;
-        gverts[o * 3 + 2] = gz;
-    }
-    closs = warp_sum(closs);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = closs;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int i = 0; i < 8; ++i) s += red[i];
-        cpart[(size_t)b * gridDim.x + blockIdx.x] = s;
-    }
-}
-
-// Per body, after the decoder's backward GEMMs: assemble dL/dx (translation, 6D global
-// orientation, betas, latent, hand PCA), add d L_rec, Adam step (torch.optim.Adam defaults,
-// fitting_habitat.py:76; bias corrections in double), loss values.
-__global__ void __launch_bounds__(128)
-fit_post_kernel(FitDims d, psi_fit_config cfg, int np_sdf, int nchunk, int num_contact,
-                const float *__restrict__ x0, float *__restrict__ x, float *__restrict__ am,
-                float *__restrict__ av, int *__restrict__ step, const float *__restrict__ hand_l,
-                const float *__restrict__ hand_r, const float *__restrict__ dz,
-                const float *__restrict__ g6_root, const float *__restrict__ gpose,
-                const float *__restrict__ gshape, const float *__restrict__ gtransl,
-                const float *__restrict__ partial, const float *__restrict__ cpart,
-                float *__restrict__ losses) {
-    __shared__ float sx[96], g[96];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int Lz = d.latent;
-    const int xdim = 9 + 10 + Lz + 2 * d.ncomp;
-    const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
-    for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
-    __syncthreads();
-    if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
-    else if (tid < 9) g[tid] = g6_root[(size_t)b * 6 + tid - 3];
-    else if (tid < 19) g[tid] = gshape[(size_t)b * d.NB + tid - 9];
-    else if (tid < 19 + Lz) g[tid] = dz[(size_t)b * Lz + tid - zoff] + cfg.w_vposer * (2.0f * sx[tid] / (float)Lz);
-    else if (tid < xdim) {                       // hand PCA backward
-        const int u = tid - lhoff, c = u % d.ncomp;
-        const bool right = u >= d.ncomp;
-        const float *comp = (right ? hand_r : hand_l) + c * 45;
-        const float *gp = gpose + (size_t)b * d.J * 3 + (right ? (d.J - 15) * 3 : (d.J - 30) * 3);
-        float a = 0.f;
-        for (int k = 0; k < 45; ++k) a = fmaf(comp[k], gp[k], a);
-        g[(right ? rhoff : lhoff) + c] = a;
-    }
-    __syncthreads();
-    const int t = step[b] + 1;
-    if (tid < xdim) {
-        const float xe = sx[tid], diff = xe - x0[(size_t)b * xdim + tid];
-        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-        const float ge = g[tid] + cfg.w_rec * sgn / (float)xdim;
-        const size_t o = (size_t)b * xdim + tid;
-        const float m = cfg.beta1 * am[o] + (1.0f - cfg.beta1) * ge;
-        const float v = cfg.beta2 * av[o] + (1.0f - cfg.beta2) * ge * ge;
-        am[o] = m;
-        av[o] = v;
-        const double bc1 = 1.0 - pow((double)cfg.beta1, (double)t);
-        const double bc2 = 1.0 - pow((double)cfg.beta2, (double)t);
-        const float step_size = (float)((double)cfg.lr / bc1);
-        const float denom = sqrtf(v) / (float)sqrt(bc2) + cfg.eps;
-        x[o] = xe - (m / denom) * step_size;
-    }
-    if (tid == 96) {
-        float sn = 0.f, cn = 0.f, cs = 0.f;
-        for (int i = 0; i < np_sdf; ++i) {
-            sn += partial[((size_t)b * np_sdf + i) * 2];
-            cn += partial[((size_t)b * np_sdf + i) * 2 + 1];
-        }
-        for (int i = 0; i < nchunk; ++i) cs += cpart[(size_t)b * nchunk + i];
-        losses[(size_t)b * 4 + 2] = cfg.w_contact * (cs / (float)num_contact);
-        losses[(size_t)b * 4 + 3] = cfg.w_collision * (cn > 0.f ? sn / cn : 0.f);
-    }
-    __syncthreads();
-    if (tid == 0) step[b] = t;
 }
 
 __global__ void fit_reset_kernel(float *am, float *av, int *step, long n, int B) {
@@ -239,18 +184,24 @@ static int launch_linear(cudaStream_t st, int B, const float *A, const float *W,
     p.A = A; p.W = W; p.bias = bias; p.gate = gate; p.pre_out = pre_out; p.out_rm = out_rm; p.outA = outA;
     p.K = K; p.N = N; p.B = B; p.n_valid = n_valid; p.ld = ld; p.outA_kpad = outA_kpad; p.act = act;
     dim3 grid((unsigned)(N / kLT), (unsigned)((B + kBG - 1) / kBG));
-    const int stages = K / kKC < kLStages ? K / kKC : kLStages;
-    fit_linear_kernel<<<grid, 128, (size_t)stages * kLStageBytes, st>>>(p);
+    if (K % kKC || K / kKC > kLMaxChunks || N % kLT) return PSI_ERR_UNSUPPORTED;
+    launch_pdl(fit_linear_kernel, dim3(grid), dim3(128), (size_t)(K / kKC) * kLChunkBytes, st, p);
     PSI_LAUNCHED_K("fit_linear");
     return PSI_OK;
 }
 
-static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
+static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
     const FitDims d = {c->B, c->V, c->J, c->NB, c->latent, c->hidden, c->nbody, c->ncomp, c->num_rot};
+    launch_pdl(fit_step_kernel, dim3(c->B), dim3(128), 0, st, d, c->cfg, do_post, c->np_sdf, c->nchunk, c->num_contact,
+               c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->dz, c->g6_root, c->gpose,
+               c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl);
+    PSI_LAUNCHED_K("fit_step");
+    return PSI_OK;
+}
+
+// one iteration = 15 launches; expects the per-body inputs of fit_step_kernel's second half
+static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     const int H = c->hidden, Lz = c->latent, NO = c->nbody * 6, NOp = c->no_pad, B = c->B;
-    fit_pre_kernel<<<B, 128, 0, st>>>(d, c->x0, c->x, c->hand_l, c->hand_r, c->pose_mean, c->cfg.w_rec,
-                                      c->cfg.w_vposer, c->zA, c->rot6d, c->pose, c->shape, c->transl, c->losses);
-    PSI_LAUNCHED_K("fit_pre");
     // VPoser decode: 32 -> 512 -> 512 -> nbody*6 (the 6D vectors land behind the root's in rot6d)
     int rc = launch_linear(st, B, c->zA, c->Wf1, Lz, H, c->b1, nullptr, c->h1pre, nullptr, 0, H, c->h1A, H, 1);
     if (rc) return rc;
@@ -259,28 +210,34 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     rc = launch_linear(st, B, c->h2A, c->Wf3, H, NOp, c->b3, nullptr, nullptr, c->rot6d + 6, c->num_rot * 6, NO,
                        nullptr, 0, 0);
     if (rc) return rc;
+    // LBS forward; the skinning epilogue also samples the scene SDF at every fresh vertex
+    SdfFuse sf;
+    sf.g.grid = c->sdf;
+    sf.g.D = c->D;
+    for (int a = 0; a < 3; ++a) {
+        const float ext = c->gmax[a] - c->gmin[a];
+        sf.g.gmin[a] = c->gmin[a];
+        sf.g.inv_extent[a] = 1.0f / ext;
+        sf.g.gscale[a] = (float)(c->D - 1) / 2.0f * (2.0f / ext);
+    }
+    sf.sdfv = c->sdfv; sf.sdfg = c->sdfg; sf.partial = c->partial;
     rc = lbs_fwd_impl(c->model, B, c->shape, c->pose, c->transl, c->cam, 12, nullptr, c->rot6d, c->num_rot,
-                      c->verts, nullptr, c->saved, st);
+                      c->verts, nullptr, c->saved, &sf, st);
     if (rc) return rc;
     // contact ids are ordered by dominant joint + kd cells of the template (fused.py): 32 consecutive
     // queries are neighbours on the posed body -> the group schedule walks the index once per warp
     rc = psi_nn_index_query_mode(c->index, c->verts, (long)c->V * 3, B, c->nu, c->csel, c->nnd, c->nni,
                                  c->nnhint, c->cfg.nn_mode > 0 ? c->cfg.nn_mode : 3, st);
     if (rc) return rc;
-    rc = psi_sdf_fwd(c->sdf, 1, c->D, c->gmin, c->gmax, c->verts, B, c->V, nullptr, c->sdfv, c->sdfg,
-                     c->partial, st);
-    if (rc) return rc;
-    {
-        dim3 grid((unsigned)c->nchunk, (unsigned)B);
-        fit_vertex_grad_kernel<<<grid, 256, 0, st>>>(c->V, c->nu, c->np_sdf, c->num_contact, c->verts,
-                                                     c->scene_pts, c->sdfv, c->sdfg, c->partial, c->nnd,
-                                                     c->nni, c->cslot, c->cweight, c->cfg.w_contact,
-                                                     c->cfg.w_collision, c->cfg.robust_c, c->gverts, c->cpart);
-        PSI_LAUNCHED_K("fit_vertex_grad");
-    }
-    rc = lbs_bwd_impl(c->model, B, c->pose, c->cam, 12, c->saved, c->gverts, nullptr, c->gshape, c->gpose,
+    // LBS backward; dL/dverts of the contact + collision terms is formed at the head of its vertex kernel
+    VGradFuse vg;
+    vg.verts = c->verts; vg.scene = c->scene_pts; vg.sdfv = c->sdfv; vg.sdfg = c->sdfg; vg.partial = c->partial;
+    vg.nnd = c->nnd; vg.nni = c->nni; vg.cslot = c->cslot; vg.cweight = c->cweight;
+    vg.w_contact = c->cfg.w_contact; vg.w_coll = c->cfg.w_collision; vg.robust_c = c->cfg.robust_c;
+    vg.nu = c->nu; vg.np_sdf = c->np_sdf; vg.num_contact = c->num_contact; vg.cpart = c->cpart;
+    rc = lbs_bwd_impl(c->model, B, c->pose, c->cam, 12, c->saved, nullptr, &vg, nullptr, c->gshape, c->gpose,
                       c->gtransl, nullptr, c->num_rot, c->rot6d, c->g6_root, c->g6A, NOp, c->lbs_ws,
-                      c->lbs_ws_bytes, st, nullptr, nullptr, nullptr);
+                      c->lbs_ws_bytes, st);
     if (rc) return rc;
     // decoder backward: d h2 = (d o . W3) * lrelu', d h1 = (d h2 . W2) * lrelu', d z = d h1 . W1
     rc = launch_linear(st, B, c->g6A, c->Wb3, NOp, H, nullptr, c->h2pre, nullptr, nullptr, 0, H, c->dh2A, H, 0);
@@ -289,11 +246,7 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     if (rc) return rc;
     rc = launch_linear(st, B, c->dh1A, c->Wb1, H, Lz, nullptr, nullptr, nullptr, c->dz, Lz, Lz, nullptr, 0, 0);
     if (rc) return rc;
-    fit_post_kernel<<<B, 128, 0, st>>>(d, c->cfg, c->np_sdf, c->nchunk, c->num_contact, c->x0, c->x, c->am, c->av,
-                                       c->step, c->hand_l, c->hand_r, c->dz, c->g6_root, c->gpose, c->gshape,
-                                       c->gtransl, c->partial, c->cpart, c->losses);
-    PSI_LAUNCHED_K("fit_post");
-    return PSI_OK;
+    return launch_step(c, 1, st);       // Adam, losses, and the next iteration's per-body inputs
 }
 
 }  // namespace psi
@@ -340,12 +293,12 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         return PSI_ERR_ALLOC;
     }
     for (int a = 0; a < 3; ++a) { c->gmin[a] = h_grid_min[a]; c->gmax[a] = h_grid_max[a]; }
-    if (cudaFuncSetAttribute(fit_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLStages * kLStageBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(fit_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLMaxChunks * kLChunkBytes) != cudaSuccess) {
         psi_fit_destroy(c);
         return PSI_ERR_UNSUPPORTED;
     }
-    c->np_sdf = psi_sdf_num_partials(V);
-    c->nchunk = (V + 255) / 256;
+    c->np_sdf = (V + 255) / 256;               // rows of the skinning kernel's SDF partial sums
+    c->nchunk = lbs_vertex_chunks(model);      // rows of the vertex backward kernel's contact partial sums
     int rc = PSI_OK;
     auto dev_alloc = [&](size_t bytes) -> void * {
         void *p = nullptr;
@@ -425,7 +378,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->verts = fbuf(B * V * 3); c->saved = fbuf(psi_lbs_saved_floats(model, c->B) + 64);
     c->sdfv = fbuf(B * V); c->sdfg = fbuf(B * V * 3); c->partial = fbuf(B * c->np_sdf * 2);
     c->nnd = fbuf(B * c->nu); c->nni = (int *)dev_alloc(B * c->nu * sizeof(int));
-    c->nnhint = (int *)dev_alloc(B * c->nu * sizeof(int)); c->gverts = fbuf(B * V * 3);
+    c->nnhint = (int *)dev_alloc(B * c->nu * sizeof(int));
     c->cpart = fbuf(B * c->nchunk); c->gshape = fbuf(B * NB); c->gpose = fbuf(B * J * 3);
     c->gtransl = fbuf(B * 3); c->losses = fbuf(B * 4);
     c->step = (int *)dev_alloc(B * sizeof(int));
@@ -463,7 +416,8 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
         if (e != cudaSuccess) return (int)e;
         if (!c->exec) {
             // warm the lazily-initialised pieces outside the capture (state is reset below)
-            int rc = enqueue_iteration(c, gs);
+            int rc = launch_step(c, 0, gs);
+            if (rc == PSI_OK) rc = enqueue_iteration(c, gs);
             if (rc) return rc;
             cudaGraph_t graph = nullptr;
             e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal);
@@ -480,6 +434,8 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
             fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gs>>>(c->am, c->av, c->step, (long)n, c->B);
             PSI_LAUNCHED();
         }
+        const int rc = launch_step(c, 0, gs);
+        if (rc) return rc;
         for (int it = 0; it < num_iter; ++it) {
             e = cudaGraphLaunch(c->exec, gs);
             if (e != cudaSuccess) return (int)e;
@@ -488,10 +444,9 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
         if (e != cudaSuccess) return (int)e;
         c->pending_join = 1;
     } else {
-        for (int it = 0; it < num_iter; ++it) {
-            const int rc = enqueue_iteration(c, st);
-            if (rc) return rc;
-        }
+        int rc = launch_step(c, 0, st);
+        for (int it = 0; it < num_iter && rc == PSI_OK; ++it) rc = enqueue_iteration(c, st);
+        if (rc) return rc;
         c->pending_join = 0;
     }
     return PSI_OK;
@@ -521,7 +476,7 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
     return psi_fit_end(c, xhr_out, losses_out, stream);
 }
 
-int psi_fit_launches_per_iteration(void) { return 19; }
+int psi_fit_launches_per_iteration(void) { return 15; }
 
 int psi_fit_profile(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int warm_iters,
                     int timed_iters, float *h_ms, const char **h_names, int max_launches, psi_stream_t stream) {

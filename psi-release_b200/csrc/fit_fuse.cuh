@@ -1,0 +1,25 @@
+// Pieces of the fitting loop's loss that are fused into LBS kernels (lbs.cu) when the loop runs
+// through psi_fit_* (fit.cu).  The generic psi_lbs_fwd / psi_lbs_bwd entry points pass none.
+#pragma once
+#include "sdf_sample.cuh"
+namespace psi {
+
+// scene-SDF lookup at every vertex, in the skinning kernel's epilogue (fitting_habitat.py:145-152)
+struct SdfFuse {
+    SdfGrid g;
+    float *sdfv, *sdfg;      // [B,V], [B,V,3]
+    float *partial;          // [B, vertex chunks, 2]: (sum of -sdf, count) over sdf < 0, per 256-vertex chunk
+};
+
+// dL/dverts of the contact robustifier (fitting_habitat.py:133-141) and the collision mean
+// (:155-160), evaluated at the head of the vertex backward kernel instead of a pass of its own
+struct VGradFuse {
+    const float *verts, *scene, *sdfv, *sdfg, *partial, *nnd;
+    const int *nni, *cslot;
+    const float *cweight;
+    float w_contact, w_coll, robust_c;
+    int nu, np_sdf, num_contact;
+    float *cpart;            // [B, vertex chunks]: contact-loss partial sums
+};
+
+}  // namespace psi

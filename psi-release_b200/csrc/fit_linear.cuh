@@ -15,9 +15,9 @@
 namespace psi {
 
 constexpr int kLT = 16;                                  // output columns per CTA (2 n8 tiles)
-constexpr int kLStages = 16;                             // K <= 512: every stage of a CTA is in flight at once
-constexpr int kLStageBytes = (kLT + kBG) * kKC * 4;      // 10 kB (the ring is latency bound: a 4-stage ring
-                                                         // measured 8-10 us per layer, 30 kB in flight per SM)
+constexpr int kLMaxChunks = 16;                          // K <= 512: both operands of a CTA sit in shared memory
+constexpr int kLGroup = 4;                               // chunks per arrival barrier (compute starts on the first 40 kB)
+constexpr int kLChunkBytes = (kLT + kBG) * kKC * 4;      // 2 kB of weights + 8 kB of activations per 32 k
 
 struct LinearParams {
     const float *A;        // [body group][K/32][64][32], swizzled; rows of bodies >= B are zero
@@ -30,61 +30,62 @@ struct LinearParams {
     int K, N, B, n_valid, ld, outA_kpad, act;            // act 1: leaky ReLU 0.2 after the bias
 };
 
+// The kernel is latency bound (32 CTAs, 160 kB each): everything is requested up front -- per group
+// of 4 chunks ONE bulk copy of weights and ONE of activations (both operands are contiguous over k)
+// -- and the three 3xTF32 terms of each output tile accumulate in their own registers, so the
+// 64-step K loop is six independent MMA chains per warp instead of two chains of 192.
 __global__ void __launch_bounds__(128) fit_linear_kernel(const LinearParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];     // min(K/32, kLStages) stages
-    __shared__ __align__(8) uint64_t full[kLStages], empty[kLStages];
+    extern __shared__ __align__(128) unsigned char smem_raw[];     // W [K/32][16][32] | A [K/32][64][32]
+    __shared__ __align__(8) uint64_t full[kLMaxChunks / kLGroup];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int tile = blockIdx.x, bg = blockIdx.y;
-    const int nchunks = p.K / kKC;
+    const int nchunks = p.K / kKC, ngroups = (nchunks + kLGroup - 1) / kLGroup;
     const float *__restrict__ w_t = p.W + (size_t)tile * p.K * kLT;      // [chunk][16][32]
     const float *__restrict__ a_g = p.A + (size_t)bg * p.K * kBG;        // [chunk][64][32]
+    unsigned char *sW = smem_raw, *sA = smem_raw + (size_t)nchunks * kLT * kKC * 4;
 
     if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < kLStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+        for (int i = 0; i < ngroups; ++i) mbar_init(&full[i], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](int c) {   // thread 0 only
-        const int st = c % kLStages;
-        mbar_wait(&empty[st], (uint32_t)(((c / kLStages) & 1) ^ 1));
-        unsigned char *dst = smem_raw + st * kLStageBytes;
-        mbar_arrive_expect_tx(&full[st], (uint32_t)kLStageBytes);
-        tma_load_1d(dst, w_t + (size_t)c * kLT * kKC, kLT * kKC * 4, &full[st]);
-        tma_load_1d(dst + kLT * kKC * 4, a_g + (size_t)c * kBG * kKC, kBG * kKC * 4, &full[st]);
-    };
-    if (tid == 0)
-        for (int c = 0; c < kLStages - 1 && c < nchunks; ++c) issue(c);
+    pdl_launch_dependents();
+    pdl_wait();
+    if (tid == 0) {
+        for (int g = 0; g < ngroups; ++g) {
+            const int c0 = g * kLGroup, nc = min(kLGroup, nchunks - c0);
+            mbar_arrive_expect_tx(&full[g], (uint32_t)(nc * kLChunkBytes));
+            tma_load_1d(sW + (size_t)c0 * kLT * kKC * 4, w_t + (size_t)c0 * kLT * kKC, nc * kLT * kKC * 4, &full[g]);
+            tma_load_1d(sA + (size_t)c0 * kBG * kKC * 4, a_g + (size_t)c0 * kBG * kKC, nc * kBG * kKC * 4, &full[g]);
+        }
+    }
 
-    float acc[2][4];
+    float acc[2][3][4];        // [n8 tile][term: lo*hi, hi*lo, hi*hi][fragment]
 #pragma unroll
-    for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
     const int l7 = lane & 7;
-    const uint32_t offA = (uint32_t)(kLT * kKC * 4 + (w * 16 + l7 + ((lane >> 3) & 1) * 8) * 128);
+    const uint32_t offA = (uint32_t)((w * 16 + l7 + ((lane >> 3) & 1) * 8) * 128);
     const int kcA = lane >> 4;
     const uint32_t offB = (uint32_t)((l7 + ((lane >> 4) & 1) * 8) * 128);
     const int kcB = (lane >> 3) & 1;
-    const uint32_t smem0 = smem_u32(smem_raw);
+    const uint32_t sW0 = smem_u32(sW), sA0 = smem_u32(sA);
 
     for (int c = 0; c < nchunks; ++c) {
-        if (tid == 0 && c + kLStages - 1 < nchunks) issue(c + kLStages - 1);
-        __syncwarp();
-        const int st = c % kLStages;
-        mbar_wait(&full[st], (uint32_t)((c / kLStages) & 1));
-        const uint32_t sb = smem0 + st * kLStageBytes;
+        if (c % kLGroup == 0) mbar_wait(&full[c / kLGroup], 0);
+        const uint32_t sbW = sW0 + c * (kLT * kKC * 4), sbA = sA0 + c * (kBG * kKC * 4);
 #pragma unroll
         for (int s = 0; s < kKC / 8; ++s) {
             const uint32_t ca = (uint32_t)(((2 * s + kcA) ^ l7) << 4), cb = (uint32_t)(((2 * s + kcB) ^ l7) << 4);
             uint32_t a[4], ah[4], al[4], bb[4], bh[4], bl[4];
-            ldsm_x4(a, sb + offA + ca);
-            ldsm_x4(bb, sb + offB + cb);
+            ldsm_x4(a, sbA + offA + ca);
+            ldsm_x4(bb, sbW + offB + cb);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { split_tf32(a[i], ah[i], al[i]); split_tf32(bb[i], bh[i], bl[i]); }
-            mma_3xtf32(acc[0], ah, al, bh[0], bh[1], bl[0], bl[1]);
-            mma_3xtf32(acc[1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+            mma_tf32(acc[0][0], al, bh[0], bh[1]); mma_tf32(acc[0][1], ah, bl[0], bl[1]); mma_tf32(acc[0][2], ah, bh[0], bh[1]);
+            mma_tf32(acc[1][0], al, bh[2], bh[3]); mma_tf32(acc[1][1], ah, bl[2], bl[3]); mma_tf32(acc[1][2], ah, bh[2], bh[3]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
     }
 
     // accumulator fragment: rows g, g+8 (bodies), columns 2t, 2t+1 (outputs) of each n8 tile
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(128) fit_linear_kernel(const LinearParams p) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int n = tile * kLT + nt * 8 + 2 * t + e;
-                float v = acc[nt][2 * h + e];
+                float v = (acc[nt][0][2 * h + e] + acc[nt][1][2 * h + e]) + acc[nt][2][2 * h + e];   // small terms first
                 if (n < p.n_valid) {
                     if (p.bias) v += p.bias[n];
                     if (p.pre_out) p.pre_out[(size_t)b * p.n_valid + n] = v;

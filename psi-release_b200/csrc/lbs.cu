@@ -29,6 +29,7 @@
 // All reductions use fixed orders: results are bit-reproducible run to run.
 #include "common.cuh"
 #include "rot6d.cuh"
+#include "fit_fuse.cuh"
 #include <math.h>
 #include <new>
 #include <vector>
@@ -55,8 +56,11 @@ struct psi_lbs_model {
     int *tree_buf;
     int V, J, NB, P, K, Kpad, Npad, KW, NC, NT;   // NC coordinate chunks of 32 (Npad = 32 NC), NT forward tiles of 72
     long nnz;
-    float *basis_fwd, *basis_bwd, *v_template, *Jt, *Jdirs, *skin_w, *jl_w;
-    int *skin_j, *parents, *jl_start, *jl_vert;
+    float *basis_fwd, *basis_bwd, *v_template, *Jt, *Jdirs, *skin_w, *ch_w;
+    int *skin_j, *parents, *ch_seg;
+    unsigned char *ch_lv;
+    int max_ent;                   // most skinning entries in one chunk
+    int NCH;                       // 256-vertex chunks of the vertex kernels (covers Npad/3 rows)
     size_t bytes;
 };
 
@@ -110,6 +114,8 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
                     float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
                     const float *__restrict__ rot6d, const psi_lbs_tree tree) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int j = tid; j < J; j += blockDim.x) {
@@ -195,6 +201,8 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
 
 // coefficient rows of bodies past B inside the last body group must read as zero
 __global__ void lbs_zero_coef_pad_kernel(float *coef, int B, int Kpad) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int nbg = (B + kBG - 1) / kBG;
     const int first = B % kBG;
     if (first == 0) return;
@@ -231,6 +239,8 @@ __global__ void __launch_bounds__(128, 3) lbs_blend_fwd_kernel(const BlendFwdPar
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
     auto issue = [&](int c) {   // thread 0 only
         const int st = c % kFStages;
         mbar_wait(&empty[st], (uint32_t)(((c / kFStages) & 1) ^ 1));   // first use: passes at once
@@ -307,131 +317,231 @@ __global__ void __launch_bounds__(128, 3) lbs_blend_fwd_kernel(const BlendFwdPar
 // skinning + translation + camera transform, one thread per (body, vertex): a streaming pass over
 // v_posed with gathers from the [B,J,12] transform table (169 kB at B=64, cache resident).
 // (lbs.py:108-116, body_model.py:246-247, cvae.py:141-149)
+// SDF = true (fitting loop): the scene-SDF sample + gradient + collision partial sums of the fresh
+// vertex are taken in the same thread (sdf_sample.cuh) -- no second pass over the vertices.
+template <bool SDF>
 __global__ void __launch_bounds__(256)
 lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const float *__restrict__ skin_w,
                     const float *__restrict__ A, const float *__restrict__ vp_in,
                     const float *__restrict__ transl, const float *__restrict__ cam, long cam_bstride,
-                    float *__restrict__ verts) {
+                    float *__restrict__ verts, const SdfFuse sf) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (v >= V) return;
-    const float *vp = vp_in + ((size_t)b * V + v) * 3;
-    const float x = vp[0], y = vp[1], z = vp[2];
-    float T[12];
+    float neg_sum = 0.f, neg_cnt = 0.f;
+    if (v < V) {
+        const float *vp = vp_in + ((size_t)b * V + v) * 3;
+        const float x = vp[0], y = vp[1], z = vp[2];
+        float T[12];
 #pragma unroll
-    for (int e = 0; e < 12; ++e) T[e] = 0.f;
-    const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
-    for (int k = 0; k < KW; ++k) {
-        const int j = skin_j[(size_t)v * KW + k];
-        const float wt = skin_w[(size_t)v * KW + k];
-        const float4 r0 = __ldg(Ab + j * 3), r1 = __ldg(Ab + j * 3 + 1), r2 = __ldg(Ab + j * 3 + 2);
-        T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]); T[3] = fmaf(wt, r0.w, T[3]);
-        T[4] = fmaf(wt, r1.x, T[4]); T[5] = fmaf(wt, r1.y, T[5]); T[6] = fmaf(wt, r1.z, T[6]); T[7] = fmaf(wt, r1.w, T[7]);
-        T[8] = fmaf(wt, r2.x, T[8]); T[9] = fmaf(wt, r2.y, T[9]); T[10] = fmaf(wt, r2.z, T[10]); T[11] = fmaf(wt, r2.w, T[11]);
+        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+        const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
+        for (int k = 0; k < KW; ++k) {
+            const int j = skin_j[(size_t)v * KW + k];
+            const float wt = skin_w[(size_t)v * KW + k];
+            const float4 r0 = __ldg(Ab + j * 3), r1 = __ldg(Ab + j * 3 + 1), r2 = __ldg(Ab + j * 3 + 2);
+            T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]); T[3] = fmaf(wt, r0.w, T[3]);
+            T[4] = fmaf(wt, r1.x, T[4]); T[5] = fmaf(wt, r1.y, T[5]); T[6] = fmaf(wt, r1.z, T[6]); T[7] = fmaf(wt, r1.w, T[7]);
+            T[8] = fmaf(wt, r2.x, T[8]); T[9] = fmaf(wt, r2.y, T[9]); T[10] = fmaf(wt, r2.z, T[10]); T[11] = fmaf(wt, r2.w, T[11]);
+        }
+        float ox = T[0] * x + T[1] * y + T[2] * z + T[3];
+        float oy = T[4] * x + T[5] * y + T[6] * z + T[7];
+        float oz = T[8] * x + T[9] * y + T[10] * z + T[11];
+        if (transl) {
+            ox += transl[(size_t)b * 3]; oy += transl[(size_t)b * 3 + 1]; oz += transl[(size_t)b * 3 + 2];
+        }
+        if (cam) {
+            const float *C = cam + (size_t)b * cam_bstride;
+            const float cx = C[0] * ox + C[1] * oy + C[2] * oz + C[3];
+            const float cy = C[4] * ox + C[5] * oy + C[6] * oz + C[7];
+            const float cz = C[8] * ox + C[9] * oy + C[10] * oz + C[11];
+            ox = cx; oy = cy; oz = cz;
+        }
+        const size_t o = (size_t)b * V + v;
+        verts[o * 3] = ox; verts[o * 3 + 1] = oy; verts[o * 3 + 2] = oz;
+        if (SDF) {
+            float g3[3];
+            const float val = sdf_sample(sf.g, ox, oy, oz, g3);
+            sf.sdfv[o] = val;
+            sf.sdfg[o * 3] = g3[0]; sf.sdfg[o * 3 + 1] = g3[1]; sf.sdfg[o * 3 + 2] = g3[2];
+            if (val < 0.f) { neg_sum -= val; neg_cnt += 1.f; }
+        }
     }
-    float ox = T[0] * x + T[1] * y + T[2] * z + T[3];
-    float oy = T[4] * x + T[5] * y + T[6] * z + T[7];
-    float oz = T[8] * x + T[9] * y + T[10] * z + T[11];
-    if (transl) {
-        ox += transl[(size_t)b * 3]; oy += transl[(size_t)b * 3 + 1]; oz += transl[(size_t)b * 3 + 2];
+    if (SDF) {   // per-(body, chunk) partial sums, fixed order
+        __shared__ float red[2][8];
+        neg_sum = warp_sum(neg_sum);
+        neg_cnt = warp_sum(neg_cnt);
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = neg_sum; red[1][threadIdx.x >> 5] = neg_cnt; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f, c = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s += red[0][i]; c += red[1][i]; }
+            sf.partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = s;
+            sf.partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = c;
+        }
     }
-    if (cam) {
-        const float *C = cam + (size_t)b * cam_bstride;
-        const float cx = C[0] * ox + C[1] * oy + C[2] * oz + C[3];
-        const float cy = C[4] * ox + C[5] * oy + C[6] * oz + C[7];
-        const float cz = C[8] * ox + C[9] * oy + C[10] * oz + C[11];
-        ox = cx; oy = cy; oz = cz;
-    }
-    float *o = verts + ((size_t)b * V + v) * 3;
-    o[0] = ox; o[1] = oy; o[2] = oz;
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, vertex side: gw = Rc^T g ; gvp = Tr^T gw.  gvp is the A operand of the dcoef GEMM:
-// [body group][coordinate chunk][64 bodies][32 coordinates, swizzled]; rows of bodies >= B are zero.
+// backward, vertex side, one CTA per (256-vertex chunk, body):
+//   g   = dL/dverts: read from gverts, or (FIT) evaluated here from the NN / SDF results
+//   gw  = Rc^T g ;  gvp = Tr^T gw, written as the A operand of the dcoef GEMM
+//         ([body group][coordinate chunk][64 bodies][32 coordinates, swizzled]; rows of bodies >= B zero)
+//   dA partials of the chunk: dApart[chunk][b][j][:] = sum over the chunk's vertices skinned to j of
+//         w * [gw (x) vp | gw]  (row J: sum of gw = d translation).  gw and vp of the chunk sit in
+//         shared memory; work item (j, entry e of 12) walks the chunk's entry list of joint j
+//         (ch_seg / ch_lv / ch_w, built once per model) in a fixed order.  lbs_pose_bwd adds the
+//         chunks up.  (This replaced a per-(joint, body) gather kernel that re-read gw and vp from
+//         L2 for every skinning entry: 37 us at B = 64.)
+template <bool FIT>
 __global__ void __launch_bounds__(256)
 lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restrict__ skin_j,
                       const float *__restrict__ skin_w, const float *__restrict__ A,
-                      const float *__restrict__ cam, long cam_bstride,
-                      const float *__restrict__ gverts, float *__restrict__ gw_out,
-                      float *__restrict__ gvp_out) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+                      const float *__restrict__ vp_in, const float *__restrict__ cam, long cam_bstride,
+                      const float *__restrict__ gverts, const int *__restrict__ ch_seg,
+                      const unsigned char *__restrict__ ch_lv, const float *__restrict__ ch_w, int stage_cap,
+                      float *__restrict__ gvp_out, float *__restrict__ dApart, const VGradFuse fg) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];   // the chunk's entries: stage_cap x (weight, local vertex)
+    __shared__ float s_gw[256 * 3], s_vp[256 * 3];
+    __shared__ float s_cnt, red[8], red3[24];
+    const int tid = threadIdx.x;
+    // the chunk's skinning entries are constants of the model: staged before the dependency wait
+    const int *seg = ch_seg + (size_t)blockIdx.x * (J + 1);
+    const int e0 = seg[0], nent = seg[J] - e0;
+    float *s_w = reinterpret_cast<float *>(dyn_smem);
+    unsigned char *s_lv = dyn_smem + (size_t)stage_cap * 4;
+    const bool staged = nent <= stage_cap;
+    if (staged && blockIdx.y < B)
+        for (int k = tid; k < nent; k += blockDim.x) { s_w[k] = ch_w[e0 + k]; s_lv[k] = ch_lv[e0 + k]; }
+    pdl_launch_dependents();
+    pdl_wait();
+    const int v = blockIdx.x * blockDim.x + tid;
     const int b = blockIdx.y;
-    if (v * 3 >= Npad) return;
     float *gvp_g = gvp_out + (size_t)(b / kBG) * Npad * kBG + (size_t)(b % kBG) * kKC;
     auto put = [&](int n, float x) {
         if (n < Npad) gvp_g[(size_t)(n / kKC) * (kBG * kKC) + swz(b % kBG, n % kKC)] = x;
     };
-    if (v >= V || b >= B) {
+    if (b >= B) {        // padding rows of the GEMM operand (whole CTA)
         put(3 * v, 0.f); put(3 * v + 1, 0.f); put(3 * v + 2, 0.f);
         return;
     }
-    const float *g = gverts + ((size_t)b * V + v) * 3;
-    float gx = g[0], gy = g[1], gz = g[2];
-    if (cam) {
-        const float *C = cam + (size_t)b * cam_bstride;
-        const float x = C[0] * gx + C[4] * gy + C[8] * gz;
-        const float y = C[1] * gx + C[5] * gy + C[9] * gz;
-        const float z = C[2] * gx + C[6] * gy + C[10] * gz;
-        gx = x; gy = y; gz = z;
-    }
-    float *gw = gw_out + ((size_t)b * V + v) * 3;
-    gw[0] = gx; gw[1] = gy; gw[2] = gz;
-    float T[9];
-#pragma unroll
-    for (int e = 0; e < 9; ++e) T[e] = 0.f;
-    const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
-    for (int k = 0; k < KW; ++k) {
-        const int j = skin_j[(size_t)v * KW + k];
-        const float wt = skin_w[(size_t)v * KW + k];
-        const float4 r0 = __ldg(Ab + j * 3), r1 = __ldg(Ab + j * 3 + 1), r2 = __ldg(Ab + j * 3 + 2);
-        T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]);
-        T[3] = fmaf(wt, r1.x, T[3]); T[4] = fmaf(wt, r1.y, T[4]); T[5] = fmaf(wt, r1.z, T[5]);
-        T[6] = fmaf(wt, r2.x, T[6]); T[7] = fmaf(wt, r2.y, T[7]); T[8] = fmaf(wt, r2.z, T[8]);
-    }
-    put(3 * v, T[0] * gx + T[3] * gy + T[6] * gz);
-    put(3 * v + 1, T[1] * gx + T[4] * gy + T[7] * gz);
-    put(3 * v + 2, T[2] * gx + T[5] * gy + T[8] * gz);
-}
-
-// dA[b,j,:] = sum over the vertices skinned to j of w * [gw (x) vp | gw]; block (J, b) sums gw.
-__global__ void __launch_bounds__(128)
-lbs_dA_kernel(int V, int J, const int *__restrict__ jl_start, const int *__restrict__ jl_vert,
-              const float *__restrict__ jl_w, const float *__restrict__ gw,
-              const float *__restrict__ vp, float *__restrict__ dA, float *__restrict__ dtr) {
-    const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    float acc[12];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) acc[e] = 0.f;
-    const float *gwb = gw + (size_t)b * V * 3, *vpb = vp + (size_t)b * V * 3;
-    if (j < J) {
-        const int s = jl_start[j], e_end = jl_start[j + 1];
-        for (int e = s + tid; e < e_end; e += blockDim.x) {
-            const int v = jl_vert[e];
-            const float w = jl_w[e];
-            const float g0 = w * gwb[v * 3], g1 = w * gwb[v * 3 + 1], g2 = w * gwb[v * 3 + 2];
-            const float x = vpb[v * 3], y = vpb[v * 3 + 1], z = vpb[v * 3 + 2];
-            acc[0] = fmaf(g0, x, acc[0]); acc[1] = fmaf(g0, y, acc[1]); acc[2] = fmaf(g0, z, acc[2]); acc[3] += g0;
-            acc[4] = fmaf(g1, x, acc[4]); acc[5] = fmaf(g1, y, acc[5]); acc[6] = fmaf(g1, z, acc[6]); acc[7] += g1;
-            acc[8] = fmaf(g2, x, acc[8]); acc[9] = fmaf(g2, y, acc[9]); acc[10] = fmaf(g2, z, acc[10]); acc[11] += g2;
+    if (FIT) {
+        if (tid < 32) {      // number of penetrating vertices of the body: lane-strided loads, shuffle tree (fixed order)
+            float c = 0.f;
+            for (int i = tid; i < fg.np_sdf; i += 32) c += fg.partial[((size_t)b * fg.np_sdf + i) * 2 + 1];
+            c = warp_sum(c);
+            if (tid == 0) s_cnt = c;
         }
+        __syncthreads();
+    }
+    float gx = 0.f, gy = 0.f, gz = 0.f, px = 0.f, py = 0.f, pz = 0.f, closs = 0.f;
+    if (v < V) {
+        const size_t o = (size_t)b * V + v;
+        if (FIT) {
+            if (fg.sdfv[o] < 0.f) {   // d/dv [ w * sum(-sdf)/cnt ]
+                const float k = -fg.w_coll / s_cnt;
+                gx = k * fg.sdfg[o * 3];
+                gy = k * fg.sdfg[o * 3 + 1];
+                gz = k * fg.sdfg[o * 3 + 2];
+            }
+            const int slot = fg.cslot[v];
+            if (slot >= 0) {
+                const float dd = fg.nnd[(size_t)b * fg.nu + slot];
+                const float s = sqrtf(dd + 1e-4f);
+                const float den = s + fg.robust_c;
+                const float wgt = fg.cweight[v];
+                closs = wgt * (s / den);
+                // d/dd [ s/(s+c) ] = c/(s+c)^2 * 1/(2s);   d dd/dp = 2 (p - q)   (chamfer.cu:165-168)
+                const float gd = (fg.w_contact / (float)fg.num_contact) * wgt * (fg.robust_c / (den * den)) * (0.5f / s);
+                const float g2 = gd * 2.0f;
+                const float *q = fg.scene + (size_t)fg.nni[(size_t)b * fg.nu + slot] * 3;
+                gx += g2 * (fg.verts[o * 3] - q[0]);
+                gy += g2 * (fg.verts[o * 3 + 1] - q[1]);
+                gz += g2 * (fg.verts[o * 3 + 2] - q[2]);
+            }
+        } else {
+            gx = gverts[o * 3]; gy = gverts[o * 3 + 1]; gz = gverts[o * 3 + 2];
+        }
+        if (cam) {
+            const float *C = cam + (size_t)b * cam_bstride;
+            const float x = C[0] * gx + C[4] * gy + C[8] * gz;
+            const float y = C[1] * gx + C[5] * gy + C[9] * gz;
+            const float z = C[2] * gx + C[6] * gy + C[10] * gz;
+            gx = x; gy = y; gz = z;
+        }
+        float T[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) T[e] = 0.f;
+        const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
+        for (int k = 0; k < KW; ++k) {
+            const int j = skin_j[(size_t)v * KW + k];
+            const float wt = skin_w[(size_t)v * KW + k];
+            const float4 r0 = __ldg(Ab + j * 3), r1 = __ldg(Ab + j * 3 + 1), r2 = __ldg(Ab + j * 3 + 2);
+            T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]);
+            T[3] = fmaf(wt, r1.x, T[3]); T[4] = fmaf(wt, r1.y, T[4]); T[5] = fmaf(wt, r1.z, T[5]);
+            T[6] = fmaf(wt, r2.x, T[6]); T[7] = fmaf(wt, r2.y, T[7]); T[8] = fmaf(wt, r2.z, T[8]);
+        }
+        put(3 * v, T[0] * gx + T[3] * gy + T[6] * gz);
+        put(3 * v + 1, T[1] * gx + T[4] * gy + T[7] * gz);
+        put(3 * v + 2, T[2] * gx + T[5] * gy + T[8] * gz);
+        const float *vp = vp_in + o * 3;
+        px = vp[0]; py = vp[1]; pz = vp[2];
     } else {
-        for (int v = tid; v < V; v += blockDim.x) {
-            acc[0] += gwb[v * 3]; acc[1] += gwb[v * 3 + 1]; acc[2] += gwb[v * 3 + 2];
-        }
+        put(3 * v, 0.f); put(3 * v + 1, 0.f); put(3 * v + 2, 0.f);
     }
-    __shared__ float red[4][12];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
-    if ((tid & 31) == 0) {
-#pragma unroll
-        for (int e = 0; e < 12; ++e) red[tid >> 5][e] = acc[e];
+    s_gw[tid * 3] = gx; s_gw[tid * 3 + 1] = gy; s_gw[tid * 3 + 2] = gz;
+    s_vp[tid * 3] = px; s_vp[tid * 3 + 1] = py; s_vp[tid * 3 + 2] = pz;
+    {   // per-warp sums of gw (row J of the partials = d translation) and of the contact loss
+        const float sx = warp_sum(gx), sy = warp_sum(gy), sz = warp_sum(gz);
+        if ((tid & 31) == 0) { red3[(tid >> 5) * 3] = sx; red3[(tid >> 5) * 3 + 1] = sy; red3[(tid >> 5) * 3 + 2] = sz; }
+        if (FIT) {
+            closs = warp_sum(closs);
+            if ((tid & 31) == 0) red[tid >> 5] = closs;
+        }
     }
     __syncthreads();
-    if (tid < 12) {
-        const float s = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-        if (j < J) dA[((size_t)b * J + j) * 12 + tid] = s;
-        else if (tid < 3) dtr[(size_t)b * 3 + tid] = s;
+    if (FIT && tid == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        fg.cpart[(size_t)b * gridDim.x + blockIdx.x] = s;
+    }
+    // dA partial sums of this chunk: item (j, r) = row r of sum over the entries of joint j of
+    // (w gw_r) * [vp | 1], entries in ascending vertex order (4 outputs share the entry's loads)
+    float *outp = dApart + ((size_t)blockIdx.x * B + b) * (J + 1) * 12;
+    for (int item = tid; item < (J + 1) * 3; item += blockDim.x) {
+        const int j = item / 3, r = item - j * 3;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (j < J) {
+            const int k0 = seg[j] - e0, k1 = seg[j + 1] - e0;
+            if (staged) {
+#pragma unroll 4
+                for (int k = k0; k < k1; ++k) {
+                    const int lv = s_lv[k];
+                    const float g = s_w[k] * s_gw[lv * 3 + r];
+                    a0 = fmaf(g, s_vp[lv * 3], a0); a1 = fmaf(g, s_vp[lv * 3 + 1], a1); a2 = fmaf(g, s_vp[lv * 3 + 2], a2);
+                    a3 += g;
+                }
+            } else {
+#pragma unroll 4
+                for (int k = k0; k < k1; ++k) {
+                    const int lv = ch_lv[e0 + k];
+                    const float g = ch_w[e0 + k] * s_gw[lv * 3 + r];
+                    a0 = fmaf(g, s_vp[lv * 3], a0); a1 = fmaf(g, s_vp[lv * 3 + 1], a1); a2 = fmaf(g, s_vp[lv * 3 + 2], a2);
+                    a3 += g;
+                }
+            }
+        } else {
+            for (int w8 = 0; w8 < 8; ++w8) a0 += red3[w8 * 3 + r];     // row J: entries 0..2 = sum of gw
+        }
+        if (j < J) {
+            *reinterpret_cast<float4 *>(outp + j * 12 + r * 4) = make_float4(a0, a1, a2, a3);
+        } else {
+            outp[J * 12 + r] = a0;
+            if (r == 0)
+                for (int e = 3; e < 12; ++e) outp[J * 12 + e] = 0.f;
+        }
     }
 }
 
@@ -458,6 +568,8 @@ lbs_dcoef_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
     auto issue = [&](int c) {   // thread 0 only; c counts from 0 inside this split
         const int st = c % kDStages;
         mbar_wait(&empty[st], (uint32_t)(((c / kDStages) & 1) ^ 1));
@@ -529,21 +641,29 @@ lbs_dcoef_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd
         }
 }
 
-// dsum[b][k] = sum over the N-splits, in a fixed order (4 interleaved partial sums)
+// out[i] = sum over the leading dimension of in[n][count], fixed order (4 interleaved partial sums);
+// blockIdx.y selects the array: 0 = the dcoef GEMM's N-splits, 1 = the dA chunk partials
 __global__ void __launch_bounds__(256)
-lbs_dcoef_reduce_kernel(const float *__restrict__ part, int nsplit, long per_split, float *__restrict__ dsum) {
+lbs_reduce2_kernel(const float *__restrict__ in0, int n0, long count0, float *__restrict__ out0,
+                   const float *__restrict__ in1, int n1, long count1, float *__restrict__ out1) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const float *__restrict__ in = blockIdx.y ? in1 : in0;
+    float *__restrict__ out = blockIdx.y ? out1 : out0;
+    const int n = blockIdx.y ? n1 : n0;
+    const long count = blockIdx.y ? count1 : count0;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= per_split) return;
+    if (i >= count) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int ns = 0;
-    for (; ns + 4 <= nsplit; ns += 4) {
-        s0 += part[(size_t)ns * per_split + i];
-        s1 += part[(size_t)(ns + 1) * per_split + i];
-        s2 += part[(size_t)(ns + 2) * per_split + i];
-        s3 += part[(size_t)(ns + 3) * per_split + i];
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+        s0 += in[(size_t)k * count + i];
+        s1 += in[(size_t)(k + 1) * count + i];
+        s2 += in[(size_t)(k + 2) * count + i];
+        s3 += in[(size_t)(k + 3) * count + i];
     }
-    for (; ns < nsplit; ++ns) s0 += part[(size_t)ns * per_split + i];
-    dsum[i] = (s0 + s1) + (s2 + s3);
+    for (; k < n; ++k) s0 += in[(size_t)k * count + i];
+    out[i] = (s0 + s1) + (s2 + s3);
 }
 
 // per body: run the chain and Rodrigues backward on the reduced d coef
@@ -551,16 +671,20 @@ __global__ void __launch_bounds__(128)
 lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     const float *__restrict__ Jdirs, const int *__restrict__ parents,
                     const float *__restrict__ pose, const float *__restrict__ saved, SavedLayout L,
-                    const float *__restrict__ dA, const float *__restrict__ dtr,
-                    const float *__restrict__ part, const float *__restrict__ gjoints,
+                    const float *__restrict__ dAsum, const float *__restrict__ part,
+                    const float *__restrict__ gjoints,
                     float *__restrict__ gbetas, float *__restrict__ gpose,
                     float *__restrict__ gtransl, float *__restrict__ grot, int num_rot,
                     const float *__restrict__ rot6d, float *__restrict__ g6_root, float *__restrict__ g6A,
                     int g6_kpad, const psi_lbs_tree tree) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], drel_s[kMaxJ * 3];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
     __shared__ float dbeta_direct[64];
     const int b = blockIdx.x, tid = threadIdx.x;
+    const float *dA = dAsum + (size_t)b * (J + 1) * 12;      // chunk partials already summed; row J = d translation
+    const float *dtr = dA + J * 12;
     const float *iR = saved + L.R + (size_t)b * J * 9, *iJ = saved + L.Jr + (size_t)b * J * 3;
     const float *iGr = saved + L.Gr + (size_t)b * J * 9;
     for (int e = tid; e < J * 9; e += blockDim.x) { sR[e] = iR[e]; sGr[e] = iGr[e]; }
@@ -576,7 +700,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     __syncthreads();
     // dGr = dAr - dAt J^T ; dGt = dAt (+ d posed joints) ; dJ = -Gr^T dAt
     for (int j = tid; j < J; j += blockDim.x) {
-        const float *a = dA + ((size_t)b * J + j) * 12;
+        const float *a = dA + j * 12;
         const float at[3] = {a[3], a[7], a[11]};
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -703,7 +827,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
         gbetas[(size_t)b * NB + l] = s;
     }
     if (gtransl && tid < 3) {
-        float s = dtr[(size_t)b * 3 + tid];
+        float s = dtr[tid];                      // row J of the chunk sums: sum over the vertices of gw
         if (gjoints)
             for (int j = 0; j < J; ++j) s += gjoints[((size_t)b * J + j) * 3 + tid];
         gtransl[(size_t)b * 3 + tid] = s;
@@ -711,21 +835,19 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
 }
 
 struct BwdLayout {
-    size_t gw, gvp, dA, dtr, part, dsum, total;  // in floats
+    size_t gvp, dApart, part, dsum, dA, total;  // in floats
     int Bpad;
 };
 static BwdLayout bwd_layout(const psi_lbs_model *m, int B) {
     BwdLayout l;
     l.Bpad = ((B + kBG - 1) / kBG) * kBG;
     size_t o = 0;
-    l.gw = o;   o += (size_t)B * m->V * 3;
-    o = (o + 31) & ~(size_t)31;
-    l.gvp = o;  o += (size_t)l.Bpad * m->Npad;
-    l.dA = o;   o += (size_t)B * m->J * 12;
-    l.dtr = o;  o += (size_t)B * 3;
+    l.gvp = o;     o += (size_t)l.Bpad * m->Npad;
+    l.dApart = o;  o += (size_t)m->NCH * B * (m->J + 1) * 12;
     o = (o + 3) & ~(size_t)3;
-    l.part = o; o += (size_t)kNSplit * l.Bpad * m->Kpad;
-    l.dsum = o; o += (size_t)l.Bpad * m->Kpad;
+    l.part = o;    o += (size_t)kNSplit * l.Bpad * m->Kpad;
+    l.dsum = o;    o += (size_t)l.Bpad * m->Kpad;
+    l.dA = o;      o += (size_t)B * (m->J + 1) * 12;
     l.total = o;
     return l;
 }
@@ -750,8 +872,8 @@ extern "C" {
 void psi_lbs_model_destroy(psi_lbs_model *m) {
     if (!m) return;
     cudaFree(m->basis_fwd); cudaFree(m->basis_bwd); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
-    cudaFree(m->skin_w); cudaFree(m->jl_w); cudaFree(m->skin_j); cudaFree(m->parents);
-    cudaFree(m->jl_start); cudaFree(m->jl_vert); cudaFree(m->tree_buf);
+    cudaFree(m->skin_w); cudaFree(m->ch_w); cudaFree(m->skin_j); cudaFree(m->parents);
+    cudaFree(m->ch_seg); cudaFree(m->ch_lv); cudaFree(m->tree_buf);
     delete m;
 }
 
@@ -828,7 +950,6 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     m->KW = KW;
     std::vector<int> skin_j((size_t)V * KW, 0);
     std::vector<float> skin_w((size_t)V * KW, 0.f);
-    std::vector<int> count(J + 1, 0);
     for (int v = 0; v < V; ++v) {
         int c = 0;
         for (int j = 0; j < J; ++j) {
@@ -837,24 +958,33 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
                 skin_j[(size_t)v * KW + c] = j;
                 skin_w[(size_t)v * KW + c] = w;
                 ++c;
-                ++count[j + 1];
             }
         }
     }
-    std::vector<int> jl_start(J + 1, 0);
-    for (int j = 0; j < J; ++j) jl_start[j + 1] = jl_start[j] + count[j + 1];
-    m->nnz = jl_start[J];
-    std::vector<int> jl_vert((size_t)m->nnz), fill(jl_start.begin(), jl_start.end() - 1);
-    std::vector<float> jl_w((size_t)m->nnz);
-    for (int v = 0; v < V; ++v)
-        for (int j = 0; j < J; ++j) {
-            const float w = h_weights[(size_t)v * J + j];
-            if (w != 0.f) {
-                jl_vert[fill[j]] = v;
-                jl_w[fill[j]] = w;
-                ++fill[j];
+    // per 256-vertex chunk: the skinning entries bucketed by joint (local vertex, weight), ascending
+    // vertex order inside a bucket -- the fixed summation order of the dA partials
+    m->NCH = ((m->Npad + 2) / 3 + 255) / 256;
+    std::vector<int> ch_seg((size_t)m->NCH * (J + 1), 0);
+    std::vector<unsigned char> ch_lv;
+    std::vector<float> ch_w;
+    m->nnz = 0;
+    for (int c = 0; c < m->NCH; ++c)
+        for (int j = 0; j <= J; ++j) {
+            ch_seg[(size_t)c * (J + 1) + j] = (int)ch_lv.size();
+            if (j == J) break;
+            for (int lv = 0; lv < 256; ++lv) {
+                const int v = c * 256 + lv;
+                if (v >= V) break;
+                const float w = h_weights[(size_t)v * J + j];
+                if (w != 0.f) { ch_lv.push_back((unsigned char)lv); ch_w.push_back(w); }
             }
         }
+    m->nnz = (long)ch_lv.size();
+    m->max_ent = 0;
+    for (int c = 0; c < m->NCH; ++c) {
+        const int ne = ch_seg[(size_t)c * (J + 1) + J] - ch_seg[(size_t)c * (J + 1)];
+        m->max_ent = ne > m->max_ent ? ne : m->max_ent;
+    }
     std::vector<int> parents(h_parents, h_parents + J);
     parents[0] = -1;
     // tree levels and children lists, packed: [lvl_start (J+1) | lvl_joint (J) | child_start (J+1) | child_list (J)]
@@ -882,9 +1012,9 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     if (rc == PSI_OK) rc = upload(&m->skin_j, skin_j, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->skin_w, skin_w, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->parents, parents, st, &m->bytes);
-    if (rc == PSI_OK) rc = upload(&m->jl_start, jl_start, st, &m->bytes);
-    if (rc == PSI_OK) rc = upload(&m->jl_vert, jl_vert, st, &m->bytes);
-    if (rc == PSI_OK) rc = upload(&m->jl_w, jl_w, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->ch_seg, ch_seg, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->ch_lv, ch_lv, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->ch_w, ch_w, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->tree_buf, treebuf, st, &m->bytes);
     if (rc == PSI_OK) {
         m->tree.nlev = nlev;
@@ -906,6 +1036,11 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
 }
 
 size_t psi_lbs_model_bytes(const psi_lbs_model *m) { return m ? m->bytes : 0; }
+}  // extern "C"
+namespace psi {
+int lbs_vertex_chunks(const psi_lbs_model *m) { return m ? m->NCH : 0; }
+}
+extern "C" {
 
 size_t psi_lbs_saved_floats(const psi_lbs_model *m, int B) {
     if (!m || B <= 0) return 0;
@@ -920,7 +1055,7 @@ namespace psi {
 int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float *pose,
                  const float *transl, const float *cam, long cam_bstride, const float *rot_in,
                  const float *rot6d, int num_rot, float *verts, float *joints, float *saved,
-                 cudaStream_t st) {
+                 const SdfFuse *sdf, cudaStream_t st) {
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!betas || !pose || !verts || !saved) return PSI_ERR_BAD_ARG;
@@ -928,11 +1063,11 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
     if (B > 65535) return PSI_ERR_UNSUPPORTED;
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
-    lbs_pose_fwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
+    launch_pdl(lbs_pose_fwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
                                           B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, m->tree);
     PSI_LAUNCHED_K("lbs_pose_fwd");
     if (B % kBG) {
-        lbs_zero_coef_pad_kernel<<<8, 256, 0, st>>>(saved + L.coef, B, m->Kpad);
+        launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef, B, m->Kpad);
         PSI_LAUNCHED_K("lbs_zero_coef_pad");
     }
     BlendFwdParams p;
@@ -945,13 +1080,17 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
         attr_set = true;
     }
     dim3 grid((unsigned)m->NT, (unsigned)((B + kBG - 1) / kBG));
-    lbs_blend_fwd_kernel<<<grid, 128, smem, st>>>(p);
+    launch_pdl(lbs_blend_fwd_kernel, dim3(grid), dim3(128), smem, st, p);
     PSI_LAUNCHED_K("lbs_blend_fwd");
     {
         dim3 sgrid((unsigned)((m->V + 255) / 256), (unsigned)B);
-        lbs_skin_fwd_kernel<<<sgrid, 256, 0, st>>>(m->V, m->J, m->KW, m->skin_j, m->skin_w, saved + L.A, saved + L.vp,
-                                                   transl, cam, cam_bstride, verts);
-        PSI_LAUNCHED_K("lbs_skin_fwd");
+        if (sdf)
+            launch_pdl(lbs_skin_fwd_kernel<true>, sgrid, dim3(256), 0, st, m->V, m->J, m->KW, m->skin_j, m->skin_w,
+                       saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, *sdf);
+        else
+            launch_pdl(lbs_skin_fwd_kernel<false>, sgrid, dim3(256), 0, st, m->V, m->J, m->KW, m->skin_j, m->skin_w,
+                       saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, SdfFuse());
+        PSI_LAUNCHED_K(sdf ? "lbs_skin_sdf_fwd" : "lbs_skin_fwd");
     }
     return PSI_OK;
 }
@@ -964,7 +1103,7 @@ int psi_lbs_fwd(const psi_lbs_model *m, int B, const float *betas, const float *
                 int num_rot, float *verts, float *joints, float *saved, psi_stream_t stream) {
     if (num_rot > 0 && !rot_in) return PSI_ERR_BAD_ARG;
     return psi::lbs_fwd_impl(m, B, betas, pose, transl, cam, cam_bstride, rot_in, nullptr, num_rot, verts,
-                             joints, saved, (cudaStream_t)stream);
+                             joints, saved, nullptr, (cudaStream_t)stream);
 }
 
 size_t psi_lbs_bwd_workspace_bytes(const psi_lbs_model *m, int B) {
@@ -978,44 +1117,35 @@ namespace psi {
 // psi_lbs_bwd2 + the 6D variant: with rot6d the gradient of the leading joints is returned through
 // the Gram-Schmidt backward (g6_root [B,6], g6A = GEMM operand layout, see lbs_pose_bwd_kernel)
 int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *cam, long cam_bstride,
-                 const float *saved, const float *grad_verts, const float *grad_joints, float *grad_betas,
-                 float *grad_pose, float *grad_transl, float *grad_rot, int num_rot, const float *rot6d,
-                 float *g6_root, float *g6A, int g6_kpad, void *workspace, size_t workspace_bytes,
-                 psi_stream_t stream, psi_stream_t side_stream, void *ev_fork, void *ev_join) {
-    // optional side stream: lbs_dA runs next to lbs_dcoef (both only depend on lbs_vertex_bwd)
-    cudaStream_t side = (side_stream && ev_fork && ev_join) ? (cudaStream_t)side_stream : nullptr;
+                 const float *saved, const float *grad_verts, const VGradFuse *vg, const float *grad_joints,
+                 float *grad_betas, float *grad_pose, float *grad_transl, float *grad_rot, int num_rot,
+                 const float *rot6d, float *g6_root, float *g6A, int g6_kpad, void *workspace,
+                 size_t workspace_bytes, cudaStream_t st) {
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
-    if (!pose || !saved || !grad_verts || !grad_betas || !grad_pose || !workspace) return PSI_ERR_BAD_ARG;
+    if (!pose || !saved || (!grad_verts && !vg) || !grad_betas || !grad_pose || !workspace) return PSI_ERR_BAD_ARG;
     if (num_rot < 0 || num_rot > m->J || (num_rot > 0 && !grad_rot && !rot6d)) return PSI_ERR_BAD_ARG;
     if (rot6d && (!g6_root || !g6A || g6_kpad < (num_rot - 1) * 6)) return PSI_ERR_BAD_ARG;
     if (B > 65535) return PSI_ERR_UNSUPPORTED;
     const BwdLayout W = bwd_layout(m, B);
     if (workspace_bytes < W.total * sizeof(float)) return PSI_ERR_WORKSPACE;
     if (((uintptr_t)workspace & 15u) != 0) return PSI_ERR_BAD_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
     float *ws = reinterpret_cast<float *>(workspace);
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     {
-        dim3 grid((unsigned)(((m->Npad + 2) / 3 + 255) / 256), (unsigned)W.Bpad);
-        lbs_vertex_bwd_kernel<<<grid, 256, 0, st>>>(m->V, m->J, m->KW, m->Npad, B, m->skin_j,
-                                                    m->skin_w, saved + L.A, cam, cam_bstride,
-                                                    grad_verts, ws + W.gw, ws + W.gvp);
-        PSI_LAUNCHED_K("lbs_vertex_bwd");
-    }
-    {
-        cudaStream_t sa = st;
-        if (side) {
-            if (cudaEventRecord((cudaEvent_t)ev_fork, st) != cudaSuccess ||
-                cudaStreamWaitEvent(side, (cudaEvent_t)ev_fork, 0) != cudaSuccess)
-                return PSI_ERR_BAD_ARG;
-            sa = side;
-        }
-        dim3 grid((unsigned)(m->J + 1), (unsigned)B);
-        lbs_dA_kernel<<<grid, 128, 0, sa>>>(m->V, m->J, m->jl_start, m->jl_vert, m->jl_w,
-                                            ws + W.gw, saved + L.vp, ws + W.dA, ws + W.dtr);
-        PSI_LAUNCHED_K("lbs_dA");
-        if (side && cudaEventRecord((cudaEvent_t)ev_join, side) != cudaSuccess) return PSI_ERR_BAD_ARG;
+        dim3 grid((unsigned)m->NCH, (unsigned)W.Bpad);
+        // the chunk's skinning entries are staged in shared memory when they fit (5 bytes each)
+        const int cap = m->max_ent <= 8192 ? ((m->max_ent + 3) & ~3) : 0;
+        const size_t smem = (size_t)cap * 5;
+        if (vg)
+            launch_pdl(lbs_vertex_bwd_kernel<true>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
+                       m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
+                       m->ch_w, cap, ws + W.gvp, ws + W.dApart, *vg);
+        else
+            launch_pdl(lbs_vertex_bwd_kernel<false>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
+                       m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
+                       m->ch_w, cap, ws + W.gvp, ws + W.dApart, VGradFuse());
+        PSI_LAUNCHED_K(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd");
     }
     {
         const size_t smem = (size_t)kDStages * kDStageBytes;
@@ -1025,17 +1155,20 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
             attr_set = true;
         }
         dim3 grid((unsigned)(m->Kpad / kDK), (unsigned)kNSplit, (unsigned)(W.Bpad / kBG));
-        lbs_dcoef_kernel<<<grid, 256, smem, st>>>(m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp, ws + W.part, kNSplit);
+        launch_pdl(lbs_dcoef_kernel, grid, dim3(256), smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp,
+                   ws + W.part, kNSplit);
         PSI_LAUNCHED_K("lbs_dcoef");
-        const long per_split = (long)W.Bpad * m->Kpad;
-        lbs_dcoef_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(ws + W.part, kNSplit, per_split, ws + W.dsum);
-        PSI_LAUNCHED_K("lbs_dcoef_reduce");
     }
-    if (side && cudaStreamWaitEvent(st, (cudaEvent_t)ev_join, 0) != cudaSuccess) return PSI_ERR_BAD_ARG;
-    lbs_pose_bwd_kernel<<<B, 128, 0, st>>>(m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
-                                          m->parents, pose, saved, L, ws + W.dA, ws + W.dtr,
-                                          ws + W.dsum, grad_joints, grad_betas, grad_pose,
-                                          grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree);
+    {
+        const long c0 = (long)W.Bpad * m->Kpad, c1 = (long)B * (m->J + 1) * 12;
+        dim3 grid((unsigned)(((c0 > c1 ? c0 : c1) + 255) / 256), 2);
+        launch_pdl(lbs_reduce2_kernel, grid, dim3(256), 0, st, ws + W.part, kNSplit, c0, ws + W.dsum, ws + W.dApart,
+                   m->NCH, c1, ws + W.dA);
+        PSI_LAUNCHED_K("lbs_reduce2");
+    }
+    launch_pdl(lbs_pose_bwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
+               m->parents, pose, saved, L, ws + W.dA, ws + W.dsum, grad_joints, grad_betas,
+               grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree);
     PSI_LAUNCHED_K("lbs_pose_bwd");
     return PSI_OK;
 }
@@ -1048,11 +1181,11 @@ int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, const float 
                  const float *grad_joints, float *grad_betas, float *grad_pose, float *grad_transl,
                  float *grad_rot, int num_rot, void *workspace, size_t workspace_bytes,
                  psi_stream_t stream, psi_stream_t side_stream, void *ev_fork, void *ev_join) {
-    (void)betas;
-    if (num_rot > 0 && !grad_rot) return PSI_ERR_BAD_ARG;
-    return psi::lbs_bwd_impl(m, B, pose, cam, cam_bstride, saved, grad_verts, grad_joints, grad_betas, grad_pose,
-                             grad_transl, grad_rot, num_rot, nullptr, nullptr, nullptr, 0, workspace,
-                             workspace_bytes, stream, side_stream, ev_fork, ev_join);
+    (void)betas; (void)side_stream; (void)ev_fork; (void)ev_join;   // the backward is 3 launches on one stream now
+    if (!grad_verts || (num_rot > 0 && !grad_rot)) return PSI_ERR_BAD_ARG;
+    return psi::lbs_bwd_impl(m, B, pose, cam, cam_bstride, saved, grad_verts, nullptr, grad_joints, grad_betas,
+                             grad_pose, grad_transl, grad_rot, num_rot, nullptr, nullptr, nullptr, 0, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
 }
 
 int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *pose,

@@ -136,6 +136,8 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         __syncthreads();
         boxes = s4;
     }
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long warps = (long)gridDim.x * (blockDim.x >> 5);
     for (long t = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += warps) {
@@ -241,6 +243,8 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
         for (int i = threadIdx.x; i < ntop2 * 3; i += blockDim.x) s4[i] = __ldg(ix.box2 + i);
         __syncthreads();
     }
+    pdl_launch_dependents();
+    pdl_wait();
     const int sbase = ix.mpad, cbase = ix.mpad + ix.num_supers;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
         const long b = t / n;
@@ -443,6 +447,8 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         top_lo = s4;
         top_hi = s4 + ntop;
     }
+    pdl_launch_dependents();
+    pdl_wait();
     const float4 *__restrict__ c_lo = ix.boxes + ntop, *__restrict__ c_hi = ix.boxes + ix.nbox + ntop;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -742,9 +748,9 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         if (blocks > cap) blocks = cap;
         const size_t top_bytes = (size_t)2 * (ix->mpad + ix->num_supers) * sizeof(float4);
         if (top_bytes <= 24 * 1024)
-            nn_index_group_kernel<true><<<(unsigned)blocks, kGrpThreads, top_bytes, st>>>(*ix, q, q_bstride, n, qsel, B, dist, idx, hint);
+            launch_pdl(nn_index_group_kernel<true>, dim3((unsigned)blocks), dim3(kGrpThreads), top_bytes, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint);
         else
-            nn_index_group_kernel<false><<<(unsigned)blocks, kGrpThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, B, dist, idx, hint);
+            launch_pdl(nn_index_group_kernel<false>, dim3((unsigned)blocks), dim3(kGrpThreads), 0, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint);
     } else if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
         // one thread per query: enough queries to fill the machine with 256-thread CTAs
         long blocks = (total + 255) / 256;
@@ -753,17 +759,17 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         const size_t top_bytes = (size_t)3 * ((ix->mpad + ix->num_supers) / 2) * sizeof(float4);
         // 64 registers (no spills with the packed pairs), 4 CTAs/SM; measured best of 3/4/5/6/8
         if (top_bytes <= 24 * 1024)
-            nn_index_thread_kernel<true><<<(unsigned)blocks, 256, top_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            launch_pdl(nn_index_thread_kernel<true>, dim3((unsigned)blocks), dim3(256), top_bytes, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
         else
-            nn_index_thread_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            launch_pdl(nn_index_thread_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     } else {
         long blocks = (total + wpb - 1) / wpb;
         const long cap = (long)PSI_NUM_SMS * (smem ? 3 : 4);
         if (blocks > cap) blocks = cap;
         if (smem)
-            nn_index_query_kernel<true><<<(unsigned)blocks, kIdxThreads, box_bytes, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            launch_pdl(nn_index_query_kernel<true>, dim3((unsigned)blocks), dim3(kIdxThreads), box_bytes, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
         else
-            nn_index_query_kernel<false><<<(unsigned)blocks, kIdxThreads, 0, st>>>(*ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            launch_pdl(nn_index_query_kernel<false>, dim3((unsigned)blocks), dim3(kIdxThreads), 0, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
     }
     PSI_LAUNCHED_K(mode == 3 ? "nn_index_group" : "nn_index_query");
     return PSI_OK;

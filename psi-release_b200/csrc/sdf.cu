@@ -10,6 +10,7 @@
 // registers; per-(body, chunk) partial sums of (-sdf, 1) over sdf<0 are reduced in a fixed
 // order (shuffle tree + fixed-order smem pass) so the collision term is reproducible.
 #include "common.cuh"
+#include "sdf_sample.cuh"
 
 namespace psi {
 
@@ -29,10 +30,20 @@ sdf_fwd_kernel(const float *__restrict__ sdf, int D, const SdfScenes sc,
                const float *__restrict__ verts, int V, const int *__restrict__ body_scene,
                float *__restrict__ out, float *__restrict__ grad, float *__restrict__ partial,
                int num_partials) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     const int scene = body_scene ? body_scene[b] : 0;
     const float *__restrict__ grid = sdf + (size_t)scene * D * D * D;
-    const float dm1 = (float)(D - 1);
+    SdfGrid gp;
+    gp.grid = grid;
+    gp.D = D;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        gp.gmin[a] = sc.gmin[scene][a];
+        gp.inv_extent[a] = sc.inv_extent[scene][a];
+        gp.gscale[a] = sc.gscale[scene][a];
+    }
     float neg_sum = 0.f, neg_cnt = 0.f;
 
 #pragma unroll
@@ -40,56 +51,13 @@ sdf_fwd_kernel(const float *__restrict__ sdf, int D, const SdfScenes sc,
         const int v = blockIdx.x * kSdfChunk + r * kSdfThreads + threadIdx.x;
         if (v >= V) continue;
         const size_t o = (size_t)b * V + v;
-        float f[3], gm[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float x = __ldg(verts + o * 3 + a);
-            // reference operation order: (v-min)/(max-min)*2-1, then ((u+1)/2)*(D-1)
-            const float u = (x - sc.gmin[scene][a]) * sc.inv_extent[scene][a] * 2.0f - 1.0f;
-            float c = ((u + 1.0f) * 0.5f) * dm1;
-            float mult = sc.gscale[scene][a];
-            if (!(c > 0.0f)) { c = 0.0f; mult = 0.0f; }          // border clamp, zero gradient
-            else if (c >= dm1) { c = dm1; mult = 0.0f; }
-            f[a] = c;
-            gm[a] = mult;
-        }
-        int i0[3];
-        float w0[3], w1[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float fl = floorf(f[a]);
-            i0[a] = (int)fl;
-            w1[a] = f[a] - fl;
-            w0[a] = (fl + 1.0f) - f[a];
-        }
-        const int x1 = min(i0[0] + 1, D - 1), y1 = min(i0[1] + 1, D - 1), z1 = min(i0[2] + 1, D - 1);
-        // corners past the border carry weight 0 (f is clamped to D-1 => w1 == 0): clamping the
-        // index keeps the load in bounds without changing the value.
-        const size_t r00 = ((size_t)i0[0] * D + i0[1]) * D, r01 = ((size_t)i0[0] * D + y1) * D;
-        const size_t r10 = ((size_t)x1 * D + i0[1]) * D, r11 = ((size_t)x1 * D + y1) * D;
-        const float s000 = __ldg(grid + r00 + i0[2]), s001 = __ldg(grid + r00 + z1);
-        const float s010 = __ldg(grid + r01 + i0[2]), s011 = __ldg(grid + r01 + z1);
-        const float s100 = __ldg(grid + r10 + i0[2]), s101 = __ldg(grid + r10 + z1);
-        const float s110 = __ldg(grid + r11 + i0[2]), s111 = __ldg(grid + r11 + z1);
-        const bool xin = i0[0] + 1 <= D - 1, yin = i0[1] + 1 <= D - 1, zin = i0[2] + 1 <= D - 1;
-        const float wx0 = w0[0], wx1 = xin ? w1[0] : 0.f;
-        const float wy0 = w0[1], wy1 = yin ? w1[1] : 0.f;
-        const float wz0 = w0[2], wz1 = zin ? w1[2] : 0.f;
-        // interpolate along z, then y, then x
-        const float c00 = s000 * wz0 + s001 * wz1, c01 = s010 * wz0 + s011 * wz1;
-        const float c10 = s100 * wz0 + s101 * wz1, c11 = s110 * wz0 + s111 * wz1;
-        const float c0 = c00 * wy0 + c01 * wy1, c1 = c10 * wy0 + c11 * wy1;
-        const float val = c0 * wx0 + c1 * wx1;
+        float g3[3];
+        const float val = sdf_sample(gp, __ldg(verts + o * 3), __ldg(verts + o * 3 + 1), __ldg(verts + o * 3 + 2), g3);
         out[o] = val;
         if (grad) {
-            const float gx = xin ? (c1 - c0) : 0.f;
-            const float gy = yin ? ((c01 - c00) * wx0 + (c11 - c10) * wx1) : 0.f;
-            const float d00 = zin ? (s001 - s000) : 0.f, d01 = zin ? (s011 - s010) : 0.f;
-            const float d10 = zin ? (s101 - s100) : 0.f, d11 = zin ? (s111 - s110) : 0.f;
-            const float gz = (d00 * wy0 + d01 * wy1) * wx0 + (d10 * wy0 + d11 * wy1) * wx1;
-            grad[o * 3 + 0] = gx * gm[0];
-            grad[o * 3 + 1] = gy * gm[1];
-            grad[o * 3 + 2] = gz * gm[2];
+            grad[o * 3 + 0] = g3[0];
+            grad[o * 3 + 1] = g3[1];
+            grad[o * 3 + 2] = g3[2];
         }
         if (val < 0.f) {
             neg_sum -= val;
@@ -154,7 +122,7 @@ int psi_sdf_fwd(const float *sdf, int S, int D, const float *h_grid_min, const f
         }
     const int np = psi_sdf_num_partials(V);
     dim3 grid((unsigned)np, (unsigned)B);
-    psi::sdf_fwd_kernel<<<grid, psi::kSdfThreads, 0, (cudaStream_t)stream>>>(
+    launch_pdl(psi::sdf_fwd_kernel, dim3(grid), dim3(psi::kSdfThreads), 0, (cudaStream_t)stream, 
         sdf, D, sc, verts, V, body_scene, out, grad, partial, np);
     PSI_LAUNCHED_K("sdf_fwd");
     return PSI_OK;
