@@ -392,13 +392,21 @@ __device__ __forceinline__ unsigned box_lb_group(const float4 lo, const float4 h
     return __float_as_uint(__fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy))));
 }
 
-// minimum distance from (qx,qy,qz) (given negated, duplicated) to the 32 points of leaf c
-__device__ __forceinline__ float leaf_min(const float4 *__restrict__ pts2, int c, float2 n2x, float2 n2y, float2 n2z) {
+// minimum distance from (qx,qy,qz) (given negated, duplicated) to the 32 points of leaf c (warp-uniform).
+// The leaf (1 kB) is fetched by the warp with two coalesced 512-byte loads into its shared-memory
+// slot and then read back as broadcasts: one L1 round trip per leaf instead of 32 uniform loads.
+__device__ __forceinline__ float leaf_min(const float4 *__restrict__ pts2, int c, float4 *wbuf, int lane,
+                                          float2 n2x, float2 n2y, float2 n2z) {
     const float4 *p = pts2 + (size_t)c * kLeaf;                 // 16 pairs x 2 float4
+    const float4 v0 = __ldg(p + lane), v1 = __ldg(p + 32 + lane);
+    __syncwarp();                                               // the previous leaf has been consumed
+    wbuf[lane] = v0;
+    wbuf[32 + lane] = v1;
+    __syncwarp();
     float lm = CUDART_INF_F;
 #pragma unroll 8
     for (int i = 0; i < kLeaf / 2; ++i) {
-        const float4 u = __ldg(p + 2 * i), w = __ldg(p + 2 * i + 1);
+        const float4 u = wbuf[2 * i], w = wbuf[2 * i + 1];
         const float2 dx = __fadd2_rn(make_float2(u.x, u.y), n2x);
         const float2 dy = __fadd2_rn(make_float2(u.z, u.w), n2y);
         const float2 dz = __fadd2_rn(make_float2(w.x, w.y), n2z);
@@ -435,6 +443,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
     // mega + super boxes (lo | hi, SoA) in shared memory; cluster boxes come through L1
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float4 s_sub[kGrpThreads / 32][4][2];            // per warp: 4 sub-group query boxes {lo, ub bits | hi}
+    __shared__ float4 s_leaf[kGrpThreads / 32][2 * kLeaf];      // per warp: the leaf being evaluated
     const int ntop = ix.mpad + ix.num_supers;
     const float4 *top_lo = ix.boxes, *top_hi = ix.boxes + ix.nbox;
     if (SMEM) {
@@ -485,7 +494,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         int bleaf = -1;              // ... the leaf it was found in ...
         int bi = -1;                 // ... and its original index once known (-1: not recovered yet)
         auto visit = [&](int c) {    // all lanes, warp-uniform c
-            const float lm = leaf_min(ix.pts2, c, n2x, n2y, n2z);
+            const float lm = leaf_min(ix.pts2, c, s_leaf[threadIdx.x >> 5], lane, n2x, n2y, n2z);
             if (lm < bd) {
                 bd = lm; bleaf = c; bi = -1;
             } else if (lm == bd && c != bleaf && bleaf >= 0) {   // exact tie between two leaves
@@ -743,8 +752,9 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
     if (mode == 3) {
         // one warp per 32 consecutive queries of a body (coherent query order: the fitting loop)
         const long ngroups = (long)B * ((n + 31) / 32);
+        // one group per warp: the hardware block scheduler balances the uneven walks
         long blocks = (ngroups + kGrpThreads / 32 - 1) / (kGrpThreads / 32);
-        const long cap = (long)PSI_NUM_SMS * 16;
+        const long cap = 1L << 20;
         if (blocks > cap) blocks = cap;
         const size_t top_bytes = (size_t)2 * (ix->mpad + ix->num_supers) * sizeof(float4);
         if (top_bytes <= 24 * 1024)
