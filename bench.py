@@ -152,15 +152,18 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
         "lbs_blend_fwd": basis + B * 506 * 4 + B * V * 12,
         "lbs_dcoef": basis + B * V * 12 + B * 506 * 4,
         "lbs_skin_fwd": 2 * B * V * 12 + V * 55 * 4 + B * 55 * 48,
+        # skinning (v_posed in, vertices out, dense weights) + the SDF lookup's 32 B gathered, value + gradient out
+        "lbs_skin_sdf_fwd": 2 * B * V * 12 + V * 55 * 4 + B * 55 * 48 + B * V * (32 + 4 + 12),
         "lbs_vertex_bwd": 3 * B * V * 12 + V * 55 * 4 + B * 55 * 48,
-        "lbs_dA": 2 * B * V * 12 + V * 55 * 4 + B * 55 * 48,
-        "lbs_dcoef_reduce": 75 * B * 512 * 4,
+        # loss gradient inputs (sdf value+gradient, NN dist+idx, vertex, scene point) + v_posed in, gvp out, weights
+        "lbs_vertex_bwd_fit": B * V * (4 + 12 + 8 + 12 + 12) + 2 * B * V * 12 + V * 55 * 4 + B * 55 * 48,
+        "lbs_reduce2": 75 * B * 512 * 4 + 42 * B * 56 * 48,
         "lbs_pose_fwd": B * (740 + 55 * 48 + 506 * 4) + 55 * 3 * 21 * 4,
         "lbs_pose_bwd": B * (55 * 48 + 506 * 4 + 740) + 55 * 3 * 21 * 4,
         "sdf_fwd": B * V * (32 + 12 + 4 + 12),
         "fit_vertex_grad": B * V * (12 + 4 + 12 + 8 + 12 + 12),
         "fit_linear": hid * hid * 4 + 2 * B * hid * 4,
-        "fit_pre": B * 75 * 8, "fit_post": B * 75 * 24,
+        "fit_step": B * 75 * 32,
     }
     agg = {}
     for name, ms in prof:
@@ -174,7 +177,8 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
         tot, n = agg[name]
         per = tot / n
         ach = alg.get(name, 0) / (per * 1e-3) / 1e9
-        tr = next((v for k, v in traffic.items() if name in k), None)
+        base = name.replace("lbs_skin_sdf_fwd", "lbs_skin_fwd").replace("lbs_vertex_bwd_fit", "lbs_vertex_bwd")
+        tr = next((v for k, v in traffic.items() if base in k), None)
         return {"kernel": "psi::" + name + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "peak_source": peak_src,
                 "traffic": None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"]),

@@ -1,18 +1,21 @@
 // Fused scene-fitting loop: the whole iteration of FittingOP.cal_loss + backward + Adam
-// (source/fitting_habitat.py:103-164,177-191) as 11 kernel launches, captured once in a CUDA graph.
+// (source/fitting_habitat.py:103-164,177-191) as 15 kernel launches, captured once in a CUDA graph.
 //
-//   fit_prologue   per body: xhr_rec[75] -> translation, 6D -> R (cvae.py:46-55), betas, VPoser
-//                  decode (MLP 32->512->512->126, leaky 0.2, vposer_smpl.py:107-121) -> 21 x 6D -> R,
-//                  hand PCA + pose_mean (smplx), L_rec and L_vposer of this body
-//   psi_lbs_fwd    (lbs.cu) joints 0..21 take R directly: the reference's R -> axis-angle
-//                  (torchgeometry) -> Rodrigues round trip is the identity on SO(3) up to rounding,
-//                  and so is its Jacobian on the tangent directions that reach it
-//   psi_nn_index_query / psi_sdf_fwd     contact NN distance, SDF value + gradient + partials
-//   fit_vertex_grad  dL/dverts of the contact robustifier (fitting_habitat.py:141) and of the
-//                  collision mean (:155-160) + per-chunk contact-loss partials
-//   psi_lbs_bwd    -> d betas, d hand axis-angles, d translation, d R (joints 0..21)
-//   fit_epilogue   per body: Gram-Schmidt / MLP / PCA backward, loss-term gradients, Adam step
-//                  (torch.optim.Adam defaults, fitting_habitat.py:76), loss values
+//   fit_linear x3    VPoser decode over the whole batch (MLP 32->512->512->126, leaky 0.2,
+//                    vposer_smpl.py:107-121) as tensor-core GEMMs; the 21 x 6D outputs land behind the
+//                    root's 6D vector
+//   lbs_fwd_impl     (lbs.cu) pose kernel: 6D -> R by Gram-Schmidt (cvae.py:46-55) for joints 0..21 --
+//                    the reference's R -> axis-angle (torchgeometry) -> Rodrigues round trip is the
+//                    identity on SO(3) up to rounding, and so is its Jacobian on the tangent directions
+//                    that reach it; blend GEMM; skinning, whose epilogue samples the
+//                    scene SDF at every fresh vertex (value + gradient + collision partial sums)
+//   psi_nn_index_query_mode  contact NN distance (group schedule, hints from the last iteration)
+//   lbs_bwd_impl     vertex kernel forms dL/dverts of the contact robustifier (fitting_habitat.py:141)
+//                    and the collision mean (:155-160) in place; -> d betas, d hand axis-angles,
+//                    d translation, d 6D (root) and the decoder-output gradient as a GEMM operand
+//   fit_linear x3    decoder backward
+//   fit_step         per body: loss-term gradients, Adam step (torch.optim.Adam defaults,
+//                    fitting_habitat.py:76), loss values, and the inputs of the next iteration
 // Loss semantics: the SUM over bodies of the reference's B=1 loss ('independent' mode) -- every
 // body is optimised exactly as the shipped batch_size-1 scripts do, bodies never interact.
 // All reductions have a fixed order: results are bit-reproducible and independent of B.
