@@ -166,7 +166,9 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
         "fit_step": B * 75 * 32,
     }
     agg = {}
+    gemm_path = "tcgen05 kind::tf32, 3xTF32" if any(n.endswith("_tc5") for n, _ in prof) else "mma.sync 3xTF32"
     for name, ms in prof:
+        name = name[:-4] if name.endswith("_tc5") else name
         a = agg.setdefault(name, [0.0, 0])
         a[0] += ms
         a[1] += 1
@@ -198,11 +200,11 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
     gemm = 2.0 * B * 512 * 3 * V
     roofline["note"] = ("the exact box-tree NN evaluates a few of the 1563 leaf clusters per query: an instruction/"
                         "latency-bound tree walk over L2-resident data, neither HBM- nor tensor-bound; "
-                        "brute-force-equivalent rate = %.3g pair/s.  LBS blend GEMMs (3xTF32 mma.sync): forward %.1f, "
+                        "brute-force-equivalent rate = %.3g pair/s.  LBS blend GEMMs (GEMMPATH): forward %.1f, "
                         "dcoef %.1f TFLOP/s FP32-equivalent (nominal FP32 CUDA-core peak %.1f)"
                         % (B * V * M / (agg[nn_name][0] / agg[nn_name][1] * 1e-3) if nn_name else 0.0,
                            gemm / (agg["lbs_blend_fwd"][0] * 1e-3) / 1e12, gemm / (agg["lbs_dcoef"][0] * 1e-3) / 1e12,
-                           fp32_peak))
+                           fp32_peak)).replace("GEMMPATH", gemm_path)
     return roofline
 
 

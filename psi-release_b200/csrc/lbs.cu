@@ -30,19 +30,25 @@
 #include "common.cuh"
 #include "rot6d.cuh"
 #include "fit_fuse.cuh"
+#include "tc5.cuh"
+#include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
 namespace psi {
 
 constexpr int kMaxJ = 64;
+constexpr int kUnitLen = 16;      // entries per work unit of the dA partial sums (lbs_vertex_bwd)
+constexpr int kMaxUnits = 160;    // units per 256-vertex chunk held in shared memory; more -> per-joint loop
 constexpr int kFT = 72;         // forward tile: 72 vertex coordinates (9 n8 tiles); 3V/72 = 437 tiles at
                                 // V = 10475 = 2.95 per SM -> one balanced wave at 3 CTAs per SM
 constexpr int kFStages = 4;     // forward ring: 4 x 17 kB
 constexpr int kDK = 128;        // dcoef tile: 128 coefficients x 64 bodies per CTA
 constexpr int kDStages = 4;     // dcoef ring: 4 x 24 kB, 2 CTAs per SM
-constexpr int kNSplit = 74;     // dcoef split of the coordinate reduction: 4 k-tiles x 74 = 2 CTAs per SM
+constexpr int kNSplit = 74;     // dcoef split of the coordinate reduction: 4 k-tiles x 74 = 2 CTAs per SM (mma.sync path)
+constexpr int kNSplitTc5 = 37;  // tcgen05 path: 4 k-tiles x 37 = one persistent CTA per SM
 
 }  // namespace psi
 
@@ -54,10 +60,11 @@ struct psi_lbs_tree {          // kinematic tree by levels (root = level 0) + ch
 struct psi_lbs_model {
     psi_lbs_tree tree;
     int *tree_buf;
-    int V, J, NB, P, K, Kpad, Npad, KW, NC, NT;   // NC coordinate chunks of 32 (Npad = 32 NC), NT forward tiles of 72
+    int V, J, NB, P, K, Kpad, Npad, KW, NC, NT, FT;   // NC coordinate chunks of 32 (Npad = 32 NC), NT forward tiles of 72
     long nnz;
     float *basis_fwd, *basis_bwd, *v_template, *Jt, *Jdirs, *skin_w, *ch_w;
-    int *skin_j, *parents, *ch_seg;
+    int *skin_j, *parents, *ch_seg, *ch_ju, *unit_desc;
+    int max_units;                 // most work units in one chunk
     unsigned char *ch_lv;
     int max_ent;                   // most skinning entries in one chunk
     int NCH;                       // 256-vertex chunks of the vertex kernels (covers Npad/3 rows)
@@ -66,8 +73,19 @@ struct psi_lbs_model {
 
 namespace psi {
 
+// PSI_LBS_GEMM=tc5 selects the tcgen05 + TMEM blend GEMMs; default: the mma.sync GEMMs.  Measured
+// at B = 64 (r01r): forward 44 vs 41 us, dcoef 39 vs 37 us -- with only 64 bodies as the N dimension
+// and FP32 operands split three ways, a tcgen05.mma (128 x 64 x 8) re-reads 6 kB of operands from
+// shared memory for 65 k MACs and runs at ~128 cycles (tensor pipe busy 47 % of the kernel); the
+// path pays off from ~128 bodies per GPU up.  Read once per process: the model's forward basis
+// layout depends on it.
+static bool lbs_gemm_tc5() {
+    static const bool on = [] { const char *e = getenv("PSI_LBS_GEMM"); return e && e[0] == 't'; }();
+    return on;
+}
+
 struct SavedLayout {
-    size_t R, Jr, Gr, Gt, A, vp, coef, total;
+    size_t R, Jr, Gr, Gt, A, vp, coef, coef_lo, total;
 };
 __host__ __device__ inline SavedLayout saved_layout(int B, int J, int V, int Kpad) {
     SavedLayout s;
@@ -81,6 +99,7 @@ __host__ __device__ inline SavedLayout saved_layout(int B, int J, int V, int Kpa
     s.vp = o;   o += (size_t)B * V * 3;
     o = (o + 31) & ~(size_t)31;                 // 128-byte aligned for the bulk copies
     s.coef = o; o += (size_t)((B + kBG - 1) / kBG) * Kpad * kBG;
+    s.coef_lo = o; o += (size_t)((B + kBG - 1) / kBG) * Kpad * kBG;   // tcgen05 path: coef = hi, coef_lo = lo (3xTF32 split)
     s.total = o;
     return s;
 }
@@ -113,7 +132,7 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ betas, const float *__restrict__ pose,
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
                     float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
-                    const float *__restrict__ rot6d, const psi_lbs_tree tree) {
+                    const float *__restrict__ rot6d, int split, const psi_lbs_tree tree) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
@@ -195,7 +214,14 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
         } else if (k < P + NB) {
             v = betas[(size_t)b * NB + (k - P)];
         }
-        coef[(size_t)(k / kKC) * (kBG * kKC) + swz(b % kBG, k % kKC)] = v;
+        const size_t at = (size_t)(k / kKC) * (kBG * kKC) + swz(b % kBG, k % kKC);
+        if (split) {     // tcgen05 GEMM: operands pre-split into TF32 hi + lo (x = hi + lo exactly)
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            coef[at] = hi;
+            coef[at + (L.coef_lo - L.coef)] = v - hi;
+        } else {
+            coef[at] = v;
+        }
     }
 }
 
@@ -337,13 +363,26 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
 #pragma unroll
         for (int e = 0; e < 12; ++e) T[e] = 0.f;
         const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
-        for (int k = 0; k < KW; ++k) {
-            const int j = skin_j[(size_t)v * KW + k];
-            const float wt = skin_w[(size_t)v * KW + k];
-            const float4 r0 = __ldg(Ab + j * 3), r1 = __ldg(Ab + j * 3 + 1), r2 = __ldg(Ab + j * 3 + 2);
+        auto blend = [&](int j, float wt, float4 r0, float4 r1, float4 r2) {
+            (void)j;
             T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]); T[3] = fmaf(wt, r0.w, T[3]);
             T[4] = fmaf(wt, r1.x, T[4]); T[5] = fmaf(wt, r1.y, T[5]); T[6] = fmaf(wt, r1.z, T[6]); T[7] = fmaf(wt, r1.w, T[7]);
             T[8] = fmaf(wt, r2.x, T[8]); T[9] = fmaf(wt, r2.y, T[9]); T[10] = fmaf(wt, r2.z, T[10]); T[11] = fmaf(wt, r2.w, T[11]);
+        };
+        if (KW == 4) {     // SMPL-X: <= 4 weights per vertex: one 16-byte load each for ids and weights, 12 independent gathers
+            const int4 jj = __ldg(reinterpret_cast<const int4 *>(skin_j) + v);
+            const float4 ww = __ldg(reinterpret_cast<const float4 *>(skin_w) + v);
+            const float4 a0 = __ldg(Ab + jj.x * 3), a1 = __ldg(Ab + jj.x * 3 + 1), a2 = __ldg(Ab + jj.x * 3 + 2);
+            const float4 b0 = __ldg(Ab + jj.y * 3), b1 = __ldg(Ab + jj.y * 3 + 1), b2 = __ldg(Ab + jj.y * 3 + 2);
+            const float4 c0 = __ldg(Ab + jj.z * 3), c1 = __ldg(Ab + jj.z * 3 + 1), c2 = __ldg(Ab + jj.z * 3 + 2);
+            const float4 d0 = __ldg(Ab + jj.w * 3), d1 = __ldg(Ab + jj.w * 3 + 1), d2 = __ldg(Ab + jj.w * 3 + 2);
+            blend(jj.x, ww.x, a0, a1, a2); blend(jj.y, ww.y, b0, b1, b2); blend(jj.z, ww.z, c0, c1, c2); blend(jj.w, ww.w, d0, d1, d2);
+        } else {
+            for (int k = 0; k < KW; ++k) {
+                const int j = skin_j[(size_t)v * KW + k];
+                const float wt = skin_w[(size_t)v * KW + k];
+                blend(j, wt, __ldg(Ab + j * 3), __ldg(Ab + j * 3 + 1), __ldg(Ab + j * 3 + 2));
+            }
         }
         float ox = T[0] * x + T[1] * y + T[2] * z + T[3];
         float oy = T[4] * x + T[5] * y + T[6] * z + T[7];
@@ -402,10 +441,13 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
                       const float *__restrict__ vp_in, const float *__restrict__ cam, long cam_bstride,
                       const float *__restrict__ gverts, const int *__restrict__ ch_seg,
                       const unsigned char *__restrict__ ch_lv, const float *__restrict__ ch_w, int stage_cap,
-                      float *__restrict__ gvp_out, float *__restrict__ dApart, const VGradFuse fg) {
+                      const int *__restrict__ ch_ju, const int *__restrict__ unit_desc, int use_units,
+                      float *__restrict__ gvp_out, float *__restrict__ gvp_lo, float *__restrict__ dApart,
+                      const VGradFuse fg) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // the chunk's entries: stage_cap x (weight, local vertex)
     __shared__ float s_gw[256 * 3], s_vp[256 * 3];
     __shared__ float s_cnt, red[8], red3[24];
+    __shared__ float4 s_part[kMaxUnits * 3];          // per (unit, row): partial sums of up to kUnitLen entries
     const int tid = threadIdx.x;
     // the chunk's skinning entries are constants of the model: staged before the dependency wait
     const int *seg = ch_seg + (size_t)blockIdx.x * (J + 1);
@@ -420,8 +462,17 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     const int v = blockIdx.x * blockDim.x + tid;
     const int b = blockIdx.y;
     float *gvp_g = gvp_out + (size_t)(b / kBG) * Npad * kBG + (size_t)(b % kBG) * kKC;
+    const size_t lo_off = gvp_lo ? (size_t)(gvp_lo - gvp_out) : 0;   // tcgen05 GEMM: operand pre-split into TF32 hi + lo
     auto put = [&](int n, float x) {
-        if (n < Npad) gvp_g[(size_t)(n / kKC) * (kBG * kKC) + swz(b % kBG, n % kKC)] = x;
+        if (n >= Npad) return;
+        const size_t at = (size_t)(n / kKC) * (kBG * kKC) + swz(b % kBG, n % kKC);
+        if (lo_off) {
+            const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+            gvp_g[at] = hi;
+            gvp_g[at + lo_off] = x - hi;
+        } else {
+            gvp_g[at] = x;
+        }
     };
     if (b >= B) {        // padding rows of the GEMM operand (whole CTA)
         put(3 * v, 0.f); put(3 * v + 1, 0.f); put(3 * v + 2, 0.f);
@@ -475,13 +526,25 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
         const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
-        for (int k = 0; k < KW; ++k) {
-            const int j = skin_j[(size_t)v * KW + k];
-            const float wt = skin_w[(size_t)v * KW + k];
-            const float4 r0 = __ldg(Ab + j * 3), r1 = __ldg(Ab + j * 3 + 1), r2 = __ldg(Ab + j * 3 + 2);
+        auto blend = [&](float wt, float4 r0, float4 r1, float4 r2) {
             T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]);
             T[3] = fmaf(wt, r1.x, T[3]); T[4] = fmaf(wt, r1.y, T[4]); T[5] = fmaf(wt, r1.z, T[5]);
             T[6] = fmaf(wt, r2.x, T[6]); T[7] = fmaf(wt, r2.y, T[7]); T[8] = fmaf(wt, r2.z, T[8]);
+        };
+        if (KW == 4) {     // one 16-byte load each for ids and weights, 12 independent gathers
+            const int4 jj = __ldg(reinterpret_cast<const int4 *>(skin_j) + v);
+            const float4 ww = __ldg(reinterpret_cast<const float4 *>(skin_w) + v);
+            const float4 a0 = __ldg(Ab + jj.x * 3), a1 = __ldg(Ab + jj.x * 3 + 1), a2 = __ldg(Ab + jj.x * 3 + 2);
+            const float4 b0 = __ldg(Ab + jj.y * 3), b1 = __ldg(Ab + jj.y * 3 + 1), b2 = __ldg(Ab + jj.y * 3 + 2);
+            const float4 c0 = __ldg(Ab + jj.z * 3), c1 = __ldg(Ab + jj.z * 3 + 1), c2 = __ldg(Ab + jj.z * 3 + 2);
+            const float4 d0 = __ldg(Ab + jj.w * 3), d1 = __ldg(Ab + jj.w * 3 + 1), d2 = __ldg(Ab + jj.w * 3 + 2);
+            blend(ww.x, a0, a1, a2); blend(ww.y, b0, b1, b2); blend(ww.z, c0, c1, c2); blend(ww.w, d0, d1, d2);
+        } else {
+            for (int k = 0; k < KW; ++k) {
+                const int j = skin_j[(size_t)v * KW + k];
+                const float wt = skin_w[(size_t)v * KW + k];
+                blend(wt, __ldg(Ab + j * 3), __ldg(Ab + j * 3 + 1), __ldg(Ab + j * 3 + 2));
+            }
         }
         put(3 * v, T[0] * gx + T[3] * gy + T[6] * gz);
         put(3 * v + 1, T[1] * gx + T[4] * gy + T[7] * gz);
@@ -507,9 +570,49 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         for (int i = 0; i < 8; ++i) s += red[i];
         fg.cpart[(size_t)b * gridDim.x + blockIdx.x] = s;
     }
-    // dA partial sums of this chunk: item (j, r) = row r of sum over the entries of joint j of
-    // (w gw_r) * [vp | 1], entries in ascending vertex order (4 outputs share the entry's loads)
+    // dA partial sums of this chunk: row r of sum over the entries of joint j of (w gw_r) * [vp | 1], entries in
+    // ascending vertex order.  Joints own very different numbers of entries (the root collects every
+    // vertex skinned to an ancestor chain through it), so the entry lists are cut into UNITS of at most
+    // kUnitLen entries (unit_desc, built with the model): phase 1 = one thread per (unit, row), phase 2 =
+    // one thread per (joint, row) adds that joint's units in order.
     float *outp = dApart + ((size_t)blockIdx.x * B + b) * (J + 1) * 12;
+    if (use_units && staged) {
+        const int *ju = ch_ju + (size_t)blockIdx.x * (J + 1);
+        const int u0 = ju[0], nunits = ju[J] - u0;
+        for (int item = tid; item < nunits * 3; item += blockDim.x) {
+            const int u = item / 3, r = item - u * 3;
+            const int d = unit_desc[u0 + u];
+            const int k0 = d >> 8, len = d & 255;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int k = k0; k < k0 + len; ++k) {
+                const int lv = s_lv[k];
+                const float g = s_w[k] * s_gw[lv * 3 + r];
+                a0 = fmaf(g, s_vp[lv * 3], a0); a1 = fmaf(g, s_vp[lv * 3 + 1], a1); a2 = fmaf(g, s_vp[lv * 3 + 2], a2);
+                a3 += g;
+            }
+            s_part[item] = make_float4(a0, a1, a2, a3);
+        }
+        __syncthreads();
+        for (int item = tid; item < (J + 1) * 3; item += blockDim.x) {
+            const int j = item / 3, r = item - j * 3;
+            if (j < J) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = ju[j] - u0; u < ju[j + 1] - u0; ++u) {
+                    const float4 p = s_part[u * 3 + r];
+                    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+                }
+                *reinterpret_cast<float4 *>(outp + j * 12 + r * 4) = acc;
+            } else {
+                float a0 = 0.f;
+                for (int w8 = 0; w8 < 8; ++w8) a0 += red3[w8 * 3 + r];     // row J: entries 0..2 = sum of gw
+                outp[J * 12 + r] = a0;
+                if (r == 0)
+                    for (int e = 3; e < 12; ++e) outp[J * 12 + e] = 0.f;
+            }
+        }
+        return;
+    }
     for (int item = tid; item < (J + 1) * 3; item += blockDim.x) {
         const int j = item / 3, r = item - j * 3;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -639,6 +742,223 @@ lbs_dcoef_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd
             for (int nt = 0; nt < 4; ++nt)
                 *reinterpret_cast<float2 *>(o + nt * 8) = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
         }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The two blend GEMMs on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Both are D[128 x 64 bodies] = BASIS_TILE[128 x K] * ACT[64 x K]^T with the basis as the M = 128
+// operand (full-rate datapath, cta_group::1) and the per-body operand (blend coefficients, or the
+// vertex gradient gvp) as N = 64; the accumulator lives in tensor memory (64 columns), operands are
+// read by the tensor core straight from 128-byte-swizzled shared-memory tiles (tc5.cuh).
+//   forward : rows = 128 vertex coordinates, K = blend coefficients  -> v_posed
+//   backward: rows = 128 blend coefficients, K = a range of vertex coordinates -> d coef partials
+// 3xTF32: the per-body operand arrives pre-split from its producer (hi and lo arrays); the basis tile
+// is split in shared memory by the CTA's 128 worker threads (raw -> hi | lo) while the previous
+// chunk's MMAs run; per 8-wide k step the elected thread issues hi*lo, lo*hi, hi*hi into the same
+// accumulator.  Three rings decouple the latencies: RAW basis tiles (5 x 16 kB, HBM stream, freed by
+// the workers right after the split), ACT tiles (4 x 16 kB, L2, freed by tcgen05.commit) and the
+// OPERAND slots the split writes (2 x 32 kB, freed by tcgen05.commit).  Warp 4 / warp 5 (one lane
+// each) are the TMA producers of the RAW / ACT rings.  CTAs are persistent over work items; the
+// epilogue reads TMEM with tcgen05.ld: lane = row, so a warp stores 32 consecutive floats per body.
+// (mma.sync kept these GEMMs tensor-pipe bound at 41 / 37 us.)
+constexpr int kTM = 128;                       // rows of a basis tile = M of the MMA
+constexpr int kTRaw = 5, kTAct = 4, kTOp = 2;  // ring depths
+constexpr int kTThreads = 192;                 // 4 worker warps + 2 producer warps
+constexpr int kTTileB = kTM * kKC * 4;         // 16 kB: one basis tile (raw, hi or lo)
+constexpr int kTTileA = kBG * kKC * 4;         // 8 kB: one per-body tile (hi or lo)
+constexpr int kTSmem = kTRaw * kTTileB + kTAct * 2 * kTTileA + kTOp * 2 * kTTileB;   // 208 kB
+
+struct Tc5Bars {
+    uint64_t full_raw[kTRaw], empty_raw[kTRaw], full_act[kTAct], empty_act[kTAct], empty_op[kTOp], accum;
+    uint32_t tmem_slot;
+};
+
+struct Tc5Item {                 // one accumulator's worth of work
+    const float *basis;          // first chunk of the [chunk][128][32] tile stream
+    size_t basis_stride;         // floats between chunks
+    const float *act_hi, *act_lo;   // [chunk][64][32]
+    int nchunks;
+};
+
+// Runs the K loop of `it`; g0 = number of chunks this CTA has processed before (ring phase).
+// Worker threads return with the accumulator complete in TMEM.
+__device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars, uint32_t tmem_d, const Tc5Item &it,
+                                             int g0, int item_parity) {
+    const int tid = threadIdx.x;
+    unsigned char *raw = smem, *act = smem + kTRaw * kTTileB, *op = act + kTAct * 2 * kTTileA;
+    if (tid >= 128) {
+        if (tid == 128) {                               // ---- producer: raw basis tiles (HBM)
+            for (int c = 0; c < it.nchunks; ++c) {
+                const int g = g0 + c, st = g % kTRaw;
+                mbar_wait(&bars.empty_raw[st], (uint32_t)(((g / kTRaw) & 1) ^ 1));
+                mbar_arrive_expect_tx(&bars.full_raw[st], (uint32_t)kTTileB);
+                tma_load_1d(raw + (size_t)st * kTTileB, it.basis + (size_t)c * it.basis_stride, kTTileB, &bars.full_raw[st]);
+            }
+        } else if (tid == 160) {                        // ---- producer: per-body tiles (L2)
+            for (int c = 0; c < it.nchunks; ++c) {
+                const int g = g0 + c, st = g % kTAct;
+                mbar_wait(&bars.empty_act[st], (uint32_t)(((g / kTAct) & 1) ^ 1));
+                mbar_arrive_expect_tx(&bars.full_act[st], (uint32_t)(2 * kTTileA));
+                tma_load_1d(act + (size_t)st * 2 * kTTileA, it.act_hi + (size_t)c * (kBG * kKC), kTTileA, &bars.full_act[st]);
+                tma_load_1d(act + (size_t)st * 2 * kTTileA + kTTileA, it.act_lo + (size_t)c * (kBG * kKC), kTTileA,
+                            &bars.full_act[st]);
+            }
+        }
+        return;
+    }
+    constexpr uint32_t idesc = tc5::idesc_tf32(kTM, kBG);
+    for (int c = 0; c < it.nchunks; ++c) {
+        const int g = g0 + c, sr = g % kTRaw, so = g % kTOp, sa = g % kTAct;
+        mbar_wait(&bars.full_raw[sr], (uint32_t)((g / kTRaw) & 1));
+        mbar_wait(&bars.empty_op[so], (uint32_t)(((g / kTOp) & 1) ^ 1));       // the MMAs that read this slot are done
+        const uint4 *src = reinterpret_cast<const uint4 *>(raw + (size_t)sr * kTTileB);
+        uint4 *hi = reinterpret_cast<uint4 *>(op + (size_t)so * 2 * kTTileB);
+        float4 *lo = reinterpret_cast<float4 *>(op + (size_t)so * 2 * kTTileB + kTTileB);
+#pragma unroll 4
+        for (int e = tid; e < kTM * kKC / 4; e += 128) {   // element-wise: the swizzle does not matter
+            const uint4 x = src[e];
+            const uint4 h = make_uint4(x.x & 0xffffe000u, x.y & 0xffffe000u, x.z & 0xffffe000u, x.w & 0xffffe000u);
+            hi[e] = h;
+            lo[e] = make_float4(__uint_as_float(x.x) - __uint_as_float(h.x), __uint_as_float(x.y) - __uint_as_float(h.y),
+                                __uint_as_float(x.z) - __uint_as_float(h.z), __uint_as_float(x.w) - __uint_as_float(h.w));
+        }
+        tc5::fence_proxy_async();
+        mbar_arrive(&bars.empty_raw[sr]);               // 128 arrivals free the raw slot
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+            mbar_wait(&bars.full_act[sa], (uint32_t)((g / kTAct) & 1));
+            tc5::fence_after_sync();
+            const uint32_t sop = smem_u32(op + (size_t)so * 2 * kTTileB), sac = smem_u32(act + (size_t)sa * 2 * kTTileA);
+            const uint64_t dbh = tc5::smem_desc_k_sw128(sop), dbl = tc5::smem_desc_k_sw128(sop + kTTileB);
+            const uint64_t dah = tc5::smem_desc_k_sw128(sac), dal = tc5::smem_desc_k_sw128(sac + kTTileA);
+#pragma unroll
+            for (int k = 0; k < kKC / 8; ++k) {          // 32 bytes of every 128-byte row per step: start address + 2
+                tc5::mma_tf32(tmem_d, dbh + 2 * k, dal + 2 * k, idesc, (c | k) != 0);
+                tc5::mma_tf32(tmem_d, dbl + 2 * k, dah + 2 * k, idesc, 1u);
+                tc5::mma_tf32(tmem_d, dbh + 2 * k, dah + 2 * k, idesc, 1u);
+            }
+            tc5::commit(&bars.empty_op[so]);
+            tc5::commit(&bars.empty_act[sa]);
+            if (c == it.nchunks - 1) tc5::commit(&bars.accum);
+        }
+    }
+    mbar_wait(&bars.accum, (uint32_t)item_parity);
+    tc5::fence_after_sync();
+}
+
+__device__ __forceinline__ uint32_t tc5_setup(Tc5Bars &bars) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kTRaw; ++i) { mbar_init(&bars.full_raw[i], 1); mbar_init(&bars.empty_raw[i], 128); }
+        for (int i = 0; i < kTAct; ++i) { mbar_init(&bars.full_act[i], 1); mbar_init(&bars.empty_act[i], 1); }
+        for (int i = 0; i < kTOp; ++i) mbar_init(&bars.empty_op[i], 1);
+        mbar_init(&bars.accum, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x >= 160) {                   // warp 5 owns the TMEM allocation
+        tc5::tmem_alloc(&bars.tmem_slot, 64);
+        tc5::tmem_relinquish();
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    return bars.tmem_slot;
+}
+
+__device__ __forceinline__ void tc5_teardown(uint32_t tmem_d) {
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x >= 160) tc5::tmem_dealloc(tmem_d, 64);
+}
+
+struct BlendFwdTc5Params {
+    const float *basis_fwd, *v_template, *coef_hi, *coef_lo;
+    float *vp_out;
+    int V, Kpad, B, ntiles, nbg;
+};
+
+// v_posed[b][n] = v_template[n] + sum_k coef[b][k] * basis[k][n]; work item = (128 coordinates, body group)
+__global__ void __launch_bounds__(kTThreads, 1) lbs_blend_fwd_tc5_kernel(const BlendFwdTc5Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_tc5[];
+    unsigned char *smem_raw = smem_tc5 + ((1024u - (smem_u32(smem_tc5) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
+    __shared__ __align__(8) Tc5Bars bars;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t tmem_d = tc5_setup(bars);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nchunks = p.Kpad / kKC, N = 3 * p.V;
+    int g0 = 0, par = 0;
+    for (int item = blockIdx.x; item < p.ntiles * p.nbg; item += gridDim.x, g0 += nchunks, par ^= 1) {
+        const int tile = item % p.ntiles, bg = item / p.ntiles;
+        Tc5Item it;
+        it.basis = p.basis_fwd + (size_t)tile * p.Kpad * kTM;
+        it.basis_stride = (size_t)kTM * kKC;
+        it.act_hi = p.coef_hi + (size_t)bg * p.Kpad * kBG;
+        it.act_lo = p.coef_lo + (size_t)bg * p.Kpad * kBG;
+        it.nchunks = nchunks;
+        tc5_mainloop(smem_raw, bars, tmem_d, it, g0, par);
+        if (w < 4) {
+            const int n = tile * kTM + w * 32 + lane;          // TMEM lane = accumulator row = coordinate
+            const float vt = n < N ? p.v_template[n] : 0.f;
+#pragma unroll 2
+            for (int c8 = 0; c8 < kBG / 8; ++c8) {
+                float v[8];
+                tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(c8 * 8), v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int b = bg * kBG + c8 * 8 + e;
+                    if (n < N && b < p.B) p.vp_out[(size_t)b * N + n] = v[e] + vt;
+                }
+            }
+            tc5::fence_before_sync();                          // TMEM reads done before the next item's first MMA
+        }
+    }
+    tc5_teardown(tmem_d);
+}
+
+// part[ns][b][k] = sum_{n in split ns} gvp[b][n] * basis[k][n]; work item = (128 coefficients, split, body group)
+__global__ void __launch_bounds__(kTThreads, 1)
+lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd, const float *__restrict__ gvp_hi,
+                     const float *__restrict__ gvp_lo, float *__restrict__ part, int nsplit) {
+    extern __shared__ __align__(1024) unsigned char smem_tc5[];
+    unsigned char *smem_raw = smem_tc5 + ((1024u - (smem_u32(smem_tc5) & 1023u)) & 1023u);
+    __shared__ __align__(8) Tc5Bars bars;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t tmem_d = tc5_setup(bars);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nkt = Kpad / kTM, nbg = Bpad / kBG;
+    int g0 = 0, par = 0;
+    for (int item = blockIdx.x; item < nkt * nsplit * nbg; item += gridDim.x) {
+        const int kt = item % nkt, ns = (item / nkt) % nsplit, bg = item / (nkt * nsplit);
+        const int c_begin = (int)((long)ns * NC / nsplit), c_end = (int)((long)(ns + 1) * NC / nsplit);
+        float *o = part + ((size_t)ns * Bpad + (size_t)bg * kBG) * Kpad + kt * kTM + w * 32 + lane;
+        if (c_end == c_begin) {                    // more splits than chunks (small models): an empty split
+            if (w < 4)
+                for (int b = 0; b < kBG; ++b) o[(size_t)b * Kpad] = 0.f;
+            continue;
+        }
+        Tc5Item it;
+        it.basis = basis_bwd + (size_t)c_begin * Kpad * kKC + (size_t)kt * kTM * kKC;
+        it.basis_stride = (size_t)Kpad * kKC;
+        it.act_hi = gvp_hi + (size_t)bg * NC * (kBG * kKC) + (size_t)c_begin * (kBG * kKC);
+        it.act_lo = gvp_lo + (size_t)bg * NC * (kBG * kKC) + (size_t)c_begin * (kBG * kKC);
+        it.nchunks = c_end - c_begin;
+        tc5_mainloop(smem_raw, bars, tmem_d, it, g0, par);
+        g0 += it.nchunks;
+        par ^= 1;
+        if (w < 4) {
+#pragma unroll 2
+            for (int c8 = 0; c8 < kBG / 8; ++c8) {
+                float v[8];
+                tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(c8 * 8), v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[(size_t)(c8 * 8 + e) * Kpad] = v[e];     // lane = coefficient: coalesced per body
+            }
+            tc5::fence_before_sync();
+        }
+    }
+    tc5_teardown(tmem_d);
 }
 
 // out[i] = sum over the leading dimension of in[n][count], fixed order (4 interleaved partial sums);
@@ -835,7 +1155,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
 }
 
 struct BwdLayout {
-    size_t gvp, dApart, part, dsum, dA, total;  // in floats
+    size_t gvp, gvp_lo, dApart, part, dsum, dA, total;  // in floats
     int Bpad;
 };
 static BwdLayout bwd_layout(const psi_lbs_model *m, int B) {
@@ -843,6 +1163,7 @@ static BwdLayout bwd_layout(const psi_lbs_model *m, int B) {
     l.Bpad = ((B + kBG - 1) / kBG) * kBG;
     size_t o = 0;
     l.gvp = o;     o += (size_t)l.Bpad * m->Npad;
+    l.gvp_lo = o;  o += (size_t)l.Bpad * m->Npad;
     l.dApart = o;  o += (size_t)m->NCH * B * (m->J + 1) * 12;
     o = (o + 3) & ~(size_t)3;
     l.part = o;    o += (size_t)kNSplit * l.Bpad * m->Kpad;
@@ -873,7 +1194,7 @@ void psi_lbs_model_destroy(psi_lbs_model *m) {
     if (!m) return;
     cudaFree(m->basis_fwd); cudaFree(m->basis_bwd); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
     cudaFree(m->skin_w); cudaFree(m->ch_w); cudaFree(m->skin_j); cudaFree(m->parents);
-    cudaFree(m->ch_seg); cudaFree(m->ch_lv); cudaFree(m->tree_buf);
+    cudaFree(m->ch_seg); cudaFree(m->ch_lv); cudaFree(m->tree_buf); cudaFree(m->ch_ju); cudaFree(m->unit_desc);
     delete m;
 }
 
@@ -895,7 +1216,9 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     m->Kpad = ((m->K + kDK - 1) / kDK) * kDK;   // multiple of the dcoef k tile (and of kKC)
     m->NC = (3 * V + kKC - 1) / kKC;
     m->Npad = m->NC * kKC;
-    m->NT = (3 * V + kFT - 1) / kFT;
+    const int FT = lbs_gemm_tc5() ? kTM : kFT;      // rows of a forward basis tile
+    m->FT = FT;
+    m->NT = (3 * V + FT - 1) / FT;
     m->bytes = 0;
     const int P = m->P, Kpad = m->Kpad, Npad = m->Npad;
     const size_t N = (size_t)3 * V;
@@ -904,17 +1227,17 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     // GEMM with the reduction index contiguous in swizzled 128-byte rows:
     //   forward  [tile n/72][chunk k/32][row n%72][32 k]     (reduction over k)
     //   backward [chunk n/32][row k][32 n]                    (reduction over n)
-    std::vector<float> bf((size_t)m->NT * Kpad * kFT, 0.f), bb((size_t)m->NC * Kpad * kKC, 0.f);
+    std::vector<float> bf((size_t)m->NT * Kpad * FT, 0.f), bb((size_t)m->NC * Kpad * kKC, 0.f);
     auto put = [&](int k, size_t n, float x) {
-        const int r = (int)(n % kFT);
-        bf[(n / kFT) * (size_t)Kpad * kFT + (size_t)(k / kKC) * (kFT * kKC) + (size_t)r * kKC + swz(r, k % kKC)] = x;
+        const int r = (int)(n % FT);
+        bf[(n / FT) * (size_t)Kpad * FT + (size_t)(k / kKC) * (FT * kKC) + (size_t)r * kKC + swz(r, k % kKC)] = x;
         bb[(n / kKC) * (size_t)Kpad * kKC + (size_t)k * kKC + swz(k, (int)(n % kKC))] = x;
     };
     for (int k = 0; k < P; ++k)
         for (size_t n = 0; n < N; ++n) put(k, n, h_posedirs[(size_t)k * N + n]);
     for (int l = 0; l < NB; ++l)
         for (size_t n = 0; n < N; ++n) put(P + l, n, h_shapedirs[n * NB + l]);
-    std::vector<float> vt((size_t)m->NT * kFT, 0.f);
+    std::vector<float> vt((size_t)m->NT * FT, 0.f);
     for (size_t n = 0; n < N; ++n) vt[n] = h_v_template[n];
     (void)Npad;
 
@@ -985,6 +1308,24 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
         const int ne = ch_seg[(size_t)c * (J + 1) + J] - ch_seg[(size_t)c * (J + 1)];
         m->max_ent = ne > m->max_ent ? ne : m->max_ent;
     }
+    // work units: every joint's entry list of a chunk cut into pieces of <= kUnitLen entries;
+    // unit_desc = (first entry relative to the chunk) << 8 | length, ch_ju = per (chunk, joint) first unit
+    std::vector<int> ch_ju((size_t)m->NCH * (J + 1), 0), unit_desc;
+    m->max_units = 0;
+    for (int c = 0; c < m->NCH; ++c) {
+        const int e0 = ch_seg[(size_t)c * (J + 1)];
+        const int ubegin = (int)unit_desc.size();
+        for (int j = 0; j <= J; ++j) {
+            ch_ju[(size_t)c * (J + 1) + j] = (int)unit_desc.size();
+            if (j == J) break;
+            for (int k = ch_seg[(size_t)c * (J + 1) + j]; k < ch_seg[(size_t)c * (J + 1) + j + 1]; k += kUnitLen) {
+                const int len = std::min(kUnitLen, ch_seg[(size_t)c * (J + 1) + j + 1] - k);
+                unit_desc.push_back(((k - e0) << 8) | len);
+            }
+        }
+        m->max_units = std::max(m->max_units, (int)unit_desc.size() - ubegin);
+    }
+    if (unit_desc.empty()) unit_desc.push_back(0);
     std::vector<int> parents(h_parents, h_parents + J);
     parents[0] = -1;
     // tree levels and children lists, packed: [lvl_start (J+1) | lvl_joint (J) | child_start (J+1) | child_list (J)]
@@ -1015,6 +1356,8 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     if (rc == PSI_OK) rc = upload(&m->ch_seg, ch_seg, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->ch_lv, ch_lv, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->ch_w, ch_w, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->ch_ju, ch_ju, st, &m->bytes);
+    if (rc == PSI_OK) rc = upload(&m->unit_desc, unit_desc, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->tree_buf, treebuf, st, &m->bytes);
     if (rc == PSI_OK) {
         m->tree.nlev = nlev;
@@ -1063,25 +1406,46 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
     if (B > 65535) return PSI_ERR_UNSUPPORTED;
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
+    const bool tc5 = lbs_gemm_tc5();
     launch_pdl(lbs_pose_fwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, m->tree);
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, tc5 ? 1 : 0, m->tree);
     PSI_LAUNCHED_K("lbs_pose_fwd");
     if (B % kBG) {
         launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef, B, m->Kpad);
         PSI_LAUNCHED_K("lbs_zero_coef_pad");
-    }
-    BlendFwdParams p;
-    p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef = saved + L.coef;
-    p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B;
-    const size_t smem = (size_t)kFStages * kFStageBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(lbs_blend_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        if (tc5) {
+            launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef_lo, B, m->Kpad);
+            PSI_LAUNCHED_K("lbs_zero_coef_pad");
+        }
     }
     dim3 grid((unsigned)m->NT, (unsigned)((B + kBG - 1) / kBG));
-    launch_pdl(lbs_blend_fwd_kernel, dim3(grid), dim3(128), smem, st, p);
-    PSI_LAUNCHED_K("lbs_blend_fwd");
+    if (tc5) {
+        BlendFwdTc5Params p;
+        p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef_hi = saved + L.coef; p.coef_lo = saved + L.coef_lo;
+        p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B; p.ntiles = m->NT; p.nbg = (B + kBG - 1) / kBG;
+        const size_t smem = (size_t)kTSmem + 1024;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(lbs_blend_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        const int items = p.ntiles * p.nbg;
+        launch_pdl(lbs_blend_fwd_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
+                   smem, st, p);
+        PSI_LAUNCHED_K("lbs_blend_fwd_tc5");
+    } else {
+        BlendFwdParams p;
+        p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef = saved + L.coef;
+        p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B;
+        const size_t smem = (size_t)kFStages * kFStageBytes;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(lbs_blend_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        launch_pdl(lbs_blend_fwd_kernel, grid, dim3(128), smem, st, p);
+        PSI_LAUNCHED_K("lbs_blend_fwd");
+    }
     {
         dim3 sgrid((unsigned)((m->V + 255) / 256), (unsigned)B);
         if (sdf)
@@ -1132,41 +1496,57 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
     if (((uintptr_t)workspace & 15u) != 0) return PSI_ERR_BAD_ARG;
     float *ws = reinterpret_cast<float *>(workspace);
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
+    const bool tc5 = lbs_gemm_tc5();
+    const int nsplit = tc5 ? kNSplitTc5 : kNSplit;
     {
         dim3 grid((unsigned)m->NCH, (unsigned)W.Bpad);
         // the chunk's skinning entries are staged in shared memory when they fit (5 bytes each)
         const int cap = m->max_ent <= 8192 ? ((m->max_ent + 3) & ~3) : 0;
         const size_t smem = (size_t)cap * 5;
+        const int units = (cap > 0 && m->max_units <= kMaxUnits) ? 1 : 0;
         if (vg)
             launch_pdl(lbs_vertex_bwd_kernel<true>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                        m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
-                       m->ch_w, cap, ws + W.gvp, ws + W.dApart, *vg);
+                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, *vg);
         else
             launch_pdl(lbs_vertex_bwd_kernel<false>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                        m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
-                       m->ch_w, cap, ws + W.gvp, ws + W.dApart, VGradFuse());
+                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, VGradFuse());
         PSI_LAUNCHED_K(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd");
     }
     {
-        const size_t smem = (size_t)kDStages * kDStageBytes;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(lbs_dcoef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
         dim3 grid((unsigned)(m->Kpad / kDK), (unsigned)kNSplit, (unsigned)(W.Bpad / kBG));
-        launch_pdl(lbs_dcoef_kernel, grid, dim3(256), smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp,
-                   ws + W.part, kNSplit);
-        PSI_LAUNCHED_K("lbs_dcoef");
+        if (tc5) {
+            const size_t smem = (size_t)kTSmem + 1024;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(lbs_dcoef_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set = true;
+            }
+            const int items = (m->Kpad / kTM) * nsplit * (W.Bpad / kBG);
+            launch_pdl(lbs_dcoef_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
+                       smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp, ws + W.gvp_lo, ws + W.part, nsplit);
+            PSI_LAUNCHED_K("lbs_dcoef_tc5");
+        } else {
+            const size_t smem = (size_t)kDStages * kDStageBytes;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(lbs_dcoef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set = true;
+            }
+            launch_pdl(lbs_dcoef_kernel, grid, dim3(256), smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp,
+                       ws + W.part, kNSplit);
+            PSI_LAUNCHED_K("lbs_dcoef");
+        }
     }
     {
         const long c0 = (long)W.Bpad * m->Kpad, c1 = (long)B * (m->J + 1) * 12;
         dim3 grid((unsigned)(((c0 > c1 ? c0 : c1) + 255) / 256), 2);
-        launch_pdl(lbs_reduce2_kernel, grid, dim3(256), 0, st, ws + W.part, kNSplit, c0, ws + W.dsum, ws + W.dApart,
+        launch_pdl(lbs_reduce2_kernel, grid, dim3(256), 0, st, ws + W.part, nsplit, c0, ws + W.dsum, ws + W.dApart,
                    m->NCH, c1, ws + W.dA);
         PSI_LAUNCHED_K("lbs_reduce2");
     }
-    launch_pdl(lbs_pose_bwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, W.Bpad, kNSplit, m->Jdirs,
+    launch_pdl(lbs_pose_bwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, W.Bpad, nsplit, m->Jdirs,
                m->parents, pose, saved, L, ws + W.dA, ws + W.dsum, grad_joints, grad_betas,
                grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree);
     PSI_LAUNCHED_K("lbs_pose_bwd");

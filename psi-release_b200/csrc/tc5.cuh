@@ -1,0 +1,77 @@
+// tcgen05 (5th-generation tensor core) helpers for sm_100a: TMEM allocation, shared-memory matrix
+// descriptors, single-thread MMA issue, completion commits, TMEM loads.
+//
+// Used by the LBS blend GEMMs (lbs.cu).  Operand tiles are K-major rows of 32 floats (128 bytes)
+// in the 128-byte swizzle (16-byte chunk c of row r at chunk c ^ (r & 7), 8-row groups 1024 bytes
+// apart, tile base 1024-byte aligned) -- the layout common.cuh's swz() produces and TMA bulk copies
+// move as is.  kind::tf32 reads FP32 words from shared memory; the 3xTF32 split (x = hi + lo, hi
+// with the low 13 mantissa bits cleared) is made explicit in shared memory so the result does not
+// depend on how the hardware narrows FP32 to TF32.
+#pragma once
+#include <stdint.h>
+
+namespace psi {
+namespace tc5 {
+
+// ---- TMEM ------------------------------------------------------------------------------------
+// whole warp (.sync.aligned); ncols a power of two >= 32; the base address lands in *smem_dst
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- descriptors -----------------------------------------------------------------------------
+// K-major operand tile, 128-byte swizzle: start address (>>4) | LBO 1 (unused for swizzled K-major)
+// | SBO = 1024 B between 8-row groups | descriptor version 1 (sm_100) | layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, dense, M x N
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- MMA issue (ONE thread) --------------------------------------------------------------------
+// D[tmem] (+)= A[smem] * B[smem]^T, K = 8 TF32 per instruction
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+// arrive on `bar` once every MMA issued so far by this thread has completed (implies
+// tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- TMEM -> registers (whole warp): lane t reads datapath lane (taddr.lane + t), 8 consecutive columns
+__device__ __forceinline__ void ld_32x32b_x8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace tc5
+}  // namespace psi

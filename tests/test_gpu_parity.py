@@ -428,3 +428,37 @@ def test_nn_index_group_schedule_coherent_queries_ties_and_qsel(n, m):
     assert L.psi_nn_index_query_mode(ix.h, _lib.ptr(tq), rows * 3, B, n, _lib.ptr(sel), _lib.ptr(dist), None,
                                      None, 3, _lib.stream_ptr()) == 0
     assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o))
+
+
+def test_lbs_tcgen05_gemm_path_matches_golden_in_subprocess(golden_dir):
+    """PSI_LBS_GEMM=tc5 switches the two blend GEMMs to the tcgen05 + TMEM kernels (the flag is read
+    once per process, hence the subprocess): forward and backward against the reference-lbs.py
+    goldens, on the small model (splits with no chunks, ragged tiles) and the full one."""
+    import subprocess, sys
+    code = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from psi_release_b200 import body_model, synthetic
+def rel(a, b): return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+for name in ("lbs_small.npz", "lbs_full.npz"):
+    g = np.load(os.path.join(%r, name))
+    model = synthetic.make_smplx_model(seed=int(g["model_seed"]), num_verts=int(g["num_verts"]))
+    m = body_model.SMPLX(model_data=model, num_pca_comps=12, batch_size=g["betas"].shape[0]).cuda()
+    h = m.handle()
+    betas = torch.tensor(g["betas"], device="cuda", requires_grad=True)
+    pose = torch.tensor(g["pose"], device="cuda", requires_grad=True)
+    verts, joints = body_model.lbs(betas, pose, h, want_joints=True)
+    assert rel(verts.detach().cpu().numpy(), g["verts"]) < 1e-4, name
+    B, V = g["verts"].shape[:2]
+    probe = np.random.default_rng(int(g["probe_seed"]))
+    probe.standard_normal((B, 20)); probe.standard_normal((B, 165))
+    w = probe.standard_normal((B, V, 3)).astype(np.float32)
+    (verts * torch.tensor(w, device="cuda")).sum().backward()
+    assert rel(betas.grad.cpu().numpy(), g["grad_betas"]) < 2e-4, name
+    mask = np.ones_like(g["grad_pose"], dtype=bool); mask[0, 3:9] = False
+    assert rel(pose.grad.cpu().numpy()[mask], g["grad_pose"][mask]) < 2e-4, name
+print("tc5 ok")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), golden_dir)
+    env = dict(os.environ, PSI_LBS_GEMM="tc5")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "tc5 ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
