@@ -104,6 +104,16 @@ class FittingOP:
 
         self.xhr_rec = torch.randn(B, 75, device=self.device).requires_grad_(True)
         self.optimizer = _Adam(self.xhr_rec, lr=self.init_lr_h)
+        # 'adam': the fitting scripts' optimiser (fitting_habitat.py:76).  'lbfgs': the second mode of
+        # SURVEY.md T7 / 8(d) -- L-BFGS, history 100, strong-Wolfe line search as
+        # human_body_prior/optimizers/lbfgs_ls.py:214-222 (the same algorithm as torch.optim.LBFGS, of
+        # which that file is a copy), driven through the closure; num_iter = max_iter, the number of
+        # closure evaluations is reported in self.closure_evals.  It couples the bodies of a batch
+        # through the shared curvature history, so it runs on the autograd engine only.
+        self.opt_name = getattr(self, "optimizer_name", "adam")
+        if self.opt_name not in ("adam", "lbfgs"):
+            raise ValueError("fittingconfig['optimizer_name'] must be 'adam' or 'lbfgs'")
+        self.closure_evals = 0
 
         # --- scene sdf + vertices (fitting_habitat.py:80-96): ONE copy, shared by the batch
         scene = getattr(self, "scene", None)
@@ -129,8 +139,10 @@ class FittingOP:
                                   torch.equal(self.contact_ids, torch.arange(self.contact_ids.numel(), device=self.device)))
         # 'fused': the whole iteration in libpsi_b200 (psi_fit_run, 11 launches/iteration);
         # 'autograd': torch autograd over the psi ops (any loss_mode, any nn mode)
-        self.engine = getattr(self, "engine", "fused" if (self.loss_mode == "independent" and
-                                                          self.nn_mode == "index") else "autograd")
+        self.engine = getattr(self, "engine", "fused" if (self.loss_mode == "independent" and self.nn_mode == "index"
+                                                          and self.opt_name == "adam") else "autograd")
+        if self.opt_name == "lbfgs" and self.engine == "fused":
+            raise ValueError("optimizer_name='lbfgs' runs on engine='autograd'")
         if self.engine not in ("fused", "autograd"):
             raise ValueError("fittingconfig['engine'] must be 'fused' or 'autograd'")
         self._fused = None
@@ -229,6 +241,26 @@ class FittingOP:
                     self.xhr_rec.copy_(fitted)
                 self.last_losses = losses.sum(dim=0)
                 return GeometryTransformer.convert_to_3D_rot(fitted)
+            if self.opt_name == "lbfgs":
+                with torch.no_grad():
+                    self.xhr_rec.copy_(xhr)
+                opt = torch.optim.LBFGS([self.xhr_rec], lr=float(getattr(self, "lbfgs_lr", 1.0)), max_iter=int(num_iter),
+                                        max_eval=int(num_iter) * 5 // 4, tolerance_grad=float(getattr(self, "tolerance_grad", 1e-7)),
+                                        tolerance_change=float(getattr(self, "tolerance_change", 1e-9)), history_size=100,
+                                        line_search_fn="strong_wolfe")
+                self.closure_evals = 0
+
+                def closure():
+                    opt.zero_grad()
+                    terms = self.cal_loss(xhr, cam_ext)
+                    loss = terms[0] + terms[1] + terms[2] + terms[3]
+                    loss.backward()
+                    self.last_losses = torch.stack([t.detach() for t in terms])
+                    self.closure_evals += 1
+                    return loss
+
+                opt.step(closure)
+                return GeometryTransformer.convert_to_3D_rot(self.xhr_rec.detach())
             if self.use_cuda_graph:
                 if self._graph is None or self._static_cam.shape != cam_ext.shape:
                     self._build_graph()

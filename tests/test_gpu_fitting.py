@@ -216,3 +216,50 @@ def test_training_geometry_block_matches_train_s2_definition(small_model):
     # before 75 % of the epochs the block is skipped (the reference multiplies it by 0.0)
     lc0, lv0, lp0 = blk(x, cams.cuda(), scene_ids, ep=3, epochs=30)
     assert float(lc0) == 0.0 and float(lp0) == 0.0 and float(lv0) > 0
+
+
+def test_lbfgs_mode_decreases_the_loss_and_counts_closures(small_model):
+    """optimizer_name='lbfgs' (the optional second mode): strong-Wolfe L-BFGS over the same
+    cal_loss closure; it must lower the loss, count its closure evaluations and leave Adam untouched."""
+    from psi_release_b200.fitting import FittingOP
+    from psi_release_b200.geometry import GeometryTransformer
+    scene, xh, cid, cfg = _world(small_model, 2)
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0).cuda()
+    op = FittingOP(dict(cfg, optimizer_name="lbfgs", num_iter=12), W)
+    assert op.engine == "autograd"
+    x0 = torch.tensor(xh).cuda()
+    xhr0 = GeometryTransformer.convert_to_6D_rot(x0)
+    with torch.no_grad():
+        op.xhr_rec.copy_(xhr0)
+    before = float(sum(op.cal_loss(xhr0, cam)))
+    out = op.fit(x0, cam)
+    after = float(op.last_losses.sum())
+    assert out.shape == (2, 72) and torch.isfinite(out).all()
+    assert 1 <= op.closure_evals <= 12 * 5 // 4 + 1
+    assert after < before
+    with pytest.raises(ValueError):
+        FittingOP(dict(cfg, optimizer_name="lbfgs", engine="fused"), W)
+
+
+def test_rooms_pipeline_generate_fit_score_write(small_model, tmp_path):
+    """pipeline.fit_rooms (BASELINE config 5 shape: rooms x samples): every room's samples are one batch,
+    results equal per-room FittingOP.fit, scores equal evaluate.collision_scores, pickles are written
+    in the reference's per-body layout."""
+    from psi_release_b200 import evaluate, io, pipeline, synthetic
+    from psi_release_b200.fitting import FittingOP
+    rooms = [synthetic.make_scene(seed=s, dim=24, num_points=1500) for s in (11, 12, 13)]
+    cid = synthetic.make_contact_ids(431, "parts")
+    base = dict(model_data=small_model, vposer_weights=synthetic.make_vposer_weights(), contact_ids=cid,
+                init_lr_h=0.1, num_iter=3, device="cuda")
+    gen = lambda r, n: synthetic.make_body_params(rooms[r], n, seed=50 + r)
+    res = pipeline.fit_rooms(rooms, gen, 4, base, W, out_dir=str(tmp_path))
+    assert res["fitted"].shape == (12, 72) and res["non_collision"].shape == (12,) and res["contact"].shape == (12,)
+    for r in range(3):
+        op = FittingOP(dict(base, scene=rooms[r], batch_size=4), W)
+        cam = torch.tensor(rooms[r].cam_ext).unsqueeze(0).cuda()
+        ref = op.fit(torch.tensor(gen(r, 4)).cuda(), cam)
+        assert torch.equal(res["fitted"][4 * r:4 * r + 4], ref)
+        nc, ct = evaluate.collision_scores(op, ref, cam)
+        assert torch.equal(res["non_collision"][4 * r:4 * r + 4], nc) and torch.equal(res["contact"][4 * r:4 * r + 4], ct)
+        d = io.read_body_pickle(str(tmp_path / ("room_%03d" % r) / "body_gen_000002.pkl"))
+        np.testing.assert_array_equal(d["transl"][0], ref[2, :3].cpu().numpy())
