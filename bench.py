@@ -329,6 +329,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PSI_BENCH_NCCL_DEBUG", "WARN")   # stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     model, scene, xh = make_world(args, rank)
     cfg = dict(model_data=model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
@@ -418,7 +419,7 @@ def run_ours(args):
         "roofline": roofline,
         "engine": op.engine,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed at N = 1 only
         out["cpu_baseline"] = cpu_baseline(args, seconds=args.cpu_baseline_seconds)
     print(json.dumps(out), flush=True)
     if world > 1:
