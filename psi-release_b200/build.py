@@ -31,7 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("PSI_EXTRA_NVCC_FLAGS", "").split()
     cmd = [_nvcc(), *flags, "-shared", "-o", out, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -2,9 +2,17 @@
 #include "common.cuh"
 #include <atomic>
 #include <stdlib.h>
+#include <string.h>
 
 namespace psi {
 static std::atomic<unsigned long long> g_launches{0};
+// Ablation timing: with PSI_SKIP_KERNEL=<name> every launch tagged <name> is skipped, so the captured
+// iteration shows that kernel's marginal cost inside the graph (eager per-launch timings overstate the
+// short kernels).  The results of such a run are meaningless; bench.py never sets it.
+bool skip_kernel(const char *name) {
+    static const char *skip = getenv("PSI_SKIP_KERNEL");
+    return skip && name && strcmp(skip, name) == 0;
+}
 bool pdl_enabled() {
     // opt-in: measured SLOWER on B200 for this chain (460 vs 535 bodies/s at r01p: the early-scheduled
     // dependents do not shorten the chain, the graph's programmatic edges cost more than they save)

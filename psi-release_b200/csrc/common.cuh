@@ -72,6 +72,7 @@ int lbs_vertex_chunks(const psi_lbs_model *m);   // 256-vertex chunks = rows of 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+bool skip_kernel(const char *name);   // api.cu: measurement aid, PSI_SKIP_KERNEL=<name> drops that launch (results invalid)
 bool pdl_enabled();   // api.cu: true only when PSI_PDL=1 (measured slower, see api.cu)
 // launch `kernel`; it MUST call pdl_wait() before touching global memory other than constants
 template <typename... KArgs, typename... Args>

@@ -188,16 +188,16 @@ static int launch_linear(cudaStream_t st, int B, const float *A, const float *W,
     p.K = K; p.N = N; p.B = B; p.n_valid = n_valid; p.ld = ld; p.outA_kpad = outA_kpad; p.act = act;
     dim3 grid((unsigned)(N / kLT), (unsigned)((B + kBG - 1) / kBG));
     if (K % kKC || K / kKC > kLMaxChunks || N % kLT) return PSI_ERR_UNSUPPORTED;
-    launch_pdl(fit_linear_kernel, dim3(grid), dim3(128), (size_t)(K / kKC) * kLChunkBytes, st, p);
+    (psi::skip_kernel("fit_linear") ? cudaSuccess : launch_pdl(fit_linear_kernel, dim3(grid), dim3(128), (size_t)(K / kKC) * kLChunkBytes, st, p));
     PSI_LAUNCHED_K("fit_linear");
     return PSI_OK;
 }
 
 static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
     const FitDims d = {c->B, c->V, c->J, c->NB, c->latent, c->hidden, c->nbody, c->ncomp, c->num_rot};
-    launch_pdl(fit_step_kernel, dim3(c->B), dim3(128), 0, st, d, c->cfg, do_post, c->np_sdf, c->nchunk, c->num_contact,
+    (psi::skip_kernel("fit_step") ? cudaSuccess : launch_pdl(fit_step_kernel, dim3(c->B), dim3(128), 0, st, d, c->cfg, do_post, c->np_sdf, c->nchunk, c->num_contact,
                c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->dz, c->g6_root, c->gpose,
-               c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl);
+               c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl));
     PSI_LAUNCHED_K("fit_step");
     return PSI_OK;
 }

@@ -1407,14 +1407,14 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     const bool tc5 = lbs_gemm_tc5();
-    launch_pdl(lbs_pose_fwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, tc5 ? 1 : 0, m->tree);
+    (psi::skip_kernel("lbs_pose_fwd") ? cudaSuccess : launch_pdl(lbs_pose_fwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, tc5 ? 1 : 0, m->tree));
     PSI_LAUNCHED_K("lbs_pose_fwd");
     if (B % kBG) {
-        launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef, B, m->Kpad);
+        (psi::skip_kernel("lbs_zero_coef_pad") ? cudaSuccess : launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef, B, m->Kpad));
         PSI_LAUNCHED_K("lbs_zero_coef_pad");
         if (tc5) {
-            launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef_lo, B, m->Kpad);
+            (psi::skip_kernel("lbs_zero_coef_pad") ? cudaSuccess : launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef_lo, B, m->Kpad));
             PSI_LAUNCHED_K("lbs_zero_coef_pad");
         }
     }
@@ -1430,8 +1430,8 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
             attr_set = true;
         }
         const int items = p.ntiles * p.nbg;
-        launch_pdl(lbs_blend_fwd_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
-                   smem, st, p);
+        (psi::skip_kernel("lbs_blend_fwd_tc5") ? cudaSuccess : launch_pdl(lbs_blend_fwd_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
+                   smem, st, p));
         PSI_LAUNCHED_K("lbs_blend_fwd_tc5");
     } else {
         BlendFwdParams p;
@@ -1443,17 +1443,17 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
             cudaFuncSetAttribute(lbs_blend_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        launch_pdl(lbs_blend_fwd_kernel, grid, dim3(128), smem, st, p);
+        (psi::skip_kernel("lbs_blend_fwd") ? cudaSuccess : launch_pdl(lbs_blend_fwd_kernel, grid, dim3(128), smem, st, p));
         PSI_LAUNCHED_K("lbs_blend_fwd");
     }
     {
         dim3 sgrid((unsigned)((m->V + 255) / 256), (unsigned)B);
         if (sdf)
-            launch_pdl(lbs_skin_fwd_kernel<true>, sgrid, dim3(256), 0, st, m->V, m->J, m->KW, m->skin_j, m->skin_w,
-                       saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, *sdf);
+            (psi::skip_kernel(sdf ? "lbs_skin_sdf_fwd" : "lbs_skin_fwd") ? cudaSuccess : launch_pdl(lbs_skin_fwd_kernel<true>, sgrid, dim3(256), 0, st, m->V, m->J, m->KW, m->skin_j, m->skin_w,
+                       saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, *sdf));
         else
-            launch_pdl(lbs_skin_fwd_kernel<false>, sgrid, dim3(256), 0, st, m->V, m->J, m->KW, m->skin_j, m->skin_w,
-                       saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, SdfFuse());
+            (psi::skip_kernel(sdf ? "lbs_skin_sdf_fwd" : "lbs_skin_fwd") ? cudaSuccess : launch_pdl(lbs_skin_fwd_kernel<false>, sgrid, dim3(256), 0, st, m->V, m->J, m->KW, m->skin_j, m->skin_w,
+                       saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, SdfFuse()));
         PSI_LAUNCHED_K(sdf ? "lbs_skin_sdf_fwd" : "lbs_skin_fwd");
     }
     return PSI_OK;
@@ -1505,13 +1505,13 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
         const size_t smem = (size_t)cap * 5;
         const int units = (cap > 0 && m->max_units <= kMaxUnits) ? 1 : 0;
         if (vg)
-            launch_pdl(lbs_vertex_bwd_kernel<true>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
+            (psi::skip_kernel(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd") ? cudaSuccess : launch_pdl(lbs_vertex_bwd_kernel<true>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                        m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
-                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, *vg);
+                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, *vg));
         else
-            launch_pdl(lbs_vertex_bwd_kernel<false>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
+            (psi::skip_kernel(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd") ? cudaSuccess : launch_pdl(lbs_vertex_bwd_kernel<false>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                        m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
-                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, VGradFuse());
+                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, VGradFuse()));
         PSI_LAUNCHED_K(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd");
     }
     {
@@ -1524,8 +1524,8 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
                 attr_set = true;
             }
             const int items = (m->Kpad / kTM) * nsplit * (W.Bpad / kBG);
-            launch_pdl(lbs_dcoef_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
-                       smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp, ws + W.gvp_lo, ws + W.part, nsplit);
+            (psi::skip_kernel("lbs_dcoef_tc5") ? cudaSuccess : launch_pdl(lbs_dcoef_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
+                       smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp, ws + W.gvp_lo, ws + W.part, nsplit));
             PSI_LAUNCHED_K("lbs_dcoef_tc5");
         } else {
             const size_t smem = (size_t)kDStages * kDStageBytes;
@@ -1534,21 +1534,21 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
                 cudaFuncSetAttribute(lbs_dcoef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 attr_set = true;
             }
-            launch_pdl(lbs_dcoef_kernel, grid, dim3(256), smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp,
-                       ws + W.part, kNSplit);
+            (psi::skip_kernel("lbs_dcoef") ? cudaSuccess : launch_pdl(lbs_dcoef_kernel, grid, dim3(256), smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp,
+                       ws + W.part, kNSplit));
             PSI_LAUNCHED_K("lbs_dcoef");
         }
     }
     {
         const long c0 = (long)W.Bpad * m->Kpad, c1 = (long)B * (m->J + 1) * 12;
         dim3 grid((unsigned)(((c0 > c1 ? c0 : c1) + 255) / 256), 2);
-        launch_pdl(lbs_reduce2_kernel, grid, dim3(256), 0, st, ws + W.part, nsplit, c0, ws + W.dsum, ws + W.dApart,
-                   m->NCH, c1, ws + W.dA);
+        (psi::skip_kernel("lbs_reduce2") ? cudaSuccess : launch_pdl(lbs_reduce2_kernel, grid, dim3(256), 0, st, ws + W.part, nsplit, c0, ws + W.dsum, ws + W.dApart,
+                   m->NCH, c1, ws + W.dA));
         PSI_LAUNCHED_K("lbs_reduce2");
     }
-    launch_pdl(lbs_pose_bwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, W.Bpad, nsplit, m->Jdirs,
+    (psi::skip_kernel("lbs_pose_bwd") ? cudaSuccess : launch_pdl(lbs_pose_bwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, W.Bpad, nsplit, m->Jdirs,
                m->parents, pose, saved, L, ws + W.dA, ws + W.dsum, grad_joints, grad_betas,
-               grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree);
+               grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree));
     PSI_LAUNCHED_K("lbs_pose_bwd");
     return PSI_OK;
 }

@@ -435,6 +435,14 @@ __device__ __noinline__ int leaf_arg(const float4 *__restrict__ pts2, int c, flo
 
 constexpr int kGrpThreads = 256;
 
+// -DPSI_NN_STATS: event counters of the group walk (debug builds only; tools/nn_stats.py)
+#ifdef PSI_NN_STATS
+__device__ unsigned long long g_nn_stats[8];
+#define NN_STAT(i) do { if (lane == 0) atomicAdd(&g_nn_stats[i], 1ull); } while (0)
+#else
+#define NN_STAT(i) do { } while (0)
+#endif
+
 template <bool SMEM>
 __global__ void __launch_bounds__(kGrpThreads, 4)
 nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, long q_bstride, int n,
@@ -474,6 +482,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         const float *qp = q_in + b * q_bstride + (qsel ? (long)__ldg(qsel + jj) : (long)jj) * 3;
         const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
         const float2 n2x = make_float2(-qx, -qx), n2y = make_float2(-qy, -qy), n2z = make_float2(-qz, -qz);
+        NN_STAT(0);
         // query boxes: the 4 sub-groups (shared memory) and the whole group (registers)
         float lx, ly, lz, hx, hy, hz;
         {
@@ -539,6 +548,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
             unsigned todo = full;
             while (todo) {
                 const int c = __shfl_sync(full, h, __ffs(todo) - 1);
+                NN_STAT(1);
                 visit(c);
                 if (lane == nvis) myvis = c;
                 ++nvis;
@@ -552,12 +562,14 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
             // (pad megas never enter: with ub = +inf -- NaN queries -- their children would be out of range)
             unsigned mmask = __ballot_sync(full, lbm <= ub && r * 32 + lane < ix.num_megas);
             while (mmask) {
+                NN_STAT(2);
                 const int src = take4(mmask, lane);
                 const int my_super = (r * 32 + (src < 0 ? 0 : src)) * kFan + (lane & 7);
                 unsigned slb = 0x7f800000u;
                 if (src >= 0) slb = box_lb_group(top_lo[ix.mpad + my_super], top_hi[ix.mpad + my_super], lx, ly, lz, hx, hy, hz);
                 unsigned smask = __ballot_sync(full, src >= 0 && slb <= ub);
                 while (smask) {
+                    NN_STAT(3);
                     const int src2 = take4(smask, lane);
                     const int cid = __shfl_sync(full, my_super, src2 < 0 ? 0 : src2) * kFan + (lane & 7);
                     // lane = cluster: admitted if any of the 4 sub-groups (tighter boxes, tighter bounds) may need it
@@ -577,9 +589,11 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
                         const int cl = __ffs(cmask) - 1;
                         cmask &= cmask - 1;
                         const int c = __shfl_sync(full, cid, cl);
+                        NN_STAT(4);
                         // lane = query: does any lane still need leaf c?
                         const float lbl = __uint_as_float(box_lb(__ldg(c_lo + c), __ldg(c_hi + c), qx, qy, qz));
                         if (__any_sync(full, lbl <= bd)) {
+                            NN_STAT(5);
                             visit(c);
                             publish_bounds();
                         }
@@ -731,6 +745,15 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
 
 size_t psi_nn_index_bytes(const psi_nn_index *ix) { return ix ? ix->bytes : 0; }
 
+#ifdef PSI_NN_STATS
+__attribute__((visibility("default"))) int psi_debug_nn_stats(unsigned long long *h_out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h_out, psi::g_nn_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(psi::g_nn_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 // mode 0: pick by query count; 1: warp per query; 2: thread per query
 static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
                                const int *qsel, float *dist, int *idx, int *hint, int mode,
@@ -758,9 +781,9 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         if (blocks > cap) blocks = cap;
         const size_t top_bytes = (size_t)2 * (ix->mpad + ix->num_supers) * sizeof(float4);
         if (top_bytes <= 24 * 1024)
-            launch_pdl(nn_index_group_kernel<true>, dim3((unsigned)blocks), dim3(kGrpThreads), top_bytes, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint);
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_group_kernel<true>, dim3((unsigned)blocks), dim3(kGrpThreads), top_bytes, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint));
         else
-            launch_pdl(nn_index_group_kernel<false>, dim3((unsigned)blocks), dim3(kGrpThreads), 0, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint);
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_group_kernel<false>, dim3((unsigned)blocks), dim3(kGrpThreads), 0, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint));
     } else if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
         // one thread per query: enough queries to fill the machine with 256-thread CTAs
         long blocks = (total + 255) / 256;
@@ -769,17 +792,17 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         const size_t top_bytes = (size_t)3 * ((ix->mpad + ix->num_supers) / 2) * sizeof(float4);
         // 64 registers (no spills with the packed pairs), 4 CTAs/SM; measured best of 3/4/5/6/8
         if (top_bytes <= 24 * 1024)
-            launch_pdl(nn_index_thread_kernel<true>, dim3((unsigned)blocks), dim3(256), top_bytes, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_thread_kernel<true>, dim3((unsigned)blocks), dim3(256), top_bytes, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint));
         else
-            launch_pdl(nn_index_thread_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_thread_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint));
     } else {
         long blocks = (total + wpb - 1) / wpb;
         const long cap = (long)PSI_NUM_SMS * (smem ? 3 : 4);
         if (blocks > cap) blocks = cap;
         if (smem)
-            launch_pdl(nn_index_query_kernel<true>, dim3((unsigned)blocks), dim3(kIdxThreads), box_bytes, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_query_kernel<true>, dim3((unsigned)blocks), dim3(kIdxThreads), box_bytes, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint));
         else
-            launch_pdl(nn_index_query_kernel<false>, dim3((unsigned)blocks), dim3(kIdxThreads), 0, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint);
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_query_kernel<false>, dim3((unsigned)blocks), dim3(kIdxThreads), 0, st, *ix, q, q_bstride, n, qsel, total, dist, idx, hint));
     }
     PSI_LAUNCHED_K(mode == 3 ? "nn_index_group" : "nn_index_query");
     return PSI_OK;

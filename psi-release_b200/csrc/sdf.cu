@@ -122,8 +122,8 @@ int psi_sdf_fwd(const float *sdf, int S, int D, const float *h_grid_min, const f
         }
     const int np = psi_sdf_num_partials(V);
     dim3 grid((unsigned)np, (unsigned)B);
-    launch_pdl(psi::sdf_fwd_kernel, dim3(grid), dim3(psi::kSdfThreads), 0, (cudaStream_t)stream, 
-        sdf, D, sc, verts, V, body_scene, out, grad, partial, np);
+    (psi::skip_kernel("sdf_fwd") ? cudaSuccess : launch_pdl(psi::sdf_fwd_kernel, dim3(grid), dim3(psi::kSdfThreads), 0, (cudaStream_t)stream, 
+        sdf, D, sc, verts, V, body_scene, out, grad, partial, np));
     PSI_LAUNCHED_K("sdf_fwd");
     return PSI_OK;
 }
