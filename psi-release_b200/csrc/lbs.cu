@@ -73,14 +73,14 @@ struct psi_lbs_model {
 
 namespace psi {
 
-// PSI_LBS_GEMM=tc5 selects the tcgen05 + TMEM blend GEMMs; default: the mma.sync GEMMs.  Measured
-// at B = 64 (r01r): forward 44 vs 41 us, dcoef 39 vs 37 us -- with only 64 bodies as the N dimension
-// and FP32 operands split three ways, a tcgen05.mma (128 x 64 x 8) re-reads 6 kB of operands from
-// shared memory for 65 k MACs and runs at ~128 cycles (tensor pipe busy 47 % of the kernel); the
-// path pays off from ~128 bodies per GPU up.  Read once per process: the model's forward basis
-// layout depends on it.
+// The two blend GEMMs run on tcgen05 + TMEM (default) or on the legacy mma.sync path (PSI_LBS_GEMM=mma).
+// Measured at B = 64: forward 32 vs 43 us, dcoef 27 vs 38 us.  With only 64 bodies as the N dimension and
+// FP32 operands split three ways the tcgen05 kernels are bound by shared-memory operand traffic, not by
+// the tensor pipe; the first version (three N = 64 MMAs per k step, issued by a worker thread) was no
+// faster than mma.sync -- stacking hi|lo of the per-body operand into one N = 128 MMA and a dedicated
+// issuer warp made the difference.  Read once per process: the model's forward basis layout depends on it.
 static bool lbs_gemm_tc5() {
-    static const bool on = [] { const char *e = getenv("PSI_LBS_GEMM"); return e && e[0] == 't'; }();
+    static const bool on = [] { const char *e = getenv("PSI_LBS_GEMM"); return !(e && e[0] == 'm'); }();
     return on;
 }
 
@@ -764,13 +764,15 @@ lbs_dcoef_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd
 // (mma.sync kept these GEMMs tensor-pipe bound at 41 / 37 us.)
 constexpr int kTM = 128;                       // rows of a basis tile = M of the MMA
 constexpr int kTRaw = 5, kTAct = 4, kTOp = 2;  // ring depths
-constexpr int kTThreads = 192;                 // 4 worker warps + 2 producer warps
+constexpr int kTThreads = 224;                 // 4 worker warps + 2 producer warps + the MMA issuer's warp
 constexpr int kTTileB = kTM * kKC * 4;         // 16 kB: one basis tile (raw, hi or lo)
 constexpr int kTTileA = kBG * kKC * 4;         // 8 kB: one per-body tile (hi or lo)
 constexpr int kTSmem = kTRaw * kTTileB + kTAct * 2 * kTTileA + kTOp * 2 * kTTileB;   // 208 kB
+constexpr int kTCols = 128;                    // TMEM columns: [0,64) = hi*hi + lo*hi, [64,128) = hi*lo
 
 struct Tc5Bars {
-    uint64_t full_raw[kTRaw], empty_raw[kTRaw], full_act[kTAct], empty_act[kTAct], empty_op[kTOp], accum;
+    uint64_t full_raw[kTRaw], empty_raw[kTRaw], full_act[kTAct], empty_act[kTAct], full_op[kTOp], empty_op[kTOp];
+    uint64_t accum, tmem_free;
     uint32_t tmem_slot;
 };
 
@@ -781,10 +783,12 @@ struct Tc5Item {                 // one accumulator's worth of work
     int nchunks;
 };
 
-// Runs the K loop of `it`; g0 = number of chunks this CTA has processed before (ring phase).
-// Worker threads return with the accumulator complete in TMEM.
+// Runs the K loop of `it`; g0 = number of chunks this CTA has processed before (ring phase), item_idx =
+// number of items before.  Roles by warp: 0-3 workers (split the raw basis tile into hi | lo operand
+// tiles), 4 raw-tile producer, 5 per-body-tile producer, 6 MMA issuer.  Worker threads return with the
+// accumulator complete in TMEM; after reading it they must arrive on bars.tmem_free.
 __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars, uint32_t tmem_d, const Tc5Item &it,
-                                             int g0, int item_parity) {
+                                             int g0, int item_idx) {
     const int tid = threadIdx.x;
     unsigned char *raw = smem, *act = smem + kTRaw * kTTileB, *op = act + kTAct * 2 * kTTileA;
     if (tid >= 128) {
@@ -795,7 +799,7 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
                 mbar_arrive_expect_tx(&bars.full_raw[st], (uint32_t)kTTileB);
                 tma_load_1d(raw + (size_t)st * kTTileB, it.basis + (size_t)c * it.basis_stride, kTTileB, &bars.full_raw[st]);
             }
-        } else if (tid == 160) {                        // ---- producer: per-body tiles (L2)
+        } else if (tid == 160) {                        // ---- producer: per-body tiles (L2); hi then lo = one 128-row tile
             for (int c = 0; c < it.nchunks; ++c) {
                 const int g = g0 + c, st = g % kTAct;
                 mbar_wait(&bars.empty_act[st], (uint32_t)(((g / kTAct) & 1) ^ 1));
@@ -804,12 +808,32 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
                 tma_load_1d(act + (size_t)st * 2 * kTTileA + kTTileA, it.act_lo + (size_t)c * (kBG * kKC), kTTileA,
                             &bars.full_act[st]);
             }
+        } else if (tid == 192) {                        // ---- MMA issuer
+            constexpr uint32_t idesc_n128 = tc5::idesc_tf32(kTM, 2 * kBG), idesc_n64 = tc5::idesc_tf32(kTM, kBG);
+            mbar_wait(&bars.tmem_free, (uint32_t)((item_idx & 1) ^ 1));      // the previous item's epilogue has read TMEM
+            tc5::fence_after_sync();
+            for (int c = 0; c < it.nchunks; ++c) {
+                const int g = g0 + c, so = g % kTOp, sa = g % kTAct;
+                mbar_wait(&bars.full_op[so], (uint32_t)((g / kTOp) & 1));
+                mbar_wait(&bars.full_act[sa], (uint32_t)((g / kTAct) & 1));
+                tc5::fence_after_sync();
+                const uint32_t sop = smem_u32(op + (size_t)so * 2 * kTTileB), sac = smem_u32(act + (size_t)sa * 2 * kTTileA);
+                const uint64_t dbh = tc5::smem_desc_k_sw128(sop), dbl = tc5::smem_desc_k_sw128(sop + kTTileB);
+                const uint64_t dact = tc5::smem_desc_k_sw128(sac);      // rows 0..63 = hi, 64..127 = lo
+#pragma unroll
+                for (int k = 0; k < kKC / 8; ++k) {      // 32 bytes of every 128-byte row per step: start address + 2
+                    tc5::mma_tf32(tmem_d, dbh + 2 * k, dact + 2 * k, idesc_n128, (c | k) != 0);   // hi*[hi | lo]
+                    tc5::mma_tf32(tmem_d, dbl + 2 * k, dact + 2 * k, idesc_n64, 1u);              // lo*hi
+                }
+                tc5::commit(&bars.empty_op[so]);
+                tc5::commit(&bars.empty_act[sa]);
+                if (c == it.nchunks - 1) tc5::commit(&bars.accum);
+            }
         }
         return;
     }
-    constexpr uint32_t idesc = tc5::idesc_tf32(kTM, kBG);
     for (int c = 0; c < it.nchunks; ++c) {
-        const int g = g0 + c, sr = g % kTRaw, so = g % kTOp, sa = g % kTAct;
+        const int g = g0 + c, sr = g % kTRaw, so = g % kTOp;
         mbar_wait(&bars.full_raw[sr], (uint32_t)((g / kTRaw) & 1));
         mbar_wait(&bars.empty_op[so], (uint32_t)(((g / kTOp) & 1) ^ 1));       // the MMAs that read this slot are done
         const uint4 *src = reinterpret_cast<const uint4 *>(raw + (size_t)sr * kTTileB);
@@ -824,26 +848,10 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
                                 __uint_as_float(x.z) - __uint_as_float(h.z), __uint_as_float(x.w) - __uint_as_float(h.w));
         }
         tc5::fence_proxy_async();
+        mbar_arrive(&bars.full_op[so]);                 // 128 arrivals: the operand slot is ready for the issuer
         mbar_arrive(&bars.empty_raw[sr]);               // 128 arrivals free the raw slot
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) {
-            mbar_wait(&bars.full_act[sa], (uint32_t)((g / kTAct) & 1));
-            tc5::fence_after_sync();
-            const uint32_t sop = smem_u32(op + (size_t)so * 2 * kTTileB), sac = smem_u32(act + (size_t)sa * 2 * kTTileA);
-            const uint64_t dbh = tc5::smem_desc_k_sw128(sop), dbl = tc5::smem_desc_k_sw128(sop + kTTileB);
-            const uint64_t dah = tc5::smem_desc_k_sw128(sac), dal = tc5::smem_desc_k_sw128(sac + kTTileA);
-#pragma unroll
-            for (int k = 0; k < kKC / 8; ++k) {          // 32 bytes of every 128-byte row per step: start address + 2
-                tc5::mma_tf32(tmem_d, dbh + 2 * k, dal + 2 * k, idesc, (c | k) != 0);
-                tc5::mma_tf32(tmem_d, dbl + 2 * k, dah + 2 * k, idesc, 1u);
-                tc5::mma_tf32(tmem_d, dbh + 2 * k, dah + 2 * k, idesc, 1u);
-            }
-            tc5::commit(&bars.empty_op[so]);
-            tc5::commit(&bars.empty_act[sa]);
-            if (c == it.nchunks - 1) tc5::commit(&bars.accum);
-        }
     }
-    mbar_wait(&bars.accum, (uint32_t)item_parity);
+    mbar_wait(&bars.accum, (uint32_t)(item_idx & 1));
     tc5::fence_after_sync();
 }
 
@@ -851,12 +859,13 @@ __device__ __forceinline__ uint32_t tc5_setup(Tc5Bars &bars) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTRaw; ++i) { mbar_init(&bars.full_raw[i], 1); mbar_init(&bars.empty_raw[i], 128); }
         for (int i = 0; i < kTAct; ++i) { mbar_init(&bars.full_act[i], 1); mbar_init(&bars.empty_act[i], 1); }
-        for (int i = 0; i < kTOp; ++i) mbar_init(&bars.empty_op[i], 1);
+        for (int i = 0; i < kTOp; ++i) { mbar_init(&bars.full_op[i], 128); mbar_init(&bars.empty_op[i], 1); }
         mbar_init(&bars.accum, 1);
+        mbar_init(&bars.tmem_free, 128);
         mbar_fence_init();
     }
-    if (threadIdx.x >= 160) {                   // warp 5 owns the TMEM allocation
-        tc5::tmem_alloc(&bars.tmem_slot, 64);
+    if (threadIdx.x >= 160 && threadIdx.x < 192) {   // warp 5 owns the TMEM allocation
+        tc5::tmem_alloc(&bars.tmem_slot, kTCols);
         tc5::tmem_relinquish();
     }
     tc5::fence_before_sync();
@@ -868,7 +877,16 @@ __device__ __forceinline__ uint32_t tc5_setup(Tc5Bars &bars) {
 __device__ __forceinline__ void tc5_teardown(uint32_t tmem_d) {
     tc5::fence_before_sync();
     __syncthreads();
-    if (threadIdx.x >= 160) tc5::tmem_dealloc(tmem_d, 64);
+    if (threadIdx.x >= 160 && threadIdx.x < 192) tc5::tmem_dealloc(tmem_d, kTCols);
+}
+
+// accumulator row of this lane, bodies c8*8 .. c8*8+7: hi*hi + lo*hi (columns 0..63) + hi*lo (columns 64..127)
+__device__ __forceinline__ void tc5_load8(uint32_t tmem_d, int w, int c8, float (&v)[8]) {
+    float u[8];
+    tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(c8 * 8), v);
+    tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(kBG + c8 * 8), u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += u[e];
 }
 
 struct BlendFwdTc5Params {
@@ -887,8 +905,8 @@ __global__ void __launch_bounds__(kTThreads, 1) lbs_blend_fwd_tc5_kernel(const B
     pdl_launch_dependents();
     pdl_wait();
     const int nchunks = p.Kpad / kKC, N = 3 * p.V;
-    int g0 = 0, par = 0;
-    for (int item = blockIdx.x; item < p.ntiles * p.nbg; item += gridDim.x, g0 += nchunks, par ^= 1) {
+    int g0 = 0, idx = 0;
+    for (int item = blockIdx.x; item < p.ntiles * p.nbg; item += gridDim.x, g0 += nchunks, ++idx) {
         const int tile = item % p.ntiles, bg = item / p.ntiles;
         Tc5Item it;
         it.basis = p.basis_fwd + (size_t)tile * p.Kpad * kTM;
@@ -896,21 +914,22 @@ __global__ void __launch_bounds__(kTThreads, 1) lbs_blend_fwd_tc5_kernel(const B
         it.act_hi = p.coef_hi + (size_t)bg * p.Kpad * kBG;
         it.act_lo = p.coef_lo + (size_t)bg * p.Kpad * kBG;
         it.nchunks = nchunks;
-        tc5_mainloop(smem_raw, bars, tmem_d, it, g0, par);
+        tc5_mainloop(smem_raw, bars, tmem_d, it, g0, idx);
         if (w < 4) {
             const int n = tile * kTM + w * 32 + lane;          // TMEM lane = accumulator row = coordinate
             const float vt = n < N ? p.v_template[n] : 0.f;
 #pragma unroll 2
             for (int c8 = 0; c8 < kBG / 8; ++c8) {
                 float v[8];
-                tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(c8 * 8), v);
+                tc5_load8(tmem_d, w, c8, v);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int b = bg * kBG + c8 * 8 + e;
                     if (n < N && b < p.B) p.vp_out[(size_t)b * N + n] = v[e] + vt;
                 }
             }
-            tc5::fence_before_sync();                          // TMEM reads done before the next item's first MMA
+            tc5::fence_before_sync();
+            mbar_arrive(&bars.tmem_free);                      // TMEM has been read: the next item may overwrite it
         }
     }
     tc5_teardown(tmem_d);
@@ -928,7 +947,7 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
     pdl_launch_dependents();
     pdl_wait();
     const int nkt = Kpad / kTM, nbg = Bpad / kBG;
-    int g0 = 0, par = 0;
+    int g0 = 0, idx = 0;
     for (int item = blockIdx.x; item < nkt * nsplit * nbg; item += gridDim.x) {
         const int kt = item % nkt, ns = (item / nkt) % nsplit, bg = item / (nkt * nsplit);
         const int c_begin = (int)((long)ns * NC / nsplit), c_end = (int)((long)(ns + 1) * NC / nsplit);
@@ -944,18 +963,19 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
         it.act_hi = gvp_hi + (size_t)bg * NC * (kBG * kKC) + (size_t)c_begin * (kBG * kKC);
         it.act_lo = gvp_lo + (size_t)bg * NC * (kBG * kKC) + (size_t)c_begin * (kBG * kKC);
         it.nchunks = c_end - c_begin;
-        tc5_mainloop(smem_raw, bars, tmem_d, it, g0, par);
+        tc5_mainloop(smem_raw, bars, tmem_d, it, g0, idx);
         g0 += it.nchunks;
-        par ^= 1;
+        ++idx;
         if (w < 4) {
 #pragma unroll 2
             for (int c8 = 0; c8 < kBG / 8; ++c8) {
                 float v[8];
-                tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(c8 * 8), v);
+                tc5_load8(tmem_d, w, c8, v);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[(size_t)(c8 * 8 + e) * Kpad] = v[e];     // lane = coefficient: coalesced per body
             }
             tc5::fence_before_sync();
+            mbar_arrive(&bars.tmem_free);
         }
     }
     tc5_teardown(tmem_d);

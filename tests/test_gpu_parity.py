@@ -430,10 +430,10 @@ def test_nn_index_group_schedule_coherent_queries_ties_and_qsel(n, m):
     assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o))
 
 
-def test_lbs_tcgen05_gemm_path_matches_golden_in_subprocess(golden_dir):
-    """PSI_LBS_GEMM=tc5 switches the two blend GEMMs to the tcgen05 + TMEM kernels (the flag is read
-    once per process, hence the subprocess): forward and backward against the reference-lbs.py
-    goldens, on the small model (splits with no chunks, ragged tiles) and the full one."""
+def test_lbs_legacy_mma_gemm_path_matches_golden_in_subprocess(golden_dir):
+    """The blend GEMMs default to the tcgen05 + TMEM kernels (every other LBS test); PSI_LBS_GEMM=mma
+    switches them to the legacy mma.sync kernels (the flag is read once per process, hence the
+    subprocess): forward and backward against the reference-lbs.py goldens, small and full model."""
     import subprocess, sys
     code = r"""
 import os, sys, numpy as np, torch
@@ -457,8 +457,8 @@ for name in ("lbs_small.npz", "lbs_full.npz"):
     assert rel(betas.grad.cpu().numpy(), g["grad_betas"]) < 2e-4, name
     mask = np.ones_like(g["grad_pose"], dtype=bool); mask[0, 3:9] = False
     assert rel(pose.grad.cpu().numpy()[mask], g["grad_pose"][mask]) < 2e-4, name
-print("tc5 ok")
+print("gemm ok")
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), golden_dir)
-    env = dict(os.environ, PSI_LBS_GEMM="tc5")
+    env = dict(os.environ, PSI_LBS_GEMM="mma")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "tc5 ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0 and "gemm ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
