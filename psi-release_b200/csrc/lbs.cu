@@ -5,27 +5,26 @@
 // (source/cvae.py:141-149), which the reference runs as ~25 torch kernels plus a 54-step
 // python loop of 4x4 matmuls.
 //
-// HBM layout owned by the model handle (DESIGN.md "LBS"):
-//   basis [Kpad][Npad]  rows 0..P-1 = posedirs (P=(J-1)*9), rows P..P+NB-1 = shapedirs^T,
-//                       zero rows up to Kpad (multiple of 32); Npad = 3V rounded up to 96.
-//                       Shape and pose blend shapes become ONE contraction over K = P+NB.
+// HBM layout owned by the model handle:
+//   basis_fwd [tile n/128][chunk k/32][128 rows][32 k]   rows of k: 0..P-1 = posedirs (P=(J-1)*9), P..P+NB-1 =
+//                       shapedirs^T, zero up to Kpad; shape and pose blend shapes become ONE contraction
+//   basis_bwd [chunk n/32][Kpad rows][32 n]              the same matrix with the coordinates as the reduction index
+//                       (both with 128-byte-swizzled rows: the tcgen05 / ldmatrix operand layout)
 //   Jt [J,3], Jdirs [J,3,NB]  joint regressor folded with the template / shape basis
 //                       (J = Jt + Jdirs*beta; the reference regresses from 10 475 vertices)
-//   skin_j/skin_w [V][KW]  the non-zeros of the dense [V,J] skinning weights (ascending joint
-//                       order, so the non-zero terms are summed in the reference's order)
-//   jl_*                the same non-zeros bucketed by joint, for the backward gather-reduce
+//   skin_j/skin_w [V][KW]  the non-zeros of the dense [V,J] skinning weights (ascending joint order)
+//   ch_seg/ch_lv/ch_w, ch_ju/unit_desc   the same non-zeros per 256-vertex chunk, bucketed by joint and cut
+//                       into work units, for the backward's dA partial sums
 //
 // Kernels:
-//   lbs_pose_fwd     one CTA per body: Rodrigues, joints, kinematic chain, A = G - G*J,
-//                    blend coefficients (pose feature | beta) in the vertex kernel's layout
-//   lbs_vertex_fwd   CTA = 32 vertices x 32 bodies; the K-loop streams [32 x 96] basis tiles
-//                    and [32 x 32] coefficient tiles through a 3-stage TMA (cp.async.bulk) +
-//                    mbarrier ring; 48 FP32 accumulators per thread (3 coords x 16 bodies);
-//                    epilogue = sparse skinning + translation + camera transform, all fused
-//   lbs_vertex_bwd   d verts -> d v_posed (through T^T and the camera rotation)
-//   lbs_dA           per (joint, body) gather-reduce of w * g (x) [v_posed;1] in fixed order
-//   lbs_dcoef        split-N SIMT GEMM  d coef[b,k] = sum_n gvp[b,n] * basis[k,n]
-//   lbs_pose_bwd     partial sums -> chain / Rodrigues backward -> d beta, d pose, d transl
+//   lbs_pose_fwd      one CTA per body: Rodrigues / 6D Gram-Schmidt, joints, kinematic chain, A = G - G*J,
+//                     blend coefficients (pose feature | beta) as a GEMM operand
+//   lbs_blend_fwd_tc5 v_posed = basis * coef on tcgen05 + TMEM (3xTF32)   [lbs_blend_fwd: mma.sync variant]
+//   lbs_skin_fwd      sparse skinning + translation + camera transform (+ fused scene-SDF sample)
+//   lbs_vertex_bwd    d verts -> d v_posed (GEMM operand) + per-chunk dA partial sums (+ fused loss gradient)
+//   lbs_dcoef_tc5     d coef partials = basis^T * gvp on tcgen05 + TMEM        [lbs_dcoef: mma.sync variant]
+//   lbs_reduce2       fixed-order sums of the coordinate splits and of the chunk partials
+//   lbs_pose_bwd      chain / Rodrigues / Gram-Schmidt backward -> d beta, d pose, d transl, d 6D
 // All reductions use fixed orders: results are bit-reproducible run to run.
 #include "common.cuh"
 #include "rot6d.cuh"

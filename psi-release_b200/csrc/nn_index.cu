@@ -434,6 +434,9 @@ __device__ __noinline__ int leaf_arg(const float4 *__restrict__ pts2, int c, flo
 }
 
 constexpr int kGrpThreads = 256;
+#ifndef PSI_NN_GRP_MINB
+#define PSI_NN_GRP_MINB 4
+#endif
 
 // -DPSI_NN_STATS: event counters of the group walk (debug builds only; tools/nn_stats.py)
 #ifdef PSI_NN_STATS
@@ -444,7 +447,7 @@ __device__ unsigned long long g_nn_stats[8];
 #endif
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kGrpThreads, 4)
+__global__ void __launch_bounds__(kGrpThreads, PSI_NN_GRP_MINB)
 nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, long q_bstride, int n,
                       const int *__restrict__ qsel, int B, float *__restrict__ dist,
                       int *__restrict__ idx, int *__restrict__ hint) {
