@@ -477,6 +477,40 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         put(3 * v, 0.f); put(3 * v + 1, 0.f); put(3 * v + 2, 0.f);
         return;
     }
+    // work-unit tables of the dA partial sums (constants of the model): fetched now, used after the barriers
+    const int *ju = ch_ju + (size_t)blockIdx.x * (J + 1);
+    int u0 = 0, nunits = 0, d_first = 0, ja = 0, jb = 0;
+    if (use_units && staged) {
+        u0 = ju[0];
+        nunits = ju[J] - u0;
+        if (tid < nunits * 3) d_first = unit_desc[u0 + tid / 3];
+        if (tid < J * 3) { ja = ju[tid / 3] - u0; jb = ju[tid / 3 + 1] - u0; }
+    }
+    // The kernel is latency bound: every global load is issued at the earliest point its address is known --
+    // level 1 (addresses from v alone) before the block barrier that publishes the body's penetration count,
+    // level 2 (NN result of the vertex's contact slot), level 3 (the matched scene point).
+    const bool act = v < V;
+    const size_t o = (size_t)b * V + (act ? v : 0);
+    float sv = 0.f, sg0 = 0.f, sg1 = 0.f, sg2 = 0.f, wgt = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+    int slot = -1;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    int4 jj = make_int4(0, 0, 0, 0);
+    float4 ww = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+        const float *vp = vp_in + o * 3;
+        px = vp[0]; py = vp[1]; pz = vp[2];
+        if (KW == 4) {
+            jj = __ldg(reinterpret_cast<const int4 *>(skin_j) + v);
+            ww = __ldg(reinterpret_cast<const float4 *>(skin_w) + v);
+        }
+        if (FIT) {
+            sv = fg.sdfv[o];
+            sg0 = fg.sdfg[o * 3]; sg1 = fg.sdfg[o * 3 + 1]; sg2 = fg.sdfg[o * 3 + 2];
+            slot = fg.cslot[v];
+            wgt = fg.cweight[v];
+            vx = fg.verts[o * 3]; vy = fg.verts[o * 3 + 1]; vz = fg.verts[o * 3 + 2];
+        }
+    }
     if (FIT) {
         if (tid < 32) {      // number of penetrating vertices of the body: lane-strided loads, shuffle tree (fixed order)
             float c = 0.f;
@@ -484,32 +518,38 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
             c = warp_sum(c);
             if (tid == 0) s_cnt = c;
         }
-        __syncthreads();
     }
-    float gx = 0.f, gy = 0.f, gz = 0.f, px = 0.f, py = 0.f, pz = 0.f, closs = 0.f;
-    if (v < V) {
-        const size_t o = (size_t)b * V + v;
+    float dd = 0.f;
+    int ni = 0;
+    if (FIT && slot >= 0) {                                    // level 2
+        dd = fg.nnd[(size_t)b * fg.nu + slot];
+        ni = fg.nni[(size_t)b * fg.nu + slot];
+    }
+    if (FIT) __syncthreads();
+    float gx = 0.f, gy = 0.f, gz = 0.f, closs = 0.f;
+    if (act) {
         if (FIT) {
-            if (fg.sdfv[o] < 0.f) {   // d/dv [ w * sum(-sdf)/cnt ]
-                const float k = -fg.w_coll / s_cnt;
-                gx = k * fg.sdfg[o * 3];
-                gy = k * fg.sdfg[o * 3 + 1];
-                gz = k * fg.sdfg[o * 3 + 2];
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            if (slot >= 0) {                                   // level 3
+                const float *q = fg.scene + (size_t)ni * 3;
+                qx = q[0]; qy = q[1]; qz = q[2];
             }
-            const int slot = fg.cslot[v];
+            if (sv < 0.f) {   // d/dv [ w * sum(-sdf)/cnt ]
+                const float k = -fg.w_coll / s_cnt;
+                gx = k * sg0;
+                gy = k * sg1;
+                gz = k * sg2;
+            }
             if (slot >= 0) {
-                const float dd = fg.nnd[(size_t)b * fg.nu + slot];
                 const float s = sqrtf(dd + 1e-4f);
                 const float den = s + fg.robust_c;
-                const float wgt = fg.cweight[v];
                 closs = wgt * (s / den);
                 // d/dd [ s/(s+c) ] = c/(s+c)^2 * 1/(2s);   d dd/dp = 2 (p - q)   (chamfer.cu:165-168)
                 const float gd = (fg.w_contact / (float)fg.num_contact) * wgt * (fg.robust_c / (den * den)) * (0.5f / s);
                 const float g2 = gd * 2.0f;
-                const float *q = fg.scene + (size_t)fg.nni[(size_t)b * fg.nu + slot] * 3;
-                gx += g2 * (fg.verts[o * 3] - q[0]);
-                gy += g2 * (fg.verts[o * 3 + 1] - q[1]);
-                gz += g2 * (fg.verts[o * 3 + 2] - q[2]);
+                gx += g2 * (vx - qx);
+                gy += g2 * (vy - qy);
+                gz += g2 * (vz - qz);
             }
         } else {
             gx = gverts[o * 3]; gy = gverts[o * 3 + 1]; gz = gverts[o * 3 + 2];
@@ -530,9 +570,7 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
             T[3] = fmaf(wt, r1.x, T[3]); T[4] = fmaf(wt, r1.y, T[4]); T[5] = fmaf(wt, r1.z, T[5]);
             T[6] = fmaf(wt, r2.x, T[6]); T[7] = fmaf(wt, r2.y, T[7]); T[8] = fmaf(wt, r2.z, T[8]);
         };
-        if (KW == 4) {     // one 16-byte load each for ids and weights, 12 independent gathers
-            const int4 jj = __ldg(reinterpret_cast<const int4 *>(skin_j) + v);
-            const float4 ww = __ldg(reinterpret_cast<const float4 *>(skin_w) + v);
+        if (KW == 4) {     // ids and weights came with the level-1 loads; 12 independent gathers
             const float4 a0 = __ldg(Ab + jj.x * 3), a1 = __ldg(Ab + jj.x * 3 + 1), a2 = __ldg(Ab + jj.x * 3 + 2);
             const float4 b0 = __ldg(Ab + jj.y * 3), b1 = __ldg(Ab + jj.y * 3 + 1), b2 = __ldg(Ab + jj.y * 3 + 2);
             const float4 c0 = __ldg(Ab + jj.z * 3), c1 = __ldg(Ab + jj.z * 3 + 1), c2 = __ldg(Ab + jj.z * 3 + 2);
@@ -548,8 +586,6 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         put(3 * v, T[0] * gx + T[3] * gy + T[6] * gz);
         put(3 * v + 1, T[1] * gx + T[4] * gy + T[7] * gz);
         put(3 * v + 2, T[2] * gx + T[5] * gy + T[8] * gz);
-        const float *vp = vp_in + o * 3;
-        px = vp[0]; py = vp[1]; pz = vp[2];
     } else {
         put(3 * v, 0.f); put(3 * v + 1, 0.f); put(3 * v + 2, 0.f);
     }
@@ -576,11 +612,9 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     // one thread per (joint, row) adds that joint's units in order.
     float *outp = dApart + ((size_t)blockIdx.x * B + b) * (J + 1) * 12;
     if (use_units && staged) {
-        const int *ju = ch_ju + (size_t)blockIdx.x * (J + 1);
-        const int u0 = ju[0], nunits = ju[J] - u0;
         for (int item = tid; item < nunits * 3; item += blockDim.x) {
             const int u = item / 3, r = item - u * 3;
-            const int d = unit_desc[u0 + u];
+            const int d = item == tid ? d_first : unit_desc[u0 + u];
             const int k0 = d >> 8, len = d & 255;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
@@ -597,7 +631,8 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
             const int j = item / 3, r = item - j * 3;
             if (j < J) {
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int u = ju[j] - u0; u < ju[j + 1] - u0; ++u) {
+                const int ua = item == tid ? ja : ju[j] - u0, ub = item == tid ? jb : ju[j + 1] - u0;
+                for (int u = ua; u < ub; ++u) {
                     const float4 p = s_part[u * 3 + r];
                     acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
                 }
