@@ -64,3 +64,49 @@ class SceneLossBlock:
         cnt = neg.sum().clamp(min=1).to(body_sdf.dtype)
         loss_sdf_pene = self.weight_collision * (((-body_sdf) * neg).sum() / cnt)
         return loss_contact, loss_vposer, loss_sdf_pene
+
+
+class TrainStep:
+    """One optimisation step of CVAE stage-2 training (BASELINE config 4): the loss assembly of
+    TrainOP.cal_loss, source/train_s2.py:102-204, around ANY `model_h(xhnr, eps_g, eps_l, xs) ->
+    (xhnr_rec, mu_g, logsigma2_g, mu_l, logsigma2_l)` (the CVAE and its ResNet18 scene encoder stay stock
+    torch modules: out of scope).  The network runs under bf16 autocast (north_star:
+    "bf16, 1->8 B200 data-parallel"), the geometry block (VPoser decode, SMPL-X, contact NN, SDF) in
+    FP32 on the psi kernels.  Data parallelism is plain DDP around `model_h`: the geometry block has no
+    trainable parameters (train_s2.py:66-67), so every rank evaluates it on its own samples and only the
+    CVAE gradients are all-reduced."""
+
+    def __init__(self, model_h, block: SceneLossBlock, optimizer, weight_loss_rec_h=1.0, weight_loss_kl=1.0,
+                 epochs=30, loss_weight_anealing=True, autocast_dtype=torch.bfloat16):
+        self.model_h, self.block, self.optimizer = model_h, block, optimizer
+        self.weight_loss_rec_h, self.weight_loss_kl = weight_loss_rec_h, weight_loss_kl
+        self.epochs, self.loss_weight_anealing, self.autocast_dtype = epochs, loss_weight_anealing, autocast_dtype
+
+    def cal_loss(self, xs, xh, eps_g, eps_l, cam_ext, cam_int, max_d, scene_ids, ep):
+        """Returns the seven terms of train_s2.py:204 in its order."""
+        from .geometry import GeometryTransformer
+        import torch.nn.functional as F
+        xhn = GeometryTransformer.normalize_global_T(xh, cam_int, max_d)
+        xhnr = GeometryTransformer.convert_to_6D_rot(xhn)
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            xhnr_rec, mu_g, logsigma2_g, mu_l, logsigma2_l = self.model_h(xhnr, eps_g, eps_l, xs)
+        xhnr_rec, mu_g, logsigma2_g, mu_l, logsigma2_l = (t.float() for t in (xhnr_rec, mu_g, logsigma2_g, mu_l, logsigma2_l))
+        xhn_rec = GeometryTransformer.convert_to_3D_rot(xhnr_rec)
+        xh_rec = GeometryTransformer.recover_global_T(xhn_rec, cam_int, max_d)
+        loss_rec_t = self.weight_loss_rec_h * (0.5 * F.l1_loss(xhnr_rec[:, :3], xhnr[:, :3]) +
+                                               0.5 * F.l1_loss(xh_rec[:, :3], xh[:, :3]))
+        loss_rec_p = self.weight_loss_rec_h * F.l1_loss(xhnr_rec[:, 3:], xhnr[:, 3:])
+        fca = min(1.0, max(float(ep) / (self.epochs * 0.75), 0)) if self.loss_weight_anealing else 1.0
+        kl = lambda mu, ls: 0.5 * torch.mean(torch.exp(ls) + mu ** 2 - 1.0 - ls)
+        loss_kl_g = fca ** 2 * self.weight_loss_kl * kl(mu_g, logsigma2_g)
+        loss_kl_l = fca ** 2 * self.weight_loss_kl * kl(mu_l, logsigma2_l)
+        loss_contact, loss_vposer, loss_sdf_pene = self.block(xh_rec, cam_ext, scene_ids, ep, self.epochs)
+        return loss_rec_t, loss_rec_p, loss_kl_g, loss_kl_l, loss_contact, loss_vposer, loss_sdf_pene
+
+    def step(self, *batch, ep):
+        """forward + backward + optimizer.step (train_s2.py:253-262); returns the detached terms."""
+        self.optimizer.zero_grad(set_to_none=True)
+        terms = self.cal_loss(*batch, ep)
+        sum(terms).backward()
+        self.optimizer.step()
+        return torch.stack([t.detach() for t in terms])

@@ -263,3 +263,65 @@ def test_rooms_pipeline_generate_fit_score_write(small_model, tmp_path):
         assert torch.equal(res["non_collision"][4 * r:4 * r + 4], nc) and torch.equal(res["contact"][4 * r:4 * r + 4], ct)
         d = io.read_body_pickle(str(tmp_path / ("room_%03d" % r) / "body_gen_000002.pkl"))
         np.testing.assert_array_equal(d["transl"][0], ref[2, :3].cpu().numpy())
+
+
+def test_train_step_config4_bf16_network_fp32_geometry(small_model):
+    """training.TrainStep (BASELINE config 4 shape): a stand-in CVAE (stock torch MLPs + a conv scene
+    encoder) under bf16 autocast, the geometry block in FP32 on the psi kernels.  The seven loss terms
+    follow train_s2.py:102-204 (checked against a plain-torch restatement of the non-geometry terms),
+    gradients reach the network, the epoch gate switches the geometry terms, a few steps lower the loss."""
+    from psi_release_b200 import body_model, synthetic, training
+    from psi_release_b200.geometry import GeometryTransformer, VPoserDecoder
+    torch.manual_seed(0)
+    B = 6
+    scenes = [synthetic.make_scene(seed=s, dim=24, num_points=1200) for s in (21, 22)]
+    scene_ids = [0, 1, 0, 1, 1, 0]
+    xh = torch.tensor(np.concatenate([synthetic.make_body_params(scenes[s], 1, seed=60 + i) for i, s in enumerate(scene_ids)])).cuda()
+    xh[:, 2] = xh[:, 2].abs() + 1.5                                  # in front of the camera (normalize_global_T divides by z)
+    cams = torch.stack([torch.tensor(scenes[s].cam_ext) for s in scene_ids]).cuda()
+    cam_int = torch.tensor([[500.0, 0, 320.0], [0, 500.0, 240.0], [0, 0, 1.0]]).repeat(B, 1, 1).cuda()
+    max_d = torch.full((B,), 6.0).cuda()
+    xs = torch.rand(B, 2, 32, 32).cuda() * 2 - 1                     # depth + semantics image (train_s2: [B,2,128,128])
+
+    class TinyCVAE(torch.nn.Module):                                 # same call signature as HumanCVAES2.forward
+        def __init__(self):
+            super().__init__()
+            self.scene = torch.nn.Sequential(torch.nn.Conv2d(2, 8, 3, 2, 1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten())
+            self.enc = torch.nn.Linear(75 + 8, 64)
+            self.mu_g, self.ls_g, self.mu_l, self.ls_l = (torch.nn.Linear(64, 16) for _ in range(4))
+            self.dec = torch.nn.Sequential(torch.nn.Linear(32 + 8, 128), torch.nn.ReLU(), torch.nn.Linear(128, 75))
+
+        def forward(self, xhnr, eps_g, eps_l, xs):
+            c = self.scene(xs)
+            h = torch.relu(self.enc(torch.cat([xhnr, c], 1)))
+            mg, lg, ml, ll = self.mu_g(h), self.ls_g(h), self.mu_l(h), self.ls_l(h)
+            z = torch.cat([mg + eps_g * torch.exp(0.5 * lg), ml + eps_l * torch.exp(0.5 * ll), c], 1)
+            return xhnr + 0.1 * self.dec(z), mg, lg, ml, ll          # residual: starts near the identity
+
+    net = TinyCVAE().cuda()
+    cid = synthetic.make_contact_ids(431, "parts")
+    blk = training.SceneLossBlock(body_model.create(model_data=small_model, num_pca_comps=12, batch_size=B),
+                                  VPoserDecoder.from_weights(synthetic.make_vposer_weights()), scenes, cid, 0.001, 0.01, 0.1)
+    opt = torch.optim.Adam(net.parameters(), lr=3e-4)
+    ts = training.TrainStep(net, blk, opt, weight_loss_rec_h=1.0, weight_loss_kl=0.1, epochs=30)
+    eps_g, eps_l = torch.randn(B, 16).cuda(), torch.randn(B, 16).cuda()
+    batch = (xs, xh, eps_g, eps_l, cams, cam_int, max_d, scene_ids)
+    early = ts.cal_loss(*batch, 3)
+    assert float(early[4]) == 0.0 and float(early[6]) == 0.0        # gated off before 0.75 * epochs
+    late = ts.cal_loss(*batch, 29)
+    assert float(late[4]) > 0.0 and all(torch.isfinite(t) for t in late)
+    # non-geometry terms vs a plain-torch restatement (network evaluated under the same autocast)
+    xhnr = GeometryTransformer.convert_to_6D_rot(GeometryTransformer.normalize_global_T(xh, cam_int, max_d))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        rec, mg, lg, ml, ll = net(xhnr, eps_g, eps_l, xs)
+    rec, mg, lg = rec.float(), mg.float(), lg.float()
+    ref_p = torch.nn.functional.l1_loss(rec[:, 3:], xhnr[:, 3:])
+    ref_kl = 0.1 * 0.5 * torch.mean(torch.exp(lg) + mg ** 2 - 1.0 - lg)             # fca = 1 at ep 29
+    assert abs(float(late[1]) - float(ref_p)) < 1e-6 and abs(float(late[2]) - float(ref_kl)) < 1e-6
+    sum(late).backward()
+    g = [p.grad for p in net.parameters() if p.grad is not None]
+    assert len(g) > 0 and all(torch.isfinite(x).all() for x in g) and any(float(x.abs().max()) > 0 for x in g)
+    first = float(ts.step(*batch, ep=29).sum())
+    for _ in range(15):
+        last = float(ts.step(*batch, ep=29).sum())
+    assert last < first
