@@ -14,8 +14,9 @@ bool skip_kernel(const char *name) {
     return skip && name && strcmp(skip, name) == 0;
 }
 bool pdl_enabled() {
-    // opt-in: measured SLOWER on B200 for this chain (460 vs 535 bodies/s at r01p: the early-scheduled
-    // dependents do not shorten the chain, the graph's programmatic edges cost more than they save)
+    // opt-in: measured SLOWER on B200 for this chain inside the captured graph, with the trigger at the top of
+    // every kernel (460 vs 535 bodies/s, r01p) and with the trigger in the kernels' tails as it is now (593 vs
+    // 630 bodies/s, r01v): the graph's programmatic edges cost more than the overlapped launch latency saves
     static const bool on = [] { const char *e = getenv("PSI_PDL"); return e && e[0] == '1'; }();
     return on;
 }

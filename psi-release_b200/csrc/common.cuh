@@ -62,13 +62,13 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
 int lbs_vertex_chunks(const psi_lbs_model *m);   // 256-vertex chunks = rows of SdfFuse::partial / VGradFuse::cpart
 
 // ---- programmatic dependent launch -----------------------------------------------------------
-// The fitting iteration is a chain of ~16 short dependent kernels; with a plain stream (or graph)
-// dependency each one pays the full launch latency after its predecessor has drained.  Launched
-// with the programmatic-stream-serialization attribute, a kernel's CTAs are scheduled while the
-// predecessor is still finishing (it signals with pdl_launch_dependents at its top) and block in
-// pdl_wait until the predecessor has COMPLETED and its writes are visible -- so everything that
-// touches a predecessor's output (or overwrites its input) comes after pdl_wait; only barrier
-// initialisation and loads of constants precede it.
+// The fitting iteration is a chain of 15 short dependent kernels; with a plain stream (or graph) dependency
+// each one pays the full launch latency after its predecessor has drained.  Launched with the
+// programmatic-stream-serialization attribute, a kernel's CTAs are scheduled once every CTA of the
+// predecessor has passed pdl_launch_dependents (placed in the kernels' tails) and block in pdl_wait until
+// the predecessor has COMPLETED and its writes are visible -- so everything that touches a predecessor's
+// output (or overwrites its input) comes after pdl_wait; only barrier initialisation and loads of constants
+// precede it.  Opt-in (PSI_PDL=1): it measured slower than plain graph edges, see api.cu.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -84,7 +84,6 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
                 const float *__restrict__ cpart, float *__restrict__ losses, float *__restrict__ zA,
                 float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
                 float *__restrict__ transl) {
-    pdl_launch_dependents();
     pdl_wait();
     __shared__ float sx[96], g[96];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -149,6 +148,7 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
         if (tid == 0) step[b] = t;
         __syncthreads();
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     // inputs of the next evaluation
     if (tid < Lz) zA[a_index(b, tid, Lz)] = sx[zoff + tid];
     if (tid < 6) rot6d[(size_t)b * d.num_rot * 6 + tid] = sx[3 + tid];

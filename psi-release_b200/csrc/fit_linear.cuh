@@ -49,7 +49,6 @@ __global__ void __launch_bounds__(128) fit_linear_kernel(const LinearParams p) {
         mbar_fence_init();
     }
     __syncthreads();
-    pdl_launch_dependents();
     pdl_wait();
     if (tid == 0) {
         for (int g = 0; g < ngroups; ++g) {
@@ -88,6 +87,7 @@ __global__ void __launch_bounds__(128) fit_linear_kernel(const LinearParams p) {
         }
     }
 
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     // accumulator fragment: rows g, g+8 (bodies), columns 2t, 2t+1 (outputs) of each n8 tile
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll

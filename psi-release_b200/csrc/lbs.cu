@@ -132,7 +132,6 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
                     float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
                     const float *__restrict__ rot6d, int split, const psi_lbs_tree tree) {
-    pdl_launch_dependents();
     pdl_wait();
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -180,6 +179,7 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
         }
         __syncthreads();
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     float *oR = saved + L.R + (size_t)b * J * 9, *oJ = saved + L.Jr + (size_t)b * J * 3;
     float *oGr = saved + L.Gr + (size_t)b * J * 9, *oGt = saved + L.Gt + (size_t)b * J * 3;
     float *oA = saved + L.A + (size_t)b * J * 12;
@@ -226,7 +226,6 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
 
 // coefficient rows of bodies past B inside the last body group must read as zero
 __global__ void lbs_zero_coef_pad_kernel(float *coef, int B, int Kpad) {
-    pdl_launch_dependents();
     pdl_wait();
     const int nbg = (B + kBG - 1) / kBG;
     const int first = B % kBG;
@@ -264,7 +263,6 @@ __global__ void __launch_bounds__(128, 3) lbs_blend_fwd_kernel(const BlendFwdPar
         mbar_fence_init();
     }
     __syncthreads();
-    pdl_launch_dependents();
     pdl_wait();
     auto issue = [&](int c) {   // thread 0 only
         const int st = c % kFStages;
@@ -350,7 +348,6 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
                     const float *__restrict__ A, const float *__restrict__ vp_in,
                     const float *__restrict__ transl, const float *__restrict__ cam, long cam_bstride,
                     float *__restrict__ verts, const SdfFuse sf) {
-    pdl_launch_dependents();
     pdl_wait();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -406,6 +403,7 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
             if (val < 0.f) { neg_sum -= val; neg_cnt += 1.f; }
         }
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     if (SDF) {   // per-(body, chunk) partial sums, fixed order
         __shared__ float red[2][8];
         neg_sum = warp_sum(neg_sum);
@@ -456,7 +454,6 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     const bool staged = nent <= stage_cap;
     if (staged && blockIdx.y < B)
         for (int k = tid; k < nent; k += blockDim.x) { s_w[k] = ch_w[e0 + k]; s_lv[k] = ch_lv[e0 + k]; }
-    pdl_launch_dependents();
     pdl_wait();
     const int v = blockIdx.x * blockDim.x + tid;
     const int b = blockIdx.y;
@@ -605,6 +602,7 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         for (int i = 0; i < 8; ++i) s += red[i];
         fg.cpart[(size_t)b * gridDim.x + blockIdx.x] = s;
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     // dA partial sums of this chunk: row r of sum over the entries of joint j of (w gw_r) * [vp | 1], entries in
     // ascending vertex order.  Joints own very different numbers of entries (the root collects every
     // vertex skinned to an ancestor chain through it), so the entry lists are cut into UNITS of at most
@@ -705,7 +703,6 @@ lbs_dcoef_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd
         mbar_fence_init();
     }
     __syncthreads();
-    pdl_launch_dependents();
     pdl_wait();
     auto issue = [&](int c) {   // thread 0 only; c counts from 0 inside this split
         const int st = c % kDStages;
@@ -936,7 +933,6 @@ __global__ void __launch_bounds__(kTThreads, 1) lbs_blend_fwd_tc5_kernel(const B
     __shared__ __align__(8) Tc5Bars bars;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t tmem_d = tc5_setup(bars);
-    pdl_launch_dependents();
     pdl_wait();
     const int nchunks = p.Kpad / kKC, N = 3 * p.V;
     int g0 = 0, idx = 0;
@@ -966,6 +962,7 @@ __global__ void __launch_bounds__(kTThreads, 1) lbs_blend_fwd_tc5_kernel(const B
             mbar_arrive(&bars.tmem_free);                      // TMEM has been read: the next item may overwrite it
         }
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     tc5_teardown(tmem_d);
 }
 
@@ -978,7 +975,6 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
     __shared__ __align__(8) Tc5Bars bars;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t tmem_d = tc5_setup(bars);
-    pdl_launch_dependents();
     pdl_wait();
     const int nkt = Kpad / kTM, nbg = Bpad / kBG;
     int g0 = 0, idx = 0;
@@ -1012,6 +1008,7 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
             mbar_arrive(&bars.tmem_free);
         }
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     tc5_teardown(tmem_d);
 }
 
@@ -1020,7 +1017,6 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
 __global__ void __launch_bounds__(256)
 lbs_reduce2_kernel(const float *__restrict__ in0, int n0, long count0, float *__restrict__ out0,
                    const float *__restrict__ in1, int n1, long count1, float *__restrict__ out1) {
-    pdl_launch_dependents();
     pdl_wait();
     const float *__restrict__ in = blockIdx.y ? in1 : in0;
     float *__restrict__ out = blockIdx.y ? out1 : out0;
@@ -1038,6 +1034,7 @@ lbs_reduce2_kernel(const float *__restrict__ in0, int n0, long count0, float *__
     }
     for (; k < n; ++k) s0 += in[(size_t)k * count + i];
     out[i] = (s0 + s1) + (s2 + s3);
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
 }
 
 // per body: run the chain and Rodrigues backward on the reduced d coef
@@ -1051,7 +1048,6 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     float *__restrict__ gtransl, float *__restrict__ grot, int num_rot,
                     const float *__restrict__ rot6d, float *__restrict__ g6_root, float *__restrict__ g6A,
                     int g6_kpad, const psi_lbs_tree tree) {
-    pdl_launch_dependents();
     pdl_wait();
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], drel_s[kMaxJ * 3];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
@@ -1135,6 +1131,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
         }
         __syncthreads();
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     // Rodrigues backward (lbs.py:177-191); joints given as matrices export dR itself
     for (int j = tid; j < J; j += blockDim.x) {
         float *o = gpose + ((size_t)b * J + j) * 3;

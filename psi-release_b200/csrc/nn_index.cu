@@ -136,7 +136,6 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         __syncthreads();
         boxes = s4;
     }
-    pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const long warps = (long)gridDim.x * (blockDim.x >> 5);
@@ -243,7 +242,6 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
         for (int i = threadIdx.x; i < ntop2 * 3; i += blockDim.x) s4[i] = __ldg(ix.box2 + i);
         __syncthreads();
     }
-    pdl_launch_dependents();
     pdl_wait();
     const int sbase = ix.mpad, cbase = ix.mpad + ix.num_supers;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
@@ -467,7 +465,6 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         top_lo = s4;
         top_hi = s4 + ntop;
     }
-    pdl_launch_dependents();
     pdl_wait();
     const float4 *__restrict__ c_lo = ix.boxes + ntop, *__restrict__ c_hi = ix.boxes + ix.nbox + ntop;
     const unsigned full = 0xffffffffu;
@@ -613,6 +610,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
             if (hint) hint[t] = bleaf;
         }
     }
+    pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
 }
 
 // balanced kd bisection: reorder ids[0..n) so that consecutive runs of `leaf` are compact

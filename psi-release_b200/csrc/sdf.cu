@@ -30,7 +30,6 @@ sdf_fwd_kernel(const float *__restrict__ sdf, int D, const SdfScenes sc,
                const float *__restrict__ verts, int V, const int *__restrict__ body_scene,
                float *__restrict__ out, float *__restrict__ grad, float *__restrict__ partial,
                int num_partials) {
-    pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y;
     const int scene = body_scene ? body_scene[b] : 0;
