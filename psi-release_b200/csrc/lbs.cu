@@ -103,6 +103,19 @@ __host__ __device__ inline SavedLayout saved_layout(int B, int J, int V, int Kpa
     return s;
 }
 
+// The kinematic tree (levels, children, parents: constants of the model) staged into shared memory: walking it
+// from global memory cost three dependent L2 round trips per tree level (40 % of the pose kernels' stalls).
+struct TreeSmem {
+    int lvl_start[kMaxJ + 1], lvl_joint[kMaxJ], child_start[kMaxJ + 1], child_list[kMaxJ], parents[kMaxJ];
+};
+__device__ __forceinline__ void stage_tree(TreeSmem &t, const psi_lbs_tree &tree, const int *__restrict__ parents, int J) {
+    for (int i = threadIdx.x; i <= J; i += blockDim.x) {
+        t.lvl_start[i] = tree.lvl_start[i];
+        t.child_start[i] = tree.child_start[i];
+        if (i < J) { t.lvl_joint[i] = tree.lvl_joint[i]; t.child_list[i] = tree.child_list[i]; t.parents[i] = parents[i]; }
+    }
+}
+
 __device__ __forceinline__ void rodrigues(const float *r, float *R) {
     // lbs.py:177-191: eps is added to the vector inside the norm, direction uses raw r
     const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
@@ -132,9 +145,11 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
                     float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
                     const float *__restrict__ rot6d, int split, const psi_lbs_tree tree) {
-    pdl_wait();
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
+    __shared__ TreeSmem st;
     const int b = blockIdx.x, tid = threadIdx.x;
+    stage_tree(st, tree, parents, J);          // constants: before the dependency wait
+    pdl_wait();
     for (int j = tid; j < J; j += blockDim.x) {
         if (j < num_rot && rot6d) {   // 6D representation -> R by Gram-Schmidt (cvae.py:46-55), fused here
             float R[9];
@@ -156,14 +171,14 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
     __syncthreads();
     // kinematic chain, one tree level at a time (joints of a level are independent)
     for (int l = 0; l < tree.nlev; ++l) {
-        for (int q = tree.lvl_start[l] + tid; q < tree.lvl_start[l + 1]; q += blockDim.x) {
-            const int j = tree.lvl_joint[q];
+        for (int q = st.lvl_start[l] + tid; q < st.lvl_start[l + 1]; q += blockDim.x) {
+            const int j = st.lvl_joint[q];
             if (j == 0) {
                 for (int e = 0; e < 9; ++e) sGr[e] = sR[e];
                 for (int e = 0; e < 3; ++e) sGt[e] = sJ[e];
                 continue;
             }
-            const int p = parents[j];
+            const int p = st.parents[j];
             const float *Gp = sGr + p * 9, *Rj = sR + j * 9;
             float rel[3] = {sJ[j * 3] - sJ[p * 3], sJ[j * 3 + 1] - sJ[p * 3 + 1],
                             sJ[j * 3 + 2] - sJ[p * 3 + 2]};
@@ -1048,11 +1063,13 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     float *__restrict__ gtransl, float *__restrict__ grot, int num_rot,
                     const float *__restrict__ rot6d, float *__restrict__ g6_root, float *__restrict__ g6A,
                     int g6_kpad, const psi_lbs_tree tree) {
-    pdl_wait();
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], drel_s[kMaxJ * 3];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
-    __shared__ float dbeta_direct[64];
+    __shared__ float dbeta_direct[64], dbeta_part[6][32];
+    __shared__ TreeSmem st;
     const int b = blockIdx.x, tid = threadIdx.x;
+    stage_tree(st, tree, parents, J);          // constants: before the dependency wait
+    pdl_wait();
     const float *dA = dAsum + (size_t)b * (J + 1) * 12;      // chunk partials already summed; row J = d translation
     const float *dtr = dA + J * 12;
     const float *iR = saved + L.R + (size_t)b * J * 9, *iJ = saved + L.Jr + (size_t)b * J * 3;
@@ -1086,15 +1103,15 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     // chain backward, deepest tree level first.  A joint first PULLS from its children (fixed
     // child order: deterministic, race free), then finishes its own dR / d rel.
     for (int l = tree.nlev - 1; l >= 0; --l) {
-        for (int q = tree.lvl_start[l] + tid; q < tree.lvl_start[l + 1]; q += blockDim.x) {
-            const int j = tree.lvl_joint[q];
+        for (int q = st.lvl_start[l] + tid; q < st.lvl_start[l + 1]; q += blockDim.x) {
+            const int j = st.lvl_joint[q];
             float g[9], gt[3], dj[3];
 #pragma unroll
             for (int e = 0; e < 9; ++e) g[e] = dGr[j * 9 + e];
 #pragma unroll
             for (int e = 0; e < 3; ++e) { gt[e] = dGt[j * 3 + e]; dj[e] = dJ[j * 3 + e]; }
-            for (int ci = tree.child_start[j]; ci < tree.child_start[j + 1]; ++ci) {
-                const int c = tree.child_list[ci];
+            for (int ci = st.child_start[j]; ci < st.child_start[j + 1]; ++ci) {
+                const int c = st.child_list[ci];
                 const float *Rc = sR + c * 9, *gc = dGr + c * 9, *gtc = dGt + c * 3;
                 const float rel[3] = {sJ[c * 3] - sJ[j * 3], sJ[c * 3 + 1] - sJ[j * 3 + 1], sJ[c * 3 + 2] - sJ[j * 3 + 2]};
 #pragma unroll
@@ -1115,7 +1132,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
 #pragma unroll
                 for (int e = 0; e < 3; ++e) dj[e] += gt[e];
             } else {
-                const float *Gp = sGr + parents[j] * 9;
+                const float *Gp = sGr + st.parents[j] * 9;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -1192,10 +1209,27 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
         o[1] = dn1 / a + da * ey / a;
         o[2] = dn2 / a + da * ez / a;
     }
-    for (int l = tid; l < NB; l += blockDim.x) {
-        float s = dbeta_direct[l];
-        for (int e = 0; e < J * 3; ++e) s = fmaf(Jdirs[(size_t)e * NB + l], dJ[e], s);
-        gbetas[(size_t)b * NB + l] = s;
+    // d beta = direct term + Jdirs^T dJ: (l, slice of the joint coordinates) per thread, six slices summed in order
+    if (NB <= 32) {
+        const int l = tid % 32, part = tid / 32;                 // 128 threads: 4 slices active, parts 4, 5 done by a second pass
+        for (int pp = part; pp < 6; pp += 4) {
+            float s = 0.f;
+            if (l < NB)
+                for (int e = pp; e < J * 3; e += 6) s = fmaf(Jdirs[(size_t)e * NB + l], dJ[e], s);
+            dbeta_part[pp][l] = s;
+        }
+        __syncthreads();
+        if (tid < NB) {
+            float s = dbeta_direct[tid];
+            for (int pp = 0; pp < 6; ++pp) s += dbeta_part[pp][tid];
+            gbetas[(size_t)b * NB + tid] = s;
+        }
+    } else {
+        for (int l = tid; l < NB; l += blockDim.x) {
+            float s = dbeta_direct[l];
+            for (int e = 0; e < J * 3; ++e) s = fmaf(Jdirs[(size_t)e * NB + l], dJ[e], s);
+            gbetas[(size_t)b * NB + l] = s;
+        }
     }
     if (gtransl && tid < 3) {
         float s = dtr[tid];                      // row J of the chunk sums: sum over the vertices of gw
