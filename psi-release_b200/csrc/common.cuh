@@ -134,6 +134,23 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
         : "memory");
 }
 
+// The same copy with an L2 eviction hint.  The two blend bases (2 x 64 MB) stream through the 126 MB L2 once per
+// iteration and cannot stay; loaded evict-first they stop pushing out what is re-used (scene SDF tiles, vertices,
+// gradients, the NN index, decoder weights).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
 // ---- tensor-core helpers: legacy mma.sync path (HMMA.1688.F32.TF32), FP32 accumulate ----
 // ldmatrix moves 8x8 b16 matrices = 8 rows x 16 bytes; with 32-bit elements a matrix is 8 rows x 4
 // words and lane l receives word (l % 4) of row (l / 4): exactly the m16n8k8 TF32 fragments when

@@ -91,6 +91,13 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;   // 75
     const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
     for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
+    // Adam state of this thread's component: requested now, consumed two barriers later
+    float x0e = 0.f, ame = 0.f, ave = 0.f;
+    int t_prev = 0;
+    if (do_post) {
+        t_prev = step[b];
+        if (tid < xdim) { x0e = x0[(size_t)b * xdim + tid]; ame = am[(size_t)b * xdim + tid]; ave = av[(size_t)b * xdim + tid]; }
+    }
     __syncthreads();
     if (do_post) {
         if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
@@ -125,15 +132,15 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
             }
         }
         __syncthreads();
-        const int t = step[b] + 1;
+        const int t = t_prev + 1;
         float xn = 0.f;
         if (tid < xdim) {
-            const float xe = sx[tid], diff = xe - x0[(size_t)b * xdim + tid];
+            const float xe = sx[tid], diff = xe - x0e;
             const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
             const float ge = g[tid] + cfg.w_rec * sgn / (float)xdim;
             const size_t o = (size_t)b * xdim + tid;
-            const float m = cfg.beta1 * am[o] + (1.0f - cfg.beta1) * ge;
-            const float v = cfg.beta2 * av[o] + (1.0f - cfg.beta2) * ge * ge;
+            const float m = cfg.beta1 * ame + (1.0f - cfg.beta1) * ge;
+            const float v = cfg.beta2 * ave + (1.0f - cfg.beta2) * ge * ge;
             am[o] = m;
             av[o] = v;
             const double bc1 = 1.0 - pow((double)cfg.beta1, (double)t);

@@ -838,12 +838,14 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
     const int tid = threadIdx.x;
     unsigned char *raw = smem, *act = smem + kTRaw * kTTileB, *op = act + kTAct * 2 * kTTileA;
     if (tid >= 128) {
-        if (tid == 128) {                               // ---- producer: raw basis tiles (HBM)
+        if (tid == 128) {                               // ---- producer: raw basis tiles (HBM), streamed evict-first
+            const uint64_t pol = l2_policy_evict_first();
             for (int c = 0; c < it.nchunks; ++c) {
                 const int g = g0 + c, st = g % kTRaw;
                 mbar_wait(&bars.empty_raw[st], (uint32_t)(((g / kTRaw) & 1) ^ 1));
                 mbar_arrive_expect_tx(&bars.full_raw[st], (uint32_t)kTTileB);
-                tma_load_1d(raw + (size_t)st * kTTileB, it.basis + (size_t)c * it.basis_stride, kTTileB, &bars.full_raw[st]);
+                tma_load_1d_hint(raw + (size_t)st * kTTileB, it.basis + (size_t)c * it.basis_stride, kTTileB,
+                                 &bars.full_raw[st], pol);
             }
         } else if (tid == 160) {                        // ---- producer: per-body tiles (L2); hi then lo = one 128-row tile
             for (int c = 0; c < it.nchunks; ++c) {
