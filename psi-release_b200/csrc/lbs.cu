@@ -447,7 +447,7 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
 //         chunks up.  (This replaced a per-(joint, body) gather kernel that re-read gw and vp from
 //         L2 for every skinning entry: 37 us at B = 64.)
 template <bool FIT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)      // (minBlocks 5 / 6 measured slower: 59.4 vs 56.1 us)
 lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restrict__ skin_j,
                       const float *__restrict__ skin_w, const float *__restrict__ A,
                       const float *__restrict__ vp_in, const float *__restrict__ cam, long cam_bstride,

@@ -435,6 +435,11 @@ constexpr int kGrpThreads = 256;
 #ifndef PSI_NN_GRP_MINB
 #define PSI_NN_GRP_MINB 4
 #endif
+#ifndef PSI_NN_SUBGROUPS
+#define PSI_NN_SUBGROUPS 4
+#endif
+constexpr int kSubGroups = PSI_NN_SUBGROUPS;       // sub-groups of a 32-query group with their own box and bound (8 measured slower: 129 vs 118 us)
+constexpr int kSubSize = 32 / kSubGroups;
 
 // -DPSI_NN_STATS: event counters of the group walk (debug builds only; tools/nn_stats.py)
 #ifdef PSI_NN_STATS
@@ -451,7 +456,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
                       int *__restrict__ idx, int *__restrict__ hint) {
     // mega + super boxes (lo | hi, SoA) in shared memory; cluster boxes come through L1
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float4 s_sub[kGrpThreads / 32][4][2];            // per warp: 4 sub-group query boxes {lo, ub bits | hi}
+    __shared__ float4 s_sub[kGrpThreads / 32][kSubGroups][2];   // per warp: sub-group query boxes {lo, ub bits | hi}
     __shared__ float4 s_leaf[kGrpThreads / 32][2 * kLeaf];      // per warp: the leaf being evaluated
     const int ntop = ix.mpad + ix.num_supers;
     const float4 *top_lo = ix.boxes, *top_hi = ix.boxes + ix.nbox;
@@ -469,7 +474,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
     const float4 *__restrict__ c_lo = ix.boxes + ntop, *__restrict__ c_hi = ix.boxes + ix.nbox + ntop;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned submask = 0xffu << (lane & 24);               // my sub-group: 8 consecutive queries
+    const unsigned submask = ((1u << kSubSize) - 1u) << (lane & ~(kSubSize - 1));   // my sub-group: kSubSize consecutive queries
     float4(*sub)[2] = s_sub[threadIdx.x >> 5];
     const int wpb = (n + 31) / 32;                               // warps (groups) per body
     const long ngroups = (long)B * wpb;
@@ -491,9 +496,9 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
             const unsigned ay = __reduce_min_sync(submask, ky), by = __reduce_max_sync(submask, ky);
             const unsigned az = __reduce_min_sync(submask, kz), bz = __reduce_max_sync(submask, kz);
             __syncwarp();
-            if ((lane & 7) == 0) {
-                sub[lane >> 3][0] = make_float4(fkey_inv(ax), fkey_inv(ay), fkey_inv(az), CUDART_INF_F);
-                sub[lane >> 3][1] = make_float4(fkey_inv(bx), fkey_inv(by), fkey_inv(bz), 0.f);
+            if ((lane & (kSubSize - 1)) == 0) {
+                sub[lane / kSubSize][0] = make_float4(fkey_inv(ax), fkey_inv(ay), fkey_inv(az), CUDART_INF_F);
+                sub[lane / kSubSize][1] = make_float4(fkey_inv(bx), fkey_inv(by), fkey_inv(bz), 0.f);
             }
             lx = fkey_inv(__reduce_min_sync(full, ax)); hx = fkey_inv(__reduce_max_sync(full, bx));
             ly = fkey_inv(__reduce_min_sync(full, ay)); hy = fkey_inv(__reduce_max_sync(full, by));
@@ -516,7 +521,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         auto publish_bounds = [&]() {
             const unsigned mine = __reduce_max_sync(submask, __float_as_uint(bd));
             ub = __reduce_max_sync(full, mine);
-            if ((lane & 7) == 0) sub[lane >> 3][0].w = __uint_as_float(mine);
+            if ((lane & (kSubSize - 1)) == 0) sub[lane / kSubSize][0].w = __uint_as_float(mine);
             __syncwarp();
         };
         // ---- seeds: last iteration's winning leaves, or a greedy descent for the lanes without one
@@ -577,7 +582,7 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
                     if (src2 >= 0) {
                         const float4 clo = __ldg(c_lo + cid), chi = __ldg(c_hi + cid);
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < kSubGroups; ++g) {
                             const float4 sl = sub[g][0], sh = sub[g][1];
                             adm |= box_lb_group(clo, chi, sl.x, sl.y, sl.z, sh.x, sh.y, sh.z) <= __float_as_uint(sl.w);
                         }
