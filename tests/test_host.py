@@ -201,3 +201,37 @@ def test_oracle_fit_loop_reduces_loss_and_modes_agree_at_b1(small_model):
     both = oracle.fit_loop(xh, cam.expand(2, -1, -1), 3, 0.1, loss_mode="independent", **kw)
     one = oracle.fit_loop(xh[1:2], cam, 3, 0.1, loss_mode="independent", **kw)
     np.testing.assert_allclose(both[1:2].numpy(), one.numpy(), atol=2e-5)
+
+
+def test_contact_query_order_is_a_permutation_grouped_by_joint():
+    """fused._spatial_order: the NN group schedule wants 32 consecutive contact ids to be neighbours on the
+    posed body -- ids grouped by dominant skinning joint (depth-first over the kinematic tree), kd cells
+    inside a joint; duplicates of an id stay adjacent; the multiset of ids is preserved."""
+    import numpy as np
+    from psi_release_b200 import synthetic
+    from psi_release_b200.fused import _spatial_order
+    m = synthetic.make_smplx_model(seed=1234, num_verts=1500)
+    parents = m["kintree_table"][0]
+    ids = np.concatenate([np.arange(1500), np.array([7, 7, 900, 3])])
+    o = _spatial_order(ids, m["v_template"], m["weights"], parents)
+    assert sorted(o.tolist()) == sorted(ids.tolist())
+    pos7 = np.nonzero(o == 7)[0]
+    assert len(pos7) == 3 and pos7.max() - pos7.min() == 2               # duplicates adjacent
+    owner = m["weights"].argmax(1)[o]
+    changes = int((owner[1:] != owner[:-1]).sum())
+    assert changes <= len(parents) - 1                                   # one contiguous run per joint
+    # inside a joint the aligned 32-runs are compact kd cells: tighter than the id order
+    def extent(order):
+        tot = 0.0
+        for j in np.unique(owner):
+            v = m["v_template"][order[owner_of(order) == j]]
+            for s in range(0, len(v) - 31, 32):
+                tot += float((v[s:s + 32].max(0) - v[s:s + 32].min(0)).max())
+        return tot
+    owner_of = lambda order: m["weights"].argmax(1)[order]
+    uniq = np.unique(ids)
+    by_id = uniq[np.argsort(owner_of(uniq), kind="stable")]
+    assert extent(np.unique(o, return_index=True)[0][np.argsort(np.unique(o, return_index=True)[1])]) < extent(by_id)
+    # without skinning information it falls back to kd cells of the template
+    o2 = _spatial_order(np.arange(1500), m["v_template"])
+    assert sorted(o2.tolist()) == list(range(1500))
