@@ -809,7 +809,13 @@ lbs_dcoef_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis_bwd
 // epilogue reads TMEM with tcgen05.ld: lane = row, so a warp stores 32 consecutive floats per body.
 // (mma.sync kept these GEMMs tensor-pipe bound at 41 / 37 us.)
 constexpr int kTM = 128;                       // rows of a basis tile = M of the MMA
-constexpr int kTRaw = 5, kTAct = 4, kTOp = 2;  // ring depths
+#ifndef PSI_TC5_RAW
+#define PSI_TC5_RAW 5
+#endif
+#ifndef PSI_TC5_ACT
+#define PSI_TC5_ACT 4
+#endif
+constexpr int kTRaw = PSI_TC5_RAW, kTAct = PSI_TC5_ACT, kTOp = 2;  // ring depths
 constexpr int kTThreads = 224;                 // 4 worker warps + 2 producer warps + the MMA issuer's warp
 constexpr int kTTileB = kTM * kKC * 4;         // 16 kB: one basis tile (raw, hi or lo)
 constexpr int kTTileA = kBG * kKC * 4;         // 8 kB: one per-body tile (hi or lo)

@@ -431,7 +431,10 @@ __device__ __noinline__ int leaf_arg(const float4 *__restrict__ pts2, int c, flo
     return li;
 }
 
-constexpr int kGrpThreads = 256;
+#ifndef PSI_NN_GRP_THREADS
+#define PSI_NN_GRP_THREADS 256
+#endif
+constexpr int kGrpThreads = PSI_NN_GRP_THREADS;
 #ifndef PSI_NN_GRP_MINB
 #define PSI_NN_GRP_MINB 4
 #endif
