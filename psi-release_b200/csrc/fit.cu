@@ -502,7 +502,10 @@ int psi_fit_profile(psi_fit_ctx *c, const float *xhr_init, const float *cam, lon
     LaunchRecorder rec;
     rec.st = st;
     for (int i = 0; i < 65; ++i)
-        if (cudaEventCreate(&rec.ev[i]) != cudaSuccess) return PSI_ERR_ALLOC;
+        if (cudaEventCreate(&rec.ev[i]) != cudaSuccess) {
+            for (int k = 0; k < i; ++k) cudaEventDestroy(rec.ev[k]);
+            return PSI_ERR_ALLOC;
+        }
     int n = 0;
     for (int i = 0; i < max_launches; ++i) h_ms[i] = 0.f;
     for (int it = 0; it < timed_iters && rc == PSI_OK; ++it) {
