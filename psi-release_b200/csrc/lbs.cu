@@ -367,32 +367,47 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     float neg_sum = 0.f, neg_cnt = 0.f;
+    // the body's [J,3,4] transform table (2.6 kB) staged in shared memory: every thread gathers 3 x KW rows of
+    // it, and from global memory those scattered 16-byte loads were what the kernel waited on
+    __shared__ float4 sA[kMaxJ * 3];
+    {
+        const float4 *__restrict__ Ag = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
+        for (int i = threadIdx.x; i < J * 3; i += blockDim.x) sA[i] = Ag[i];
+    }
+    float x = 0.f, y = 0.f, z = 0.f;
+    int4 jj = make_int4(0, 0, 0, 0);
+    float4 ww = make_float4(0.f, 0.f, 0.f, 0.f);
     if (v < V) {
         const float *vp = vp_in + ((size_t)b * V + v) * 3;
-        const float x = vp[0], y = vp[1], z = vp[2];
+        x = vp[0]; y = vp[1]; z = vp[2];
+        if (KW == 4) {     // SMPL-X: <= 4 weights per vertex: one 16-byte load each for ids and weights
+            jj = __ldg(reinterpret_cast<const int4 *>(skin_j) + v);
+            ww = __ldg(reinterpret_cast<const float4 *>(skin_w) + v);
+        }
+    }
+    __syncthreads();
+    if (v < V) {
         float T[12];
 #pragma unroll
         for (int e = 0; e < 12; ++e) T[e] = 0.f;
-        const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
+        const float4 *Ab = sA;
         auto blend = [&](int j, float wt, float4 r0, float4 r1, float4 r2) {
             (void)j;
             T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]); T[3] = fmaf(wt, r0.w, T[3]);
             T[4] = fmaf(wt, r1.x, T[4]); T[5] = fmaf(wt, r1.y, T[5]); T[6] = fmaf(wt, r1.z, T[6]); T[7] = fmaf(wt, r1.w, T[7]);
             T[8] = fmaf(wt, r2.x, T[8]); T[9] = fmaf(wt, r2.y, T[9]); T[10] = fmaf(wt, r2.z, T[10]); T[11] = fmaf(wt, r2.w, T[11]);
         };
-        if (KW == 4) {     // SMPL-X: <= 4 weights per vertex: one 16-byte load each for ids and weights, 12 independent gathers
-            const int4 jj = __ldg(reinterpret_cast<const int4 *>(skin_j) + v);
-            const float4 ww = __ldg(reinterpret_cast<const float4 *>(skin_w) + v);
-            const float4 a0 = __ldg(Ab + jj.x * 3), a1 = __ldg(Ab + jj.x * 3 + 1), a2 = __ldg(Ab + jj.x * 3 + 2);
-            const float4 b0 = __ldg(Ab + jj.y * 3), b1 = __ldg(Ab + jj.y * 3 + 1), b2 = __ldg(Ab + jj.y * 3 + 2);
-            const float4 c0 = __ldg(Ab + jj.z * 3), c1 = __ldg(Ab + jj.z * 3 + 1), c2 = __ldg(Ab + jj.z * 3 + 2);
-            const float4 d0 = __ldg(Ab + jj.w * 3), d1 = __ldg(Ab + jj.w * 3 + 1), d2 = __ldg(Ab + jj.w * 3 + 2);
+        if (KW == 4) {     // 12 independent shared-memory gathers
+            const float4 a0 = (Ab[jj.x * 3]), a1 = (Ab[jj.x * 3 + 1]), a2 = (Ab[jj.x * 3 + 2]);
+            const float4 b0 = (Ab[jj.y * 3]), b1 = (Ab[jj.y * 3 + 1]), b2 = (Ab[jj.y * 3 + 2]);
+            const float4 c0 = (Ab[jj.z * 3]), c1 = (Ab[jj.z * 3 + 1]), c2 = (Ab[jj.z * 3 + 2]);
+            const float4 d0 = (Ab[jj.w * 3]), d1 = (Ab[jj.w * 3 + 1]), d2 = (Ab[jj.w * 3 + 2]);
             blend(jj.x, ww.x, a0, a1, a2); blend(jj.y, ww.y, b0, b1, b2); blend(jj.z, ww.z, c0, c1, c2); blend(jj.w, ww.w, d0, d1, d2);
         } else {
             for (int k = 0; k < KW; ++k) {
                 const int j = skin_j[(size_t)v * KW + k];
                 const float wt = skin_w[(size_t)v * KW + k];
-                blend(j, wt, __ldg(Ab + j * 3), __ldg(Ab + j * 3 + 1), __ldg(Ab + j * 3 + 2));
+                blend(j, wt, Ab[j * 3], Ab[j * 3 + 1], Ab[j * 3 + 2]);
             }
         }
         float ox = T[0] * x + T[1] * y + T[2] * z + T[3];
@@ -470,6 +485,11 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     if (staged && blockIdx.y < B)
         for (int k = tid; k < nent; k += blockDim.x) { s_w[k] = ch_w[e0 + k]; s_lv[k] = ch_lv[e0 + k]; }
     pdl_wait();
+    __shared__ float4 sA[kMaxJ * 3];                  // the body's transform table: gathered 3 x KW rows per thread
+    if (blockIdx.y < B) {
+        const float4 *__restrict__ Ag = reinterpret_cast<const float4 *>(A + (size_t)blockIdx.y * J * 12);
+        for (int i = tid; i < J * 3; i += blockDim.x) sA[i] = Ag[i];
+    }
     const int v = blockIdx.x * blockDim.x + tid;
     const int b = blockIdx.y;
     float *gvp_g = gvp_out + (size_t)(b / kBG) * Npad * kBG + (size_t)(b % kBG) * kKC;
@@ -537,7 +557,7 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         dd = fg.nnd[(size_t)b * fg.nu + slot];
         ni = fg.nni[(size_t)b * fg.nu + slot];
     }
-    if (FIT) __syncthreads();
+    __syncthreads();
     float gx = 0.f, gy = 0.f, gz = 0.f, closs = 0.f;
     if (act) {
         if (FIT) {
@@ -576,23 +596,23 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         float T[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
-        const float4 *__restrict__ Ab = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
+        const float4 *Ab = sA;
         auto blend = [&](float wt, float4 r0, float4 r1, float4 r2) {
             T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]);
             T[3] = fmaf(wt, r1.x, T[3]); T[4] = fmaf(wt, r1.y, T[4]); T[5] = fmaf(wt, r1.z, T[5]);
             T[6] = fmaf(wt, r2.x, T[6]); T[7] = fmaf(wt, r2.y, T[7]); T[8] = fmaf(wt, r2.z, T[8]);
         };
         if (KW == 4) {     // ids and weights came with the level-1 loads; 12 independent gathers
-            const float4 a0 = __ldg(Ab + jj.x * 3), a1 = __ldg(Ab + jj.x * 3 + 1), a2 = __ldg(Ab + jj.x * 3 + 2);
-            const float4 b0 = __ldg(Ab + jj.y * 3), b1 = __ldg(Ab + jj.y * 3 + 1), b2 = __ldg(Ab + jj.y * 3 + 2);
-            const float4 c0 = __ldg(Ab + jj.z * 3), c1 = __ldg(Ab + jj.z * 3 + 1), c2 = __ldg(Ab + jj.z * 3 + 2);
-            const float4 d0 = __ldg(Ab + jj.w * 3), d1 = __ldg(Ab + jj.w * 3 + 1), d2 = __ldg(Ab + jj.w * 3 + 2);
+            const float4 a0 = Ab[jj.x * 3], a1 = Ab[jj.x * 3 + 1], a2 = Ab[jj.x * 3 + 2];
+            const float4 b0 = Ab[jj.y * 3], b1 = Ab[jj.y * 3 + 1], b2 = Ab[jj.y * 3 + 2];
+            const float4 c0 = Ab[jj.z * 3], c1 = Ab[jj.z * 3 + 1], c2 = Ab[jj.z * 3 + 2];
+            const float4 d0 = Ab[jj.w * 3], d1 = Ab[jj.w * 3 + 1], d2 = Ab[jj.w * 3 + 2];
             blend(ww.x, a0, a1, a2); blend(ww.y, b0, b1, b2); blend(ww.z, c0, c1, c2); blend(ww.w, d0, d1, d2);
         } else {
             for (int k = 0; k < KW; ++k) {
                 const int j = skin_j[(size_t)v * KW + k];
                 const float wt = skin_w[(size_t)v * KW + k];
-                blend(wt, __ldg(Ab + j * 3), __ldg(Ab + j * 3 + 1), __ldg(Ab + j * 3 + 2));
+                blend(wt, Ab[j * 3], Ab[j * 3 + 1], Ab[j * 3 + 2]);
             }
         }
         put(3 * v, T[0] * gx + T[3] * gy + T[6] * gz);
