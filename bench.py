@@ -241,7 +241,7 @@ def roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak
 
     nn_target = op.s_index if op.s_index is not None else op.s_verts
     if op.s_index is not None:
-        # the loop's own configuration: contact queries in Morton order of the template + last
+        # the loop's own configuration: contact queries ordered by dominant joint + kd cells of the template + last
         # iteration's hints (psi_fit_run keeps them); one call outside the timing warms the hints
         from psi_release_b200.fused import _spatial_order
         sel = torch.tensor(_spatial_order(np.arange(NUM_VERTS), model["v_template"], model["weights"],
@@ -279,7 +279,7 @@ def roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak
         "lbs_bwd": model_bytes + B * (NUM_VERTS * 24 + 740),
         "sdf": B * NUM_VERTS * (32 + 12 + 4 + 12),
     }
-    names = {"nn": ("psi::nn_index_thread_kernel<true> (exact box-tree NN, Morton-ordered queries + hints)" if op.s_index is not None
+    names = {"nn": ("psi::nn_index_group_kernel<true> (exact box-tree NN, joint/kd-ordered queries + hints)" if op.s_index is not None
                     else "psi::nn_fwd_kernel<8,16,256,1024,2> (brute-force NN)"),
              "lbs_fwd": "psi::lbs_pose_fwd_kernel + psi::lbs_blend_fwd_kernel + psi::lbs_skin_fwd_kernel",
              "lbs_bwd": "psi::lbs_vertex_bwd/dA/dcoef/pose_bwd kernels", "sdf": "psi::sdf_fwd_kernel"}

@@ -16,7 +16,11 @@
 // already evaluated, so every skipped point has d > final minimum and cannot win or tie.
 // Visited points are compared lexicographically on (d, original index).
 //
-// Execution: one warp per query.  A 32-lane round evaluates 32 mega boxes, or the 8 children of
+// Three schedules return the same bits (psi_nn_index_query_mode): one warp per query (below; generic,
+// incoherent query sets), one thread per query, and one warp per GROUP of 32 consecutive queries sharing
+// one tree walk (nn_index_group_kernel, what the fitting loop uses).
+//
+// Warp-per-query execution.  A 32-lane round evaluates 32 mega boxes, or the 8 children of
 // up to 4 admitted parents at once (lane = parent slot*8 + child); an admitted cluster is ONE
 // coalesced 512-byte load, one point per lane; the running bound is a warp-wide redux.sync.min on
 // the distance bits (d >= 0: the IEEE pattern is monotone).  The bound is seeded either
