@@ -329,7 +329,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PSI_BENCH_NCCL_DEBUG", "WARN")   # stdout carries ONE JSON line
+        # stdout carries ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION
+        if "PSI_BENCH_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["PSI_BENCH_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     model, scene, xh = make_world(args, rank)
     cfg = dict(model_data=model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
