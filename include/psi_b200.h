@@ -39,7 +39,7 @@ typedef void *psi_stream_t; /* cudaStream_t */
 #define PSI_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels were built for */
 #define PSI_ERR_ALLOC (-4)        /* device allocation failed (model upload only) */
 
-#define PSI_ABI_VERSION 1
+#define PSI_ABI_VERSION 2   /* 2: psi_fit_config.nn_mode, psi_fit_profile, psi_nn_index_query_mode mode 3 */
 
 /* ABI version of the loaded library (PSI_ABI_VERSION it was built with). */
 PSI_API int psi_abi_version(void);

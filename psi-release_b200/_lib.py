@@ -86,8 +86,8 @@ def lib():
         fn = getattr(L, name)      # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if L.psi_abi_version() != 1:
-        raise PsiError(f"libpsi_b200 ABI {L.psi_abi_version()} != 1")
+    if L.psi_abi_version() != 2:
+        raise PsiError(f"libpsi_b200 ABI {L.psi_abi_version()} != 2")
     _LIB = L
     return L
 

@@ -24,7 +24,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert sorted(_lib.EXPORTS) == declared          # the Python binding covers the whole header
     lib = _lib.lib()
-    assert lib.psi_abi_version() == 1
+    assert lib.psi_abi_version() == 2
     assert b"workspace" in lib.psi_error_string(-2)
     assert lib.psi_sdf_num_partials(10475) == 11 and lib.psi_nn_workspace_bytes(2, 10, 30) == 2 * 30 * 8
 
