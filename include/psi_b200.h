@@ -10,7 +10,11 @@
  *   - outputs are caller-owned and OVERWRITTEN (no pre-zero contract, unlike
  *     chamfer_pytorch/chamfer.cu:177-178 whose memsets are commented out);
  *   - work is enqueued on `stream` (a cudaStream_t) and the call returns without
- *     synchronising; no global state, re-entrant, never prints;
+ *     synchronising; never prints; handles (model / index / fit context) belong to the device
+ *     that was current when they were created and calls on them must be made with that device
+ *     current; different handles may be used from different threads and on different devices of
+ *     one process (process-wide state: a launch counter and a mutex-guarded cache of the
+ *     per-device kernel attributes);
  *   - return value: 0 = ok, >0 = a cudaError_t from the launch, <0 = PSI_ERR_*.
  *
  * Each entry point names the reference interface it replaces.
@@ -39,7 +43,8 @@ typedef void *psi_stream_t; /* cudaStream_t */
 #define PSI_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels were built for */
 #define PSI_ERR_ALLOC (-4)        /* device allocation failed (model upload only) */
 
-#define PSI_ABI_VERSION 2   /* 2: psi_fit_config.nn_mode, psi_fit_profile, psi_nn_index_query_mode mode 3 */
+#define PSI_ABI_VERSION 3   /* 3: psi_fit_config.{loop_mode,loss_mode}, psi_fit_trace, psi_fit_trace_bytes;
+                               2: psi_fit_config.nn_mode, psi_fit_profile, psi_nn_index_query_mode mode 3 */
 
 /* ABI version of the loaded library (PSI_ABI_VERSION it was built with). */
 PSI_API int psi_abi_version(void);
@@ -58,7 +63,9 @@ PSI_API const char *psi_error_string(int code);
  *
  * Distance definition (bit-exact with the reference build):
  *   dx = s.x - q.x ...;  d = fma(dz,dz, fma(dx,dx, rn(dy*dy)));  first minimum wins
- *   (lowest index on ties).  Inputs must be finite.
+ *   (lowest index on ties).  Scene points must be finite.  A query whose distances are all NaN
+ *   or all +inf (a diverged body) gets index 0 and its distance to point 0, which is what the
+ *   reference's `k == 0 ||` clauses return (chamfer.cu:36,121,126).
  * ---------------------------------------------------------------------------------------- */
 
 /* Bytes of scratch psi_nn_fwd / psi_chamfer_fwd need for these sizes (may be 0). */
@@ -220,6 +227,11 @@ typedef struct psi_fit_config {
     float robust_c;       /* 1.0 (fitting_habitat.py:141) or 0.01 (fitting_proxe.py:139) */
     float lr, beta1, beta2, eps;                     /* torch.optim.Adam: init_lr_h, .9, .999, 1e-8 */
     int nn_mode;          /* schedule of the in-loop NN query (psi_nn_index_query_mode); 0 = default (3) */
+    int loop_mode;        /* with use_graph: 0 = the WHOLE loop as one graph launch (a conditional WHILE node whose
+                             body is the iteration, counted down on the device), 1 = one graph launch per iteration */
+    int loss_mode;        /* 0 = independent: sum over bodies of the reference's B=1 loss (the shipped scripts,
+                             fitting_habitat.py:254); 1 = batch: the reference's batch-coupled means
+                             (fitting_proxe.py:105,110,139,155-160 with B > 1; demo.ipynb cell 16) */
 } psi_fit_config;
 
 typedef struct psi_fit_ctx psi_fit_ctx;
@@ -252,6 +264,29 @@ PSI_API int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *ca
                   int num_iter, psi_stream_t stream);
 PSI_API int psi_fit_end(psi_fit_ctx *c, float *xhr_out, float *losses_out, psi_stream_t stream);
 PSI_API int psi_fit_launches_per_iteration(void);
+
+/* Trace of the most recent iteration the context evaluated (parity tests, debugging): copies one of the
+ * loop's own buffers to `dst` (device memory, psi_fit_trace_bytes(what) bytes) on `stream`, ordered after
+ * the loop.  After psi_fit_run(num_iter = k) the "last iteration" is iteration k-1: X_EVAL is the vector it
+ * was evaluated at, GRAD_X = dL/dx there (all four loss terms, before Adam), VERTS / SDF / NN are what its
+ * kernels produced, X is the vector after its Adam step.  NN arrays are in QUERY order: slot s is body
+ * vertex QUERY_IDS[s] (the unique contact ids in the order the loop queries them). */
+#define PSI_FIT_TRACE_X_EVAL 0     /* float [B,75] */
+#define PSI_FIT_TRACE_GRAD_X 1     /* float [B,75] */
+#define PSI_FIT_TRACE_VERTS 2      /* float [B,V,3] scene frame */
+#define PSI_FIT_TRACE_SDF 3        /* float [B,V] */
+#define PSI_FIT_TRACE_SDF_GRAD 4   /* float [B,V,3] */
+#define PSI_FIT_TRACE_NN_DIST 5    /* float [B,nu] */
+#define PSI_FIT_TRACE_NN_IDX 6     /* int   [B,nu] original scene point index */
+#define PSI_FIT_TRACE_QUERY_IDS 7  /* int   [nu] */
+#define PSI_FIT_TRACE_LOSSES 8     /* float [B,4] */
+#define PSI_FIT_TRACE_X 9          /* float [B,75] */
+#define PSI_FIT_TRACE_ADAM_M 10    /* float [B,75] */
+#define PSI_FIT_TRACE_ADAM_V 11    /* float [B,75] */
+#define PSI_FIT_TRACE_POSE6D 12    /* float [B,nbody+1,6]: root 6D + VPoser decoder output of the last iteration */
+PSI_API size_t psi_fit_trace_bytes(const psi_fit_ctx *c, int what);   /* 0 for an unknown `what` */
+PSI_API int psi_fit_trace(psi_fit_ctx *c, int what, void *dst, size_t dst_bytes, psi_stream_t stream);
+
 /* Measurement aid (bench.py `roofline`): runs warm_iters + timed_iters iterations EAGERLY on
  * `stream` with a CUDA event recorded behind every kernel launch and returns the launch count n
  * of one iteration (< 0 on error); h_ms[i] (host) = average duration of launch i over the timed

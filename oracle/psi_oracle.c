@@ -18,7 +18,8 @@
  *       /root/reference/source/fitting_habitat.py:145-152
  *       (align_corners=True, padding_mode='border')
  *
- * Parity pin: on a GPU box tests/test_chamfer_gpu.py checks this file against the
+ * Parity pin: on a GPU box tests/test_gpu_parity.py
+ * (test_chamfer_matches_reference_cuda_build_bit_exact) checks this file against the
  * reference's own chamfer.cu compiled unmodified into oracle/_ref/ (bit-exact
  * dist + idx), and against the reference test's matmul formula
  * (chamfer_pytorch/test_chamfer.py:35-54, sum sq err < 1e-8).
@@ -106,6 +107,9 @@ static void nn_one_avx2(float qx, float qy, float qz, const float *sx, const flo
     int bi = 0;
     for (int l = 0; l < 8; ++l)
         if (bl[l] < best || (bl[l] == best && il[l] < bi)) { best = bl[l]; bi = il[l]; }
+    /* no distance compared below +inf (NaN or overflowing query): the reference's `k == 0 ||` clauses
+     * (chamfer.cu:36,121,126) leave point 0 and its distance, as the scalar scan above does */
+    if (k > 0 && !(best < INFINITY)) { best = ref_dist(qx, qy, qz, sx[0], sy[0], sz[0]); bi = 0; }
     if (k == 0) { best = 0.0f; bi = 0; }
     for (; k < m; ++k) {
         float d = ref_dist(qx, qy, qz, sx[k], sy[k], sz[k]);
@@ -142,6 +146,9 @@ static void nn_one_avx512(float qx, float qy, float qz, const float *sx, const f
     int bi = 0;
     for (int l = 0; l < 16; ++l)
         if (bl[l] < best || (bl[l] == best && il[l] < bi)) { best = bl[l]; bi = il[l]; }
+    /* no distance compared below +inf (NaN or overflowing query): the reference's `k == 0 ||` clauses
+     * (chamfer.cu:36,121,126) leave point 0 and its distance, as the scalar scan above does */
+    if (k > 0 && !(best < INFINITY)) { best = ref_dist(qx, qy, qz, sx[0], sy[0], sz[0]); bi = 0; }
     if (k == 0) { best = 0.0f; bi = 0; }
     for (; k < m; ++k) {
         float d = ref_dist(qx, qy, qz, sx[k], sy[k], sz[k]);

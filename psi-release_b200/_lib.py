@@ -22,7 +22,14 @@ _f = ctypes.c_float
 class FitConfig(ctypes.Structure):
     """struct psi_fit_config (include/psi_b200.h)."""
     _fields_ = [("B", _i), ("use_graph", _i), ("w_rec", _f), ("w_vposer", _f), ("w_contact", _f),
-                ("w_collision", _f), ("robust_c", _f), ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("nn_mode", _i)]
+                ("w_collision", _f), ("robust_c", _f), ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("nn_mode", _i),
+                ("loop_mode", _i), ("loss_mode", _i)]
+
+
+# psi_fit_trace selectors (PSI_FIT_TRACE_* in include/psi_b200.h): name -> (code, is_int)
+FIT_TRACE = {"x_eval": (0, False), "grad_x": (1, False), "verts": (2, False), "sdf": (3, False), "sdf_grad": (4, False),
+             "nn_dist": (5, False), "nn_idx": (6, True), "query_ids": (7, True), "losses": (8, False), "x": (9, False),
+             "adam_m": (10, False), "adam_v": (11, False), "pose6d": (12, False)}
 
 
 class PsiError(RuntimeError):
@@ -81,13 +88,15 @@ def lib():
         "psi_fit_end": (_i, [_vp, _vp, _vp, _vp]),
         "psi_fit_launches_per_iteration": (_i, []),
         "psi_fit_profile": (_i, [_vp, _vp, _vp, _l, _i, _i, _vp, _vp, _i, _vp]),
+        "psi_fit_trace_bytes": (_sz, [_vp, _i]),
+        "psi_fit_trace": (_i, [_vp, _i, _vp, _sz, _vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)      # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if L.psi_abi_version() != 2:
-        raise PsiError(f"libpsi_b200 ABI {L.psi_abi_version()} != 2")
+    if L.psi_abi_version() != 3:
+        raise PsiError(f"libpsi_b200 ABI {L.psi_abi_version()} != 3 (rebuild: python -m psi_release_b200.build)")
     _LIB = L
     return L
 
@@ -98,7 +107,7 @@ EXPORTS = ["psi_abi_version", "psi_error_string", "psi_launch_count", "psi_nn_wo
            "psi_sdf_bwd", "psi_lbs_model_create", "psi_lbs_model_destroy", "psi_lbs_model_bytes",
            "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd", "psi_lbs_bwd2", "psi_fit_profile",
            "psi_fit_create", "psi_fit_destroy", "psi_fit_run", "psi_fit_begin", "psi_fit_end",
-           "psi_fit_launches_per_iteration"]
+           "psi_fit_launches_per_iteration", "psi_fit_trace_bytes", "psi_fit_trace"]
 
 
 def check(rc: int, what: str) -> None:

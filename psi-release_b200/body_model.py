@@ -132,6 +132,11 @@ def lbs(betas, pose, handle, transl=None, cam=None, want_joints=False):
     return _LBS.apply(betas, pose, transl, cam, handle, want_joints)
 
 
+# npz keys read from an SMPL-X model file (human_body_prior/body_model/body_model.py:86-135 plus smplx's hand PCA)
+MODEL_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "kintree_table", "weights", "f",
+              "hands_componentsl", "hands_componentsr", "hands_meanl", "hands_meanr")
+
+
 class SMPLX(nn.Module):
     """`smplx.create(model_path, model_type='smplx', ...)` result.  Same keyword surface as the
     reference's call; every `create_*` flag makes a zero nn.Parameter of shape [batch_size, .]."""
@@ -153,8 +158,15 @@ class SMPLX(nn.Module):
                 model_path = os.path.join(model_path, f"SMPLX_{gender.upper()}.{ext}")
             if not os.path.exists(model_path):
                 raise FileNotFoundError(model_path)
-            model_data = dict(np.load(model_path, allow_pickle=False))
-        self._model_data = {k: np.asarray(v) for k, v in model_data.items()}
+            # only the keys the path reads: the published SMPLX_*.npz also carries object-dtype
+            # entries (joint2num, part2num, ...) that np.load refuses with allow_pickle=False and that smplx
+            # itself unpickles -- they are never touched here, so nothing has to be unpickled
+            with np.load(model_path, allow_pickle=False) as z:
+                missing = [k for k in MODEL_KEYS if k not in z.files]
+                if missing:
+                    raise KeyError(f"{model_path}: missing SMPL-X keys {missing}")
+                model_data = {k: z[k] for k in MODEL_KEYS}
+        self._model_data = {k: np.asarray(v) for k, v in model_data.items() if k in MODEL_KEYS}
         md = self._model_data
         self.batch_size = batch_size
         self.num_betas, self.num_expression_coeffs = num_betas, num_expression_coeffs

@@ -1,8 +1,11 @@
 // ABI version and error strings for libpsi_b200.
 #include "common.cuh"
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
 
 namespace psi {
 static std::atomic<unsigned long long> g_launches{0};
@@ -19,6 +22,24 @@ bool pdl_enabled() {
     // 630 bodies/s, r01v): the graph's programmatic edges cost more than the overlapped launch latency saves
     static const bool on = [] { const char *e = getenv("PSI_PDL"); return e && e[0] == '1'; }();
     return on;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs
+// through the C ABI has to opt every kernel in on every device it launches on.  (device, function) pairs that
+// already hold at least `bytes` are remembered; the map is the only mutable process-wide state besides the
+// launch counter and is guarded by a mutex.
+int ensure_max_dyn_smem(const void *func, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, int> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find({dev, func});
+    if (it != done.end() && it->second >= bytes) return PSI_OK;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    done[{dev, func}] = bytes;
+    return PSI_OK;
 }
 static thread_local LaunchRecorder *g_rec = nullptr;
 void recorder_set(LaunchRecorder *r) { g_rec = r; }

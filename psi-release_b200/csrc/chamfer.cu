@@ -186,12 +186,20 @@ __global__ void __launch_bounds__(THREADS, MINB) nn_fwd_kernel(const NNParams p)
             if (d == best[i]) bi = k;
         }
         const long o = p.shared_scene ? t : (long)group * p.n + t;
+        float bd = best[i];
+        if (!(bd < CUDART_INF_F)) {
+            // nothing compared below +inf (every distance NaN or +inf: a diverged body): the reference's
+            // `k == 0 ||` clauses (chamfer.cu:36,121,126) leave point 0 and its distance
+            if (k_begin != 0) continue;               // another chunk owns point 0; the key stays all-ones
+            bi = 0;
+            bd = ref_dist(__ldg(s), __ldg(s + 1), __ldg(s + 2), qx[i], qy[i], qz[i]);
+        }
         if (p.num_chunks == 1) {
-            p.dist[o] = best[i];
+            p.dist[o] = bd;
             if (p.idx) p.idx[o] = bi;
         } else {
             const unsigned long long key =
-                ((unsigned long long)__float_as_uint(best[i]) << 32) | (unsigned int)bi;
+                ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned int)bi;
             atomicMin(p.packed + o, key);
         }
     }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/psi_b200.h"
 
 #define PSI_RETURN_IF_LAUNCH_FAILED()                  \
@@ -24,6 +25,14 @@
 struct psi_lbs_model;
 
 namespace psi {
+
+// NVTX range around a C-ABI entry point (header-only NVTX3: a no-op unless a profiler is attached)
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range &) = delete;
+    Range &operator=(const Range &) = delete;
+};
 
 void count_launch(const char *name);   // api.cu
 // per-launch timing for psi_fit_profile: while a recorder is active on this thread, every counted
@@ -71,6 +80,13 @@ int lbs_vertex_chunks(const psi_lbs_model *m);   // 256-vertex chunks = rows of 
 // precede it.  Opt-in (PSI_PDL=1): it measured slower than plain graph edges, see api.cu.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// opt `func` in to `bytes` of dynamic shared memory on the CURRENT device (once per device; api.cu); 0 or a cudaError_t
+int ensure_max_dyn_smem(const void *func, int bytes);
+template <typename... KArgs>
+inline int ensure_max_dyn_smem(void (*kernel)(KArgs...), size_t bytes) {
+    return ensure_max_dyn_smem(reinterpret_cast<const void *>(kernel), (int)bytes);
+}
 
 bool skip_kernel(const char *name);   // api.cu: measurement aid, PSI_SKIP_KERNEL=<name> drops that launch (results invalid)
 bool pdl_enabled();   // api.cu: true only when PSI_PDL=1 (measured slower, see api.cu)

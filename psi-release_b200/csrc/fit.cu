@@ -16,9 +16,16 @@
 //   fit_linear x3    decoder backward
 //   fit_step         per body: loss-term gradients, Adam step (torch.optim.Adam defaults,
 //                    fitting_habitat.py:76), loss values, and the inputs of the next iteration
-// Loss semantics: the SUM over bodies of the reference's B=1 loss ('independent' mode) -- every
-// body is optimised exactly as the shipped batch_size-1 scripts do, bodies never interact.
-// All reductions have a fixed order: results are bit-reproducible and independent of B.
+// Loss semantics: loss_mode 0 = the SUM over bodies of the reference's B=1 loss ('independent') -- every
+// body is optimised exactly as the shipped batch_size-1 scripts do, bodies never interact, results are
+// independent of B; loss_mode 1 = the reference's batch-coupled means (fitting_proxe.py:105,110,139,155-160
+// with B > 1, demo.ipynb cell 16): the terms are means over the whole batch and the collision term divides by
+// the batch-wide number of penetrating vertices (an integer counted with atomics, so still deterministic).
+// All reductions have a fixed order: results are bit-reproducible.
+//
+// The loop itself is ONE graph launch: a conditional WHILE node whose body is the captured iteration; the
+// last kernel of the body counts the remaining iterations down on the device (cudaGraphSetConditional).
+// loop_mode 1 keeps the older form, one graph launch per iteration.
 #include "common.cuh"
 #include "rot6d.cuh"
 #include "fit_fuse.cuh"
@@ -40,11 +47,17 @@ struct psi_fit_ctx {
     // state + scratch.  *A buffers are GEMM A operands ([body group][K/32][64][32], rows >= B zero)
     float *x0, *x, *am, *av, *cam, *rot6d, *pose, *shape, *transl, *zA, *h1pre, *h1A, *h2pre, *h2A,
         *g6_root, *g6A, *dh2A, *dh1A, *dz, *verts, *saved, *sdfv, *sdfg, *partial, *nnd, *cpart,
-        *gshape, *gpose, *gtransl, *lbs_ws, *losses;
+        *gshape, *gpose, *gtransl, *lbs_ws, *losses, *gx, *xeval;
     int *nni, *step, *nnhint;
+    int *neg_cnt;                  // loss_mode 1: batch-wide count of penetrating vertices, [2] by iteration parity
+    int *loop_left;                // iterations the WHILE node still has to run
     size_t lbs_ws_bytes;
-    cudaGraphExec_t exec;
+    cudaGraphExec_t exec;          // one iteration (loop_mode 1)
+    cudaGraphExec_t loop_exec;     // the whole loop (loop_mode 0)
+    cudaGraphConditionalHandle loop_cond;
+    int capturing_loop;            // enqueue_iteration is recording the WHILE body: fit_step gets the handle
     int pending_join;
+    int ev_out_recorded;           // ev_out marks the end of the last loop run on gstream
     cudaStream_t gstream;          // graphs cannot be captured on the legacy default stream
     cudaEvent_t ev_in, ev_out;
     std::vector<void *> owned;
@@ -83,7 +96,8 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
                 const float *__restrict__ gtransl, const float *__restrict__ partial,
                 const float *__restrict__ cpart, float *__restrict__ losses, float *__restrict__ zA,
                 float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
-                float *__restrict__ transl) {
+                float *__restrict__ transl, float *__restrict__ gx_out, float *__restrict__ xeval_out,
+                int *__restrict__ neg_cnt, int *__restrict__ loop_left, cudaGraphConditionalHandle loop_cond) {
     pdl_wait();
     __shared__ float sx[96], g[96];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -99,11 +113,14 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
         if (tid < xdim) { x0e = x0[(size_t)b * xdim + tid]; ame = am[(size_t)b * xdim + tid]; ave = av[(size_t)b * xdim + tid]; }
     }
     __syncthreads();
+    // loss_mode 1: the L1 / L2 terms are means over the whole batch (the contact and collision terms are scaled
+    // where their gradients are formed, lbs_vertex_bwd<FIT>)
+    const float bdiv = cfg.loss_mode == 1 ? (float)d.B : 1.0f;
     if (do_post) {
         if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
         else if (tid < 9) g[tid] = g6_root[(size_t)b * 6 + tid - 3];
         else if (tid < 19) g[tid] = gshape[(size_t)b * d.NB + tid - 9];
-        else if (tid < 19 + Lz) g[tid] = dz[(size_t)b * Lz + tid - zoff] + cfg.w_vposer * (2.0f * sx[tid] / (float)Lz);
+        else if (tid < 19 + Lz) g[tid] = dz[(size_t)b * Lz + tid - zoff] + cfg.w_vposer * (2.0f * sx[tid] / ((float)Lz * bdiv));
         else if (tid < xdim) {                       // hand PCA backward
             const int u = tid - lhoff, c = u % d.ncomp;
             const bool right = u >= d.ncomp;
@@ -124,10 +141,12 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
             }
             for (int i = ln; i < nchunk; i += 32) cs += cpart[(size_t)b * nchunk + i];
             r = warp_sum(r); zz = warp_sum(zz); sn = warp_sum(sn); cn = warp_sum(cn); cs = warp_sum(cs);
+            // loss_mode 1: this body's share of the batch means (the rows add up to the reference's scalars)
+            if (cfg.loss_mode == 1) cn = (float)neg_cnt[t_prev & 1];
             if (ln == 0) {
-            losses[(size_t)b * 4 + 0] = cfg.w_rec * (r / (float)xdim);
-            losses[(size_t)b * 4 + 1] = cfg.w_vposer * (zz / (float)Lz);
-            losses[(size_t)b * 4 + 2] = cfg.w_contact * (cs / (float)num_contact);
+            losses[(size_t)b * 4 + 0] = cfg.w_rec * (r / ((float)xdim * bdiv));
+            losses[(size_t)b * 4 + 1] = cfg.w_vposer * (zz / ((float)Lz * bdiv));
+            losses[(size_t)b * 4 + 2] = cfg.w_contact * (cs / ((float)num_contact * bdiv));
             losses[(size_t)b * 4 + 3] = cfg.w_collision * (cn > 0.f ? sn / cn : 0.f);
             }
         }
@@ -137,8 +156,10 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
         if (tid < xdim) {
             const float xe = sx[tid], diff = xe - x0e;
             const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-            const float ge = g[tid] + cfg.w_rec * sgn / (float)xdim;
+            const float ge = g[tid] + cfg.w_rec * sgn / ((float)xdim * bdiv);
             const size_t o = (size_t)b * xdim + tid;
+            gx_out[o] = ge;          // trace: dL/dx of the iteration just evaluated, and where it was evaluated
+            xeval_out[o] = xe;
             const float m = cfg.beta1 * ame + (1.0f - cfg.beta1) * ge;
             const float v = cfg.beta2 * ave + (1.0f - cfg.beta2) * ge * ge;
             am[o] = m;
@@ -153,6 +174,15 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
         __syncthreads();           // everyone has read sx / step[b]
         if (tid < xdim) sx[tid] = xn;
         if (tid == 0) step[b] = t;
+        if (b == 0 && tid == 0) {
+            // the next iteration's penetration counter (its parity is t & 1; nobody reads it during this kernel)
+            if (neg_cnt) neg_cnt[t & 1] = 0;
+            if (loop_left) {           // body of the WHILE node: one iteration done
+                const int left = *loop_left - 1;
+                *loop_left = left;
+                cudaGraphSetConditional(loop_cond, left > 0 ? 1u : 0u);
+            }
+        }
         __syncthreads();
     }
     pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
@@ -176,11 +206,18 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     if (tid < 3) transl[(size_t)b * 3 + tid] = sx[tid];
 }
 
-__global__ void fit_reset_kernel(float *am, float *av, int *step, long n, int B) {
+__global__ void fit_reset_kernel(float *am, float *av, int *step, long n, int B, int *neg_cnt) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { am[i] = 0.f; av[i] = 0.f; }
     if (i < B) step[i] = 0;
+    if (i < 2) neg_cnt[i] = 0;
 }
+
+// head of the loop graph: arm the WHILE node with the iteration count psi_fit_begin stored
+__global__ void fit_loop_head_kernel(cudaGraphConditionalHandle cond, const int *loop_left) {
+    cudaGraphSetConditional(cond, *loop_left > 0 ? 1u : 0u);
+}
+__global__ void fit_loop_set_kernel(int *loop_left, int n) { *loop_left = n; }
 
 __global__ void fit_cam_kernel(const float *cam, long stride, int B, float *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,7 +241,9 @@ static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
     const FitDims d = {c->B, c->V, c->J, c->NB, c->latent, c->hidden, c->nbody, c->ncomp, c->num_rot};
     (psi::skip_kernel("fit_step") ? cudaSuccess : launch_pdl(fit_step_kernel, dim3(c->B), dim3(128), 0, st, d, c->cfg, do_post, c->np_sdf, c->nchunk, c->num_contact,
                c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->dz, c->g6_root, c->gpose,
-               c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl));
+               c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl,
+               c->gx, c->xeval, c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr,
+               c->capturing_loop ? c->loop_left : nullptr, c->loop_cond));
     PSI_LAUNCHED_K("fit_step");
     return PSI_OK;
 }
@@ -231,6 +270,7 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
         sf.g.gscale[a] = (float)(c->D - 1) / 2.0f * (2.0f / ext);
     }
     sf.sdfv = c->sdfv; sf.sdfg = c->sdfg; sf.partial = c->partial;
+    sf.neg_cnt = c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr; sf.step = c->step;
     rc = lbs_fwd_impl(c->model, B, c->shape, c->pose, c->transl, c->cam, 12, nullptr, c->rot6d, c->num_rot,
                       c->verts, nullptr, c->saved, &sf, st);
     if (rc) return rc;
@@ -245,6 +285,8 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     vg.nnd = c->nnd; vg.nni = c->nni; vg.cslot = c->cslot; vg.cweight = c->cweight;
     vg.w_contact = c->cfg.w_contact; vg.w_coll = c->cfg.w_collision; vg.robust_c = c->cfg.robust_c;
     vg.nu = c->nu; vg.np_sdf = c->np_sdf; vg.num_contact = c->num_contact; vg.cpart = c->cpart;
+    vg.neg_cnt = c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr; vg.step = c->step;
+    vg.bdiv = c->cfg.loss_mode == 1 ? (float)B : 1.0f;
     rc = lbs_bwd_impl(c->model, B, c->pose, c->cam, 12, c->saved, nullptr, &vg, nullptr, c->gshape, c->gpose,
                       c->gtransl, nullptr, c->num_rot, c->rot6d, c->g6_root, c->g6A, NOp, c->lbs_ws,
                       c->lbs_ws_bytes, st);
@@ -266,6 +308,7 @@ extern "C" {
 void psi_fit_destroy(psi_fit_ctx *c) {
     if (!c) return;
     if (c->exec) cudaGraphExecDestroy(c->exec);
+    if (c->loop_exec) cudaGraphExecDestroy(c->loop_exec);
     if (c->gstream) cudaStreamDestroy(c->gstream);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
@@ -286,6 +329,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         !h_W2 || !h_b2 || !h_W3 || !h_b3 || !h_hand_l || !h_hand_r || !h_pose_mean || !h_contact_ids || !cfg)
         return PSI_ERR_BAD_ARG;
     if (cfg->B < 1 || num_contact < 1 || D < 1 || V < 1) return PSI_ERR_BAD_ARG;
+    if (cfg->loss_mode < 0 || cfg->loss_mode > 1 || cfg->loop_mode < 0 || cfg->loop_mode > 1) return PSI_ERR_BAD_ARG;
     if (hidden != 512 || latent != 32 || nbody * 6 > 128 || nbody + 1 > J || ncomp > 16 ||
         J < 31 || NB < 10 || hidden % 32)
         return PSI_ERR_UNSUPPORTED;
@@ -296,6 +340,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->B = cfg->B; c->V = V; c->J = J; c->NB = NB; c->latent = latent; c->hidden = hidden; c->nbody = nbody;
     c->ncomp = ncomp; c->num_rot = nbody + 1; c->D = D; c->sdf = sdf; c->scene_pts = scene_points;
     c->num_contact = num_contact; c->exec = nullptr; c->pending_join = 0; c->gstream = nullptr; c->ev_in = c->ev_out = nullptr;
+    c->loop_exec = nullptr; c->capturing_loop = 0; c->loop_cond = 0; c->ev_out_recorded = 0;
     if (cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -303,7 +348,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         return PSI_ERR_ALLOC;
     }
     for (int a = 0; a < 3; ++a) { c->gmin[a] = h_grid_min[a]; c->gmax[a] = h_grid_max[a]; }
-    if (cudaFuncSetAttribute(fit_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLMaxChunks * kLChunkBytes) != cudaSuccess) {
+    if (ensure_max_dyn_smem(fit_linear_kernel, (size_t)kLMaxChunks * kLChunkBytes) != PSI_OK) {
         psi_fit_destroy(c);
         return PSI_ERR_UNSUPPORTED;
     }
@@ -390,8 +435,11 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->nnd = fbuf(B * c->nu); c->nni = (int *)dev_alloc(B * c->nu * sizeof(int));
     c->nnhint = (int *)dev_alloc(B * c->nu * sizeof(int));
     c->cpart = fbuf(B * c->nchunk); c->gshape = fbuf(B * NB); c->gpose = fbuf(B * J * 3);
-    c->gtransl = fbuf(B * 3); c->losses = fbuf(B * 4);
+    c->gtransl = fbuf(B * 3); c->losses = zbuf(B * 4);
+    c->gx = zbuf(B * xd); c->xeval = zbuf(B * xd);
     c->step = (int *)dev_alloc(B * sizeof(int));
+    c->neg_cnt = (int *)dev_alloc(2 * sizeof(int));
+    c->loop_left = (int *)dev_alloc(sizeof(int));
     c->lbs_ws_bytes = psi_lbs_bwd_workspace_bytes(model, c->B) + 64;
     c->lbs_ws = (float *)dev_alloc(c->lbs_ws_bytes);
     if (rc == PSI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PSI_ERR_ALLOC;
@@ -400,9 +448,67 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     return PSI_OK;
 }
 
+// loop_mode 1: one iteration as an executable graph, replayed num_iter times by the host
+static int build_iteration_graph(psi_fit_ctx *c) {
+    cudaStream_t gs = c->gstream;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return (int)e;
+    const int rc = psi::enqueue_iteration(c, gs);
+    e = cudaStreamEndCapture(gs, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGraphInstantiate(&c->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    return e == cudaSuccess ? PSI_OK : (int)e;
+}
+
+// loop_mode 0: head kernel -> conditional WHILE node whose body graph is the captured iteration.  The body's
+// last kernel (fit_step) decrements *loop_left and re-arms the condition, so the host launches the whole
+// num_iter-iteration loop once (300 cudaGraphLaunch calls per fit before).
+static int build_loop_graph(psi_fit_ctx *c) {
+    cudaStream_t gs = c->gstream;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaGraphCreate(&g, 0);
+    if (e != cudaSuccess) return (int)e;
+    int rc = PSI_OK;
+    do {
+        e = cudaGraphConditionalHandleCreate(&c->loop_cond, g, 0, 0);
+        if (e != cudaSuccess) break;
+        cudaGraphNode_t head = nullptr, loop = nullptr;
+        cudaKernelNodeParams kp = {};
+        void *args[] = {&c->loop_cond, &c->loop_left};
+        kp.func = (void *)psi::fit_loop_head_kernel;
+        kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
+        e = cudaGraphAddKernelNode(&head, g, nullptr, 0, &kp);
+        if (e != cudaSuccess) break;
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = c->loop_cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        e = cudaGraphAddNode(&loop, g, &head, 1, &np);
+        if (e != cudaSuccess) break;
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        e = cudaStreamBeginCaptureToGraph(gs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) break;
+        c->capturing_loop = 1;
+        rc = psi::enqueue_iteration(c, gs);
+        c->capturing_loop = 0;
+        cudaGraph_t captured = nullptr;
+        e = cudaStreamEndCapture(gs, &captured);     // == body
+        if (rc != PSI_OK || e != cudaSuccess) break;
+        e = cudaGraphInstantiate(&c->loop_exec, g, 0);
+    } while (0);
+    cudaGraphDestroy(g);
+    if (rc != PSI_OK) return rc;
+    return e == cudaSuccess ? PSI_OK : (int)e;
+}
+
 int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int num_iter,
                   psi_stream_t stream) {
     using namespace psi;
+    Range nvtx_range("psi_fit_begin");
     if (!c || !xhr_init || !cam || num_iter < 0) return PSI_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t xd = 9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp, n = (size_t)c->B * xd;
@@ -414,50 +520,53 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
     // one [3x4] transform per body (stride 0 broadcasts a shared one)
     fit_cam_kernel<<<(unsigned)((c->B * 12 + 255) / 256), 256, 0, st>>>(cam, cam_bstride, c->B, c->cam);
     PSI_LAUNCHED();
-    fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B);
+    fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt);
     PSI_LAUNCHED();
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
     if (c->cfg.use_graph && cs == cudaStreamCaptureStatusNone && num_iter > 1) {
         // the loop runs on the context's own stream, ordered after / before the caller's stream
         cudaStream_t gs = c->gstream;
+        const bool whole = c->cfg.loop_mode == 0;
         e = cudaEventRecord(c->ev_in, st);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(gs, c->ev_in, 0);
         if (e != cudaSuccess) return (int)e;
-        if (!c->exec) {
+        if (whole ? !c->loop_exec : !c->exec) {
             // warm the lazily-initialised pieces outside the capture (state is reset below)
             int rc = launch_step(c, 0, gs);
             if (rc == PSI_OK) rc = enqueue_iteration(c, gs);
+            if (rc == PSI_OK) rc = whole ? build_loop_graph(c) : build_iteration_graph(c);
             if (rc) return rc;
-            cudaGraph_t graph = nullptr;
-            e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal);
-            if (e != cudaSuccess) return (int)e;
-            rc = enqueue_iteration(c, gs);
-            e = cudaStreamEndCapture(gs, &graph);
-            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (e != cudaSuccess) return (int)e;
-            e = cudaGraphInstantiate(&c->exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) return (int)e;
             e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, gs);
             if (e != cudaSuccess) return (int)e;
-            fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gs>>>(c->am, c->av, c->step, (long)n, c->B);
+            e = cudaMemsetAsync(c->nnhint, 0xff, (size_t)c->B * c->nu * sizeof(int), gs);
+            if (e != cudaSuccess) return (int)e;
+            fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gs>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt);
             PSI_LAUNCHED();
         }
         const int rc = launch_step(c, 0, gs);
         if (rc) return rc;
-        for (int it = 0; it < num_iter; ++it) {
-            e = cudaGraphLaunch(c->exec, gs);
+        if (whole) {
+            fit_loop_set_kernel<<<1, 1, 0, gs>>>(c->loop_left, num_iter);
+            PSI_LAUNCHED();
+            e = cudaGraphLaunch(c->loop_exec, gs);
             if (e != cudaSuccess) return (int)e;
+        } else {
+            for (int it = 0; it < num_iter; ++it) {
+                e = cudaGraphLaunch(c->exec, gs);
+                if (e != cudaSuccess) return (int)e;
+            }
         }
         e = cudaEventRecord(c->ev_out, gs);
         if (e != cudaSuccess) return (int)e;
         c->pending_join = 1;
+        c->ev_out_recorded = 1;
     } else {
         int rc = launch_step(c, 0, st);
         for (int it = 0; it < num_iter && rc == PSI_OK; ++it) rc = enqueue_iteration(c, st);
         if (rc) return rc;
         c->pending_join = 0;
+        c->ev_out_recorded = 0;
     }
     return PSI_OK;
 }
@@ -487,6 +596,48 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
 }
 
 int psi_fit_launches_per_iteration(void) { return 15; }
+
+// (buffer, bytes) of a traceable object
+static const void *trace_buffer(const psi_fit_ctx *c, int what, size_t *bytes) {
+    const size_t B = (size_t)c->B, xd = 9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp, f = sizeof(float);
+    switch (what) {
+        case PSI_FIT_TRACE_X_EVAL: *bytes = B * xd * f; return c->xeval;
+        case PSI_FIT_TRACE_GRAD_X: *bytes = B * xd * f; return c->gx;
+        case PSI_FIT_TRACE_VERTS: *bytes = B * c->V * 3 * f; return c->verts;
+        case PSI_FIT_TRACE_SDF: *bytes = B * c->V * f; return c->sdfv;
+        case PSI_FIT_TRACE_SDF_GRAD: *bytes = B * c->V * 3 * f; return c->sdfg;
+        case PSI_FIT_TRACE_NN_DIST: *bytes = B * c->nu * f; return c->nnd;
+        case PSI_FIT_TRACE_NN_IDX: *bytes = B * c->nu * sizeof(int); return c->nni;
+        case PSI_FIT_TRACE_QUERY_IDS: *bytes = (size_t)c->nu * sizeof(int); return c->csel;
+        case PSI_FIT_TRACE_LOSSES: *bytes = B * 4 * f; return c->losses;
+        case PSI_FIT_TRACE_X: *bytes = B * xd * f; return c->x;
+        case PSI_FIT_TRACE_ADAM_M: *bytes = B * xd * f; return c->am;
+        case PSI_FIT_TRACE_ADAM_V: *bytes = B * xd * f; return c->av;
+        case PSI_FIT_TRACE_POSE6D: *bytes = B * c->num_rot * 6 * f; return c->rot6d;
+        default: *bytes = 0; return nullptr;
+    }
+}
+
+size_t psi_fit_trace_bytes(const psi_fit_ctx *c, int what) {
+    size_t bytes = 0;
+    if (c) trace_buffer(c, what, &bytes);
+    return bytes;
+}
+
+int psi_fit_trace(psi_fit_ctx *c, int what, void *dst, size_t dst_bytes, psi_stream_t stream) {
+    if (!c || !dst) return PSI_ERR_BAD_ARG;
+    size_t bytes = 0;
+    const void *src = trace_buffer(c, what, &bytes);
+    if (!src) return PSI_ERR_BAD_ARG;
+    if (dst_bytes < bytes) return PSI_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->ev_out_recorded) {   // the loop ran (or still runs) on the context's own stream
+        const cudaError_t e = cudaStreamWaitEvent(st, c->ev_out, 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+    return e == cudaSuccess ? PSI_OK : (int)e;
+}
 
 int psi_fit_profile(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int warm_iters,
                     int timed_iters, float *h_ms, const char **h_names, int max_launches, psi_stream_t stream) {

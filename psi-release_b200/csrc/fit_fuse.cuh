@@ -9,6 +9,10 @@ struct SdfFuse {
     SdfGrid g;
     float *sdfv, *sdfg;      // [B,V], [B,V,3]
     float *partial;          // [B, vertex chunks, 2]: (sum of -sdf, count) over sdf < 0, per 256-vertex chunk
+    // batch-coupled loss (psi_fit_config.loss_mode 1): the batch-wide count of penetrating vertices is
+    // accumulated with integer atomics into neg_cnt[iteration & 1] (iteration = step[0]); NULL otherwise
+    int *neg_cnt;
+    const int *step;
 };
 
 // dL/dverts of the contact robustifier (fitting_habitat.py:133-141) and the collision mean
@@ -20,6 +24,9 @@ struct VGradFuse {
     float w_contact, w_coll, robust_c;
     int nu, np_sdf, num_contact;
     float *cpart;            // [B, vertex chunks]: contact-loss partial sums
+    const int *neg_cnt;      // loss_mode 1: batch-wide penetration count [2] (see SdfFuse), else NULL
+    const int *step;
+    float bdiv;              // loss_mode 1: bodies in the batch (the contact mean runs over B x Nc), else 1
 };
 
 }  // namespace psi

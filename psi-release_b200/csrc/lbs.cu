@@ -446,6 +446,7 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
             for (int i = 0; i < 8; ++i) { s += red[0][i]; c += red[1][i]; }
             sf.partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = s;
             sf.partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = c;
+            if (sf.neg_cnt && c > 0.f) atomicAdd(sf.neg_cnt + (sf.step[0] & 1), (int)c);   // integer: order-independent
         }
     }
 }
@@ -544,7 +545,9 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
         }
     }
     if (FIT) {
-        if (tid < 32) {      // number of penetrating vertices of the body: lane-strided loads, shuffle tree (fixed order)
+        if (fg.neg_cnt) {    // batch-coupled loss: penetrating vertices of the WHOLE batch (fitting_proxe.py:155-158)
+            if (tid == 0) s_cnt = (float)fg.neg_cnt[fg.step[0] & 1];
+        } else if (tid < 32) {      // number of penetrating vertices of the body: lane-strided loads, shuffle tree (fixed order)
             float c = 0.f;
             for (int i = tid; i < fg.np_sdf; i += 32) c += fg.partial[((size_t)b * fg.np_sdf + i) * 2 + 1];
             c = warp_sum(c);
@@ -577,7 +580,7 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
                 const float den = s + fg.robust_c;
                 closs = wgt * (s / den);
                 // d/dd [ s/(s+c) ] = c/(s+c)^2 * 1/(2s);   d dd/dp = 2 (p - q)   (chamfer.cu:165-168)
-                const float gd = (fg.w_contact / (float)fg.num_contact) * wgt * (fg.robust_c / (den * den)) * (0.5f / s);
+                const float gd = (fg.w_contact / ((float)fg.num_contact * fg.bdiv)) * wgt * (fg.robust_c / (den * den)) * (0.5f / s);
                 const float g2 = gd * 2.0f;
                 gx += g2 * (vx - qx);
                 gy += g2 * (vy - qy);
@@ -1537,11 +1540,7 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
         p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef_hi = saved + L.coef; p.coef_lo = saved + L.coef_lo;
         p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B; p.ntiles = m->NT; p.nbg = (B + kBG - 1) / kBG;
         const size_t smem = (size_t)kTSmem + 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(lbs_blend_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
+        if (const int arc = ensure_max_dyn_smem(lbs_blend_fwd_tc5_kernel, smem)) return arc;
         const int items = p.ntiles * p.nbg;
         (psi::skip_kernel("lbs_blend_fwd_tc5") ? cudaSuccess : launch_pdl(lbs_blend_fwd_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
                    smem, st, p));
@@ -1551,11 +1550,7 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
         p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef = saved + L.coef;
         p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B;
         const size_t smem = (size_t)kFStages * kFStageBytes;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(lbs_blend_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
+        if (const int arc = ensure_max_dyn_smem(lbs_blend_fwd_kernel, smem)) return arc;
         (psi::skip_kernel("lbs_blend_fwd") ? cudaSuccess : launch_pdl(lbs_blend_fwd_kernel, grid, dim3(128), smem, st, p));
         PSI_LAUNCHED_K("lbs_blend_fwd");
     }
@@ -1631,22 +1626,14 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
         dim3 grid((unsigned)(m->Kpad / kDK), (unsigned)kNSplit, (unsigned)(W.Bpad / kBG));
         if (tc5) {
             const size_t smem = (size_t)kTSmem + 1024;
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(lbs_dcoef_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set = true;
-            }
+            if (const int arc = ensure_max_dyn_smem(lbs_dcoef_tc5_kernel, smem)) return arc;
             const int items = (m->Kpad / kTM) * nsplit * (W.Bpad / kBG);
             (psi::skip_kernel("lbs_dcoef_tc5") ? cudaSuccess : launch_pdl(lbs_dcoef_tc5_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kTThreads),
                        smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp, ws + W.gvp_lo, ws + W.part, nsplit));
             PSI_LAUNCHED_K("lbs_dcoef_tc5");
         } else {
             const size_t smem = (size_t)kDStages * kDStageBytes;
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(lbs_dcoef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set = true;
-            }
+            if (const int arc = ensure_max_dyn_smem(lbs_dcoef_kernel, smem)) return arc;
             (psi::skip_kernel("lbs_dcoef") ? cudaSuccess : launch_pdl(lbs_dcoef_kernel, grid, dim3(256), smem, st, m->Kpad, m->NC, W.Bpad, m->basis_bwd, ws + W.gvp,
                        ws + W.part, kNSplit));
             PSI_LAUNCHED_K("lbs_dcoef");

@@ -52,6 +52,7 @@ struct psi_nn_index {
     float4 *box2;   // thread kernel: node PAIRS {lo.x0,lo.x1,lo.y0,lo.y1},{lo.z0,lo.z1,-hi.x0,-hi.x1},
                     //                {-hi.y0,-hi.y1,-hi.z0,-hi.z1}   [nbox/2][3]  (levels start at even nodes)
     int nbox;       // mpad + num_supers + num_clusters
+    float p0x, p0y, p0z;   // original point 0: the answer for a query no point compares below +inf for
     size_t bytes;
 };
 
@@ -62,6 +63,14 @@ __device__ __forceinline__ unsigned box_lb(const float4 lo, const float4 hi, flo
     const float gy = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
     const float gz = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
     return __float_as_uint(__fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy))));
+}
+
+// No point won (every distance NaN or +inf: a diverged body).  The reference's `k == 0 ||` clauses
+// (chamfer.cu:36,121,126) then leave index 0 with its distance, and so does the brute-force kernel; an
+// INT_MAX "no index" would be dereferenced by the gradient kernels.
+__device__ __forceinline__ float dist_point0(const psi_nn_index &ix, float qx, float qy, float qz) {
+    const float dx = __fsub_rn(ix.p0x, qx), dy = __fsub_rn(ix.p0y, qy), dz = __fsub_rn(ix.p0z, qz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 struct Query {
@@ -208,9 +217,10 @@ nn_index_query_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
         const bool win = __float_as_uint(q.bd) == dmin;
         const unsigned imin = __reduce_min_sync(0xffffffffu, win ? (unsigned)q.bi : 0x7fffffffu);
         if (lane == 0) {
-            dist[t] = __uint_as_float(dmin);
-            if (idx) idx[t] = (int)imin;
-            if (hint) hint[t] = (imin < (unsigned)ix.m) ? __ldg(ix.pos_of + imin) / kLeaf : -1;
+            const bool none = imin >= (unsigned)ix.m;
+            dist[t] = none ? dist_point0(ix, q.x, q.y, q.z) : __uint_as_float(dmin);
+            if (idx) idx[t] = none ? 0 : (int)imin;
+            if (hint) hint[t] = none ? -1 : __ldg(ix.pos_of + imin) / kLeaf;
         }
     }
 }
@@ -356,9 +366,10 @@ nn_index_thread_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lo
                 }
             }
         }
-        dist[t] = bd;
-        if (idx) idx[t] = bi;
-        if (hint) hint[t] = ((unsigned)bi < (unsigned)ix.m) ? __ldg(ix.pos_of + bi) / kLeaf : -1;
+        const bool none = (unsigned)bi >= (unsigned)ix.m;
+        dist[t] = none ? dist_point0(ix, qx, qy, qz) : bd;
+        if (idx) idx[t] = none ? 0 : bi;
+        if (hint) hint[t] = none ? -1 : __ldg(ix.pos_of + bi) / kLeaf;
     }
 }
 
@@ -615,7 +626,10 @@ nn_index_group_kernel(const psi_nn_index ix, const float *__restrict__ q_in, lon
                 mmask &= __ballot_sync(full, lbm <= ub);
             }
         }
-        if (bi < 0) bi = bleaf >= 0 ? leaf_arg(ix.pts2, bleaf, bd, qx, qy, qz) : 0x7fffffff;
+        if (bi < 0) {
+            if (bleaf >= 0) bi = leaf_arg(ix.pts2, bleaf, bd, qx, qy, qz);
+            else { bi = 0; bd = dist_point0(ix, qx, qy, qz); }
+        }
         if (j < n) {
             dist[t] = bd;
             if (idx) idx[t] = bi;
@@ -682,6 +696,7 @@ int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_st
     if (!ix) return PSI_ERR_ALLOC;
     ix->pts = nullptr; ix->boxes = nullptr; ix->pos_of = nullptr; ix->pts2 = nullptr; ix->box2 = nullptr;
     ix->m = m;
+    ix->p0x = h_points[0]; ix->p0y = h_points[1]; ix->p0z = h_points[2];
     ix->num_megas = num_megas;
     ix->rounds = rounds;
     ix->mpad = rounds * 32;
@@ -780,11 +795,7 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
     const size_t box_bytes = (size_t)2 * ix->nbox * sizeof(float4);
     const bool smem = box_bytes <= kIdxSmemMax;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(nn_index_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemMax);
-        attr = true;
-    }
+    if (const int arc = ensure_max_dyn_smem(nn_index_query_kernel<true>, kIdxSmemMax)) return arc;
     if (mode == 3) {
         // one warp per 32 consecutive queries of a body (coherent query order: the fitting loop)
         const long ngroups = (long)B * ((n + 31) / 32);

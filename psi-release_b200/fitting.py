@@ -19,7 +19,7 @@ What changed underneath (none of it changes B=1 results beyond float rounding):
     every body is optimised exactly as the shipped scripts do (batch_size 1,
     fitting_habitat.py:254) and results do not depend on how bodies are sharded;
     `loss_mode='batch'` reproduces the demo notebook's batch-coupled means (demo.ipynb cell 16,
-    SURVEY.md T9);
+    SURVEY.md T9); both run on the fused engine;
   * the whole iteration (loss, backward, Adam) is captured in a CUDA graph and replayed.
 """
 from __future__ import annotations
@@ -85,10 +85,15 @@ class FittingOP:
 
         # --- VPoser decoder (fitting_habitat.py:54): a real checkpoint dir or synthetic weights
         vw = getattr(self, "vposer_weights", None)
-        if vw is None:
-            raise FileNotFoundError("no VPoser checkpoint is available offline: pass "
-                                    "fittingconfig['vposer_weights'] (synthetic.make_vposer_weights())")
-        self.vposer = VPoserDecoder.from_weights(vw).to(self.device)
+        if vw is not None:
+            self.vposer = VPoserDecoder.from_weights(vw)
+        elif getattr(self, "vposer_ckpt_path", None):
+            # the reference's key: load_vposer(vposer_ckpt_path, vp_model='snapshot'), fitting_habitat.py:54
+            self.vposer = VPoserDecoder.from_checkpoint_dir(self.vposer_ckpt_path)
+        else:
+            raise FileNotFoundError("fittingconfig needs 'vposer_ckpt_path' (a VPoser experiment directory with "
+                                    "snapshots/*.pt) or 'vposer_weights' (e.g. synthetic.make_vposer_weights())")
+        self.vposer = self.vposer.to(self.device)
         for p_ in self.vposer.parameters():
             p_.requires_grad_(False)
 
@@ -139,23 +144,26 @@ class FittingOP:
                                   torch.equal(self.contact_ids, torch.arange(self.contact_ids.numel(), device=self.device)))
         # 'fused': the whole iteration in libpsi_b200 (psi_fit_run, 15 launches/iteration);
         # 'autograd': torch autograd over the psi ops (any loss_mode, any nn mode)
-        self.engine = getattr(self, "engine", "fused" if (self.loss_mode == "independent" and self.nn_mode == "index"
-                                                          and self.opt_name == "adam") else "autograd")
+        if self.loss_mode not in ("independent", "batch"):
+            raise ValueError("fittingconfig['loss_mode'] must be 'independent' or 'batch'")
+        self.engine = getattr(self, "engine", "fused" if (self.nn_mode == "index" and self.opt_name == "adam")
+                              else "autograd")
         if self.opt_name == "lbfgs" and self.engine == "fused":
             raise ValueError("optimizer_name='lbfgs' runs on engine='autograd'")
         if self.engine not in ("fused", "autograd"):
             raise ValueError("fittingconfig['engine'] must be 'fused' or 'autograd'")
         self._fused = None
         if self.engine == "fused":
-            if self.loss_mode != "independent" or self.nn_mode != "index":
-                raise ValueError("engine='fused' needs loss_mode='independent' and nn='index'")
+            if self.nn_mode != "index":
+                raise ValueError("engine='fused' needs nn='index'")
             from .fused import FusedFit
             lossw = {k: getattr(self, k) for k in ("weight_loss_rec", "weight_loss_vposer", "weight_contact",
                                                    "weight_collision")}
             self._fused = FusedFit(B, self.body_mesh_model.handle(self.device), self.body_mesh_model,
                                    self.s_index, self.scene_sdf, self.vposer, self.contact_ids.cpu().numpy(),
                                    lossw, self.robust_c, self.init_lr_h, use_graph=self.use_cuda_graph,
-                                   num_streams=getattr(self, "num_streams", None))
+                                   num_streams=getattr(self, "num_streams", None), loss_mode=self.loss_mode,
+                                   loop_mode=getattr(self, "loop_mode", None))
         self._graph = None
         self._static_xhr = None
         self._static_cam = None
@@ -283,6 +291,12 @@ class FittingOP:
                         print("[INFO][fitting] iter={:d}, l_rec={:f}, l_vposer={:f}, l_contact={:f}, "
                               "l_collision={:f}".format(ii, *l))
             return GeometryTransformer.convert_to_3D_rot(self.xhr_rec.detach())
+
+    def trace(self, what):
+        """Fused engine only: a buffer of the last iteration the loop evaluated (FusedFit.trace / psi_fit_trace)."""
+        if self._fused is None:
+            raise _lib.PsiError("trace needs engine='fused'")
+        return self._fused.trace(what)
 
     def profile_iteration(self, xh, cam_ext, warm_iters=20, timed_iters=50):
         """Fused engine only: [(kernel name, mean ms per launch)] of one fitting iteration, each

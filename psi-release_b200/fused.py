@@ -69,7 +69,7 @@ class FusedFit:
     """Owns psi_fit_ctx objects bound to (body model handle, scene index, scene SDF, VPoser decoder)."""
 
     def __init__(self, batch_size, model_handle, body_model, scene_index, scene_sdf, vposer, contact_ids,
-                 weights, robust_c, lr, use_graph=True, num_streams=None):
+                 weights, robust_c, lr, use_graph=True, num_streams=None, loss_mode="independent", loop_mode=None):
         if scene_sdf.num_scenes != 1:
             raise ValueError("the fused loop fits one scene per context")
         self.device = model_handle.device
@@ -90,6 +90,16 @@ class FusedFit:
         if num_streams is None:
             num_streams = 1     # measured: two half-batch contexts are not faster (kernels do not shrink with B)
         num_streams = max(1, min(int(num_streams), self.B))
+        if loss_mode not in ("independent", "batch"):
+            raise ValueError("loss_mode must be 'independent' or 'batch'")
+        if loss_mode == "batch" and num_streams != 1:
+            raise ValueError("loss_mode='batch' couples the bodies of a batch: one context (num_streams=1)")
+        # 'whole' = all iterations in ONE graph launch (conditional WHILE node); 'replay' = one launch per iteration
+        if loop_mode is None:
+            loop_mode = os.environ.get("PSI_FIT_LOOP", "whole")
+        if loop_mode not in ("whole", "replay"):
+            raise ValueError("loop_mode must be 'whole' or 'replay'")
+        self.loss_mode, self.loop_mode = loss_mode, loop_mode
         base, rem = divmod(self.B, num_streams)
         self.parts = []                  # (start, size, handle)
         self.xdim = 19 + W1.shape[1] + 2 * hl.shape[0]
@@ -101,7 +111,8 @@ class FusedFit:
                                  w_rec=float(weights["weight_loss_rec"]), w_vposer=float(weights["weight_loss_vposer"]),
                                  w_contact=float(weights["weight_contact"]), w_collision=float(weights["weight_collision"]),
                                  robust_c=float(robust_c), lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8,
-                                 nn_mode=int(os.environ.get("PSI_FIT_NN_MODE", "0")))
+                                 nn_mode=int(os.environ.get("PSI_FIT_NN_MODE", "0")),
+                                 loop_mode=0 if loop_mode == "whole" else 1, loss_mode=1 if loss_mode == "batch" else 0)
             h = ctypes.c_void_p()
             with torch.cuda.device(self.device):
                 rc = _lib.lib().psi_fit_create(
@@ -137,6 +148,25 @@ class FusedFit:
                 rc = L.psi_fit_end(h, _lib.ptr(out[s:s + nb]), _lib.ptr(losses[s:s + nb]), st)
                 _lib.check(rc, "psi_fit_end")
         return out, losses
+
+    def trace(self, what):
+        """One buffer of the most recent iteration the loop evaluated (psi_fit_trace): 'x_eval' [B,75] (where it
+        was evaluated), 'grad_x' [B,75] (dL/dx there, before Adam), 'verts' [B,V,3], 'sdf' [B,V], 'sdf_grad'
+        [B,V,3], 'nn_dist' / 'nn_idx' [B,nu] in query order, 'query_ids' [nu] (body vertex of each query slot),
+        'losses' [B,4], 'x' [B,75] (after the step), 'adam_m' / 'adam_v', 'pose6d' [B,22,6].  Device tensors."""
+        code, is_int = _lib.FIT_TRACE[what]
+        L = _lib.lib()
+        outs = []
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr()
+            for _, nb, h in self.parts:
+                nbytes = int(L.psi_fit_trace_bytes(h, code))
+                t = torch.empty(nbytes // 4, dtype=torch.int32 if is_int else torch.float32, device=self.device)
+                _lib.check(L.psi_fit_trace(h, code, _lib.ptr(t), nbytes, st), "psi_fit_trace")
+                outs.append(t if what == "query_ids" else t.view(nb, -1))
+        if what == "query_ids":
+            return outs[0]
+        return torch.cat(outs, 0)
 
     def profile(self, xhr, cam_ext, warm_iters=20, timed_iters=50):
         """Per-kernel timing of one fitting iteration (psi_fit_profile: eager launches with a CUDA

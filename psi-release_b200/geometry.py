@@ -225,6 +225,32 @@ class VPoserDecoder(nn.Module):
         m.load_state_dict({k: torch.as_tensor(v) for k, v in weights.items()}, strict=True)
         return m.eval()
 
+    @classmethod
+    def from_checkpoint_dir(cls, expr_dir: str):
+        """What load_vposer(expr_dir, vp_model='snapshot') yields for the decode half
+        (human_body_prior/tools/model_loader.py:30,43-72): the NEWEST `snapshots/*.pt` by mtime, a state_dict
+        of the full VPoser; only the `bodyprior_dec_*` tensors are used (the encoder never runs while fitting).
+        Also accepts the `weights_npy/vposerWeights.npz` dump of extract_weights_asnumpy (:75-90)."""
+        import glob
+        import os
+        snaps = sorted(glob.glob(os.path.join(expr_dir, "snapshots", "*.pt")), key=os.path.getmtime)
+        if snaps:
+            sd = torch.load(snaps[-1], map_location="cpu", weights_only=True)
+            if isinstance(sd, dict) and "state_dict" in sd and "bodyprior_dec_fc1.weight" not in sd:
+                sd = sd["state_dict"]
+            sd = {k[7:] if k.startswith("module.") else k: v for k, v in sd.items()}     # nn.DataParallel prefix
+        else:
+            npz = os.path.join(expr_dir, "weights_npy", "vposerWeights.npz")
+            if not os.path.exists(npz):
+                raise FileNotFoundError(f"no snapshots/*.pt and no weights_npy/vposerWeights.npz under {expr_dir}")
+            with np.load(npz, allow_pickle=False) as z:
+                sd = {k: z[k] for k in z.files}
+        keys = [f"bodyprior_dec_{n}.{t}" for n in ("fc1", "fc2", "out") for t in ("weight", "bias")]
+        missing = [k for k in keys if k not in sd]
+        if missing:
+            raise KeyError(f"VPoser checkpoint under {expr_dir} lacks {missing}")
+        return cls.from_weights({k: sd[k] for k in keys})
+
     def decode(self, Zin, output_type="matrot"):
         assert output_type in ("matrot", "aa")
         x = F.leaky_relu(self.bodyprior_dec_fc1(Zin), negative_slope=0.2)

@@ -18,6 +18,9 @@ from torch.autograd import Function
 from . import _lib
 
 
+MAX_SCENES = 16     # kMaxScenes in csrc/sdf.cu
+
+
 class SceneSDF:
     """S scenes: sdf [S,D,D,D] on the device, grid_min / grid_max [S,3] on the host."""
 
@@ -103,18 +106,33 @@ def sdf_lookup(scene: SceneSDF, verts, body_scene=None, with_partials=False):
 def grid_sample_sdf(input, grid, padding_mode="border", grid_min=None, grid_max=None):
     """Shim with F.grid_sample's call shape for unchanged reference code:
         F.grid_sample(s_sdf.unsqueeze(1), norm_verts[:,:,[2,1,0]].view(-1,V,1,1,3), padding_mode='border')
-    `input` [B,1,D,D,D] (every batch entry must be the same scene -- only entry 0 is read),
-    `grid` [B,V,1,1,3] already normalised to [-1,1] in (z,y,x) order.  Returns [B,1,V,1,1]."""
+    `input` [B,1,D,D,D]: one grid per batch entry (train_s2.py:182-189 samples a different scene per body); a
+    batch-expanded single scene (stride 0, what `.expand` gives) is read once.  The reference's `.repeat`ed
+    copies (fitting_proxe.py:90) work too, as B grids.  `grid` [B,V,1,1,3] already normalised to [-1,1] in
+    (z,y,x) order; gradients flow to `grid`.  Returns [B,1,V,1,1]."""
     if padding_mode != "border":
         raise ValueError("only padding_mode='border' is used on the PSI path")
     B, V = grid.shape[0], grid.shape[1]
     D = input.shape[-1]
-    scene = SceneSDF.__new__(SceneSDF)
-    scene.sdf = input[0:1, 0].contiguous()
-    scene.num_scenes, scene.dim = 1, D
-    scene.grid_min = np.full((1, 3), -1.0, dtype=np.float32)
-    scene.grid_max = np.full((1, 3), 1.0, dtype=np.float32)
-    scene._gmin_t = torch.from_numpy(scene.grid_min)
-    scene._gmax_t = torch.from_numpy(scene.grid_max)
+    shared = input.shape[0] == 1 or input.stride(0) == 0
     verts = grid.reshape(B, V, 3)[:, :, [2, 1, 0]].contiguous()   # back to (x,y,z), still in [-1,1]
-    return sdf_lookup(scene, verts).view(B, 1, V, 1, 1)
+
+    def unit_bank(vol):                                            # [S,D,D,D] sampled over [-1,1]^3
+        scene = SceneSDF.__new__(SceneSDF)
+        scene.sdf = vol.contiguous()
+        S = int(vol.shape[0])
+        scene.num_scenes, scene.dim = S, D
+        scene.grid_min = np.full((S, 3), -1.0, dtype=np.float32)
+        scene.grid_max = np.full((S, 3), 1.0, dtype=np.float32)
+        scene._gmin_t = torch.from_numpy(scene.grid_min)
+        scene._gmax_t = torch.from_numpy(scene.grid_max)
+        return scene
+
+    if shared:
+        return sdf_lookup(unit_bank(input[0:1, 0]), verts).view(B, 1, V, 1, 1)
+    outs = []
+    for b0 in range(0, B, MAX_SCENES):                             # psi_sdf_fwd addresses up to 16 grids per call
+        nb = min(MAX_SCENES, B - b0)
+        ids = torch.arange(nb, dtype=torch.int32, device=grid.device)
+        outs.append(sdf_lookup(unit_bank(input[b0:b0 + nb, 0]), verts[b0:b0 + nb], ids))
+    return torch.cat(outs, 0).view(B, 1, V, 1, 1)

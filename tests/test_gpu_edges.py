@@ -107,3 +107,70 @@ def test_lbs_dense_skinning_weights_and_small_tree():
     (v * _cuda(wv)).sum().backward()
     assert rel(cb.grad.cpu().numpy(), tb.grad.numpy()) < 3e-4
     assert rel(cp.grad.cpu().numpy(), tp.grad.numpy()) < 3e-4
+
+
+def test_nan_and_overflowing_queries_return_point_zero_like_the_reference():
+    """A diverged body (NaN or overflowing vertices) must not produce an out-of-range index: every NN path
+    returns index 0 and the distance to point 0, which is what the reference's `k == 0 ||` clauses leave
+    (chamfer.cu:36,121,126) and what the oracle restates; the other queries of the call are untouched."""
+    from psi_release_b200 import _lib, chamfer
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    m, n, B = 5000, 130, 2
+    s = torch.rand(m, 3, generator=g).cuda()
+    q = torch.rand(B, n, 3, generator=g)
+    q[0, 7] = float("nan")
+    q[1, 64, 1] = float("nan")
+    q[1, 100] = 3e30                      # squares overflow to +inf: no distance compares below +inf
+    q = q.cuda()
+    do, io = oracle.nn_fwd(q.cpu().numpy(), s.cpu().numpy())
+    assert io[0, 7] == 0 and io[1, 64] == 0 and io[1, 100] == 0 and np.isnan(do[0, 7]) and np.isinf(do[1, 100])
+    ix = chamfer.SceneIndex(s)
+    outs = {"brute": chamfer.nn_forward(q, s)}
+    for mode in (1, 2, 3):
+        d = torch.empty(B, n, device="cuda")
+        i = torch.empty(B, n, dtype=torch.int32, device="cuda")
+        h = torch.full((B, n), -1, dtype=torch.int32, device="cuda")
+        for _ in range(2):                # second call: with the hints of the first
+            rc = L.psi_nn_index_query_mode(ix.h, _lib.ptr(q), n * 3, B, n, None, _lib.ptr(d), _lib.ptr(i), _lib.ptr(h),
+                                           mode, _lib.stream_ptr())
+            assert rc == 0
+        outs["index mode %d" % mode] = (d, i)
+    for name, (d, i) in outs.items():
+        i, d = i.cpu().numpy(), d.cpu().numpy()
+        assert i.min() >= 0 and i.max() < m, name
+        assert np.array_equal(i, io), name
+        assert np.array_equal(np.isnan(d), np.isnan(do)), name
+        ok = ~np.isnan(do)
+        assert np.array_equal(d[ok].view(np.uint32), do[ok].view(np.uint32)), name
+    # and the gradient gather can consume the result (an INT_MAX index would fault here)
+    qg = q.clone().requires_grad_(True)
+    dist, _ = chamfer.nn_distance(qg, ix)
+    (gq,) = torch.autograd.grad(dist.nan_to_num(0.0, 0.0, 0.0).sum(), qg)
+    torch.cuda.synchronize()
+    assert torch.isfinite(gq[0, 0]).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices_through_the_c_abi(small_model):
+    """The opt-in to > 48 kB of dynamic shared memory (tcgen05 blend GEMMs, the warp-per-query NN walk) is a
+    per-DEVICE function attribute: a second GPU driven from the same process must get it too."""
+    from psi_release_b200 import synthetic
+    from psi_release_b200.fitting import FittingOP
+    scene = synthetic.make_scene(seed=1, dim=32, num_points=60000)       # > 58 kB of boxes: the big NN opt-in too
+    xh = torch.tensor(synthetic.make_body_params(scene, 3, seed=3))
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        from psi_release_b200 import chamfer
+        op = FittingOP(dict(model_data=small_model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
+                            contact_ids=synthetic.make_contact_ids(431, "parts"), init_lr_h=0.1, num_iter=3,
+                            batch_size=3, device=dev), dict(weight_loss_rec=1, weight_loss_vposer=0.01,
+                                                            weight_contact=0.1, weight_collision=0.5))
+        outs.append(op.fit(xh.to(dev), cam.to(dev)).cpu())
+        with torch.cuda.device(dev):
+            q = torch.rand(1, 40, 3, device=dev)
+            d, i = chamfer.nn_forward(q, op.s_index)                     # warp-per-query schedule (few queries)
+            do, io = oracle.nn_fwd(q.cpu().numpy(), scene.points)
+            assert np.array_equal(i.cpu().numpy(), io)
+    assert torch.equal(outs[0], outs[1])

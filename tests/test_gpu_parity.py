@@ -462,3 +462,157 @@ print("gemm ok")
     env = dict(os.environ, PSI_LBS_GEMM="mma")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "gemm ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_sdf_at_baseline_resolution_and_full_scene_bank():
+    """D = 256 (BASELINE configs[1]) and a 4-scene bank of 256^3 grids (configs[2]: 4 x 64 MiB; offsets of the
+    last grid are past 2^26 floats), random grid values so that a wrong corner offset cannot hide; the
+    reference call shape through the grid_sample shim on the same data."""
+    from psi_release_b200 import sdf as sdf_mod
+    rng = np.random.default_rng(21)
+    D, S, B, V = 256, 4, 6, 10475
+    grids = rng.standard_normal((S, D, D, D), dtype=np.float32)
+    gmin = np.array([[-3, -3, -3], [-2, -3, -1], [-3.5, -2, -3], [0, 0, 0]], np.float32)
+    gmax = np.array([[3, 3, 3], [4, 3, 2], [3, 2.5, 3], [5, 6, 7]], np.float32)
+    which = np.array([3, 0, 2, 1, 3, 3], np.int32)
+    v = np.stack([rng.uniform(gmin[s] - 0.3, gmax[s] + 0.3, (V, 3)).astype(np.float32) for s in which])
+    v[0, 0] = gmax[3]; v[0, 1] = gmin[3]                       # the last voxel of the last grid, and its first
+    scene = sdf_mod.SceneSDF(grids, gmin, gmax)
+    out, grad, partial = sdf_mod.sdf_forward(scene, _cuda(v), _cuda(which), want_grad=True, want_partials=True)
+    out, grad = out.cpu().numpy(), grad.cpu().numpy()
+    for b, s in enumerate(which):
+        vo, go = oracle.sdf_fwd(grids[s], gmin[s], gmax[s], v[b])
+        np.testing.assert_allclose(out[b], vo, rtol=1e-4, atol=1e-4 * np.abs(vo).max())
+        np.testing.assert_allclose(grad[b], go, rtol=1e-4, atol=1e-4 * np.abs(go).max())
+        assert int(partial[b, :, 1].sum()) == int((vo < 0).sum())
+    assert out[0, 0] == grids[3, -1, -1, -1] and out[0, 1] == grids[3, 0, 0, 0]
+    # F.grid_sample's call shape with one grid PER BODY (train_s2.py:182-189) vs torch's own kernel, align_corners=True
+    per_body = _cuda(grids[which[:3]])
+    norm = (_cuda(v[:3]) - _cuda(gmin[which[:3]])[:, None]) / (_cuda(gmax[which[:3]]) - _cuda(gmin[which[:3]]))[:, None] * 2 - 1
+    g5 = norm[:, :, [2, 1, 0]].view(-1, V, 1, 1, 3)
+    shim = sdf_mod.grid_sample_sdf(per_body.unsqueeze(1), g5, padding_mode="border")
+    ref = torch.nn.functional.grid_sample(per_body.unsqueeze(1), g5, padding_mode="border", align_corners=True)
+    np.testing.assert_allclose(shim.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=2e-4)
+
+
+def test_unchanged_reference_call_lines_run_on_the_psi_kernels(small_model, tmp_path):
+    """shims.install(), then the reference's own statements: the imports of fitting_habitat.py:32-34, the
+    constructor calls of :56-73, and the hot-path calls of cal_loss (:126-152) -- smplx module call,
+    ext.chamferDist()(a, b), F.grid_sample(sdf.unsqueeze(1), grid, padding_mode='border') with align_corners
+    left unset.  The four loss terms must equal the CPU restatement, and F.grid_sample must have been served by
+    the psi SDF kernel (today's torch would silently sample with align_corners=False)."""
+    import importlib
+    import torch.nn.functional as F
+    from psi_release_b200 import _lib, shims, synthetic
+    from psi_release_b200.geometry import BodyParamParser, GeometryTransformer
+    scene = synthetic.make_scene(seed=1, dim=32, num_points=3000)
+    B = 3
+    # the files a reference user has: a model directory with an npz that ALSO holds object-dtype entries (the
+    # published SMPLX_NEUTRAL.npz does), and a VPoser experiment directory with snapshots/*.pt
+    md = dict(small_model)
+    md["joint2num"] = np.array({"Pelvis": 0}, dtype=object)
+    md["part2num"] = np.array({"Global": 0}, dtype=object)
+    (tmp_path / "models" / "smplx").mkdir(parents=True)
+    np.savez(str(tmp_path / "models" / "smplx" / "SMPLX_NEUTRAL.npz"), **md)
+    (tmp_path / "vposer_v1_0" / "snapshots").mkdir(parents=True)
+    vw = synthetic.make_vposer_weights()
+    sd = {k: torch.tensor(v) for k, v in vw.items()}
+    sd["bodyprior_enc_fc1.weight"] = torch.zeros(4, 4)                       # encoder tensors are ignored
+    torch.save(sd, str(tmp_path / "vposer_v1_0" / "snapshots" / "TR00_E096.pt"))
+
+    shims.install()
+    try:
+        smplx = importlib.import_module("smplx")
+        ext = importlib.import_module("chamfer_pytorch.dist_chamfer")
+        load_vposer = importlib.import_module("human_body_prior.tools.model_loader").load_vposer
+        device = torch.device("cuda")
+        batch_size = B
+        vposer, _ = load_vposer(str(tmp_path / "vposer_v1_0"), vp_model='snapshot')
+        body_mesh_model = smplx.create(str(tmp_path / "models"), model_type='smplx',
+                                       gender='neutral', ext='npz',
+                                       num_pca_comps=12,
+                                       create_global_orient=True,
+                                       create_body_pose=True,
+                                       create_betas=True,
+                                       create_left_hand_pose=True,
+                                       create_right_hand_pose=True,
+                                       create_expression=True,
+                                       create_jaw_pose=True,
+                                       create_leye_pose=True,
+                                       create_reye_pose=True,
+                                       create_transl=True,
+                                       batch_size=batch_size
+                                       )
+        vposer.to(device)
+        body_mesh_model.to(device)
+        s_grid_min_batch = torch.tensor(scene.grid_min, dtype=torch.float32, device=device).unsqueeze(0)
+        s_grid_max_batch = torch.tensor(scene.grid_max, dtype=torch.float32, device=device).unsqueeze(0)
+        s_sdf_batch = torch.tensor(scene.sdf, dtype=torch.float32, device=device).unsqueeze(0).repeat(B, 1, 1, 1)
+        s_verts_batch = torch.tensor(scene.points, dtype=torch.float32, device=device).unsqueeze(0).repeat(B, 1, 1)
+        vid = synthetic.make_contact_ids(431, "parts")
+        xh = torch.tensor(synthetic.make_body_params(scene, B, seed=3))
+        cam_ext = torch.tensor(scene.cam_ext).unsqueeze(0).repeat(B, 1, 1).to(device)
+        xhr = GeometryTransformer.convert_to_6D_rot(xh.to(device))
+        xhr_rec = (xhr + 0.01 * torch.randn(xhr.shape, generator=torch.Generator().manual_seed(0)).to(device)).requires_grad_(True)
+        launches0 = _lib.lib().psi_launch_count()
+
+        # ---- cal_loss as written in the reference
+        loss_rec = W_REF["weight_loss_rec"] * F.l1_loss(xhr, xhr_rec)
+        xh_rec = GeometryTransformer.convert_to_3D_rot(xhr_rec)
+        vposer_pose = xh_rec[:, 16:48]
+        loss_vposer = W_REF["weight_loss_vposer"] * torch.mean(vposer_pose**2)
+        body_param_rec = BodyParamParser.body_params_encapsulate_batch(xh_rec)
+        joint_rot_batch = vposer.decode(body_param_rec['body_pose_vp'],
+                                        output_type='aa').view(batch_size, -1)
+        body_param_ = {}
+        for key in body_param_rec.keys():
+            if key in ['body_pose_vp']:
+                continue
+            else:
+                body_param_[key] = body_param_rec[key]
+        smplx_output = body_mesh_model(return_verts=True,
+                                       body_pose=joint_rot_batch,
+                                       **body_param_)
+        body_verts_batch = smplx_output.vertices
+        body_verts_batch = GeometryTransformer.verts_transform(body_verts_batch, cam_ext)
+        body_verts_contact_batch = body_verts_batch[:, vid, :]
+        dist_chamfer_contact = ext.chamferDist()
+        contact_dist, _ = dist_chamfer_contact(body_verts_contact_batch.contiguous(),
+                                               s_verts_batch.contiguous())
+        loss_contact = W_REF["weight_contact"] * torch.mean(torch.sqrt(contact_dist+1e-4)/(torch.sqrt(contact_dist+1e-4)+1.0))
+        s_grid_min_batch = s_grid_min_batch.unsqueeze(1)
+        s_grid_max_batch = s_grid_max_batch.unsqueeze(1)
+        norm_verts_batch = (body_verts_batch - s_grid_min_batch) / (s_grid_max_batch - s_grid_min_batch) * 2 - 1
+        n_verts = norm_verts_batch.shape[1]
+        body_sdf_batch = F.grid_sample(s_sdf_batch.unsqueeze(1),
+                                       norm_verts_batch[:, :, [2, 1, 0]].view(-1, n_verts, 1, 1, 3),
+                                       padding_mode='border')
+        if body_sdf_batch.lt(0).sum().item() < 1:
+            loss_sdf_pene = torch.tensor(0.0, dtype=torch.float32, device=device)
+        else:
+            loss_sdf_pene = body_sdf_batch[body_sdf_batch < 0].abs().mean()
+        loss_collision = W_REF["weight_collision"] * loss_sdf_pene
+        loss = loss_rec + loss_vposer + loss_contact + loss_collision
+        loss.backward()
+        # ----
+        assert _lib.lib().psi_launch_count() - launches0 >= 8       # LBS fwd/bwd, chamfer fwd/bwd, SDF fwd/bwd ran in libpsi_b200
+        assert body_sdf_batch.shape == (B, 1, n_verts, 1, 1)
+    finally:
+        shims.uninstall()
+    assert F.grid_sample.__module__ == "torch.nn.functional"
+    kw = dict(smplx_model=oracle.SMPLXOracle(small_model), vposer=oracle.VPoserDecoderOracle(vw),
+              sdf=torch.tensor(scene.sdf), gmin=torch.tensor(scene.grid_min), gmax=torch.tensor(scene.grid_max),
+              scene_points=torch.tensor(scene.points), contact_ids=vid, weights=W_REF)
+    ref_rec = xhr_rec.detach().cpu().clone().requires_grad_(True)
+    rterms = oracle.cal_loss(xhr.cpu(), ref_rec, cam_ext.cpu(), loss_mode="batch", **kw)
+    (rg,) = torch.autograd.grad(sum(rterms), ref_rec)
+    for a, b in zip((loss_rec, loss_vposer, loss_contact, loss_collision), rterms):
+        assert abs(float(a) - float(b)) <= 1e-4 * max(1.0, abs(float(b)))
+    assert float((xhr_rec.grad.cpu() - rg).abs().max()) <= 2e-4 * float(rg.abs().max())
+    # the same line WITHOUT the shim is a different function on today's torch
+    plain = F.grid_sample(s_sdf_batch.unsqueeze(1), norm_verts_batch.detach()[:, :, [2, 1, 0]].view(-1, n_verts, 1, 1, 3),
+                          padding_mode='border')
+    assert float((plain - body_sdf_batch.detach()).abs().max()) > 1e-3
+
+
+W_REF = dict(weight_loss_rec=1, weight_loss_vposer=0.01, weight_contact=0.1, weight_collision=0.5)

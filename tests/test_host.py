@@ -24,7 +24,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert sorted(_lib.EXPORTS) == declared          # the Python binding covers the whole header
     lib = _lib.lib()
-    assert lib.psi_abi_version() == 2
+    assert lib.psi_abi_version() == 3
     assert b"workspace" in lib.psi_error_string(-2)
     assert lib.psi_sdf_num_partials(10475) == 11 and lib.psi_nn_workspace_bytes(2, 10, 30) == 2 * 30 * 8
 
@@ -235,3 +235,116 @@ def test_contact_query_order_is_a_permutation_grouped_by_joint():
     # without skinning information it falls back to kd cells of the template
     o2 = _spatial_order(np.arange(1500), m["v_template"])
     assert sorted(o2.tolist()) == list(range(1500))
+
+
+def test_rotation_restatements_against_an_independent_implementation():
+    """torchgeometry 0.1.2 (requirements.txt:103) is absent, so its matrix <-> axis-angle conversions
+    (cvae.py:72-91, vposer_smpl.py:153-171) are restated from the published algorithm in BOTH oracle.py and
+    geometry.py -- comparing those two only compares a text with itself.  This pins them to an independent
+    implementation of the same mathematical maps (scipy.spatial.transform.Rotation), including angles near 0
+    and near pi and every quaternion branch of rotation_matrix_to_quaternion."""
+    from scipy.spatial.transform import Rotation
+    from psi_release_b200 import geometry
+    rng = np.random.default_rng(3)
+    axes = rng.standard_normal((400, 3))
+    axes /= np.linalg.norm(axes, axis=1, keepdims=True)
+    ang = np.concatenate([rng.uniform(0.05, 3.0, 340), rng.uniform(1e-4, 2e-3, 20), rng.uniform(3.0, 3.13, 40)])
+    aa = (axes * ang[:, None]).astype(np.float32)
+    R_ref = Rotation.from_rotvec(aa.astype(np.float64)).as_matrix()
+    for mod in (oracle, geometry):
+        to_R = mod.aa_to_matrix if mod is oracle else mod.angle_axis_to_rotation_matrix
+        to_aa = mod.matrix_to_aa if mod is oracle else mod.rotation_matrix_to_angle_axis
+        R = to_R(torch.tensor(aa)).numpy()
+        # (torchgeometry divides by theta + 1e-6: measured deviation 1.5e-6)
+        np.testing.assert_allclose(R, R_ref, atol=4e-6)
+        back = to_aa(torch.tensor(R_ref.astype(np.float32))).numpy()
+        np.testing.assert_allclose(back, Rotation.from_matrix(R_ref).as_rotvec(), atol=2e-6)
+        q = (oracle.rotation_matrix_to_quaternion if mod is oracle else geometry.rotation_matrix_to_quaternion)(
+            torch.tensor(R_ref.astype(np.float32))).numpy()
+        qs = Rotation.from_matrix(R_ref).as_quat()           # (x, y, z, w)
+        qs = np.concatenate([qs[:, 3:], qs[:, :3]], 1)
+        sign = np.sign((q * qs).sum(1, keepdims=True))
+        np.testing.assert_allclose(q, qs * sign, atol=1e-6)
+    m00, m11, m22 = R_ref[:, 0, 0], R_ref[:, 1, 1], R_ref[:, 2, 2]
+    for taken in ((m22 < 1e-6) & (m00 > m11), (m22 < 1e-6) & ~(m00 > m11), ~(m22 < 1e-6) & (m00 < -m11),
+                  ~(m22 < 1e-6) & ~(m00 < -m11)):
+        assert taken.sum() > 5                               # every quaternion branch is exercised by the sample
+    # 6D -> matrix (cvae.py:46-55): Gram-Schmidt of the first two columns
+    x6 = rng.standard_normal((50, 6)).astype(np.float32)
+    Rg = oracle.rot6d_to_matrix(torch.tensor(x6)).numpy()
+    a1, a2 = x6.reshape(-1, 3, 2)[:, :, 0].astype(np.float64), x6.reshape(-1, 3, 2)[:, :, 1].astype(np.float64)
+    b1 = a1 / np.linalg.norm(a1, axis=1, keepdims=True)
+    b2 = a2 - (b1 * a2).sum(1, keepdims=True) * b1
+    b2 /= np.linalg.norm(b2, axis=1, keepdims=True)
+    np.testing.assert_allclose(Rg, np.stack([b1, b2, np.cross(b1, b2)], -1), atol=2e-6)
+
+
+def test_real_model_files_load(tmp_path, small_model):
+    """smplx.create(<model dir>): the published SMPLX_NEUTRAL.npz also carries object-dtype entries, which
+    np.load refuses with allow_pickle=False -- only the keys the path reads may be touched.  And the VPoser
+    experiment directory of fittingconfig['vposer_ckpt_path'] (load_vposer, model_loader.py:30,43-72): newest
+    snapshots/*.pt by mtime, decode-half tensors only."""
+    from psi_release_b200 import body_model, shims, synthetic
+    from psi_release_b200.geometry import VPoserDecoder
+    md = dict(small_model)
+    md["joint2num"] = np.array({"Pelvis": 0}, dtype=object)
+    md["part2num"] = np.array({"Global": 0}, dtype=object)
+    (tmp_path / "models" / "smplx").mkdir(parents=True)
+    np.savez(str(tmp_path / "models" / "smplx" / "SMPLX_NEUTRAL.npz"), **md)
+    with pytest.raises(ValueError):
+        dict(np.load(str(tmp_path / "models" / "smplx" / "SMPLX_NEUTRAL.npz"), allow_pickle=False))   # the old loader
+    m = body_model.create(str(tmp_path / "models"), model_type="smplx", gender="neutral", ext="npz",
+                          num_pca_comps=12, batch_size=2)
+    assert m.faces.shape[1] == 3 and m.left_hand_components.shape == (12, 45) and m.num_joints == 55
+    np.testing.assert_array_equal(m._model_data["v_template"], small_model["v_template"])
+    assert "joint2num" not in m._model_data
+    bad = {k: v for k, v in small_model.items() if k != "weights"}
+    np.savez(str(tmp_path / "bad.npz"), **bad)
+    with pytest.raises(KeyError):
+        body_model.SMPLX(str(tmp_path / "bad.npz"))
+    # VPoser checkpoint directory
+    snap = tmp_path / "vposer_v1_0" / "snapshots"
+    snap.mkdir(parents=True)
+    old, new = synthetic.make_vposer_weights(seed=1), synthetic.make_vposer_weights(seed=2)
+    for name, w, t in (("TR00_E010.pt", old, 1_000_000_000), ("TR00_E096.pt", new, 1_500_000_000)):
+        sd = {"module." + k: torch.tensor(v) for k, v in w.items()}      # nn.DataParallel prefix, as the trainer saves
+        sd["module.bodyprior_enc_fc1.weight"] = torch.zeros(3, 3)
+        torch.save(sd, str(snap / name))
+        os.utime(str(snap / name), (t, t))
+    dec = VPoserDecoder.from_checkpoint_dir(str(tmp_path / "vposer_v1_0"))
+    np.testing.assert_array_equal(dec.bodyprior_dec_out.weight.detach().numpy(), new["bodyprior_dec_out.weight"])
+    vp, ps = shims.load_vposer(str(tmp_path / "vposer_v1_0"), vp_model="snapshot")
+    assert ps is None and vp.decode(torch.zeros(2, 32), output_type="aa").shape == (2, 1, 21, 3)
+    with pytest.raises(FileNotFoundError):
+        VPoserDecoder.from_checkpoint_dir(str(tmp_path / "nothing_here"))
+
+
+def test_shims_route_only_the_reference_call_shape():
+    """install() aliases the reference's import names and routes F.grid_sample's PSI call shape to the psi SDF
+    op; anything else (CPU tensors, 4-D inputs, zeros padding) reaches torch's own grid_sample; uninstall()
+    restores everything."""
+    import importlib
+    import torch.nn.functional as F
+    from psi_release_b200 import body_model, chamfer, shims
+    orig = F.grid_sample
+    shims.install()
+    try:
+        assert importlib.import_module("smplx") is body_model
+        assert importlib.import_module("chamfer_pytorch.dist_chamfer").chamferDist is chamfer.chamferDist
+        assert importlib.import_module("human_body_prior.tools.model_loader").load_vposer is shims.load_vposer
+        assert F.grid_sample is not orig
+        vol, grid = torch.rand(2, 1, 4, 4, 4), torch.rand(2, 5, 1, 1, 3) * 2 - 1
+        assert not shims._is_psi_sdf_call(vol, grid, "bilinear", "border", None)          # CPU tensors: torch's kernel
+        np.testing.assert_array_equal(F.grid_sample(vol, grid, padding_mode="border", align_corners=True).numpy(),
+                                      orig(vol, grid, padding_mode="border", align_corners=True).numpy())
+        img, g2 = torch.rand(1, 3, 8, 8), torch.rand(1, 4, 4, 2) * 2 - 1
+        np.testing.assert_array_equal(F.grid_sample(img, g2, align_corners=False).numpy(), orig(img, g2, align_corners=False).numpy())
+
+        meta_vol, meta_grid = torch.empty(2, 1, 4, 4, 4, device="meta"), torch.empty(2, 5, 1, 1, 3, device="meta")
+        assert not shims._is_psi_sdf_call(meta_vol, meta_grid, "bilinear", "border", None)
+    finally:
+        shims.uninstall()
+    assert F.grid_sample is orig and "smplx" not in sys.modules and "chamfer_pytorch" not in sys.modules
+    with shims.routed_grid_sample():
+        assert F.grid_sample is not orig
+    assert F.grid_sample is orig
