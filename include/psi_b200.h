@@ -43,7 +43,7 @@ typedef void *psi_stream_t; /* cudaStream_t */
 #define PSI_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels were built for */
 #define PSI_ERR_ALLOC (-4)        /* device allocation failed (model upload only) */
 
-#define PSI_ABI_VERSION 3   /* 3: psi_fit_config.{loop_mode,loss_mode}, psi_fit_trace, psi_fit_trace_bytes;
+#define PSI_ABI_VERSION 3   /* 3: psi_fit_config.{loop_mode,loop_unroll,loss_mode}, psi_fit_trace, psi_fit_trace_bytes;
                                2: psi_fit_config.nn_mode, psi_fit_profile, psi_nn_index_query_mode mode 3 */
 
 /* ABI version of the loaded library (PSI_ABI_VERSION it was built with). */
@@ -229,6 +229,8 @@ typedef struct psi_fit_config {
     int nn_mode;          /* schedule of the in-loop NN query (psi_nn_index_query_mode); 0 = default (3) */
     int loop_mode;        /* with use_graph: 0 = the WHOLE loop as one graph launch (a conditional WHILE node whose
                              body is the iteration, counted down on the device), 1 = one graph launch per iteration */
+    int loop_unroll;      /* loop_mode 0: iterations captured per pass of the WHILE body (0 = default); a remainder
+                             of num_iter runs as single-iteration launches first */
     int loss_mode;        /* 0 = independent: sum over bodies of the reference's B=1 loss (the shipped scripts,
                              fitting_habitat.py:254); 1 = batch: the reference's batch-coupled means
                              (fitting_proxe.py:105,110,139,155-160 with B > 1; demo.ipynb cell 16) */

@@ -23,7 +23,7 @@ class FitConfig(ctypes.Structure):
     """struct psi_fit_config (include/psi_b200.h)."""
     _fields_ = [("B", _i), ("use_graph", _i), ("w_rec", _f), ("w_vposer", _f), ("w_contact", _f),
                 ("w_collision", _f), ("robust_c", _f), ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("nn_mode", _i),
-                ("loop_mode", _i), ("loss_mode", _i)]
+                ("loop_mode", _i), ("loop_unroll", _i), ("loss_mode", _i)]
 
 
 # psi_fit_trace selectors (PSI_FIT_TRACE_* in include/psi_b200.h): name -> (code, is_int)

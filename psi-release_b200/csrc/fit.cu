@@ -56,6 +56,7 @@ struct psi_fit_ctx {
     cudaGraphExec_t loop_exec;     // the whole loop (loop_mode 0)
     cudaGraphConditionalHandle loop_cond;
     int capturing_loop;            // enqueue_iteration is recording the WHILE body: fit_step gets the handle
+    int unroll;                    // iterations per pass of the WHILE body
     int pending_join;
     int ev_out_recorded;           // ev_out marks the end of the last loop run on gstream
     cudaStream_t gstream;          // graphs cannot be captured on the legacy default stream
@@ -67,6 +68,8 @@ namespace psi {
 
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.2f * v; }
 __device__ __forceinline__ float lrelu_grad(float pre) { return pre > 0.f ? 1.0f : 0.2f; }
+
+constexpr int kDefaultUnroll = 15;   // iterations per pass of the WHILE body when psi_fit_config.loop_unroll == 0
 
 struct FitDims {
     int B, V, J, NB, latent, hidden, nbody, ncomp, num_rot;
@@ -329,7 +332,9 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         !h_W2 || !h_b2 || !h_W3 || !h_b3 || !h_hand_l || !h_hand_r || !h_pose_mean || !h_contact_ids || !cfg)
         return PSI_ERR_BAD_ARG;
     if (cfg->B < 1 || num_contact < 1 || D < 1 || V < 1) return PSI_ERR_BAD_ARG;
-    if (cfg->loss_mode < 0 || cfg->loss_mode > 1 || cfg->loop_mode < 0 || cfg->loop_mode > 1) return PSI_ERR_BAD_ARG;
+    if (cfg->loss_mode < 0 || cfg->loss_mode > 1 || cfg->loop_mode < 0 || cfg->loop_mode > 1 || cfg->loop_unroll < 0 ||
+        cfg->loop_unroll > 64)
+        return PSI_ERR_BAD_ARG;
     if (hidden != 512 || latent != 32 || nbody * 6 > 128 || nbody + 1 > J || ncomp > 16 ||
         J < 31 || NB < 10 || hidden % 32)
         return PSI_ERR_UNSUPPORTED;
@@ -341,6 +346,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->ncomp = ncomp; c->num_rot = nbody + 1; c->D = D; c->sdf = sdf; c->scene_pts = scene_points;
     c->num_contact = num_contact; c->exec = nullptr; c->pending_join = 0; c->gstream = nullptr; c->ev_in = c->ev_out = nullptr;
     c->loop_exec = nullptr; c->capturing_loop = 0; c->loop_cond = 0; c->ev_out_recorded = 0;
+    c->unroll = cfg->loop_unroll > 0 ? cfg->loop_unroll : kDefaultUnroll;
     if (cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -492,8 +498,11 @@ static int build_loop_graph(psi_fit_ctx *c) {
         cudaGraph_t body = np.conditional.phGraph_out[0];
         e = cudaStreamBeginCaptureToGraph(gs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) break;
-        c->capturing_loop = 1;
-        rc = psi::enqueue_iteration(c, gs);
+        // `unroll` iterations per pass of the WHILE body: the conditional node costs a few microseconds per pass
+        for (int u = 0; u < c->unroll && rc == PSI_OK; ++u) {
+            c->capturing_loop = u == c->unroll - 1;      // the last fit_step of the body counts the pass
+            rc = psi::enqueue_iteration(c, gs);
+        }
         c->capturing_loop = 0;
         cudaGraph_t captured = nullptr;
         e = cudaStreamEndCapture(gs, &captured);     // == body
@@ -535,7 +544,8 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
             // warm the lazily-initialised pieces outside the capture (state is reset below)
             int rc = launch_step(c, 0, gs);
             if (rc == PSI_OK) rc = enqueue_iteration(c, gs);
-            if (rc == PSI_OK) rc = whole ? build_loop_graph(c) : build_iteration_graph(c);
+            if (rc == PSI_OK && whole) rc = build_loop_graph(c);
+            if (rc == PSI_OK && !c->exec && (!whole || c->unroll > 1)) rc = build_iteration_graph(c);
             if (rc) return rc;
             e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, gs);
             if (e != cudaSuccess) return (int)e;
@@ -547,10 +557,16 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
         const int rc = launch_step(c, 0, gs);
         if (rc) return rc;
         if (whole) {
-            fit_loop_set_kernel<<<1, 1, 0, gs>>>(c->loop_left, num_iter);
-            PSI_LAUNCHED();
-            e = cudaGraphLaunch(c->loop_exec, gs);
-            if (e != cudaSuccess) return (int)e;
+            for (int it = 0; it < num_iter % c->unroll; ++it) {      // the remainder, one launch per iteration
+                e = cudaGraphLaunch(c->exec, gs);
+                if (e != cudaSuccess) return (int)e;
+            }
+            if (num_iter / c->unroll > 0) {
+                fit_loop_set_kernel<<<1, 1, 0, gs>>>(c->loop_left, num_iter / c->unroll);
+                PSI_LAUNCHED();
+                e = cudaGraphLaunch(c->loop_exec, gs);
+                if (e != cudaSuccess) return (int)e;
+            }
         } else {
             for (int it = 0; it < num_iter; ++it) {
                 e = cudaGraphLaunch(c->exec, gs);

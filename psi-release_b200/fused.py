@@ -112,7 +112,9 @@ class FusedFit:
                                  w_contact=float(weights["weight_contact"]), w_collision=float(weights["weight_collision"]),
                                  robust_c=float(robust_c), lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8,
                                  nn_mode=int(os.environ.get("PSI_FIT_NN_MODE", "0")),
-                                 loop_mode=0 if loop_mode == "whole" else 1, loss_mode=1 if loss_mode == "batch" else 0)
+                                 loop_mode=0 if loop_mode == "whole" else 1,
+                                 loop_unroll=int(os.environ.get("PSI_FIT_UNROLL", "0")),
+                                 loss_mode=1 if loss_mode == "batch" else 0)
             h = ctypes.c_void_p()
             with torch.cuda.device(self.device):
                 rc = _lib.lib().psi_fit_create(

@@ -483,7 +483,10 @@ def test_sdf_at_baseline_resolution_and_full_scene_bank():
     for b, s in enumerate(which):
         vo, go = oracle.sdf_fwd(grids[s], gmin[s], gmax[s], v[b])
         np.testing.assert_allclose(out[b], vo, rtol=1e-4, atol=1e-4 * np.abs(vo).max())
-        np.testing.assert_allclose(grad[b], go, rtol=1e-4, atol=1e-4 * np.abs(go).max())
+        # the slope jumps across voxel faces (random grid values): compare it away from them
+        f = (v[b].astype(np.float64) - gmin[s]) / (gmax[s] - gmin[s]) * (D - 1)
+        inner = (np.abs(f - np.round(f)) > 2e-3).all(-1)
+        np.testing.assert_allclose(grad[b][inner], go[inner], rtol=1e-4, atol=1e-4 * np.abs(go).max())
         assert int(partial[b, :, 1].sum()) == int((vo < 0).sum())
     assert out[0, 0] == grids[3, -1, -1, -1] and out[0, 1] == grids[3, 0, 0, 0]
     # F.grid_sample's call shape with one grid PER BODY (train_s2.py:182-189) vs torch's own kernel, align_corners=True

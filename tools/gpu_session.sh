@@ -1,0 +1,28 @@
+#!/bin/bash
+# One gpurun call = several measurement stages; every stage logs under gpurun_out/.
+#   tools/gpu_session.sh <tag> stage [stage...]      stages: probe tests bench bench_replay launches ncu_full report
+set -u
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.csv" 2>&1
+for stage in "$@"; do
+  echo "=== $stage $(date +%T)"
+  case $stage in
+    probe) ./tools/probes/cond_graph_probe.bin > "$OUT/probe.log" 2>&1; tail -2 "$OUT/probe.log" ;;
+    tests) timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > "$OUT/tests.log" 2>&1; tail -25 "$OUT/tests.log" ;;
+    tests_new) timeout 1200 python -m pytest tests/test_gpu_trace.py tests/test_gpu_edges.py -m gpu -q --tb=short -p no:cacheprovider > "$OUT/tests_new.log" 2>&1; tail -25 "$OUT/tests_new.log" ;;
+    bench) timeout 900 python bench.py --steps 5 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; tail -c 600 "$OUT/bench.json"; tail -3 "$OUT/bench.err" ;;
+    bench_quick) timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$OUT/bench_quick.json" 2> "$OUT/bench_quick.err"; python tools/bench_brief.py "$OUT/bench_quick.json"; tail -3 "$OUT/bench_quick.err" ;;
+    bench_replay) PSI_FIT_LOOP=replay timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$OUT/bench_replay.json" 2> "$OUT/bench_replay.err"; python tools/bench_brief.py "$OUT/bench_replay.json"; tail -3 "$OUT/bench_replay.err" ;;
+    bench_u*) U=${stage#bench_u}; PSI_FIT_UNROLL=$U timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$OUT/$stage.json" 2> "$OUT/$stage.err"; python tools/bench_brief.py "$OUT/$stage.json" | head -1; tail -3 "$OUT/$stage.err" ;;
+    tests_k) timeout 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "$TESTS_K" > "$OUT/tests_k.log" 2>&1; tail -25 "$OUT/tests_k.log" ;;
+    bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; tail -c 600 "$OUT/bench_ref.json" ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 90 --csv --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 3 --iters 30 --no-cpu-baseline > "$OUT/launches.log" 2>&1; python tools/ncu_summary.py launches "$OUT/launches.csv" | tail -30 ;;
+    ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNELS:-nn_index_group|lbs_vertex_bwd|lbs_skin_fwd|lbs_blend_fwd_tc5|lbs_dcoef_tc5}" -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-10} -o "$OUT/prof" python bench.py --steps 1 --warmup 3 --iters 30 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1; ls -la "$OUT" ;;
+    report) timeout 900 python tools/parity_report.py > "$OUT/parity_report.json" 2> "$OUT/parity_report.err"; cat "$OUT/parity_report.json"; tail -3 "$OUT/parity_report.err" ;;
+    smoke) timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > "$OUT/smoke.log" 2>&1; tail -3 "$OUT/smoke.log" ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+echo "=== done $(date +%T)"
