@@ -1,21 +1,25 @@
 """bench.py -- fitted bodies / second over the 300-iteration scene-fit loop (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fit|train_s2|rooms]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], per GPU): 64 bodies, one synthetic scene (256^3 SDF over
-[-3,3]^3, 50 000 scene points), SMPL-X-shaped model with 10 475 vertices, every vertex a contact
-vertex ("10k-vert body"), 300 iterations of {cal_loss forward, backward, Adam(lr 0.1) step}
-(fitting_habitat.py:177-191; SURVEY.md T7 on why Adam).  One STEP = fitting one batch of 64
-bodies for 300 iterations.  Bodies are independent problems: with N GPUs every rank fits its own
-64 bodies (weak scaling) and one all-gather of the fitted vectors ends the job.
+Workload `fit` (the headline; BASELINE.json configs[1] at N = 1, configs[2] at N = 8): SMPL-X-shaped model with
+10 475 vertices, every vertex a contact vertex ("10k-vert body"), synthetic scenes (256^3 SDF over [-3,3]^3,
+50 000 scene points), 300 iterations of {cal_loss forward, backward, Adam(lr 0.1) step}
+(fitting_habitat.py:177-191; SURVEY.md T7 on why Adam).  One STEP = every rank fits its 64 bodies for 300
+iterations.  N = 1: one scene, 64 bodies.  N > 1: 128 bodies per scene, two ranks per scene (N = 8: 512 bodies
+over 4 scenes = configs[2]) through `distributed.fit_scenes`; bodies are independent problems, so no collective
+runs inside the loop and ONE all-gather of the fitted vectors ends the step (inside the e2e timed region).
 
-`value`  : bodies/s with the inputs already on the device (FittingOP.fit).
-`e2e`    : bodies/s through FittingOP.fit_host -- pinned HOST body vectors + camera transform
-           copied in, fitted vectors copied out, inside the timed region.
-`--impl reference` : the reference algorithm on the host CPU (oracle/: torch-CPU LBS and
-           grid_sample, AVX brute-force NN in C/OpenMP, torch Adam), all host threads, on a
-           bounded sample (64 bodies x `--ref-iters` iterations per step, scaled to 300).
+`value`  : bodies/s with the inputs already on the device.
+`e2e`    : bodies/s through the public call with HOST inputs -- pinned body vectors + camera transform copied
+           in, the loop, the all-gather (N > 1), fitted vectors copied out -- all inside the timed region.
+`--impl reference` : the reference algorithm on the host CPU (oracle/: torch-CPU LBS and grid_sample, AVX
+           brute-force NN in C/OpenMP, torch Adam), all host threads.  Each step fits a few bodies for ALL 300
+           iterations (nothing is scaled); the body count is sized so the run ends within a few minutes.
+`reference_gpu` (N = 1, rank 0): the reference's own GPU path on the same B200 (its chamfer.cu built
+           unmodified + torch LBS / grid_sample, oracle/reference_gpu.py), one un-scaled 300-iteration step.
+Workloads `train_s2` (configs[3]) and `rooms` (configs[4]) print their own metric lines; see their functions.
 """
 from __future__ import annotations
 
@@ -47,22 +51,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fit", choices=["fit", "train_s2", "rooms"])
     ap.add_argument("--batch", type=int, default=64, help="bodies per GPU")
     ap.add_argument("--iters", type=int, default=ITERS)
     ap.add_argument("--nn", default="index", choices=["index", "bruteforce"],
                     help="index: exact cluster-pruned NN over the static scene; bruteforce: the tiled all-pairs kernel")
-    ap.add_argument("--ref-iters", type=int, default=6, help="iterations per reference-arm step")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="time budget of the whole reference-arm run")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--geometry", default="on", choices=["on", "off"], help="train_s2: geometry block active (ep > 0.75 E) or gated off")
+    ap.add_argument("--rooms", type=int, default=7)
+    ap.add_argument("--samples", type=int, default=128)
     return ap.parse_args()
 
 
+def scenes_for(world):
+    """N = 1: one scene.  N > 1: two ranks per scene, 128 bodies per scene (N = 8: configs[2], 4 scenes)."""
+    return max(1, world // 2)
+
+
 def workload_config(args, n_gpus):
-    return {"workload": "configs[1]: batch=%d bodies/GPU, 1 scene, %d-vert body, %d^3 SDF, %d-pt scene, "
-                        "%d Adam iterations, full-body contact" % (args.batch, NUM_VERTS, SDF_DIM, NUM_POINTS, args.iters),
-            "bodies_per_gpu": args.batch, "global_bodies": args.batch * n_gpus, "iterations": args.iters,
+    ns = scenes_for(n_gpus)
+    name = ("configs[1]: batch=%d bodies, 1 scene" % args.batch if n_gpus == 1 else
+            "configs[2]%s: %d bodies across %d scenes (%d per scene, 2 ranks per scene), sharded fitting with one NCCL all-gather"
+            % ("" if n_gpus == 8 else " shape at N=%d" % n_gpus, args.batch * n_gpus, ns, args.batch * n_gpus // ns))
+    return {"workload": "%s; %d-vert body, %d^3 SDF, %d-pt scene, %d Adam iterations, full-body contact"
+                        % (name, NUM_VERTS, SDF_DIM, NUM_POINTS, args.iters),
+            "bodies_per_gpu": args.batch, "global_bodies": args.batch * n_gpus, "scenes": ns, "iterations": args.iters,
             "optimizer": "adam lr=0.1", "nn": "one direction (body->scene), %s, bit-exact" % ("exact cluster index" if args.nn == "index" else "brute force"),
-            "loss_mode": "independent", "parallelism": "dp%d (bodies sharded, no data-path collective)" % n_gpus,
+            "loss_mode": "independent", "parallelism": "dp%d (bodies sharded, no data-path collective in the loop, one all-gather per step)" % n_gpus,
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -107,10 +125,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def make_world(args, rank):
+def make_world(args, rank, scene_seed=0):
     from psi_release_b200 import synthetic
     model = synthetic.make_smplx_model(seed=1234, num_verts=NUM_VERTS)
-    scene = synthetic.make_scene(seed=0, dim=SDF_DIM, num_points=NUM_POINTS)
+    scene = synthetic.make_scene(seed=scene_seed, dim=SDF_DIM, num_points=NUM_POINTS)
     xh = synthetic.make_body_params(scene, args.batch, seed=rank)
     return model, scene, xh
 
@@ -124,9 +142,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def init_dist(dev):
+    """One process per GPU over NCCL.  NCCL's own init lines are the driver's evidence of the communicator
+    (nranks): whatever NCCL_DEBUG the environment sets is kept; without one, INIT-level lines go to stderr so
+    that stdout still carries exactly one JSON line."""
+    import torch.distributed as dist
+    if "NCCL_DEBUG" not in os.environ:
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+    return dist
+
+
 # ------------------------------------------------------------------------------- rooflines
-def _latest_traffic():
-    """dram bytes per launch from the newest committed `ncu --set full` summary (profiles/*_traffic.json)."""
+def _latest_profile():
+    """Per-launch ncu numbers (dram bytes, warp instructions, issue-active %) of the newest committed
+    `ncu --set full` summary (profiles/*_traffic.json)."""
     d = os.path.join(ROOT, "profiles")
     files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json")) if os.path.isdir(d) else []
     if not files:
@@ -173,19 +205,30 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
         a[0] += ms
         a[1] += 1
     it_ms = sum(a[0] for a in agg.values())
-    traffic, tsrc = _latest_traffic()
+    ncu, nsrc = _latest_profile()
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_max * 1e6                  # warp instructions / s: 148 SMs x 4 schedulers x 1 per clock
 
     def entry(name):
         tot, n = agg[name]
         per = tot / n
         ach = alg.get(name, 0) / (per * 1e-3) / 1e9
         base = name.replace("lbs_skin_sdf_fwd", "lbs_skin_fwd").replace("lbs_vertex_bwd_fit", "lbs_vertex_bwd")
-        tr = next((v for k, v in traffic.items() if base in k), None)
-        return {"kernel": "psi::" + name + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "peak_source": peak_src,
-                "traffic": None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"]),
-                "traffic_source": tsrc if tr is not None else None, "launch_ms": per, "launches_per_iteration": n,
-                "algorithmic_bytes_per_launch": alg.get(name, 0), "share_of_iteration": tot / it_ms}
+        tr = next((v for k, v in ncu.items() if base in k), None)
+        e = {"kernel": "psi::" + name + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+             "frac": ach / hbm_peak, "peak_source": peak_src,
+             "traffic": None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"]),
+             "traffic_source": nsrc if tr is not None else None, "launch_ms": per, "launches_per_iteration": n,
+             "algorithmic_bytes_per_launch": alg.get(name, 0), "share_of_iteration": tot / it_ms}
+        if tr is not None and tr.get("warp_instructions"):
+            # the roof that binds an instruction-bound kernel: warp instructions issued (ncu, per launch) over the
+            # LIVE launch time against 148 SMs x 4 schedulers x 1 instruction per clock
+            ips = tr["warp_instructions"] / (per * 1e-3)
+            e["issue"] = {"bound": "issue slots", "achieved": ips / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-inst/s",
+                          "frac": ips / issue_peak, "warp_instructions_per_launch": tr["warp_instructions"],
+                          "ncu_issue_active_pct": tr.get("issue_active_pct"), "source": nsrc,
+                          "peak_source": "148 SMs x 4 schedulers x clocks.max.sm"}
+        return e
 
     top = max(agg, key=lambda k: agg[k][0])
     roofline = entry(top)
@@ -193,13 +236,14 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
                          "(psi_fit_profile), inputs as the loop leaves them")
     roofline["iteration_ms_eager_sum"] = it_ms
     roofline["iteration_ms_graph"] = step_ms / args.iters
+    roofline["iteration_algorithmic_bytes"] = int(sum(alg.get(k, 0) * a[1] for k, a in agg.items()))
+    roofline["iteration_hbm_frac"] = roofline["iteration_algorithmic_bytes"] / (step_ms / args.iters * 1e-3) / 1e9 / hbm_peak
     roofline["others"] = {k: entry(k) for k in sorted(agg, key=lambda k: -agg[k][0]) if k != top}
-    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     nn_name = next((k for k in agg if k.startswith("nn_")), None)
     gemm = 2.0 * B * 512 * 3 * V
     roofline["note"] = ("the exact box-tree NN evaluates a few of the 1563 leaf clusters per query: an instruction/"
-                        "latency-bound tree walk over L2-resident data, neither HBM- nor tensor-bound; "
+                        "latency-bound tree walk over L2-resident data, neither HBM- nor tensor-bound (see `issue`); "
                         "brute-force-equivalent rate = %.3g pair/s.  LBS blend GEMMs (GEMMPATH): forward %.1f, "
                         "dcoef %.1f TFLOP/s FP32-equivalent (nominal FP32 CUDA-core peak %.1f)"
                         % (B * V * M / (agg[nn_name][0] / agg[nn_name][1] * 1e-3) if nn_name else 0.0,
@@ -240,31 +284,15 @@ def roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak
         return float(np.mean(ks))
 
     nn_target = op.s_index if op.s_index is not None else op.s_verts
-    if op.s_index is not None:
-        # the loop's own configuration: contact queries ordered by dominant joint + kd cells of the template + last
-        # iteration's hints (psi_fit_run keeps them); one call outside the timing warms the hints
-        from psi_release_b200.fused import _spatial_order
-        sel = torch.tensor(_spatial_order(np.arange(NUM_VERTS), model["v_template"], model["weights"],
-                                          model["kintree_table"][0]), device=dev)
-        nnd = torch.empty(args.batch, NUM_VERTS, device=dev)
-        nni = torch.empty(args.batch, NUM_VERTS, dtype=torch.int32, device=dev)
-        nnh = torch.full((args.batch, NUM_VERTS), -1, dtype=torch.int32, device=dev)
 
-        def nn_call():
-            rc = L.psi_nn_index_query_mode(op.s_index.h, _lib.ptr(verts), NUM_VERTS * 3, args.batch, NUM_VERTS,
-                                           _lib.ptr(sel), _lib.ptr(nnd), _lib.ptr(nni), _lib.ptr(nnh),
-                                           int(os.environ.get("PSI_FIT_NN_MODE", "3")), _lib.stream_ptr())
-            assert rc == 0
-    else:
-        def nn_call():
-            chamfer.nn_forward(verts, nn_target)
+    def nn_call():
+        chamfer.nn_forward(verts, nn_target)
     kernel_ms = {
         "nn": alone(nn_call),
         "lbs_fwd": alone(lambda: bm.lbs(betas, pose, h, cam=cam_dev)),
         "lbs_bwd": alone(lambda: torch.autograd.grad(vq, (bq, pq), gq, retain_graph=True)),
         "sdf": alone(lambda: sdf_mod.sdf_forward(op.scene_sdf, verts, want_grad=True, want_partials=True)),
     }
-
     if rank != 0:
         return None
     B = args.batch
@@ -272,30 +300,23 @@ def roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak
     sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     model_bytes = h.nbytes()
-    # algorithmic bytes per launch (SURVEY.md 8(d) per-body figures x B)
     alg = {
         "nn": (B * NUM_VERTS * 12 + B * NUM_VERTS * 8 + NUM_POINTS * 12),
         "lbs_fwd": model_bytes + B * (740 + NUM_VERTS * 12),
         "lbs_bwd": model_bytes + B * (NUM_VERTS * 24 + 740),
         "sdf": B * NUM_VERTS * (32 + 12 + 4 + 12),
     }
-    names = {"nn": ("psi::nn_index_group_kernel<true> (exact box-tree NN, joint/kd-ordered queries + hints)" if op.s_index is not None
+    names = {"nn": ("psi::nn_index_thread_kernel (exact box-tree NN)" if op.s_index is not None
                     else "psi::nn_fwd_kernel<8,16,256,1024,2> (brute-force NN)"),
              "lbs_fwd": "psi::lbs_pose_fwd_kernel + psi::lbs_blend_fwd_kernel + psi::lbs_skin_fwd_kernel",
              "lbs_bwd": "psi::lbs_vertex_bwd/dA/dcoef/pose_bwd kernels", "sdf": "psi::sdf_fwd_kernel"}
     top = max(kernel_ms, key=kernel_ms.get)
 
-    traffic = {}
-
     def roof(k):
         ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
-        tr = traffic.get(k)
-        tr = None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
         return {"kernel": names[k], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "peak_source": peak_src, "traffic": tr,
-                "traffic_source": None,
-                "launch_ms": kernel_ms[k],
-                "algorithmic_bytes_per_launch": alg[k],
+                "frac": ach / hbm_peak, "peak_source": peak_src, "traffic": None, "traffic_source": None,
+                "launch_ms": kernel_ms[k], "algorithmic_bytes_per_launch": alg[k],
                 "share_of_step": kernel_ms[k] * args.iters / step_ms}
 
     roofline = roof(top)
@@ -307,20 +328,42 @@ def roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak
                             "frac": pairs * 8 / (kernel_ms["nn"] * 1e-3) / 1e12 / fp32_peak,
                             "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm (no measured FP32 peak)",
                             "pairs_per_s": pairs / (kernel_ms["nn"] * 1e-3)}
-    else:
-        roofline["note"] = ("the index evaluates ~3 of 1563 leaf clusters per query (plus ~80 box bounds): an "
-                            "instruction/latency-bound tree walk over L2-resident data, neither HBM- nor "
-                            "tensor-bound; brute-force-equivalent rate = %.3g pair/s"
-                            % (pairs / (kernel_ms["nn"] * 1e-3)))
-    roofline["lbs_fwd_fp32_frac"] = 49.3e6 * B / (kernel_ms["lbs_fwd"] * 1e-3) / 1e12 / fp32_peak
     return roofline
 
 
 # ----------------------------------------------------------------------------------- our arm
+def _timed(fn, steps, flush, dev, barrier):
+    """K steps, each bracketed by its own CUDA events on the launching stream; L2 flushed between steps outside
+    the events.  Returns (this rank's summed time in ms, last result)."""
+    tot, out = 0.0, None
+    barrier()
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        tot += e0.elapsed_time(e1)
+    barrier()
+    return tot, out
+
+
+def _over_ranks(ms, dist, world, dev):
+    """-> (max over ranks, per-rank list) of a per-rank time."""
+    if world == 1:
+        return ms, [ms]
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    per = [float(x.item()) for x in allt]
+    return max(per), per
+
+
 def run_ours(args):
-    import torch.distributed as dist
-    from psi_release_b200 import _lib, chamfer, synthetic
-    from psi_release_b200.distributed import gather_rows
+    from psi_release_b200 import _lib, body_model as bm, chamfer, sdf as sdf_mod, synthetic
+    from psi_release_b200.distributed import fit_scenes
     from psi_release_b200.fitting import FittingOP
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -328,21 +371,77 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        # stdout carries ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION
-        if "PSI_BENCH_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["PSI_BENCH_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
-        dist.init_process_group("nccl", device_id=dev)
-    model, scene, xh = make_world(args, rank)
+    dist = init_dist(dev) if world > 1 else None
+    ns = scenes_for(world)
+    my_scene = rank * ns // world                           # two ranks per scene (plan_scene_shards' layout)
+    per_scene = args.batch * world // ns
+    # ---- setup (outside every timed region, reported as setup_ms)
+    t0 = time.perf_counter()
+    model, scene, _ = make_world(args, rank, scene_seed=my_scene)
+    t_synth = time.perf_counter() - t0
+    # the bodies of scene s, the same on every rank (a rank fits its slice of them)
+    # (two ranks share a scene and draw the same array; the other scenes' rows are never read by this rank)
+    xh_scene = [(torch.tensor(synthetic.make_body_params(scene, per_scene, seed=100 + s)) if s == my_scene
+                 else torch.zeros(per_scene, 72)) for s in range(ns)] if world > 1 else []
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
     cfg = dict(model_data=model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
                contact_ids=synthetic.make_contact_ids(NUM_VERTS, "full"), init_lr_h=0.1,
                num_iter=args.iters, batch_size=args.batch, device=dev, use_cuda_graph=True, nn=args.nn)
     op = FittingOP(cfg, LOSS)
-    xh_host = torch.tensor(xh).pin_memory()
-    cam_host = torch.tensor(scene.cam_ext).unsqueeze(0).pin_memory()
-    xh_dev, cam_dev = xh_host.to(dev), cam_host.to(dev)
+    torch.cuda.synchronize(dev)
+    t_ctor = time.perf_counter() - t0
+
+    def piece(fn):
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        keep = fn()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t
+        del keep
+        return dt * 1e3
+    setup = {"fitting_op_ctor_ms": t_ctor * 1e3,
+             "of_which_nn_index_build_ms": piece(lambda: chamfer.SceneIndex(op.s_verts)) if args.nn == "index" else 0.0,
+             "of_which_model_relayout_upload_ms": piece(lambda: bm._ModelHandle(
+                 model["v_template"], op.body_mesh_model._shapedirs, op.body_mesh_model._posedirs, model["J_regressor"],
+                 model["weights"], op.body_mesh_model.parents.cpu().numpy(), dev)),
+             "of_which_sdf_upload_ms": piece(lambda: sdf_mod.SceneSDF(scene.sdf, scene.grid_min, scene.grid_max, device=dev)),
+             "synthetic_world_ms": t_synth * 1e3,
+             "note": "once per (model, scene): host kd build + box tree of the scene index, basis re-layout into the two "
+                     "GEMM operand layouts + upload, 64 MiB SDF upload; outside every timed region"}
+
+    if world == 1:
+        xh = synthetic.make_body_params(scene, args.batch, seed=rank)
+        xh_host = torch.tensor(xh).pin_memory()
+        cam_host = torch.tensor(scene.cam_ext).unsqueeze(0).pin_memory()
+        xh_dev, cam_dev = xh_host.to(dev), cam_host.to(dev)
+        fit_dev = lambda: op.fit(xh_dev, cam_dev)
+        fit_e2e = lambda: op.fit_host(xh_host, cam_host)
+        h2d = int(xh_host.numel() * 4 + cam_host.numel() * 4)
+        d2h = int(args.batch * 72 * 4)
+        api = "psi_release_b200.fitting.FittingOP.fit_host"
+    else:
+        # configs[2] shape: every scene's bodies as a host array; fit_scenes cuts them over the ranks (two per
+        # scene), fits this rank's slice and all-gathers the fitted vectors
+        cams = [torch.tensor(scene.cam_ext).unsqueeze(0).pin_memory() for _ in range(ns)]
+        xh_host_l = [x.pin_memory() for x in xh_scene]
+        lo = (rank - my_scene * (world // ns)) * args.batch
+        xh_dev_l = [x.to(dev) for x in xh_host_l]
+        cams_dev = [c.to(dev) for c in cams]
+        make = lambda s, b: op                               # this rank's scene operator, built once above
+        total = args.batch * world
+        res_pin = torch.empty(total, 72, dtype=torch.float32).pin_memory()
+        fit_dev = lambda: fit_scenes(make, xh_dev_l, cams_dev)
+
+        def fit_e2e():
+            out = fit_scenes(make, xh_host_l, cams)          # H2D of this rank's slice, loop, all-gather
+            res_pin.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return res_pin
+        xh_dev, cam_dev = xh_dev_l[my_scene][lo:lo + args.batch], cams_dev[my_scene]
+        h2d = int(args.batch * 72 * 4 + 64) * world
+        d2h = int(total * 72 * 4) * world
+        api = "psi_release_b200.distributed.fit_scenes (host inputs) + D2H of the gathered [%d,72]" % total
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     L = _lib.lib()
 
@@ -351,28 +450,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
-        """K steps, each bracketed by its own CUDA events on the launching stream; L2 flushed
-        between steps outside the events.  Returns the max over ranks of the summed time (ms)."""
-        tot = 0.0
-        barrier()
-        for _ in range(steps):
-            flush.zero_()
-            torch.cuda.synchronize(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = fn()
-            e1.record()
-            torch.cuda.synchronize(dev)
-            tot += e0.elapsed_time(e1)
-        barrier()
-        t = torch.tensor([tot], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), out
-
-    for _ in range(max(args.warmup, 3)):
-        op.fit(xh_dev, cam_dev)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    fit_dev()
+    torch.cuda.synchronize(dev)
+    setup["first_fit_graph_capture_ms"] = (time.perf_counter() - t0) * 1e3
+    for _ in range(max(args.warmup, 3) - 1):
+        fit_dev()
     # kernels launched per captured iteration (the graph replays them `iters` times per step)
     if op.engine == "fused":
         per_iter = int(L.psi_fit_launches_per_iteration())
@@ -386,13 +470,13 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, fitted = timed(lambda: op.fit(xh_dev, cam_dev), args.steps)
-    ms_e2e, fitted_h = timed(lambda: op.fit_host(xh_host, cam_host), args.steps)
+    ms_dev_r, fitted = _timed(fit_dev, args.steps, flush, dev, barrier)
+    ms_e2e_r, fitted_h = _timed(fit_e2e, args.steps, flush, dev, barrier)
     clocks = sampler.stop() if rank == 0 else None
-
-    # one all-gather of the fitted vectors ends a sharded job (not part of the per-step loop)
-    all_fitted = gather_rows(fitted, args.batch * world) if world > 1 else fitted
-    assert all_fitted.shape == (args.batch * world, 72) and torch.isfinite(all_fitted).all()
+    ms_dev, per_rank_dev = _over_ranks(ms_dev_r, dist, world, dev)
+    ms_e2e, per_rank_e2e = _over_ranks(ms_e2e_r, dist, world, dev)
+    assert fitted.shape == (args.batch * world, 72) and torch.isfinite(fitted).all()
+    assert torch.equal(fitted_h.to(fitted.device), fitted)                     # host path == device path, bit for bit
 
     hbm_peak, peak_src = peaks()
     step_ms = ms_dev / args.steps
@@ -401,33 +485,95 @@ def run_ours(args):
     else:
         roofline = roofline_alone(op, args, model, scene, xh_dev, cam_dev, flush, dev, hbm_peak, peak_src,
                                   step_ms, clocks, rank)
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        ref_gpu = reference_gpu(args, op, model, scene, xh_dev, cam_dev, flush, dev, step_ms)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     bodies = args.batch * world * args.steps
-    value = bodies / (ms_dev * 1e-3)
-    e2e = bodies / (ms_e2e * 1e-3)
     out = {
-        "metric": METRIC, "value": value, "unit": "bodies/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": bodies / (ms_dev * 1e-3), "unit": "bodies/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "e2e": {"value": e2e, "unit": "bodies/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(xh_host.numel() * 4 + cam_host.numel() * 4) * world,
-                "d2h_bytes_per_step": int(args.batch * 72 * 4) * world,
-                "api": "psi_release_b200.fitting.FittingOP.fit_host"},
+        "e2e": {"value": bodies / (ms_e2e * 1e-3), "unit": "bodies/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api,
+                "includes_allgather": world > 1},
         "gpu_launches": per_iter * args.iters * args.steps * world,
         "gpu_launches_per_iteration": per_iter,
+        "host_graph_launches_per_step": (1 + args.iters % 15) if getattr(op._fused, "loop_mode", "") == "whole" else args.iters,
+        "per_rank_ms_per_step": [x / args.steps for x in per_rank_dev],
+        "per_rank_e2e_ms_per_step": [x / args.steps for x in per_rank_e2e],
+        "setup_ms": setup,
         "clocks": clocks,
         "roofline": roofline,
         "engine": op.engine,
     }
+    if ref_gpu is not None:
+        out["reference_gpu"] = ref_gpu
     if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed at N = 1 only
         out["cpu_baseline"] = cpu_baseline(args, seconds=args.cpu_baseline_seconds)
+    time.sleep(0.3)                                   # let the other ranks' NCCL teardown lines out first
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------ reference, same GPU
+def reference_gpu(args, op, model, scene, xh_dev, cam_dev, flush, dev, our_step_ms):
+    """The reference's own GPU path on this B200 (oracle/reference_gpu.py): chamfer.cu built unmodified (both
+    directions, as dist_chamfer.py runs it) + torch LBS / grid_sample / Adam; ONE un-scaled step of the same
+    workload, and kernel-against-kernel times of the NN search."""
+    try:
+        from oracle import reference_gpu as rg
+        from psi_release_b200 import _lib, chamfer, synthetic
+        if rg.ref_ext() is None:
+            return {"unavailable": "oracle/_ref/chamfer_ref.so not built (needs /root/reference at build time)"}
+        loop = rg.ReferenceGpuLoop(model, synthetic.make_vposer_weights(), scene, np.arange(NUM_VERTS), LOSS, dev)
+        loop.fit(xh_dev, cam_dev, 3)                                   # warm-up
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = loop.fit(xh_dev, cam_dev, args.iters)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        assert torch.isfinite(out).all()
+
+        def t(fn, reps=5):
+            fn()
+            torch.cuda.synchronize(dev)
+            ks = []
+            for _ in range(reps):
+                flush.zero_()
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize(dev)
+                ks.append(a.elapsed_time(b))
+            return float(np.median(ks))
+        verts = op.body_verts(xh_dev, cam_dev).detach().contiguous()
+        pts_b = loop.points.unsqueeze(0).repeat(args.batch, 1, 1)
+        ref_both = t(lambda: rg.RefChamfer.apply(verts, pts_b))
+        ours_brute = t(lambda: chamfer.nn_forward(verts, op.s_verts))
+        ours_index = t(lambda: chamfer.nn_forward(verts, op.s_index)) if op.s_index is not None else None
+        d_ref, _ = rg.RefChamfer.apply(verts, pts_b)
+        d_ours, _ = chamfer.nn_forward(verts, op.s_index if op.s_index is not None else op.s_verts)
+        return {"value": args.batch / (ms * 1e-3), "unit": "bodies/s", "ms_per_step": ms, "iterations": args.iters,
+                "extrapolated": False, "bodies": args.batch,
+                "what": "reference chamfer.cu (unmodified, sm_100a build, both directions as dist_chamfer.py computes them) "
+                        "+ torch-CUDA lbs / grid_sample(align_corners=True) / Adam on the same GPU, one full step",
+                "ours_over_reference_gpu": (ms / our_step_ms),
+                "nn_kernel_ms": {"reference_chamfer_both_directions": ref_both, "reference_one_direction_equiv": ref_both / 2,
+                                 "ours_bruteforce_one_direction": ours_brute, "ours_exact_index_one_direction": ours_index,
+                                 "shape": "%d x %d queries against %d points" % (args.batch, NUM_VERTS, NUM_POINTS),
+                                 "distances_bit_identical": bool(torch.equal(d_ref.view(torch.int32), d_ours.view(torch.int32)))}}
+    except Exception as e:  # noqa: BLE001  (a measurement aid must not take the bench line down)
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
 # ----------------------------------------------------------------------------------- CPU arms
@@ -468,19 +614,32 @@ def _best_threads(oracle, xh, cam, kw):
     return best
 
 
+def _cpu_sample_desc(nb, iters):
+    return ("%d bodies x all %d iterations (torch-CPU LBS + grid_sample, AVX brute-force NN in C/OpenMP, torch Adam); "
+            "nothing scaled" % (nb, iters))
+
+
+def _large_batch_estimate(args, oracle, xh, cam, kw):
+    """64 bodies x 2 iterations, scaled to 300: how the port does when the fixed per-call costs (61 MB of pose
+    basis per LBS call) are spread over a large batch.  Reported next to the measured figure, flagged."""
+    nb = min(args.batch, 64)
+    _cpu_step(oracle, xh[:nb], cam, kw, 1)
+    t = _cpu_step(oracle, xh[:nb], cam, kw, 2)
+    return {"value": nb * (2 / args.iters) / t, "unit": "bodies/s", "extrapolated": True,
+            "sample": "%d bodies x 2 of %d iterations, scaled" % (nb, args.iters)}
+
+
 def cpu_baseline(args, seconds):
-    """The oracle port timed on the host cores (rank 0, N=1 legs): bounded sample."""
+    """The oracle port timed on the host cores (rank 0, N = 1): a few bodies fitted for ALL iterations."""
     oracle, xh, cam, kw = _cpu_setup(args)
-    nb = min(args.batch, 16)
-    cores = _best_threads(oracle, xh[:nb], cam, kw)
-    t1 = _cpu_step(oracle, xh[:nb], cam, kw, 1)              # warm-up + cost probe
-    iters = int(max(1, min(20, seconds / max(t1, 1e-3))))
-    t = _cpu_step(oracle, xh[:nb], cam, kw, iters)
-    val = nb * (iters / args.iters) / t
-    return {"value": val, "unit": "bodies/s", "cores": cores, "logical_cpus": os.cpu_count(),
-            "kind": "port", "simd_lanes": oracle.simd_width(),
-            "sample": "%d bodies x %d of %d iterations (torch-CPU LBS + grid_sample, C/OpenMP brute-force NN, "
-                      "torch Adam), scaled to %d iterations" % (nb, iters, args.iters, args.iters)}
+    cores = _best_threads(oracle, xh[:4], cam, kw)
+    t1 = _cpu_step(oracle, xh[:4], cam, kw, 1) / 4                       # seconds per body-iteration
+    nb = int(max(1, min(16, seconds / max(t1 * args.iters, 1e-3))))
+    t = _cpu_step(oracle, xh[:nb], cam, kw, args.iters)
+    return {"value": nb / t, "unit": "bodies/s", "cores": cores, "logical_cpus": os.cpu_count(),
+            "kind": "port", "simd_lanes": oracle.simd_width(), "extrapolated": False, "seconds": t,
+            "sample": _cpu_sample_desc(nb, args.iters),
+            "large_batch_estimate": _large_batch_estimate(args, oracle, xh, cam, kw)}
 
 
 def run_reference(args):
@@ -489,31 +648,40 @@ def run_reference(args):
     if rank != 0:
         return
     oracle, xh, cam, kw = _cpu_setup(args)
-    cores = _best_threads(oracle, xh, cam, kw)
-    it = args.ref_iters
-    for _ in range(max(1, min(args.warmup, 3))):
-        _cpu_step(oracle, xh, cam, kw, 1)
+    cores = _best_threads(oracle, xh[:4], cam, kw)
+    t1 = _cpu_step(oracle, xh[:4], cam, kw, 1) / 4                       # seconds per body-iteration
+    runs = args.steps + args.warmup
+    nb = int(max(1, min(args.batch, args.ref_seconds / runs / max(t1 * args.iters, 1e-3))))
+    for _ in range(args.warmup):
+        _cpu_step(oracle, xh[:nb], cam, kw, args.iters)
     t = 0.0
     for _ in range(args.steps):
-        t += _cpu_step(oracle, xh, cam, kw, it)
-    val = args.batch * args.steps * (it / args.iters) / t
-    sample = ("each step = %d bodies x %d of %d iterations on the host CPU (torch-CPU LBS + grid_sample, "
-              "AVX brute-force NN in C/OpenMP, torch Adam), scaled to %d iterations" % (args.batch, it, args.iters, args.iters))
+        t += _cpu_step(oracle, xh[:nb], cam, kw, args.iters)
+    val = nb * args.steps / t
     cfg = workload_config(args, world)
+    cfg["reference_sample"] = _cpu_sample_desc(nb, args.iters)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "bodies/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3 * (args.iters / it),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "extrapolated": False, "bodies_per_step": nb,
         "cpu_baseline": {"value": val, "unit": "bodies/s", "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
-                         "simd_lanes": oracle.simd_width(), "sample": sample},
+                         "simd_lanes": oracle.simd_width(), "extrapolated": False,
+                         "sample": "each step = " + _cpu_sample_desc(nb, args.iters),
+                         "large_batch_estimate": _large_batch_estimate(args, oracle, xh, cam, kw)},
         "e2e": {"value": val, "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "train_s2":
+        from tools import workloads
+        workloads.run_train_s2(a)
+    elif a.workload == "rooms":
+        from tools import workloads
+        workloads.run_rooms(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

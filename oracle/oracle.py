@@ -159,7 +159,7 @@ def batch_rodrigues(aa):
     rx, ry, rz = n[:, 0:1], n[:, 1:2], n[:, 2:3]
     z = torch.zeros_like(rx)
     K = torch.cat([z, -rz, ry, rz, z, -rx, -ry, rx, z], dim=1).view(-1, 3, 3)
-    eye = torch.eye(3, dtype=aa.dtype).unsqueeze(0)
+    eye = torch.eye(3, dtype=aa.dtype, device=aa.device).unsqueeze(0)
     return eye + s * K + (1 - c) * torch.bmm(K, K)
 
 
@@ -171,12 +171,12 @@ def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_
     v_shaped = v_template.unsqueeze(0) + torch.einsum("bl,mkl->bmk", betas, shapedirs)
     J = torch.einsum("bik,ji->bjk", v_shaped, J_regressor).contiguous()
     R = batch_rodrigues(pose.reshape(-1, 3)).view(B, nj, 3, 3)
-    pose_feature = (R[:, 1:] - torch.eye(3, dtype=betas.dtype)).reshape(B, -1)
+    pose_feature = (R[:, 1:] - torch.eye(3, dtype=betas.dtype, device=betas.device)).reshape(B, -1)
     v_posed = v_shaped + torch.matmul(pose_feature, posedirs).view(B, -1, 3)
     # kinematic chain (lbs.py:207-262)
     rel = J.clone()
     rel[:, 1:] = J[:, 1:] - J[:, parents[1:]]
-    Tm = torch.zeros(B, nj, 4, 4, dtype=betas.dtype)
+    Tm = torch.zeros(B, nj, 4, 4, dtype=betas.dtype, device=betas.device)
     Tm[:, :, :3, :3] = R
     Tm[:, :, :3, 3] = rel
     Tm[:, :, 3, 3] = 1
@@ -185,11 +185,11 @@ def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_
         chain.append(torch.matmul(chain[int(parents[i])], Tm[:, i]))
     G = torch.stack(chain, dim=1)
     posed_joints = G[:, :, :3, 3]
-    Jh = torch.cat([J, torch.zeros(B, nj, 1, dtype=betas.dtype)], dim=2).unsqueeze(-1)
+    Jh = torch.cat([J, torch.zeros(B, nj, 1, dtype=betas.dtype, device=betas.device)], dim=2).unsqueeze(-1)
     init_bone = F.pad(torch.matmul(G, Jh), [3, 0])
     A = G - init_bone
     T = torch.matmul(lbs_weights.unsqueeze(0).expand(B, -1, -1), A.view(B, nj, 16)).view(B, -1, 4, 4)
-    vh = torch.cat([v_posed, torch.ones(B, v_posed.shape[1], 1, dtype=betas.dtype)], dim=2)
+    vh = torch.cat([v_posed, torch.ones(B, v_posed.shape[1], 1, dtype=betas.dtype, device=betas.device)], dim=2)
     verts = torch.matmul(T, vh.unsqueeze(-1))[:, :, :3, 0]
     return verts, posed_joints
 
@@ -221,9 +221,16 @@ class SMPLXOracle:
         self.dtype = dtype
         self.num_expression = num_expression
 
+    def to(self, device):
+        """The same restatement with its constants on `device` (oracle/reference_gpu.py: the reference's
+        GPU path timed on the B200 next to ours)."""
+        for k in ("shapedirs", "v_template", "posedirs", "J_regressor", "weights", "lh", "rh", "pose_mean"):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
     def full_pose(self, global_orient, body_pose, left_hand_pose, right_hand_pose):
         B = global_orient.shape[0]
-        z3 = torch.zeros(B, 3, dtype=self.dtype)
+        z3 = torch.zeros(B, 3, dtype=self.dtype, device=global_orient.device)
         lh = torch.einsum("bi,ij->bj", left_hand_pose, self.lh)
         rh = torch.einsum("bi,ij->bj", right_hand_pose, self.rh)
         full = torch.cat([global_orient, body_pose, z3, z3, z3, lh, rh], dim=1)
@@ -232,7 +239,7 @@ class SMPLXOracle:
     def __call__(self, body_pose, transl, global_orient, betas, left_hand_pose, right_hand_pose):
         B = betas.shape[0]
         full = self.full_pose(global_orient, body_pose, left_hand_pose, right_hand_pose)
-        shape = torch.cat([betas, torch.zeros(B, self.num_expression, dtype=self.dtype)], dim=-1)
+        shape = torch.cat([betas, torch.zeros(B, self.num_expression, dtype=self.dtype, device=betas.device)], dim=-1)
         verts, joints = lbs(shape, full, self.v_template, self.shapedirs, self.posedirs,
                             self.J_regressor, self.parents, self.weights)
         return verts + transl.unsqueeze(1), joints + transl.unsqueeze(1)
@@ -321,6 +328,10 @@ class VPoserDecoderOracle:
 
     def __init__(self, weights: dict):
         self.w = {k: torch.tensor(v) for k, v in weights.items()}
+
+    def to(self, device):
+        self.w = {k: v.to(device) for k, v in self.w.items()}
+        return self
 
     def decode(self, z):
         w = self.w

@@ -222,7 +222,9 @@ class SMPLX(nn.Module):
             return value
         p = getattr(self, name, None)
         if p is not None:
-            return p
+            # smplx fixes the batch size at construction; a module shared by operators of several batch sizes
+            # (pipeline.fit_rooms) broadcasts the first row of its default parameter instead of failing
+            return p if p.shape[0] == B else p[:1].expand(B, -1)
         return torch.zeros(B, dim, dtype=torch.float32, device=self.pose_mean.device)
 
     def assemble(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,

@@ -98,12 +98,15 @@ class FittingOP:
             p_.requires_grad_(False)
 
         # --- body model (fitting_habitat.py:57-73)
-        self.body_mesh_model = smplx_b200.create(
+        # (fittingconfig['body_mesh_model']: an already created module, so that operators for several scenes
+        # share ONE device copy of the model constants instead of re-laying the 2 x 64 MB bases out per scene)
+        shared_model = getattr(self, "body_mesh_model", None)
+        self.body_mesh_model = (shared_model if shared_model is not None else smplx_b200.create(
             getattr(self, "human_model_path", None), model_type="smplx", gender="neutral", ext="npz",
             num_pca_comps=12, create_global_orient=True, create_body_pose=True, create_betas=True,
             create_left_hand_pose=True, create_right_hand_pose=True, create_expression=True,
             create_jaw_pose=True, create_leye_pose=True, create_reye_pose=True, create_transl=True,
-            batch_size=B, model_data=getattr(self, "model_data", None)).to(self.device)
+            batch_size=B, model_data=getattr(self, "model_data", None))).to(self.device)
         for p_ in self.body_mesh_model.parameters():
             p_.requires_grad_(False)
 

@@ -32,6 +32,12 @@ def fit_rooms(rooms, generate, samples_per_room, fittingconfig, lossconfig, out_
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     counts = [int(samples_per_room)] * len(rooms)
     outs, ncs, cts, dev = [], [], [], None
+    if "body_mesh_model" not in fittingconfig:
+        # one device copy of the SMPL-X constants for every room this rank touches
+        from . import body_model
+        fittingconfig = dict(fittingconfig, body_mesh_model=body_model.create(
+            fittingconfig.get("human_model_path"), model_type="smplx", gender="neutral", ext="npz", num_pca_comps=12,
+            batch_size=int(samples_per_room), model_data=fittingconfig.get("model_data")))
     for r, a, b in plan_scene_shards(counts, world)[rank]:
         scene = rooms[r]
         xh = torch.as_tensor(generate(r, counts[r]), dtype=torch.float32)[a:b]     # same samples whatever the sharding

@@ -71,21 +71,35 @@ def _check_iteration(op, kw, scene, cid, x0_6d, cam, loss_mode="independent", gr
     for a, b in zip(losses.tolist(), terms):
         assert abs(a - float(b)) <= 1e-4 * max(1.0, abs(float(b))), (losses.tolist(), [float(t) for t in terms])
     g = op.trace("grad_x").cpu()
-    # The reference loss is DISCONTINUOUS where a vertex crosses sdf = 0 (the mean's denominator changes,
-    # fitting_habitat.py:155-158) and its gradient where a vertex's nearest scene point changes.  The CPU chain
-    # evaluates its own vertices (within 1e-5 of the kernel's): a body that sits on such a discontinuity
-    # is compared loosely, and there may only be a few of them.
-    svc, _ = oracle.sdf_fwd(scene.sdf, scene.grid_min, scene.grid_max, vo.numpy(), want_grad=False)
-    _, ioc = oracle.nn_fwd(vo[:, qid].contiguous().numpy(), scene.points)
-    crossing = ((sv < 0).sum(1) != (svc < 0).sum(1)) | (nni != ioc).any(1)
-    if loss_mode == "batch":
-        crossing[:] = crossing.any()                  # one shared denominator
-    assert crossing.sum() <= max(1, B // 8), f"{int(crossing.sum())} of {B} bodies on a loss discontinuity"
+    # The reference loss has KINKS: the trilinear SDF slope jumps across voxel faces, a vertex crossing sdf = 0
+    # changes the mean's denominator (fitting_habitat.py:155-158), a vertex between two scene points changes its
+    # nearest one.  The CPU chain evaluates its own vertices (within ~2e-5 m of the kernel's), so on a kink the two
+    # sides take different -- equally valid -- one-sided derivatives.  The slack per body is the L1 difference of
+    # dL/dverts evaluated from the kernel's inputs and from the CPU chain's inputs (times a lever arm of 3 for the
+    # rotations); away from kinks it is ~1e-7 and the plain tolerance decides.
+    svc, sgc = oracle.sdf_fwd(scene.sdf, scene.grid_min, scene.grid_max, vo.numpy())
+    doc, ioc = oracle.nn_fwd(vo[:, qid].contiguous().numpy(), scene.points)
+    mult = np.bincount(np.asarray(cid, dtype=np.int64), minlength=V)[qid.numpy()].astype(np.float64)
+
+    def vertex_grad(v, val, slope, nd, ni):
+        gv = np.zeros((B, V, 3))
+        neg = val < 0
+        cnt = np.maximum(neg.sum() if loss_mode == "batch" else neg.sum(1, keepdims=True), 1)
+        gv -= (W["weight_collision"] / cnt)[..., None] * slope * neg[..., None] if loss_mode != "batch" else \
+            (W["weight_collision"] / cnt) * slope * neg[..., None]
+        sq = np.sqrt(nd.astype(np.float64) + 1e-4)
+        gd = W["weight_contact"] / (len(cid) * (B if loss_mode == "batch" else 1)) * mult * (1.0 / (sq + 1.0) ** 2) * (0.5 / sq)
+        gv[:, qid.numpy()] += 2 * gd[..., None] * (v[:, qid.numpy()] - scene.points[ni])
+        return gv
+    slack = 3 * np.abs(vertex_grad(verts.numpy().astype(np.float64), sv, sg, nnd, nni) -
+                       vertex_grad(vo.numpy().astype(np.float64), svc, sgc, doc, ioc)).sum((1, 2))
+    on_kink = slack > 1e-5
+    assert on_kink.sum() <= max(2, B // 4), f"{int(on_kink.sum())} of {B} bodies on a kink of the loss"
     for b in range(B):
         scale = float(go[b].abs().max())
         err = float((g[b] - go[b]).abs().max())
-        tol = 5e-2 if crossing[b] else grad_tol
-        assert err <= tol * scale, f"body {b}: |dL/dx - oracle| = {err:.3e} vs scale {scale:.3e} (crossing: {bool(crossing[b])})"
+        assert err <= grad_tol * scale + slack[b], \
+            f"body {b}: |dL/dx - oracle| = {err:.3e} vs scale {scale:.3e}, kink slack {slack[b]:.3e}"
     return x_eval, g
 
 
@@ -169,7 +183,6 @@ def test_loop_forms_are_bit_identical(small_model):
         assert torch.equal(whole.trace("x_eval"), eager.trace("x_eval"))
         assert torch.equal(whole.trace("grad_x"), eager.trace("grad_x"))
     assert not torch.equal(whole.fit(xh, cam, num_iter=30), whole.fit(xh, cam, num_iter=29))
-    one_per_pass = _make(small_model, scene, cid, B, loop_mode="whole")
     import os
     os.environ["PSI_FIT_UNROLL"] = "1"
     try:

@@ -86,9 +86,21 @@ def full(rep, prefix):
             v, u = vals.get(m, ("0", "byte"))
             f = float(v.replace(",", "") or 0)
             return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        def num(m):
+            v, _ = vals.get(m, ("0", ""))
+            try:
+                return float(v.replace(",", "") or 0)
+            except ValueError:
+                return 0.0
+        dur, du = vals.get("gpu__time_duration.sum", ("0", "us"))
+        dur = float(dur.replace(",", "") or 0) * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(du, 1.0)
         traffic[name.split("(")[0].replace("void ", "").strip()] = {
             "kernel": name[:80], "dram_bytes_read": to_bytes("dram__bytes_read.sum"),
-            "dram_bytes_write": to_bytes("dram__bytes_write.sum")}
+            "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
+            "warp_instructions": num("smsp__inst_executed.sum"),
+            "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "tensor_pipe_pct": num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+            "registers": num("launch__registers_per_thread"), "ncu_duration_us": dur}
     open(prefix + "_ncu_full_summary.md", "w").write(
         "# `ncu --set full --clock-control none --import-source on`, first captured launch of each kernel\n\nSource: %s (not committed)\n\n" % rep + "\n".join(out))
     json.dump({"source": prefix + "_ncu_full_summary.md", "kernels": traffic}, open(prefix + "_traffic.json", "w"), indent=1)
