@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--iters", type=int, default=ITERS)
     ap.add_argument("--nn", default="index", choices=["index", "bruteforce"],
                     help="index: exact cluster-pruned NN over the static scene; bruteforce: the tiled all-pairs kernel")
+    ap.add_argument("--optimizer", default="adam", choices=["adam", "lbfgs"],
+                    help="adam: the fitting scripts' optimiser (the headline).  lbfgs: per-body L-BFGS / strong Wolfe, --iters closure "
+                         "evaluations (the literal wording of BASELINE.json's metric; SURVEY.md T7)")
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="time budget of the whole reference-arm run")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -79,7 +82,8 @@ def workload_config(args, n_gpus):
     return {"workload": "%s; %d-vert body, %d^3 SDF, %d-pt scene, %d Adam iterations, full-body contact"
                         % (name, NUM_VERTS, SDF_DIM, NUM_POINTS, args.iters),
             "bodies_per_gpu": args.batch, "global_bodies": args.batch * n_gpus, "scenes": ns, "iterations": args.iters,
-            "optimizer": "adam lr=0.1", "nn": "one direction (body->scene), %s, bit-exact" % ("exact cluster index" if args.nn == "index" else "brute force"),
+            "optimizer": "adam lr=0.1" if getattr(args, "optimizer", "adam") == "adam" else
+                         "per-body L-BFGS (history 100, strong Wolfe, lr 1.0), %d closure evaluations" % args.iters, "nn": "one direction (body->scene), %s, bit-exact" % ("exact cluster index" if args.nn == "index" else "brute force"),
             "loss_mode": "independent", "parallelism": "dp%d (bodies sharded, no data-path collective in the loop, one all-gather per step)" % n_gpus,
             "l2": "flushed between timed steps (256 MiB write)"}
 
@@ -143,16 +147,30 @@ def peaks():
 
 
 def init_dist(dev):
-    """One process per GPU over NCCL.  NCCL's own init lines are the driver's evidence of the communicator
-    (nranks): whatever NCCL_DEBUG the environment sets is kept; without one, INIT-level lines go to stderr so
-    that stdout still carries exactly one JSON line."""
+    """One process per GPU over NCCL.  NCCL's own init lines are the evidence of the communicator (nranks): whatever
+    NCCL_DEBUG / NCCL_DEBUG_FILE the environment sets is kept untouched; without one, INIT-level lines go to a
+    per-process file that `nccl_init_lines` reads back into the JSON line (stdout then carries only NCCL's version
+    banner before the ONE JSON line, which is printed last)."""
     import torch.distributed as dist
     if "NCCL_DEBUG" not in os.environ:
         os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/psi_bench_nccl_%p.log")
     dist.init_process_group("nccl", device_id=dev)
     return dist
+
+
+def nccl_init_lines():
+    """This process's NCCL init lines that name the communicator size (from the file init_dist pointed NCCL at)."""
+    path = os.environ.get("NCCL_DEBUG_FILE", "").replace("%p", str(os.getpid()))
+    if "%h" in path:
+        import socket
+        path = path.replace("%h", socket.gethostname())
+    try:
+        with open(path) as f:
+            return [l.strip()[-220:] for l in f if "nranks" in l][:4]
+    except OSError:
+        return []
 
 
 # ------------------------------------------------------------------------------- rooflines
@@ -387,7 +405,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     cfg = dict(model_data=model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
                contact_ids=synthetic.make_contact_ids(NUM_VERTS, "full"), init_lr_h=0.1,
-               num_iter=args.iters, batch_size=args.batch, device=dev, use_cuda_graph=True, nn=args.nn)
+               num_iter=args.iters, batch_size=args.batch, device=dev, use_cuda_graph=True, nn=args.nn,
+               optimizer_name=args.optimizer)
     op = FittingOP(cfg, LOSS)
     torch.cuda.synchronize(dev)
     t_ctor = time.perf_counter() - t0
@@ -488,6 +507,7 @@ def run_ours(args):
     ref_gpu = None
     if rank == 0 and world == 1 and not args.no_reference_gpu:
         ref_gpu = reference_gpu(args, op, model, scene, xh_dev, cam_dev, flush, dev, step_ms)
+    nccl_lines = nccl_init_lines() if world > 1 else None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -512,6 +532,8 @@ def run_ours(args):
         "roofline": roofline,
         "engine": op.engine,
     }
+    if world > 1:
+        out["nccl_init"] = nccl_lines
     if ref_gpu is not None:
         out["reference_gpu"] = ref_gpu
     if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed at N = 1 only

@@ -43,7 +43,7 @@ typedef void *psi_stream_t; /* cudaStream_t */
 #define PSI_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels were built for */
 #define PSI_ERR_ALLOC (-4)        /* device allocation failed (model upload only) */
 
-#define PSI_ABI_VERSION 3   /* 3: psi_fit_config.{loop_mode,loop_unroll,loss_mode}, psi_fit_trace, psi_fit_trace_bytes;
+#define PSI_ABI_VERSION 3   /* 3: psi_fit_config.{loop_mode,loop_unroll,loss_mode,optimizer,lbfgs_*}, psi_fit_trace, psi_fit_trace_bytes;
                                2: psi_fit_config.nn_mode, psi_fit_profile, psi_nn_index_query_mode mode 3 */
 
 /* ABI version of the loaded library (PSI_ABI_VERSION it was built with). */
@@ -234,6 +234,14 @@ typedef struct psi_fit_config {
     int loss_mode;        /* 0 = independent: sum over bodies of the reference's B=1 loss (the shipped scripts,
                              fitting_habitat.py:254); 1 = batch: the reference's batch-coupled means
                              (fitting_proxe.py:105,110,139,155-160 with B > 1; demo.ipynb cell 16) */
+    int optimizer;        /* 0 = Adam (the fitting scripts', fitting_habitat.py:76); 1 = L-BFGS with strong-Wolfe line search
+                             (human_body_prior/optimizers/lbfgs_ls.py:54-183,275-463), one independent optimiser per
+                             body, num_iter = closure evaluations; loss_mode 0 only */
+    float lbfgs_lr;             /* initial step of every line search (lbfgs_ls.py lr; 0 = 1.0) */
+    float lbfgs_tolerance_grad;     /* stop when |g|_1 <= this   (0 = 1e-5, lbfgs_ls.py:214-216) */
+    float lbfgs_tolerance_change;   /* stop on a step / loss change below this (0 = 1e-9) */
+    int lbfgs_history;          /* curvature pairs kept (0 = 100) */
+    int lbfgs_zoom_max;         /* zoom-phase iteration bound (0 = 300: the reference passes the optimiser's max_iter) */
 } psi_fit_config;
 
 typedef struct psi_fit_ctx psi_fit_ctx;
@@ -286,6 +294,9 @@ PSI_API int psi_fit_launches_per_iteration(void);
 #define PSI_FIT_TRACE_ADAM_M 10    /* float [B,75] */
 #define PSI_FIT_TRACE_ADAM_V 11    /* float [B,75] */
 #define PSI_FIT_TRACE_POSE6D 12    /* float [B,nbody+1,6]: root 6D + VPoser decoder output of the last iteration */
+#define PSI_FIT_TRACE_LBFGS_STATE 13   /* int [B,4]: (phase 0 start / 1 bracket / 2 zoom / 3 done, outer iterations, closure
+                                          evaluations, curvature pairs held); optimizer 1 only */
+#define PSI_FIT_TRACE_LBFGS_BEST 14    /* float [B,75]: last accepted point (+ best sufficient-decrease step of a search in progress) */
 PSI_API size_t psi_fit_trace_bytes(const psi_fit_ctx *c, int what);   /* 0 for an unknown `what` */
 PSI_API int psi_fit_trace(psi_fit_ctx *c, int what, void *dst, size_t dst_bytes, psi_stream_t stream);
 

@@ -23,13 +23,15 @@ class FitConfig(ctypes.Structure):
     """struct psi_fit_config (include/psi_b200.h)."""
     _fields_ = [("B", _i), ("use_graph", _i), ("w_rec", _f), ("w_vposer", _f), ("w_contact", _f),
                 ("w_collision", _f), ("robust_c", _f), ("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("nn_mode", _i),
-                ("loop_mode", _i), ("loop_unroll", _i), ("loss_mode", _i)]
+                ("loop_mode", _i), ("loop_unroll", _i), ("loss_mode", _i), ("optimizer", _i), ("lbfgs_lr", _f),
+                ("lbfgs_tolerance_grad", _f), ("lbfgs_tolerance_change", _f), ("lbfgs_history", _i), ("lbfgs_zoom_max", _i)]
 
 
 # psi_fit_trace selectors (PSI_FIT_TRACE_* in include/psi_b200.h): name -> (code, is_int)
 FIT_TRACE = {"x_eval": (0, False), "grad_x": (1, False), "verts": (2, False), "sdf": (3, False), "sdf_grad": (4, False),
              "nn_dist": (5, False), "nn_idx": (6, True), "query_ids": (7, True), "losses": (8, False), "x": (9, False),
-             "adam_m": (10, False), "adam_v": (11, False), "pose6d": (12, False)}
+             "adam_m": (10, False), "adam_v": (11, False), "pose6d": (12, False), "lbfgs_state": (13, True),
+             "lbfgs_best": (14, False)}
 
 
 class PsiError(RuntimeError):

@@ -360,6 +360,7 @@ size_t psi_nn_workspace_bytes(int B, int n, int m) {
 int psi_nn_fwd(const float *q, long q_bstride, int B, int n, const float *s, long s_bstride,
                int m, float *dist, int *idx, void *workspace, size_t workspace_bytes,
                psi_stream_t stream) {
+    psi::Range nvtx_range("psi_nn_fwd");
     return psi::nn_fwd_launch(q, q_bstride, B, n, s, s_bstride, m, dist, idx, workspace,
                               workspace_bytes, (cudaStream_t)stream);
 }
@@ -367,6 +368,7 @@ int psi_nn_fwd(const float *q, long q_bstride, int B, int n, const float *s, lon
 int psi_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int n, int m, float *dist1,
                     float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
                     psi_stream_t stream) {
+    psi::Range nvtx_range("psi_chamfer_fwd");
     int rc = psi::nn_fwd_launch(xyz1, (long)n * 3, B, n, xyz2, (long)m * 3, m, dist1, idx1,
                                 workspace, workspace_bytes, (cudaStream_t)stream);
     if (rc != PSI_OK) return rc;
@@ -378,6 +380,7 @@ int psi_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int n, int m, f
 
 int psi_nn_bwd(const float *q, long q_bstride, int B, int n, const float *s, long s_bstride,
                int m, const float *graddist, const int *idx, float *grad_q, psi_stream_t stream) {
+    psi::Range nvtx_range("psi_nn_bwd");
     if (B < 0 || n < 0 || m < 0) return PSI_ERR_BAD_ARG;
     if (B == 0 || n == 0) return PSI_OK;
     if (!q || !s || !graddist || !idx || !grad_q || m == 0) return PSI_ERR_BAD_ARG;
@@ -391,6 +394,7 @@ int psi_nn_bwd(const float *q, long q_bstride, int B, int n, const float *s, lon
 int psi_chamfer_bwd(const float *xyz1, const float *xyz2, int B, int n, int m,
                     const float *graddist1, const float *graddist2, const int *idx1,
                     const int *idx2, float *gradxyz1, float *gradxyz2, psi_stream_t stream) {
+    psi::Range nvtx_range("psi_chamfer_bwd");
     if (B < 0 || n < 0 || m < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!xyz1 || !xyz2 || !gradxyz1 || !gradxyz2) return PSI_ERR_BAD_ARG;

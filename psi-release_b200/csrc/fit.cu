@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "rot6d.cuh"
 #include "fit_fuse.cuh"
+#include "fit_lbfgs.cuh"
 #include <math.h>
 #include <new>
 #include <vector>
@@ -49,6 +50,9 @@ struct psi_fit_ctx {
         *g6_root, *g6A, *dh2A, *dh1A, *dz, *verts, *saved, *sdfv, *sdfg, *partial, *nnd, *cpart,
         *gshape, *gpose, *gtransl, *lbs_ws, *losses, *gx, *xeval;
     int *nni, *step, *nnhint;
+    psi::LbfgsState lb;            // optimizer 1: per-body L-BFGS state
+    psi::LbfgsParams lbp;
+    int *lb_info;                  // trace staging [B,4]
     int *neg_cnt;                  // loss_mode 1: batch-wide count of penetrating vertices, [2] by iteration parity
     int *loop_left;                // iterations the WHILE node still has to run
     size_t lbs_ws_bytes;
@@ -89,6 +93,7 @@ namespace psi {
 //   then, for the (updated) x: the latent z as the decoder's first A operand, the root's 6D vector,
 //            betas, translation, hand PCA + pose_mean (smplx) for the LBS kernels.
 // psi_fit_begin launches it once with do_post = 0.
+template <int OPT>      // 0 = Adam, 1 = per-body L-BFGS (fit_lbfgs.cuh)
 __global__ void __launch_bounds__(128)
 fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchunk, int num_contact,
                 const float *__restrict__ x0, float *__restrict__ x, float *__restrict__ am,
@@ -100,9 +105,11 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
                 const float *__restrict__ cpart, float *__restrict__ losses, float *__restrict__ zA,
                 float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
                 float *__restrict__ transl, float *__restrict__ gx_out, float *__restrict__ xeval_out,
-                int *__restrict__ neg_cnt, int *__restrict__ loop_left, cudaGraphConditionalHandle loop_cond) {
+                int *__restrict__ neg_cnt, int *__restrict__ loop_left, cudaGraphConditionalHandle loop_cond,
+                const LbfgsParams lbp, const LbfgsState lbs) {
     pdl_wait();
     __shared__ float sx[96], g[96];
+    __shared__ float s_loss;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int Lz = d.latent;
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;   // 75
@@ -151,18 +158,31 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
             losses[(size_t)b * 4 + 1] = cfg.w_vposer * (zz / ((float)Lz * bdiv));
             losses[(size_t)b * 4 + 2] = cfg.w_contact * (cs / ((float)num_contact * bdiv));
             losses[(size_t)b * 4 + 3] = cfg.w_collision * (cn > 0.f ? sn / cn : 0.f);
+            s_loss = ((cfg.w_rec * (r / ((float)xdim * bdiv)) + cfg.w_vposer * (zz / ((float)Lz * bdiv))) +
+                      cfg.w_contact * (cs / ((float)num_contact * bdiv))) + cfg.w_collision * (cn > 0.f ? sn / cn : 0.f);
             }
         }
         __syncthreads();
         const int t = t_prev + 1;
         float xn = 0.f;
+        float ge = 0.f;
         if (tid < xdim) {
             const float xe = sx[tid], diff = xe - x0e;
             const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-            const float ge = g[tid] + cfg.w_rec * sgn / ((float)xdim * bdiv);
+            ge = g[tid] + cfg.w_rec * sgn / ((float)xdim * bdiv);
             const size_t o = (size_t)b * xdim + tid;
             gx_out[o] = ge;          // trace: dL/dx of the iteration just evaluated, and where it was evaluated
             xeval_out[o] = xe;
+        }
+        if (OPT == 1) {
+            // L-BFGS: one warp advances this body's line search / direction by one evaluation
+            __syncthreads();                       // every thread has read g[tid]
+            if (tid < xdim) g[tid] = ge;
+            __syncthreads();
+            if (tid < 32) lbfgs_feed_body(lbp, lbs, b, xdim, (double)s_loss, g, sx, x, tid);
+        } else if (tid < xdim) {
+            const float xe = sx[tid];
+            const size_t o = (size_t)b * xdim + tid;
             const float m = cfg.beta1 * ame + (1.0f - cfg.beta1) * ge;
             const float v = cfg.beta2 * ave + (1.0f - cfg.beta2) * ge * ge;
             am[o] = m;
@@ -175,7 +195,7 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
             x[o] = xn;
         }
         __syncthreads();           // everyone has read sx / step[b]
-        if (tid < xdim) sx[tid] = xn;
+        if (OPT == 0 && tid < xdim) sx[tid] = xn;
         if (tid == 0) step[b] = t;
         if (b == 0 && tid == 0) {
             // the next iteration's penetration counter (its parity is t & 1; nobody reads it during this kernel)
@@ -216,6 +236,23 @@ __global__ void fit_reset_kernel(float *am, float *av, int *step, long n, int B,
     if (i < 2) neg_cnt[i] = 0;
 }
 
+__global__ void fit_lbfgs_reset_kernel(LbfgsScalars *sc, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        LbfgsScalars z = {};
+        z.phase = LB_START;
+        z.H = 1.0;
+        sc[i] = z;
+    }
+}
+__global__ void fit_lbfgs_info_kernel(const LbfgsScalars *sc, int B, int *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        out[i * 4 + 0] = sc[i].phase; out[i * 4 + 1] = sc[i].n_iter;
+        out[i * 4 + 2] = sc[i].evals; out[i * 4 + 3] = sc[i].hist_count;
+    }
+}
+
 // head of the loop graph: arm the WHILE node with the iteration count psi_fit_begin stored
 __global__ void fit_loop_head_kernel(cudaGraphConditionalHandle cond, const int *loop_left) {
     cudaGraphSetConditional(cond, *loop_left > 0 ? 1u : 0u);
@@ -242,11 +279,17 @@ static int launch_linear(cudaStream_t st, int B, const float *A, const float *W,
 
 static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
     const FitDims d = {c->B, c->V, c->J, c->NB, c->latent, c->hidden, c->nbody, c->ncomp, c->num_rot};
-    (psi::skip_kernel("fit_step") ? cudaSuccess : launch_pdl(fit_step_kernel, dim3(c->B), dim3(128), 0, st, d, c->cfg, do_post, c->np_sdf, c->nchunk, c->num_contact,
-               c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->dz, c->g6_root, c->gpose,
-               c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl,
-               c->gx, c->xeval, c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr,
-               c->capturing_loop ? c->loop_left : nullptr, c->loop_cond));
+    auto go = [&](auto kernel) {
+        return launch_pdl(kernel, dim3(c->B), dim3(128), 0, st, d, c->cfg, do_post, c->np_sdf, c->nchunk, c->num_contact,
+                          c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->dz, c->g6_root, c->gpose,
+                          c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl,
+                          c->gx, c->xeval, c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr,
+                          c->capturing_loop ? c->loop_left : nullptr, c->loop_cond, c->lbp, c->lb);
+    };
+    if (!psi::skip_kernel("fit_step")) {
+        if (c->cfg.optimizer == 1) go(fit_step_kernel<1>);
+        else go(fit_step_kernel<0>);
+    }
     PSI_LAUNCHED_K("fit_step");
     return PSI_OK;
 }
@@ -327,14 +370,16 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
                    const float *h_hand_r, const float *h_pose_mean, int ncomp,
                    const int *h_contact_ids, int num_contact, const psi_fit_config *cfg,
                    psi_stream_t stream) {
+    psi::Range nvtx_range("psi_fit_create");
     using namespace psi;
     if (!out || !model || !index || !scene_points || !sdf || !h_grid_min || !h_grid_max || !h_W1 || !h_b1 ||
         !h_W2 || !h_b2 || !h_W3 || !h_b3 || !h_hand_l || !h_hand_r || !h_pose_mean || !h_contact_ids || !cfg)
         return PSI_ERR_BAD_ARG;
     if (cfg->B < 1 || num_contact < 1 || D < 1 || V < 1) return PSI_ERR_BAD_ARG;
     if (cfg->loss_mode < 0 || cfg->loss_mode > 1 || cfg->loop_mode < 0 || cfg->loop_mode > 1 || cfg->loop_unroll < 0 ||
-        cfg->loop_unroll > 64)
+        cfg->loop_unroll > 64 || cfg->optimizer < 0 || cfg->optimizer > 1 || cfg->lbfgs_history < 0 || cfg->lbfgs_history > 1024)
         return PSI_ERR_BAD_ARG;
+    if (cfg->optimizer == 1 && cfg->loss_mode != 0) return PSI_ERR_UNSUPPORTED;   // per-body line searches need a per-body loss
     if (hidden != 512 || latent != 32 || nbody * 6 > 128 || nbody + 1 > J || ncomp > 16 ||
         J < 31 || NB < 10 || hidden % 32)
         return PSI_ERR_UNSUPPORTED;
@@ -444,6 +489,28 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->gtransl = fbuf(B * 3); c->losses = zbuf(B * 4);
     c->gx = zbuf(B * xd); c->xeval = zbuf(B * xd);
     c->step = (int *)dev_alloc(B * sizeof(int));
+    c->lb = psi::LbfgsState();
+    c->lbp = psi::LbfgsParams();
+    c->lb_info = nullptr;
+    if (cfg->optimizer == 1) {
+        const int hist = cfg->lbfgs_history > 0 ? cfg->lbfgs_history : 100;
+        c->lbp.lr = cfg->lbfgs_lr > 0.f ? (double)cfg->lbfgs_lr : 1.0;
+        c->lbp.tol_grad = cfg->lbfgs_tolerance_grad > 0.f ? (double)cfg->lbfgs_tolerance_grad : 1e-5;
+        c->lbp.tol_change = cfg->lbfgs_tolerance_change > 0.f ? (double)cfg->lbfgs_tolerance_change : 1e-9;
+        c->lbp.c1 = 1e-4; c->lbp.c2 = 0.9;                      // lbfgs_ls.py:54
+        c->lbp.history = hist;
+        c->lbp.max_iter = 1 << 30;                              // the budget is counted in closure evaluations (num_iter)
+        c->lbp.max_ls = 25;
+        c->lbp.zoom_max_iter = cfg->lbfgs_zoom_max > 0 ? cfg->lbfgs_zoom_max : 300;
+        c->lbp.reset_lr = 0;
+        c->lb.sc = (psi::LbfgsScalars *)dev_alloc(B * sizeof(psi::LbfgsScalars));
+        c->lb.x_init = zbuf(B * psi::kLbStride); c->lb.d = zbuf(B * psi::kLbStride); c->lb.g0 = zbuf(B * psi::kLbStride);
+        c->lb.g_prev = zbuf(B * psi::kLbStride); c->lb.bg = zbuf(B * 2 * psi::kLbStride);
+        c->lb.Y = zbuf(B * hist * psi::kLbStride); c->lb.S = zbuf(B * hist * psi::kLbStride);
+        c->lb.ro = (double *)dev_alloc(B * 2 * hist * sizeof(double));
+        c->lb.xbest = zbuf(B * xd);
+        c->lb_info = (int *)dev_alloc(B * 4 * sizeof(int));
+    }
     c->neg_cnt = (int *)dev_alloc(2 * sizeof(int));
     c->loop_left = (int *)dev_alloc(sizeof(int));
     c->lbs_ws_bytes = psi_lbs_bwd_workspace_bytes(model, c->B) + 64;
@@ -514,6 +581,24 @@ static int build_loop_graph(psi_fit_ctx *c) {
     return e == cudaSuccess ? PSI_OK : (int)e;
 }
 
+// the loop's starting state on stream `st`: x = xhr_init, no NN hints, optimiser state cleared
+static int reset_state(psi_fit_ctx *c, const float *xhr_init, cudaStream_t st) {
+    using namespace psi;
+    const size_t xd = 9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp, n = (size_t)c->B * xd;
+    cudaError_t e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->nnhint, 0xff, (size_t)c->B * c->nu * sizeof(int), st);   // -1: no hint yet
+    if (e != cudaSuccess) return (int)e;
+    fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt);
+    PSI_LAUNCHED();
+    if (c->cfg.optimizer == 1) {
+        e = cudaMemcpyAsync(c->lb.xbest, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+        fit_lbfgs_reset_kernel<<<(unsigned)((c->B + 127) / 128), 128, 0, st>>>(c->lb.sc, c->B);
+        PSI_LAUNCHED();
+    }
+    return PSI_OK;
+}
+
 int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int num_iter,
                   psi_stream_t stream) {
     using namespace psi;
@@ -522,14 +607,10 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t xd = 9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp, n = (size_t)c->B * xd;
     cudaError_t e = cudaMemcpyAsync(c->x0, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(c->nnhint, 0xff, (size_t)c->B * c->nu * sizeof(int), st);   // -1: no hint yet
-    if (e != cudaSuccess) return (int)e;
+    if (const int rrc = reset_state(c, xhr_init, st)) return rrc;
     // one [3x4] transform per body (stride 0 broadcasts a shared one)
     fit_cam_kernel<<<(unsigned)((c->B * 12 + 255) / 256), 256, 0, st>>>(cam, cam_bstride, c->B, c->cam);
-    PSI_LAUNCHED();
-    fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt);
     PSI_LAUNCHED();
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
@@ -547,12 +628,7 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
             if (rc == PSI_OK && whole) rc = build_loop_graph(c);
             if (rc == PSI_OK && !c->exec && (!whole || c->unroll > 1)) rc = build_iteration_graph(c);
             if (rc) return rc;
-            e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, gs);
-            if (e != cudaSuccess) return (int)e;
-            e = cudaMemsetAsync(c->nnhint, 0xff, (size_t)c->B * c->nu * sizeof(int), gs);
-            if (e != cudaSuccess) return (int)e;
-            fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gs>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt);
-            PSI_LAUNCHED();
+            if (const int rrc = reset_state(c, xhr_init, gs)) return rrc;
         }
         const int rc = launch_step(c, 0, gs);
         if (rc) return rc;
@@ -588,6 +664,7 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
 }
 
 int psi_fit_end(psi_fit_ctx *c, float *xhr_out, float *losses_out, psi_stream_t stream) {
+    psi::Range nvtx_range("psi_fit_end");
     if (!c || !xhr_out) return PSI_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
@@ -597,7 +674,8 @@ int psi_fit_end(psi_fit_ctx *c, float *xhr_out, float *losses_out, psi_stream_t 
         c->pending_join = 0;
     }
     const size_t n = (size_t)c->B * (9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp);
-    e = cudaMemcpyAsync(xhr_out, c->x, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    // Adam: the vector after the last step.  L-BFGS: the last accepted point (c->x is a trial point of a line search)
+    e = cudaMemcpyAsync(xhr_out, c->cfg.optimizer == 1 ? c->lb.xbest : c->x, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess && losses_out)
         e = cudaMemcpyAsync(losses_out, c->losses, (size_t)c->B * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
     return e == cudaSuccess ? PSI_OK : (int)e;
@@ -630,6 +708,8 @@ static const void *trace_buffer(const psi_fit_ctx *c, int what, size_t *bytes) {
         case PSI_FIT_TRACE_ADAM_M: *bytes = B * xd * f; return c->am;
         case PSI_FIT_TRACE_ADAM_V: *bytes = B * xd * f; return c->av;
         case PSI_FIT_TRACE_POSE6D: *bytes = B * c->num_rot * 6 * f; return c->rot6d;
+        case PSI_FIT_TRACE_LBFGS_STATE: *bytes = c->cfg.optimizer == 1 ? B * 4 * sizeof(int) : 0; return c->lb_info;
+        case PSI_FIT_TRACE_LBFGS_BEST: *bytes = c->cfg.optimizer == 1 ? B * xd * f : 0; return c->lb.xbest;
         default: *bytes = 0; return nullptr;
     }
 }
@@ -644,12 +724,16 @@ int psi_fit_trace(psi_fit_ctx *c, int what, void *dst, size_t dst_bytes, psi_str
     if (!c || !dst) return PSI_ERR_BAD_ARG;
     size_t bytes = 0;
     const void *src = trace_buffer(c, what, &bytes);
-    if (!src) return PSI_ERR_BAD_ARG;
+    if (!src || bytes == 0) return PSI_ERR_BAD_ARG;
     if (dst_bytes < bytes) return PSI_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (c->ev_out_recorded) {   // the loop ran (or still runs) on the context's own stream
         const cudaError_t e = cudaStreamWaitEvent(st, c->ev_out, 0);
         if (e != cudaSuccess) return (int)e;
+    }
+    if (what == PSI_FIT_TRACE_LBFGS_STATE) {
+        psi::fit_lbfgs_info_kernel<<<(unsigned)((c->B + 127) / 128), 128, 0, st>>>(c->lb.sc, c->B, c->lb_info);
+        PSI_LAUNCHED();
     }
     const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
     return e == cudaSuccess ? PSI_OK : (int)e;
@@ -657,6 +741,7 @@ int psi_fit_trace(psi_fit_ctx *c, int what, void *dst, size_t dst_bytes, psi_str
 
 int psi_fit_profile(psi_fit_ctx *c, const float *xhr_init, const float *cam, long cam_bstride, int warm_iters,
                     int timed_iters, float *h_ms, const char **h_names, int max_launches, psi_stream_t stream) {
+    psi::Range nvtx_range("psi_fit_profile");
     using namespace psi;
     if (!c || !xhr_init || !cam || !h_ms || !h_names || warm_iters < 0 || timed_iters < 1 || max_launches < 1)
         return PSI_ERR_BAD_ARG;

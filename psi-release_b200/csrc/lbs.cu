@@ -1318,6 +1318,7 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
                          const float *h_shapedirs, const float *h_posedirs,
                          const float *h_J_regressor, const float *h_weights, const int *h_parents,
                          psi_stream_t stream) {
+    psi::Range nvtx_range("psi_lbs_model_create");
     using namespace psi;
     if (!out || V < 1 || J < 1 || NB < 0 || !h_v_template || !h_shapedirs || !h_posedirs ||
         !h_J_regressor || !h_weights || !h_parents)
@@ -1515,6 +1516,7 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
                  const float *transl, const float *cam, long cam_bstride, const float *rot_in,
                  const float *rot6d, int num_rot, float *verts, float *joints, float *saved,
                  const SdfFuse *sdf, cudaStream_t st) {
+    psi::Range nvtx_range("psi_lbs_fwd");
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!betas || !pose || !verts || !saved) return PSI_ERR_BAD_ARG;
@@ -1593,6 +1595,7 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
                  float *grad_betas, float *grad_pose, float *grad_transl, float *grad_rot, int num_rot,
                  const float *rot6d, float *g6_root, float *g6A, int g6_kpad, void *workspace,
                  size_t workspace_bytes, cudaStream_t st) {
+    psi::Range nvtx_range("psi_lbs_bwd");
     if (!m || B < 0) return PSI_ERR_BAD_ARG;
     if (B == 0) return PSI_OK;
     if (!pose || !saved || (!grad_verts && !vg) || !grad_betas || !grad_pose || !workspace) return PSI_ERR_BAD_ARG;

@@ -676,6 +676,7 @@ void psi_nn_index_destroy(psi_nn_index *ix) {
 }
 
 int psi_nn_index_create(psi_nn_index **out, const float *h_points, int m, psi_stream_t stream) {
+    psi::Range nvtx_range("psi_nn_index_create");
     using namespace psi;
     if (!out || !h_points || m < 1) return PSI_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -786,6 +787,7 @@ __attribute__((visibility("default"))) int psi_debug_nn_stats(unsigned long long
 static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bstride, int B, int n,
                                const int *qsel, float *dist, int *idx, int *hint, int mode,
                                psi_stream_t stream) {
+    psi::Range nvtx_range("psi_nn_index_query");
     using namespace psi;
     if (!ix || B < 0 || n < 0) return PSI_ERR_BAD_ARG;
     if (B == 0 || n == 0) return PSI_OK;

@@ -106,6 +106,7 @@ int psi_sdf_num_partials(int V) { return V <= 0 ? 0 : (V + psi::kSdfChunk - 1) /
 int psi_sdf_fwd(const float *sdf, int S, int D, const float *h_grid_min, const float *h_grid_max,
                 const float *verts, int B, int V, const int *body_scene, float *out, float *grad,
                 float *partial, psi_stream_t stream) {
+    psi::Range nvtx_range("psi_sdf_fwd");
     if (B < 0 || V < 0 || D < 1 || S < 1) return PSI_ERR_BAD_ARG;
     if (S > psi::kMaxScenes) return PSI_ERR_UNSUPPORTED;
     if (B == 0 || V == 0) return PSI_OK;

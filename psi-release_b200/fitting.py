@@ -114,10 +114,10 @@ class FittingOP:
         self.optimizer = _Adam(self.xhr_rec, lr=self.init_lr_h)
         # 'adam': the fitting scripts' optimiser (fitting_habitat.py:76).  'lbfgs': the second mode of
         # SURVEY.md T7 / 8(d) -- L-BFGS, history 100, strong-Wolfe line search as
-        # human_body_prior/optimizers/lbfgs_ls.py:214-222 (the same algorithm as torch.optim.LBFGS, of
-        # which that file is a copy), driven through the closure; num_iter = max_iter, the number of
-        # closure evaluations is reported in self.closure_evals.  It couples the bodies of a batch
-        # through the shared curvature history, so it runs on the autograd engine only.
+        # human_body_prior/optimizers/lbfgs_ls.py:214-222.  Fused engine: one independent optimiser per body inside
+        # libpsi_b200 (csrc/fit_lbfgs.cuh), num_iter = closure evaluations.  Autograd engine: torch.optim.LBFGS
+        # (the merged form of the same PR) over the whole batch through the closure, num_iter = max_iter, closure
+        # evaluations reported in self.closure_evals -- it couples the bodies through one curvature history.
         self.opt_name = getattr(self, "optimizer_name", "adam")
         if self.opt_name not in ("adam", "lbfgs"):
             raise ValueError("fittingconfig['optimizer_name'] must be 'adam' or 'lbfgs'")
@@ -149,10 +149,12 @@ class FittingOP:
         # 'autograd': torch autograd over the psi ops (any loss_mode, any nn mode)
         if self.loss_mode not in ("independent", "batch"):
             raise ValueError("fittingconfig['loss_mode'] must be 'independent' or 'batch'")
-        self.engine = getattr(self, "engine", "fused" if (self.nn_mode == "index" and self.opt_name == "adam")
-                              else "autograd")
-        if self.opt_name == "lbfgs" and self.engine == "fused":
-            raise ValueError("optimizer_name='lbfgs' runs on engine='autograd'")
+        # fused: Adam in either loss mode, or the per-body L-BFGS (independent losses: every body runs its own
+        # line search); the batch-coupled L-BFGS of torch.optim (one history for the whole batch) stays on autograd
+        self.engine = getattr(self, "engine", "fused" if (self.nn_mode == "index" and (
+            self.opt_name == "adam" or self.loss_mode == "independent")) else "autograd")
+        if self.opt_name == "lbfgs" and self.engine == "fused" and self.loss_mode != "independent":
+            raise ValueError("optimizer_name='lbfgs' with loss_mode='batch' runs on engine='autograd'")
         if self.engine not in ("fused", "autograd"):
             raise ValueError("fittingconfig['engine'] must be 'fused' or 'autograd'")
         self._fused = None
@@ -166,7 +168,11 @@ class FittingOP:
                                    self.s_index, self.scene_sdf, self.vposer, self.contact_ids.cpu().numpy(),
                                    lossw, self.robust_c, self.init_lr_h, use_graph=self.use_cuda_graph,
                                    num_streams=getattr(self, "num_streams", None), loss_mode=self.loss_mode,
-                                   loop_mode=getattr(self, "loop_mode", None))
+                                   loop_mode=getattr(self, "loop_mode", None), optimizer=self.opt_name,
+                                   lbfgs=dict(lr=float(getattr(self, "lbfgs_lr", 1.0)),
+                                              tolerance_grad=float(getattr(self, "tolerance_grad", 1e-5)),
+                                              tolerance_change=float(getattr(self, "tolerance_change", 1e-9)),
+                                              history_size=int(getattr(self, "history_size", 100))))
         self._graph = None
         self._static_xhr = None
         self._static_cam = None

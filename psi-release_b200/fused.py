@@ -69,7 +69,8 @@ class FusedFit:
     """Owns psi_fit_ctx objects bound to (body model handle, scene index, scene SDF, VPoser decoder)."""
 
     def __init__(self, batch_size, model_handle, body_model, scene_index, scene_sdf, vposer, contact_ids,
-                 weights, robust_c, lr, use_graph=True, num_streams=None, loss_mode="independent", loop_mode=None):
+                 weights, robust_c, lr, use_graph=True, num_streams=None, loss_mode="independent", loop_mode=None,
+                 optimizer="adam", lbfgs=None):
         if scene_sdf.num_scenes != 1:
             raise ValueError("the fused loop fits one scene per context")
         self.device = model_handle.device
@@ -100,6 +101,13 @@ class FusedFit:
         if loop_mode not in ("whole", "replay"):
             raise ValueError("loop_mode must be 'whole' or 'replay'")
         self.loss_mode, self.loop_mode = loss_mode, loop_mode
+        if optimizer not in ("adam", "lbfgs"):
+            raise ValueError("optimizer must be 'adam' or 'lbfgs'")
+        if optimizer == "lbfgs" and loss_mode != "independent":
+            raise ValueError("the per-body L-BFGS needs loss_mode='independent'")
+        self.optimizer = optimizer
+        lb = dict(lr=1.0, tolerance_grad=1e-5, tolerance_change=1e-9, history_size=100, zoom_max=300)   # lbfgs_ls.py:214-222
+        lb.update(lbfgs or {})
         base, rem = divmod(self.B, num_streams)
         self.parts = []                  # (start, size, handle)
         self.xdim = 19 + W1.shape[1] + 2 * hl.shape[0]
@@ -114,7 +122,10 @@ class FusedFit:
                                  nn_mode=int(os.environ.get("PSI_FIT_NN_MODE", "0")),
                                  loop_mode=0 if loop_mode == "whole" else 1,
                                  loop_unroll=int(os.environ.get("PSI_FIT_UNROLL", "0")),
-                                 loss_mode=1 if loss_mode == "batch" else 0)
+                                 loss_mode=1 if loss_mode == "batch" else 0, optimizer=1 if optimizer == "lbfgs" else 0,
+                                 lbfgs_lr=float(lb["lr"]), lbfgs_tolerance_grad=float(lb["tolerance_grad"]),
+                                 lbfgs_tolerance_change=float(lb["tolerance_change"]), lbfgs_history=int(lb["history_size"]),
+                                 lbfgs_zoom_max=int(lb["zoom_max"]))
             h = ctypes.c_void_p()
             with torch.cuda.device(self.device):
                 rc = _lib.lib().psi_fit_create(

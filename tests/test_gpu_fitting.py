@@ -225,7 +225,7 @@ def test_lbfgs_mode_decreases_the_loss_and_counts_closures(small_model):
     from psi_release_b200.geometry import GeometryTransformer
     scene, xh, cid, cfg = _world(small_model, 2)
     cam = torch.tensor(scene.cam_ext).unsqueeze(0).cuda()
-    op = FittingOP(dict(cfg, optimizer_name="lbfgs", num_iter=12), W)
+    op = FittingOP(dict(cfg, optimizer_name="lbfgs", engine="autograd", num_iter=12), W)
     assert op.engine == "autograd"
     x0 = torch.tensor(xh).cuda()
     xhr0 = GeometryTransformer.convert_to_6D_rot(x0)
@@ -238,7 +238,8 @@ def test_lbfgs_mode_decreases_the_loss_and_counts_closures(small_model):
     assert 1 <= op.closure_evals <= 12 * 5 // 4 + 1
     assert after < before
     with pytest.raises(ValueError):
-        FittingOP(dict(cfg, optimizer_name="lbfgs", engine="fused"), W)
+        FittingOP(dict(cfg, optimizer_name="lbfgs", engine="fused", loss_mode="batch"), W)   # per-body line searches need per-body losses
+    assert FittingOP(dict(cfg, optimizer_name="lbfgs"), W).engine == "fused"
 
 
 def test_rooms_pipeline_generate_fit_score_write(small_model, tmp_path):

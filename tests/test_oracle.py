@@ -118,3 +118,41 @@ def test_rotation_chain_roundtrip():
     x = torch.cat([torch.zeros(64, 3), aa, torch.zeros(64, 66)], dim=1)
     back = oracle.convert_to_3D_rot(oracle.convert_to_6D_rot(x))
     np.testing.assert_allclose(back.numpy(), x.numpy(), atol=2e-5)
+
+
+def test_lbfgs_machine_reproduces_torch_optim_lbfgs_step_for_step():
+    """oracle/lbfgs.py restates human_body_prior/optimizers/lbfgs_ls.py (a copy of pytorch PR #8824) as a state
+    machine fed one closure evaluation at a time.  torch.optim.LBFGS(line_search_fn='strong_wolfe') is the merged
+    form of that PR: with reset_lr=True and the zoom bound at torch's max_ls the two must evaluate the SAME points,
+    on the Rosenbrock function the reference file defines (lbfgs_ls.py:15-18)."""
+    from oracle import lbfgs
+
+    def rosen(x):
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        f = (100 * (xt[1:] - xt[:-1] ** 2) ** 2 + (1 - xt[:-1]) ** 2).sum()
+        f.backward()
+        return float(f), xt.grad.numpy().copy()
+    x0 = np.array([-1.2, 1.0, 0.3, -0.7, 1.5])
+    for budget in (1, 3, 8, 21, 60):
+        p = torch.tensor(x0.copy(), requires_grad=True)
+        opt = torch.optim.LBFGS([p], lr=1.0, max_iter=25, max_eval=budget, tolerance_grad=0, tolerance_change=1e-300,
+                                history_size=100, line_search_fn="strong_wolfe")
+        pts = []
+
+        def closure():
+            opt.zero_grad()
+            f = (100 * (p[1:] - p[:-1] ** 2) ** 2 + (1 - p[:-1]) ** 2).sum()
+            f.backward()
+            pts.append(p.detach().numpy().copy())
+            return f
+        opt.step(closure)
+        m = lbfgs.LBFGSMachine(lr=1.0, history_size=100, tolerance_grad=0, tolerance_change=1e-300, max_iter=25,
+                               zoom_max_iter=25, reset_lr=True)
+        x = m.start(x0)
+        for ref_pt in pts:
+            np.testing.assert_allclose(x, ref_pt, rtol=0, atol=1e-9)       # the same point is evaluated ...
+            x = m.feed(*rosen(x))
+        np.testing.assert_allclose(m.best() if m.phase != lbfgs.DONE else m.x_init, p.detach().numpy(), atol=1e-9)   # ... and accepted
+    # a history shorter than the run exercises the ring (oldest pair dropped, lbfgs_ls.py:344-347)
+    xb, m = lbfgs.minimize(rosen, x0, 120, lr=1.0, history_size=3, tolerance_grad=0, tolerance_change=1e-300)
+    assert rosen(xb)[0] < 1e-6 and len(m.Y) == 3
