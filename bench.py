@@ -216,9 +216,10 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
         "fit_step": B * 75 * 32,
     }
     agg = {}
-    gemm_path = "tcgen05 kind::tf32, 3xTF32" if any(n.endswith("_tc5") for n, _ in prof) else "mma.sync 3xTF32"
+    gemm_path = ("tcgen05 kind::f16, bf16x3" if any(n.endswith("_bf3") for n, _ in prof) else
+                 "tcgen05 kind::tf32, 3xTF32" if any(n.endswith("_tc5") for n, _ in prof) else "mma.sync 3xTF32")
     for name, ms in prof:
-        name = name[:-4] if name.endswith("_tc5") else name
+        name = name[:-4] if name.endswith(("_tc5", "_bf3")) else name
         a = agg.setdefault(name, [0.0, 0])
         a[0] += ms
         a[1] += 1

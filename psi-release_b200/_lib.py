@@ -39,7 +39,8 @@ class PsiError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "lib", "libpsi_b200.so")
+    """lib/libpsi_b200.so; PSI_B200_LIB names another build of the same sources (A/B runs of compile-time variants)."""
+    return os.environ.get("PSI_B200_LIB") or os.path.join(_HERE, "lib", "libpsi_b200.so")
 
 
 def lib():

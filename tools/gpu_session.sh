@@ -24,6 +24,9 @@ for stage in "$@"; do
        timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG $EXTRA > "$OUT/$stage.n$NG.json" 2> "$OUT/$stage.n$NG.err"; grep '^{' "$OUT/$stage.n$NG.json" | tail -1 | cut -c1-1500; grep -i "nranks\|error\|Traceback" "$OUT/$stage.n$NG.err" | head -5 ;;
     bench_pdl) PSI_PDL=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_pdl.json" 2> "$OUT/bench_pdl.err"; python tools/bench_brief.py "$OUT/bench_pdl.json" | head -1 ;;
     bench_lbfgs) timeout 600 python bench.py --optimizer lbfgs --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_lbfgs.json" 2> "$OUT/bench_lbfgs.err"; python tools/bench_brief.py "$OUT/bench_lbfgs.json" | head -12; tail -3 "$OUT/bench_lbfgs.err" ;;
+    benchlib_*) V=${stage#benchlib_}; PSI_B200_LIB=$PWD/psi-release_b200/lib/variants/libpsi_b200_$V.so timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/$stage.json" 2> "$OUT/$stage.err"; python tools/bench_brief.py "$OUT/$stage.json" | head -12; tail -2 "$OUT/$stage.err" ;;
+    testlib_*) V=${stage#testlib_}; PSI_B200_LIB=$PWD/psi-release_b200/lib/variants/libpsi_b200_$V.so timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "${TESTS_K:-golden or baseline_size or fused_iteration}" > "$OUT/$stage.log" 2>&1; tail -4 "$OUT/$stage.log" ;;
+    bench_bf3) PSI_LBS_GEMM=bf3 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_bf3.json" 2> "$OUT/bench_bf3.err"; python tools/bench_brief.py "$OUT/bench_bf3.json" 2>/dev/null | head -12; tail -3 "$OUT/bench_bf3.err" ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; tail -c 600 "$OUT/bench_ref.json" ;;
     launches) PSI_FIT_LOOP=replay timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 90 --csv --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 3 --iters 30 --no-cpu-baseline --no-reference-gpu > "$OUT/launches.log" 2>&1; python tools/ncu_summary.py launches "$OUT/launches.csv" | tail -30 ;;
     ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNELS:-nn_index_group|lbs_vertex_bwd|lbs_skin_fwd|lbs_blend_fwd_tc5|lbs_dcoef_tc5}" -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-10} -o "$OUT/prof" python bench.py --steps 1 --warmup 3 --iters 30 --no-cpu-baseline --no-reference-gpu > "$OUT/ncu_full.log" 2>&1; ls -la "$OUT" ;;
