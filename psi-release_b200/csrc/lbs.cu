@@ -37,7 +37,7 @@
 #include <vector>
 
 #ifndef PSI_LBS_GEMM_DEFAULT
-#define PSI_LBS_GEMM_DEFAULT kGemmTc5
+#define PSI_LBS_GEMM_DEFAULT kGemmBf3
 #endif
 
 namespace psi {
@@ -1202,9 +1202,15 @@ __device__ __forceinline__ void t3_mainloop(unsigned char *smem, T3Bars &bars, u
         for (int c = 0; c < it.nchunks; ++c) {
             const int g = g0 + c, st = g % kT3Stages;
             mbar_wait(&bars.empty[st], (uint32_t)(((g / kT3Stages) & 1) ^ 1));
+            TC5_STAMP(0, g);                          // producer: stage free, TMA issued now
             mbar_arrive_expect_tx(&bars.full[st], (uint32_t)kT3Stage);
             unsigned char *dst = smem + (size_t)st * kT3Stage;
+#ifdef PSI_T3_NO_HINT
+            (void)pol;
+            tma_load_1d(dst, it.basis + (size_t)c * it.basis_stride, 3 * kT3TileA, &bars.full[st]);
+#else
             tma_load_1d_hint(dst, it.basis + (size_t)c * it.basis_stride, 3 * kT3TileA, &bars.full[st], pol);   // HBM stream
+#endif
             tma_load_1d(dst + 3 * kT3TileA, it.act + (size_t)c * (3 * kBG * kKC3), kT3TileB, &bars.full[st]);   // L2
         }
     } else if (tid == 160) {                            // ---- MMA issuer
@@ -1215,6 +1221,7 @@ __device__ __forceinline__ void t3_mainloop(unsigned char *smem, T3Bars &bars, u
         for (int c = 0; c < it.nchunks; ++c) {
             const int g = g0 + c, st = g % kT3Stages;
             mbar_wait(&bars.full[st], (uint32_t)((g / kT3Stages) & 1));
+            TC5_STAMP(4, g);                          // issuer: stage landed
             tc5::fence_after_sync();
             const uint32_t sb = smem_u32(smem + (size_t)st * kT3Stage);
             const uint64_t a1 = tc5::smem_desc_k_sw128(sb), a2 = tc5::smem_desc_k_sw128(sb + kT3TileA),
@@ -1226,6 +1233,7 @@ __device__ __forceinline__ void t3_mainloop(unsigned char *smem, T3Bars &bars, u
                 tc5::mma_bf16(d, a3 + 2 * k, bc + 2 * k, i64, 1u);              // a3 x [c1]
             }
             tc5::commit(&bars.empty[st]);
+            TC5_STAMP(6, g);                          // issuer: MMAs + commit issued
             if (c == it.nchunks - 1) tc5::commit(&bars.accum[acc]);
         }
     } else if (tid < 128) {

@@ -34,6 +34,10 @@ names = ["tma_issue", "wk_raw_ok", "wk_op_free", "wk_split_done", "is_op_ok", "i
 print("chunk " + " ".join("%13s" % n for n in names) + "   (ns since the first TMA issue; CTA 0, 2 tiles x 16 chunks)")
 for g in range(32):
     print("%5d " % g + " ".join("%13d" % (t[e, g] - t0) for e in range(7)))
+if os.environ.get("PSI_LBS_GEMM", "").startswith("b"):
+    print("bf16x3 path: 16 stages of 64 k (2 tiles): period", np.diff(t[6, 1:16]).mean(), "ns; TMA issue -> landed", (t[4, 1:16] - t[0, 1:16]).mean(),
+          "ns; landed -> MMAs issued", (t[6, 1:16] - t[4, 1:16]).mean(), "ns")
+    sys.exit(0)
 d = lambda a, b: np.diff(t[a, 2:30]).mean() if a == b else (t[a, 2:30] - t[b, 2:30]).mean()
 print("mean period per chunk (ns):", d(6, 6), " raw landed after TMA issue:", d(1, 0), " split (op free -> done):", d(3, 2),
       " issuer waits for op after split done:", d(4, 3), " issue time:", d(6, 5), " worker waits for op slot after raw:", d(2, 1))
