@@ -488,6 +488,118 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
     }
 }
 
+// The fitting loop's skinning + SDF pass with TWO vertices per thread (v and v + 256 of a 512-vertex block): the
+// pass is latency bound (eight scattered grid reads per vertex behind a dependent chain v_posed -> skin -> sample),
+// so each thread first issues the loads of both vertices, skins both, puts all sixteen SDF gathers in flight and
+// only then interpolates.  Same arithmetic and the same per-256-vertex partial sums as lbs_skin_fwd_kernel<true>.
+#ifndef PSI_SKIN2_MINB
+#define PSI_SKIN2_MINB 4
+#endif
+__global__ void __launch_bounds__(256, PSI_SKIN2_MINB)
+lbs_skin_sdf2_kernel(int V, int J, const int *__restrict__ skin_j, const float *__restrict__ skin_w,
+                     const float *__restrict__ A, const float *__restrict__ vp_in,
+                     const float *__restrict__ transl, const float *__restrict__ cam, long cam_bstride,
+                     float *__restrict__ verts, const SdfFuse sf) {
+    pdl_wait();
+    const int b = blockIdx.y, tid = threadIdx.x;
+    __shared__ float4 sA[kMaxJ * 3];
+    __shared__ float red[2][2][8];
+    {
+        const float4 *__restrict__ Ag = reinterpret_cast<const float4 *>(A + (size_t)b * J * 12);
+        for (int i = tid; i < J * 3; i += blockDim.x) sA[i] = Ag[i];
+    }
+    int v[2];
+    float x[2], y[2], z[2];
+    int4 jj[2];
+    float4 ww[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        v[h] = blockIdx.x * 512 + h * 256 + tid;
+        x[h] = y[h] = z[h] = 0.f;
+        jj[h] = make_int4(0, 0, 0, 0);
+        ww[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v[h] < V) {
+            const float *vp = vp_in + ((size_t)b * V + v[h]) * 3;
+            x[h] = vp[0]; y[h] = vp[1]; z[h] = vp[2];
+            jj[h] = __ldg(reinterpret_cast<const int4 *>(skin_j) + v[h]);
+            ww[h] = __ldg(reinterpret_cast<const float4 *>(skin_w) + v[h]);
+        }
+    }
+    float tr[3] = {0.f, 0.f, 0.f}, C[12];
+    if (transl) { tr[0] = transl[(size_t)b * 3]; tr[1] = transl[(size_t)b * 3 + 1]; tr[2] = transl[(size_t)b * 3 + 2]; }
+    if (cam) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) C[e] = cam[(size_t)b * cam_bstride + e];
+    }
+    __syncthreads();
+    float o[2][3];
+    SdfCell cell[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float T[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+        auto blend = [&](float wt, float4 r0, float4 r1, float4 r2) {
+            T[0] = fmaf(wt, r0.x, T[0]); T[1] = fmaf(wt, r0.y, T[1]); T[2] = fmaf(wt, r0.z, T[2]); T[3] = fmaf(wt, r0.w, T[3]);
+            T[4] = fmaf(wt, r1.x, T[4]); T[5] = fmaf(wt, r1.y, T[5]); T[6] = fmaf(wt, r1.z, T[6]); T[7] = fmaf(wt, r1.w, T[7]);
+            T[8] = fmaf(wt, r2.x, T[8]); T[9] = fmaf(wt, r2.y, T[9]); T[10] = fmaf(wt, r2.z, T[10]); T[11] = fmaf(wt, r2.w, T[11]);
+        };
+        const float4 a0 = sA[jj[h].x * 3], a1 = sA[jj[h].x * 3 + 1], a2 = sA[jj[h].x * 3 + 2];
+        const float4 b0 = sA[jj[h].y * 3], b1 = sA[jj[h].y * 3 + 1], b2 = sA[jj[h].y * 3 + 2];
+        const float4 c0 = sA[jj[h].z * 3], c1 = sA[jj[h].z * 3 + 1], c2 = sA[jj[h].z * 3 + 2];
+        const float4 d0 = sA[jj[h].w * 3], d1 = sA[jj[h].w * 3 + 1], d2 = sA[jj[h].w * 3 + 2];
+        blend(ww[h].x, a0, a1, a2); blend(ww[h].y, b0, b1, b2); blend(ww[h].z, c0, c1, c2); blend(ww[h].w, d0, d1, d2);
+        float ox = T[0] * x[h] + T[1] * y[h] + T[2] * z[h] + T[3];
+        float oy = T[4] * x[h] + T[5] * y[h] + T[6] * z[h] + T[7];
+        float oz = T[8] * x[h] + T[9] * y[h] + T[10] * z[h] + T[11];
+        if (transl) { ox += tr[0]; oy += tr[1]; oz += tr[2]; }
+        if (cam) {
+            const float cx = C[0] * ox + C[1] * oy + C[2] * oz + C[3];
+            const float cy = C[4] * ox + C[5] * oy + C[6] * oz + C[7];
+            const float cz = C[8] * ox + C[9] * oy + C[10] * oz + C[11];
+            ox = cx; oy = cy; oz = cz;
+        }
+        o[h][0] = ox; o[h][1] = oy; o[h][2] = oz;
+        cell[h] = sdf_prepare(sf.g, ox, oy, oz);
+    }
+    float sv[2][8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if (v[h] < V) sdf_gather(sf.g, cell[h], sv[h]);          // sixteen independent gathers in flight
+    float neg_sum[2] = {0.f, 0.f}, neg_cnt[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (v[h] < V) {
+            const size_t at = (size_t)b * V + v[h];
+            verts[at * 3] = o[h][0]; verts[at * 3 + 1] = o[h][1]; verts[at * 3 + 2] = o[h][2];
+            float g3[3];
+            const float val = sdf_finish(cell[h], sv[h], g3);
+            sf.sdfv[at] = val;
+            sf.sdfg[at * 3] = g3[0]; sf.sdfg[at * 3 + 1] = g3[1]; sf.sdfg[at * 3 + 2] = g3[2];
+            if (val < 0.f) { neg_sum[h] -= val; neg_cnt[h] += 1.f; }
+        }
+    }
+    pdl_launch_dependents();
+    // per-(body, 256-vertex chunk) partial sums, fixed order (the layout lbs_vertex_bwd<FIT> and fit_step read)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float s_ = warp_sum(neg_sum[h]), c_ = warp_sum(neg_cnt[h]);
+        if ((tid & 31) == 0) { red[h][0][tid >> 5] = s_; red[h][1][tid >> 5] = c_; }
+    }
+    __syncthreads();
+    if (tid < 2) {
+        const int h = tid, np = (V + 255) / 256, chunk = blockIdx.x * 2 + h;
+        if (chunk < np) {
+            float s_ = 0.f, c_ = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s_ += red[h][0][i]; c_ += red[h][1][i]; }
+            sf.partial[((size_t)b * np + chunk) * 2 + 0] = s_;
+            sf.partial[((size_t)b * np + chunk) * 2 + 1] = c_;
+            if (sf.neg_cnt && c_ > 0.f) atomicAdd(sf.neg_cnt + (sf.step[0] & 1), (int)c_);   // integer: order-independent
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward, vertex side, one CTA per (256-vertex chunk, body):
 //   g   = dL/dverts: read from gverts, or (FIT) evaluated here from the NN / SDF results
@@ -510,7 +622,7 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
                       float *__restrict__ gvp_out, float *__restrict__ gvp_lo, int gmode, float *__restrict__ dApart,
                       const VGradFuse fg) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // the chunk's entries: stage_cap x (weight, local vertex)
-    __shared__ float s_gw[256 * 3], s_vp[256 * 3];
+    __shared__ float4 s_gw4[256], s_vp4[256];         // gw and v_posed of the chunk's vertices (xyz, pad): one 16-byte read each
     __shared__ float s_cnt, red[8], red3[24];
     __shared__ float4 s_part[kMaxUnits * 3];          // per (unit, row): partial sums of up to kUnitLen entries
     const int tid = threadIdx.x;
@@ -532,15 +644,19 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     const int b = blockIdx.y;
     float *gvp_g = gvp_out + (size_t)(b / kBG) * Npad * kBG + (size_t)(b % kBG) * kKC;
     const size_t lo_off = gvp_lo ? (size_t)(gvp_lo - gvp_out) : 0;   // tcgen05 GEMM: operand pre-split into TF32 hi + lo
+    // bf16x3 operand: this body's row of term 0 in chunk 0 ([group][chunk n/64][term][64 bodies][64 n])
+    unsigned short *g3_body = reinterpret_cast<unsigned short *>(gvp_out) + (size_t)(b / kBG) * (Npad / kKC3) * (3 * kBG * kKC3) +
+                              (size_t)(b % kBG) * kKC3;
     auto put = [&](int n, float x) {
         if (n >= Npad) return;
-        if (gmode == 2) {        // bf16x3 GEMM operand: three bfloat16 terms (common.cuh); Npad is a multiple of 64
+        if (gmode == 2) {        // bf16x3 GEMM operand: three bfloat16 terms (a3_index, common.cuh); Npad is a multiple of 64
             unsigned short b1, b2, b3;
             split_bf16x3(x, b1, b2, b3);
-            unsigned short *g3 = reinterpret_cast<unsigned short *>(gvp_out);
-            g3[a3_index(b, 0, n, Npad)] = b1;
-            g3[a3_index(b, 1, n, Npad)] = b2;
-            g3[a3_index(b, 2, n, Npad)] = b3;
+            const int col = n & (kKC3 - 1);
+            unsigned short *q = g3_body + (size_t)(n >> 6) * (3 * kBG * kKC3) + (((((col >> 3) ^ b) & 7) << 3) | (col & 7));
+            q[0] = b1;
+            q[kBG * kKC3] = b2;
+            q[2 * kBG * kKC3] = b3;
             return;
         }
         const size_t at = (size_t)(n / kKC) * (kBG * kKC) + swz(b % kBG, n % kKC);
@@ -562,7 +678,7 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     if (use_units && staged) {
         u0 = ju[0];
         nunits = ju[J] - u0;
-        if (tid < nunits * 3) d_first = unit_desc[u0 + tid / 3];
+        if (tid < nunits) d_first = unit_desc[u0 + tid];
         if (tid < J * 3) { ja = ju[tid / 3] - u0; jb = ju[tid / 3 + 1] - u0; }
     }
     // The kernel is latency bound: every global load is issued at the earliest point its address is known --
@@ -670,8 +786,8 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     } else {
         put(3 * v, 0.f); put(3 * v + 1, 0.f); put(3 * v + 2, 0.f);
     }
-    s_gw[tid * 3] = gx; s_gw[tid * 3 + 1] = gy; s_gw[tid * 3 + 2] = gz;
-    s_vp[tid * 3] = px; s_vp[tid * 3 + 1] = py; s_vp[tid * 3 + 2] = pz;
+    s_gw4[tid] = make_float4(gx, gy, gz, 0.f);
+    s_vp4[tid] = make_float4(px, py, pz, 0.f);
     {   // per-warp sums of gw (row J of the partials = d translation) and of the contact loss
         const float sx = warp_sum(gx), sy = warp_sum(gy), sz = warp_sum(gz);
         if ((tid & 31) == 0) { red3[(tid >> 5) * 3] = sx; red3[(tid >> 5) * 3 + 1] = sy; red3[(tid >> 5) * 3 + 2] = sz; }
@@ -694,19 +810,28 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     // one thread per (joint, row) adds that joint's units in order.
     float *outp = dApart + ((size_t)blockIdx.x * B + b) * (J + 1) * 12;
     if (use_units && staged) {
-        for (int item = tid; item < nunits * 3; item += blockDim.x) {
-            const int u = item / 3, r = item - u * 3;
-            const int d = item == tid ? d_first : unit_desc[u0 + u];
+        // one thread per unit does all three rows: the entry's weight, gw and v_posed are read once (4 shared-memory
+        // loads per entry instead of 18); every (unit, row) sum keeps its entry order, so the bits do not change
+        for (int u = tid; u < nunits; u += blockDim.x) {
+            const int d = u == tid ? d_first : unit_desc[u0 + u];
             const int k0 = d >> 8, len = d & 255;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            float4 acc[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
             for (int k = k0; k < k0 + len; ++k) {
                 const int lv = s_lv[k];
-                const float g = s_w[k] * s_gw[lv * 3 + r];
-                a0 = fmaf(g, s_vp[lv * 3], a0); a1 = fmaf(g, s_vp[lv * 3 + 1], a1); a2 = fmaf(g, s_vp[lv * 3 + 2], a2);
-                a3 += g;
+                const float w = s_w[k];
+                const float4 gw = s_gw4[lv], vp = s_vp4[lv];
+                const float g3[3] = {w * gw.x, w * gw.y, w * gw.z};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    acc[r].x = fmaf(g3[r], vp.x, acc[r].x); acc[r].y = fmaf(g3[r], vp.y, acc[r].y);
+                    acc[r].z = fmaf(g3[r], vp.z, acc[r].z); acc[r].w += g3[r];
+                }
             }
-            s_part[item] = make_float4(a0, a1, a2, a3);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) s_part[u * 3 + r] = acc[r];
         }
         __syncthreads();
         for (int item = tid; item < (J + 1) * 3; item += blockDim.x) {
@@ -738,16 +863,18 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
 #pragma unroll 4
                 for (int k = k0; k < k1; ++k) {
                     const int lv = s_lv[k];
-                    const float g = s_w[k] * s_gw[lv * 3 + r];
-                    a0 = fmaf(g, s_vp[lv * 3], a0); a1 = fmaf(g, s_vp[lv * 3 + 1], a1); a2 = fmaf(g, s_vp[lv * 3 + 2], a2);
+                    const float4 vp = s_vp4[lv];
+                    const float g = s_w[k] * (&s_gw4[lv].x)[r];
+                    a0 = fmaf(g, vp.x, a0); a1 = fmaf(g, vp.y, a1); a2 = fmaf(g, vp.z, a2);
                     a3 += g;
                 }
             } else {
 #pragma unroll 4
                 for (int k = k0; k < k1; ++k) {
                     const int lv = ch_lv[e0 + k];
-                    const float g = ch_w[e0 + k] * s_gw[lv * 3 + r];
-                    a0 = fmaf(g, s_vp[lv * 3], a0); a1 = fmaf(g, s_vp[lv * 3 + 1], a1); a2 = fmaf(g, s_vp[lv * 3 + 2], a2);
+                    const float4 vp = s_vp4[lv];
+                    const float g = ch_w[e0 + k] * (&s_gw4[lv].x)[r];
+                    a0 = fmaf(g, vp.x, a0); a1 = fmaf(g, vp.y, a1); a2 = fmaf(g, vp.z, a2);
                     a3 += g;
                 }
             }
@@ -1887,7 +2014,11 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
     }
     {
         dim3 sgrid((unsigned)((m->V + 255) / 256), (unsigned)B);
-        if (sdf)
+        static const bool two = [] { const char *e = getenv("PSI_SKIN_SDF"); return !(e && e[0] == '1'); }();   // PSI_SKIN_SDF=1: one vertex per thread
+        if (sdf && two && m->KW == 4)
+            (psi::skip_kernel("lbs_skin_sdf_fwd") ? cudaSuccess : launch_pdl(lbs_skin_sdf2_kernel, dim3((unsigned)((m->V + 511) / 512), (unsigned)B), dim3(256), 0, st,
+                       m->V, m->J, m->skin_j, m->skin_w, saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, *sdf));
+        else if (sdf)
             (psi::skip_kernel(sdf ? "lbs_skin_sdf_fwd" : "lbs_skin_fwd") ? cudaSuccess : launch_pdl(lbs_skin_fwd_kernel<true>, sgrid, dim3(256), 0, st, m->V, m->J, m->KW, m->skin_j, m->skin_w,
                        saved + L.A, saved + L.vp, transl, cam, cam_bstride, verts, *sdf));
         else
