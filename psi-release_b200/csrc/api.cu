@@ -16,13 +16,16 @@ bool skip_kernel(const char *name) {
     static const char *skip = getenv("PSI_SKIP_KERNEL");
     return skip && name && strcmp(skip, name) == 0;
 }
-bool pdl_enabled() {
-    // opt-in: measured SLOWER on B200 for this chain inside the captured graph, with the trigger at the top of
-    // every kernel (460 vs 535 bodies/s, r01p) and with the trigger in the kernels' tails as it is now (593 vs
-    // 630 bodies/s, r01v): the graph's programmatic edges cost more than the overlapped launch latency saves
-    static const bool on = [] { const char *e = getenv("PSI_PDL"); return e && e[0] == '1'; }();
-    return on;
+int pdl_mode() {
+    // PSI_PDL: 0 / unset = plain graph edges (default), 1 = programmatic dependent launch on every kernel of the chain,
+    // 2 = only on the kernels that have a long constant-only prologue before their dependency wait (the NN walk
+    // stages the top of the box tree, the vertex backward kernel its skinning entries).  Mode 1 measured SLOWER
+    // inside the captured graph three times (460 vs 535, 593 vs 630, 640 vs 663 bodies/s): the graph's programmatic
+    // edges cost more than the overlapped launch latency saves.
+    static const int mode = [] { const char *e = getenv("PSI_PDL"); return e ? atoi(e) : 0; }();
+    return mode;
 }
+bool pdl_enabled() { return pdl_mode() == 1; }
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs
 // through the C ABI has to opt every kernel in on every device it launches on.  (device, function) pairs that
 // already hold at least `bytes` are remembered; the map is the only mutable process-wide state besides the

@@ -129,6 +129,7 @@ inline int ensure_max_dyn_smem(void (*kernel)(KArgs...), size_t bytes) {
 
 bool skip_kernel(const char *name);   // api.cu: measurement aid, PSI_SKIP_KERNEL=<name> drops that launch (results invalid)
 bool pdl_enabled();   // api.cu: true only when PSI_PDL=1 (measured slower, see api.cu)
+int pdl_mode();       // api.cu: PSI_PDL (0 off, 1 every kernel, 2 only launch_pdl_sel sites)
 // launch `kernel`; it MUST call pdl_wait() before touching global memory other than constants
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -143,6 +144,23 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// the same for a kernel with a long constant-only prologue: also programmatic under PSI_PDL=2
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_sel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_mode() >= 1 ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

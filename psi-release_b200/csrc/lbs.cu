@@ -2092,7 +2092,7 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
         const size_t smem = (size_t)cap * 5;
         const int units = (cap > 0 && m->max_units <= kMaxUnits) ? 1 : 0;
         if (vg)
-            (psi::skip_kernel(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd") ? cudaSuccess : launch_pdl(lbs_vertex_bwd_kernel<true>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
+            (psi::skip_kernel(vg ? "lbs_vertex_bwd_fit" : "lbs_vertex_bwd") ? cudaSuccess : launch_pdl_sel(lbs_vertex_bwd_kernel<true>, grid, dim3(256), smem, st, m->V, m->J, m->KW, m->Npad, B, m->skin_j,
                        m->skin_w, saved + L.A, saved + L.vp, cam, cam_bstride, grad_verts, m->ch_seg, m->ch_lv,
                        m->ch_w, cap, m->ch_ju, m->unit_desc, units, ws + W.gvp, tc5 ? ws + W.gvp_lo : nullptr, gmode, ws + W.dApart, *vg));
         else

@@ -807,9 +807,9 @@ static int nn_index_query_impl(const psi_nn_index *ix, const float *q, long q_bs
         if (blocks > cap) blocks = cap;
         const size_t top_bytes = (size_t)2 * (ix->mpad + ix->num_supers) * sizeof(float4);
         if (top_bytes <= 24 * 1024)
-            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_group_kernel<true>, dim3((unsigned)blocks), dim3(kGrpThreads), top_bytes, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint));
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl_sel(nn_index_group_kernel<true>, dim3((unsigned)blocks), dim3(kGrpThreads), top_bytes, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint));
         else
-            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl(nn_index_group_kernel<false>, dim3((unsigned)blocks), dim3(kGrpThreads), 0, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint));
+            (psi::skip_kernel(mode == 3 ? "nn_index_group" : "nn_index_query") ? cudaSuccess : launch_pdl_sel(nn_index_group_kernel<false>, dim3((unsigned)blocks), dim3(kGrpThreads), 0, st, *ix, q, q_bstride, n, qsel, B, dist, idx, hint));
     } else if (mode == 2 || (mode == 0 && total >= (long)PSI_NUM_SMS * 768)) {
         // one thread per query: enough queries to fill the machine with 256-thread CTAs
         long blocks = (total + 255) / 256;

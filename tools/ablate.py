@@ -11,8 +11,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = ["", "fit_linear", "lbs_pose_fwd", "lbs_blend_fwd", "lbs_skin_sdf_fwd", "nn_index_group", "lbs_vertex_bwd_fit",
-           "lbs_dcoef", "lbs_reduce2", "lbs_pose_bwd", "fit_step"]
+KERNELS = ["", "fit_linear", "lbs_pose_fwd", "lbs_blend_fwd_bf3", "lbs_skin_sdf_fwd", "nn_index_group", "lbs_vertex_bwd_fit",
+           "lbs_dcoef_bf3", "lbs_reduce2", "lbs_pose_bwd", "fit_step"]
 
 CHILD = r"""
 import sys, json, numpy as np, torch
@@ -39,10 +39,15 @@ if __name__ == "__main__":
     base = None
     rows = []
     for k in KERNELS:
-        env = dict(os.environ)
+        # one graph launch per iteration: with the whole-loop WHILE graph a skipped fit_step would never count the loop down
+        env = dict(os.environ, PSI_FIT_LOOP="replay")
         if k:
             env["PSI_SKIP_KERNEL"] = k
-        out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, cwd=ROOT)
+        try:
+            out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, cwd=ROOT, timeout=120)
+        except subprocess.TimeoutExpired:
+            print(k, "TIMED OUT")
+            continue
         try:
             us = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])["us_per_iteration"]
         except Exception:
