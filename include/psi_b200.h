@@ -43,7 +43,7 @@ typedef void *psi_stream_t; /* cudaStream_t */
 #define PSI_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels were built for */
 #define PSI_ERR_ALLOC (-4)        /* device allocation failed (model upload only) */
 
-#define PSI_ABI_VERSION 3   /* 3: psi_fit_config.{loop_mode,loop_unroll,loss_mode,optimizer,lbfgs_*}, psi_fit_trace, psi_fit_trace_bytes;
+#define PSI_ABI_VERSION 3   /* 3: psi_fit_config.{loop_mode,loop_unroll,loss_mode,optimizer,lbfgs_*}, psi_fit_trace*, psi_fit_exchange_*, psi_fit_set_peers;
                                2: psi_fit_config.nn_mode, psi_fit_profile, psi_nn_index_query_mode mode 3 */
 
 /* ABI version of the loaded library (PSI_ABI_VERSION it was built with). */
@@ -275,6 +275,25 @@ PSI_API int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *ca
 PSI_API int psi_fit_end(psi_fit_ctx *c, float *xhr_out, float *losses_out, psi_stream_t stream);
 PSI_API int psi_fit_launches_per_iteration(void);
 
+/* loss_mode 1 with the batch SHARDED over several contexts -- GPUs of one node, one process per GPU, or several
+ * contexts of one process (SURVEY.md 8(e) option 2).  The batch-coupled loss needs, every iteration, the number of
+ * penetrating vertices of the WHOLE batch (fitting_proxe.py:155-158) and the total body count for its means.  Each
+ * context owns a small exchange buffer; once the shards know each other's buffers, every iteration PUBLISHES its
+ * count into the peers' buffers with plain stores through the peer mapping (NVLink) right after the SDF pass and
+ * COLLECTS theirs right before the vertex backward kernel -- 8 bytes per peer, hidden behind the NN walk; no NCCL
+ * call, no host involvement, inside the same CUDA graph.  Results are bit-identical to one context fitting the
+ * union batch.
+ *   psi_fit_exchange_handle: the buffer's cudaIpcMemHandle_t (64 bytes, host) for ANOTHER PROCESS;
+ *   psi_fit_exchange_ptr:    its device pointer for another context of the SAME process;
+ *   psi_fit_set_peers:       rank / world (<= 16) / bodies of the whole batch, and per shard EITHER its IPC handle
+ *                            (h_handles[q], 64 bytes) OR its device pointer (ptrs[q]); entry `rank` is ignored.
+ * Every shard must run the same psi_fit_run / psi_fit_begin calls (same num_iter) with use_graph = 1. */
+#define PSI_FIT_MAX_SHARDS 16
+PSI_API int psi_fit_exchange_handle(psi_fit_ctx *c, void *h_handle64);
+PSI_API void *psi_fit_exchange_ptr(psi_fit_ctx *c);
+PSI_API int psi_fit_set_peers(psi_fit_ctx *c, int rank, int world, int batch_total, const void *const *h_handles,
+                      void *const *ptrs);
+
 /* Trace of the most recent iteration the context evaluated (parity tests, debugging): copies one of the
  * loop's own buffers to `dst` (device memory, psi_fit_trace_bytes(what) bytes) on `stream`, ordered after
  * the loop.  After psi_fit_run(num_iter = k) the "last iteration" is iteration k-1: X_EVAL is the vector it
@@ -296,6 +315,7 @@ PSI_API int psi_fit_launches_per_iteration(void);
 #define PSI_FIT_TRACE_POSE6D 12    /* float [B,nbody+1,6]: root 6D + VPoser decoder output of the last iteration */
 #define PSI_FIT_TRACE_LBFGS_STATE 13   /* int [B,4]: (phase 0 start / 1 bracket / 2 zoom / 3 done, outer iterations, closure
                                           evaluations, curvature pairs held); optimizer 1 only */
+#define PSI_FIT_TRACE_EXCHANGE 15      /* int [4]: (fit sequence number, 1 if a peer's count did not arrive in time, -, -); sharded batch loss */
 #define PSI_FIT_TRACE_LBFGS_BEST 14    /* float [B,75]: last accepted point (+ best sufficient-decrease step of a search in progress) */
 PSI_API size_t psi_fit_trace_bytes(const psi_fit_ctx *c, int what);   /* 0 for an unknown `what` */
 PSI_API int psi_fit_trace(psi_fit_ctx *c, int what, void *dst, size_t dst_bytes, psi_stream_t stream);

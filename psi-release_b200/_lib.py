@@ -31,7 +31,7 @@ class FitConfig(ctypes.Structure):
 FIT_TRACE = {"x_eval": (0, False), "grad_x": (1, False), "verts": (2, False), "sdf": (3, False), "sdf_grad": (4, False),
              "nn_dist": (5, False), "nn_idx": (6, True), "query_ids": (7, True), "losses": (8, False), "x": (9, False),
              "adam_m": (10, False), "adam_v": (11, False), "pose6d": (12, False), "lbfgs_state": (13, True),
-             "lbfgs_best": (14, False)}
+             "lbfgs_best": (14, False), "exchange": (15, True)}
 
 
 class PsiError(RuntimeError):
@@ -93,6 +93,9 @@ def lib():
         "psi_fit_profile": (_i, [_vp, _vp, _vp, _l, _i, _i, _vp, _vp, _i, _vp]),
         "psi_fit_trace_bytes": (_sz, [_vp, _i]),
         "psi_fit_trace": (_i, [_vp, _i, _vp, _sz, _vp]),
+        "psi_fit_exchange_handle": (_i, [_vp, _vp]),
+        "psi_fit_exchange_ptr": (_vp, [_vp]),
+        "psi_fit_set_peers": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)      # AttributeError here = header / library mismatch
@@ -110,7 +113,8 @@ EXPORTS = ["psi_abi_version", "psi_error_string", "psi_launch_count", "psi_nn_wo
            "psi_sdf_bwd", "psi_lbs_model_create", "psi_lbs_model_destroy", "psi_lbs_model_bytes",
            "psi_lbs_saved_floats", "psi_lbs_fwd", "psi_lbs_bwd_workspace_bytes", "psi_lbs_bwd", "psi_lbs_bwd2", "psi_fit_profile",
            "psi_fit_create", "psi_fit_destroy", "psi_fit_run", "psi_fit_begin", "psi_fit_end",
-           "psi_fit_launches_per_iteration", "psi_fit_trace_bytes", "psi_fit_trace"]
+           "psi_fit_launches_per_iteration", "psi_fit_trace_bytes", "psi_fit_trace", "psi_fit_exchange_handle",
+           "psi_fit_exchange_ptr", "psi_fit_set_peers"]
 
 
 def check(rc: int, what: str) -> None:

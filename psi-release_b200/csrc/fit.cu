@@ -31,6 +31,7 @@
 #include "fit_fuse.cuh"
 #include "fit_lbfgs.cuh"
 #include <math.h>
+#include <string.h>
 #include <new>
 #include <vector>
 
@@ -53,7 +54,14 @@ struct psi_fit_ctx {
     psi::LbfgsState lb;            // optimizer 1: per-body L-BFGS state
     psi::LbfgsParams lbp;
     int *lb_info;                  // trace staging [B,4]
-    int *neg_cnt;                  // loss_mode 1: batch-wide count of penetrating vertices, [2] by iteration parity
+    int *neg_cnt;                  // loss_mode 1: this shard's count of penetrating vertices, [2] by iteration parity
+    // loss_mode 1 sharded over several contexts (psi_fit_set_peers): exchange buffer [2][16] of (tag << 32 | count)
+    // written by the peers, the peers' buffers, the batch-wide count [2], a fit sequence number, an error flag
+    unsigned long long *xbuf;
+    unsigned long long *peer_buf[PSI_FIT_MAX_SHARDS];
+    void *ipc_opened[PSI_FIT_MAX_SHARDS];
+    int *neg_tot, *xseq, *xerr;
+    int rank, world, batch_total;
     int *loop_left;                // iterations the WHILE node still has to run
     size_t lbs_ws_bytes;
     cudaGraphExec_t exec;          // one iteration (loop_mode 1)
@@ -105,8 +113,8 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
                 const float *__restrict__ cpart, float *__restrict__ losses, float *__restrict__ zA,
                 float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
                 float *__restrict__ transl, float *__restrict__ gx_out, float *__restrict__ xeval_out,
-                int *__restrict__ neg_cnt, int *__restrict__ loop_left, cudaGraphConditionalHandle loop_cond,
-                const LbfgsParams lbp, const LbfgsState lbs) {
+                int *__restrict__ neg_cnt, const int *__restrict__ neg_tot, int batch_total, int *__restrict__ loop_left,
+                cudaGraphConditionalHandle loop_cond, const LbfgsParams lbp, const LbfgsState lbs) {
     pdl_wait();
     __shared__ float sx[96], g[96];
     __shared__ float s_loss;
@@ -125,7 +133,7 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     __syncthreads();
     // loss_mode 1: the L1 / L2 terms are means over the whole batch (the contact and collision terms are scaled
     // where their gradients are formed, lbs_vertex_bwd<FIT>)
-    const float bdiv = cfg.loss_mode == 1 ? (float)d.B : 1.0f;
+    const float bdiv = cfg.loss_mode == 1 ? (float)(neg_tot ? batch_total : d.B) : 1.0f;   // sharded: bodies of the WHOLE batch
     if (do_post) {
         if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
         else if (tid < 9) g[tid] = g6_root[(size_t)b * 6 + tid - 3];
@@ -152,7 +160,7 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
             for (int i = ln; i < nchunk; i += 32) cs += cpart[(size_t)b * nchunk + i];
             r = warp_sum(r); zz = warp_sum(zz); sn = warp_sum(sn); cn = warp_sum(cn); cs = warp_sum(cs);
             // loss_mode 1: this body's share of the batch means (the rows add up to the reference's scalars)
-            if (cfg.loss_mode == 1) cn = (float)neg_cnt[t_prev & 1];
+            if (cfg.loss_mode == 1) cn = (float)(neg_tot ? neg_tot : neg_cnt)[t_prev & 1];
             if (ln == 0) {
             losses[(size_t)b * 4 + 0] = cfg.w_rec * (r / ((float)xdim * bdiv));
             losses[(size_t)b * 4 + 1] = cfg.w_vposer * (zz / ((float)Lz * bdiv));
@@ -253,6 +261,55 @@ __global__ void fit_lbfgs_info_kernel(const LbfgsScalars *sc, int B, int *out) {
     }
 }
 
+// ---- batch-coupled loss sharded over several contexts: 8 bytes per peer per iteration through peer memory --------
+struct PeerBufs {
+    unsigned long long *p[PSI_FIT_MAX_SHARDS];
+};
+// after the SDF pass: this shard's penetration count of iteration `it` into every peer's slot [it & 1][rank]
+__global__ void fit_publish_kernel(PeerBufs peers, int rank, int world, const int *__restrict__ neg_cnt,
+                                   const int *__restrict__ step, const int *__restrict__ xseq) {
+    pdl_wait();
+    const int q = threadIdx.x;
+    if (q >= world || q == rank) return;
+    const int it = step[0], par = it & 1;
+    const unsigned long long tag = ((unsigned long long)(unsigned)xseq[0] << 16) | (unsigned long long)((it + 1) & 0xffff);
+    const unsigned long long val = (tag << 32) | (unsigned long long)(unsigned)neg_cnt[par];
+    unsigned long long *dst = peers.p[q] + par * PSI_FIT_MAX_SHARDS + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(val) : "memory");
+}
+// before the vertex backward kernel: wait for every peer's count of this iteration, add them up
+__global__ void fit_collect_kernel(const unsigned long long *__restrict__ xbuf, int rank, int world,
+                                   const int *__restrict__ neg_cnt, int *__restrict__ neg_tot,
+                                   const int *__restrict__ step, const int *__restrict__ xseq, int *__restrict__ xerr) {
+    pdl_wait();
+    const int q = threadIdx.x;
+    const int it = step[0], par = it & 1;
+    const unsigned long long tag = ((unsigned long long)(unsigned)xseq[0] << 16) | (unsigned long long)((it + 1) & 0xffff);
+    int mine = 0;
+    if (q < world && q != rank) {
+        const unsigned long long *src = xbuf + par * PSI_FIT_MAX_SHARDS + q;
+        unsigned long long v = 0;
+        long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if ((v >> 32) == tag) break;
+            if (++spins > (1L << 24)) {      // ~ a second: a peer is gone or out of step -- flag it, fall back to what we have
+                atomicExch(xerr, 1);
+                v = 0;
+                break;
+            }
+            __nanosleep(64);
+        }
+        mine = (int)(unsigned)(v & 0xffffffffull);
+    } else if (q == rank) {
+        mine = neg_cnt[par];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);     // integers: any order
+    if (q == 0) neg_tot[par] = mine;
+}
+__global__ void fit_seq_kernel(int *xseq) { xseq[0] = (xseq[0] + 1) & 0xffff; }
+
 // head of the loop graph: arm the WHILE node with the iteration count psi_fit_begin stored
 __global__ void fit_loop_head_kernel(cudaGraphConditionalHandle cond, const int *loop_left) {
     cudaGraphSetConditional(cond, *loop_left > 0 ? 1u : 0u);
@@ -284,6 +341,7 @@ static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
                           c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->dz, c->g6_root, c->gpose,
                           c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl,
                           c->gx, c->xeval, c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr,
+                          c->cfg.loss_mode == 1 && c->world > 1 ? c->neg_tot : nullptr, c->batch_total,
                           c->capturing_loop ? c->loop_left : nullptr, c->loop_cond, c->lbp, c->lb);
     };
     if (!psi::skip_kernel("fit_step")) {
@@ -320,19 +378,31 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     rc = lbs_fwd_impl(c->model, B, c->shape, c->pose, c->transl, c->cam, 12, nullptr, c->rot6d, c->num_rot,
                       c->verts, nullptr, c->saved, &sf, st);
     if (rc) return rc;
+    const bool sharded = c->cfg.loss_mode == 1 && c->world > 1;
+    if (sharded) {       // this shard's penetration count -> the peers (8 bytes each, plain stores through the peer mapping)
+        PeerBufs pb;
+        for (int q = 0; q < PSI_FIT_MAX_SHARDS; ++q) pb.p[q] = c->peer_buf[q];
+        launch_pdl(fit_publish_kernel, dim3(1), dim3(32), 0, st, pb, c->rank, c->world, c->neg_cnt, c->step, c->xseq);
+        PSI_LAUNCHED_K("fit_publish");
+    }
     // contact ids are ordered by dominant joint + kd cells of the template (fused.py): 32 consecutive
     // queries are neighbours on the posed body -> the group schedule walks the index once per warp
     rc = psi_nn_index_query_mode(c->index, c->verts, (long)c->V * 3, B, c->nu, c->csel, c->nnd, c->nni,
                                  c->nnhint, c->cfg.nn_mode > 0 ? c->cfg.nn_mode : 3, st);
     if (rc) return rc;
+    if (sharded) {       // ... and theirs, by now long arrived (the NN walk ran in between)
+        launch_pdl(fit_collect_kernel, dim3(1), dim3(32), 0, st, c->xbuf, c->rank, c->world, c->neg_cnt, c->neg_tot, c->step,
+                   c->xseq, c->xerr);
+        PSI_LAUNCHED_K("fit_collect");
+    }
     // LBS backward; dL/dverts of the contact + collision terms is formed at the head of its vertex kernel
     VGradFuse vg;
     vg.verts = c->verts; vg.scene = c->scene_pts; vg.sdfv = c->sdfv; vg.sdfg = c->sdfg; vg.partial = c->partial;
     vg.nnd = c->nnd; vg.nni = c->nni; vg.cslot = c->cslot; vg.cweight = c->cweight;
     vg.w_contact = c->cfg.w_contact; vg.w_coll = c->cfg.w_collision; vg.robust_c = c->cfg.robust_c;
     vg.nu = c->nu; vg.np_sdf = c->np_sdf; vg.num_contact = c->num_contact; vg.cpart = c->cpart;
-    vg.neg_cnt = c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr; vg.step = c->step;
-    vg.bdiv = c->cfg.loss_mode == 1 ? (float)B : 1.0f;
+    vg.neg_cnt = c->cfg.loss_mode == 1 ? (sharded ? c->neg_tot : c->neg_cnt) : nullptr; vg.step = c->step;
+    vg.bdiv = c->cfg.loss_mode == 1 ? (float)(sharded ? c->batch_total : B) : 1.0f;
     rc = lbs_bwd_impl(c->model, B, c->pose, c->cam, 12, c->saved, nullptr, &vg, nullptr, c->gshape, c->gpose,
                       c->gtransl, nullptr, c->num_rot, c->rot6d, c->g6_root, c->g6A, NOp, c->lbs_ws,
                       c->lbs_ws_bytes, st);
@@ -358,6 +428,8 @@ void psi_fit_destroy(psi_fit_ctx *c) {
     if (c->gstream) cudaStreamDestroy(c->gstream);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
+    for (int q = 0; q < PSI_FIT_MAX_SHARDS; ++q)
+        if (c->ipc_opened[q]) cudaIpcCloseMemHandle(c->ipc_opened[q]);
     for (void *p : c->owned) cudaFree(p);
     delete c;
 }
@@ -512,6 +584,16 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         c->lb_info = (int *)dev_alloc(B * 4 * sizeof(int));
     }
     c->neg_cnt = (int *)dev_alloc(2 * sizeof(int));
+    c->rank = 0; c->world = 1; c->batch_total = c->B;
+    for (int q = 0; q < PSI_FIT_MAX_SHARDS; ++q) { c->peer_buf[q] = nullptr; c->ipc_opened[q] = nullptr; }
+    c->neg_tot = (int *)dev_alloc(2 * sizeof(int));
+    {   // exchange buffer + sequence number + error flag: one allocation of its own (cudaIpcGetMemHandle needs cudaMalloc memory)
+        void *xp = dev_alloc((2 * PSI_FIT_MAX_SHARDS + 2) * sizeof(unsigned long long));
+        c->xbuf = (unsigned long long *)xp;
+        c->xseq = xp ? (int *)(c->xbuf + 2 * PSI_FIT_MAX_SHARDS) : nullptr;
+        c->xerr = xp ? c->xseq + 1 : nullptr;
+        if (xp && cudaMemsetAsync(xp, 0, (2 * PSI_FIT_MAX_SHARDS + 2) * sizeof(unsigned long long), st) != cudaSuccess) rc = PSI_ERR_ALLOC;
+    }
     c->loop_left = (int *)dev_alloc(sizeof(int));
     c->lbs_ws_bytes = psi_lbs_bwd_workspace_bytes(model, c->B) + 64;
     c->lbs_ws = (float *)dev_alloc(c->lbs_ws_bytes);
@@ -590,6 +672,10 @@ static int reset_state(psi_fit_ctx *c, const float *xhr_init, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt);
     PSI_LAUNCHED();
+    if (c->world > 1) {     // a new fit: the peers' stale slots of the last one must not match
+        fit_seq_kernel<<<1, 1, 0, st>>>(c->xseq);
+        PSI_LAUNCHED();
+    }
     if (c->cfg.optimizer == 1) {
         e = cudaMemcpyAsync(c->lb.xbest, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return (int)e;
@@ -614,7 +700,10 @@ int psi_fit_begin(psi_fit_ctx *c, const float *xhr_init, const float *cam, long 
     PSI_LAUNCHED();
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
-    if (c->cfg.use_graph && cs == cudaStreamCaptureStatusNone && num_iter > 1) {
+    const bool graph_path = c->cfg.use_graph && cs == cudaStreamCaptureStatusNone && num_iter > 1;
+    // a sharded batch waits for its peers inside the iteration: the loop must run on the context's own stream
+    if (c->cfg.loss_mode == 1 && c->world > 1 && !graph_path && num_iter > 0) return PSI_ERR_UNSUPPORTED;
+    if (graph_path) {
         // the loop runs on the context's own stream, ordered after / before the caller's stream
         cudaStream_t gs = c->gstream;
         const bool whole = c->cfg.loop_mode == 0;
@@ -691,6 +780,54 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
 
 int psi_fit_launches_per_iteration(void) { return 15; }
 
+int psi_fit_exchange_handle(psi_fit_ctx *c, void *h_handle64) {
+    if (!c || !h_handle64) return PSI_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const cudaError_t e = cudaIpcGetMemHandle((cudaIpcMemHandle_t *)h_handle64, c->xbuf);
+    return e == cudaSuccess ? PSI_OK : (int)e;
+}
+
+void *psi_fit_exchange_ptr(psi_fit_ctx *c) { return c ? (void *)c->xbuf : nullptr; }
+
+int psi_fit_set_peers(psi_fit_ctx *c, int rank, int world, int batch_total, const void *const *h_handles, void *const *ptrs) {
+    if (!c || rank < 0 || world < 1 || rank >= world || world > PSI_FIT_MAX_SHARDS || batch_total < c->B) return PSI_ERR_BAD_ARG;
+    if (c->cfg.loss_mode != 1) return PSI_ERR_UNSUPPORTED;
+    if (world > 1 && !h_handles && !ptrs) return PSI_ERR_BAD_ARG;
+    // graphs captured for another peer set hold the old pointers
+    if (c->exec) { cudaGraphExecDestroy(c->exec); c->exec = nullptr; }
+    if (c->loop_exec) { cudaGraphExecDestroy(c->loop_exec); c->loop_exec = nullptr; }
+    for (int q = 0; q < PSI_FIT_MAX_SHARDS; ++q) {
+        if (c->ipc_opened[q]) { cudaIpcCloseMemHandle(c->ipc_opened[q]); c->ipc_opened[q] = nullptr; }
+        c->peer_buf[q] = nullptr;
+    }
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) { c->peer_buf[q] = c->xbuf; continue; }
+        if (ptrs && ptrs[q]) {
+            // another context of this process; on another device the peer mapping has to be enabled once
+            cudaPointerAttributes pa;
+            int dev = 0;
+            if (cudaPointerGetAttributes(&pa, ptrs[q]) == cudaSuccess && cudaGetDevice(&dev) == cudaSuccess && pa.device != dev) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(pa.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return (int)e;
+                (void)cudaGetLastError();
+            }
+            c->peer_buf[q] = (unsigned long long *)ptrs[q];
+        } else if (h_handles && h_handles[q]) {
+            void *p = nullptr;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, h_handles[q], sizeof(h));
+            const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return (int)e;
+            c->ipc_opened[q] = p;
+            c->peer_buf[q] = (unsigned long long *)p;
+        } else {
+            return PSI_ERR_BAD_ARG;
+        }
+    }
+    c->rank = rank; c->world = world; c->batch_total = batch_total;
+    return PSI_OK;
+}
+
 // (buffer, bytes) of a traceable object
 static const void *trace_buffer(const psi_fit_ctx *c, int what, size_t *bytes) {
     const size_t B = (size_t)c->B, xd = 9 + 10 + (size_t)c->latent + 2 * (size_t)c->ncomp, f = sizeof(float);
@@ -710,6 +847,7 @@ static const void *trace_buffer(const psi_fit_ctx *c, int what, size_t *bytes) {
         case PSI_FIT_TRACE_POSE6D: *bytes = B * c->num_rot * 6 * f; return c->rot6d;
         case PSI_FIT_TRACE_LBFGS_STATE: *bytes = c->cfg.optimizer == 1 ? B * 4 * sizeof(int) : 0; return c->lb_info;
         case PSI_FIT_TRACE_LBFGS_BEST: *bytes = c->cfg.optimizer == 1 ? B * xd * f : 0; return c->lb.xbest;
+        case PSI_FIT_TRACE_EXCHANGE: *bytes = 4 * sizeof(int); return c->xseq;
         default: *bytes = 0; return nullptr;
     }
 }

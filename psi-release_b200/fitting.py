@@ -301,6 +301,14 @@ class FittingOP:
                               "l_collision={:f}".format(ii, *l))
             return GeometryTransformer.convert_to_3D_rot(self.xhr_rec.detach())
 
+    def connect_batch_shards(self, batch_total, group=None):
+        """loss_mode='batch' with the batch sharded over the ranks of a torch.distributed group (one node, one process
+        per GPU; SURVEY.md 8(e) option 2): after this call `fit` on every rank optimises the loss of the UNION batch --
+        the per-iteration exchange of the penetration counts runs inside the loop through peer memory."""
+        if self._fused is None:
+            raise _lib.PsiError("connect_batch_shards needs engine='fused'")
+        self._fused.connect_group(batch_total, group)
+
     def trace(self, what):
         """Fused engine only: a buffer of the last iteration the loop evaluated (FusedFit.trace / psi_fit_trace)."""
         if self._fused is None:

@@ -138,6 +138,58 @@ class FusedFit:
             self.parts.append((start, nb, h))
             start += nb
 
+    # ---- loss_mode='batch' sharded over several contexts / GPUs (psi_fit_set_peers) -----------------------------
+    def connect_local(self, shards, rank, batch_total):
+        """Shards living in THIS process (a list of FusedFit, this one at index `rank`): device pointers."""
+        if self.loss_mode != "batch" or len(self.parts) != 1:
+            raise ValueError("sharding the batch-coupled loss needs loss_mode='batch' and one context per shard")
+        L = _lib.lib()
+        ptrs = (ctypes.c_void_p * len(shards))(*[L.psi_fit_exchange_ptr(s.parts[0][2]) for s in shards])
+        with torch.cuda.device(self.device):
+            _lib.check(L.psi_fit_set_peers(self.parts[0][2], int(rank), len(shards), int(batch_total), None, ptrs), "psi_fit_set_peers")
+        self.world = len(shards)
+
+    def connect_group(self, batch_total, group=None):
+        """Shards = the ranks of a torch.distributed group on ONE node (one process per GPU): every rank's exchange
+        buffer is opened in every other rank through its CUDA IPC handle; no collective runs afterwards -- each
+        iteration's 8 bytes per peer travel as plain stores over the peer mapping inside the loop's graph."""
+        import torch.distributed as dist
+        if self.loss_mode != "batch" or len(self.parts) != 1:
+            raise ValueError("sharding the batch-coupled loss needs loss_mode='batch' and one context per shard")
+        L = _lib.lib()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mine = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(L.psi_fit_exchange_handle(self.parts[0][2], mine), "psi_fit_exchange_handle")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine.raw), group=group)
+        bufs = [ctypes.create_string_buffer(h, 64) for h in handles]
+        arr = (ctypes.c_void_p * world)(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+        with torch.cuda.device(self.device):
+            _lib.check(L.psi_fit_set_peers(self.parts[0][2], rank, world, int(batch_total), arr, None), "psi_fit_set_peers")
+        self.world = world
+        dist.barrier(group)                       # every rank has mapped every buffer before anyone starts a loop
+
+    def begin(self, xhr, cam_ext, num_iter):
+        """Enqueue the loop (it runs on the context's own stream) and return; `end()` collects the result.  Lets
+        several shards of one process run concurrently."""
+        _lib.require_cuda(xhr, cam_ext)
+        self._xhr = xhr.contiguous().float()
+        self._cam = cam_ext.reshape(-1, 16)[:, :12].contiguous().float()
+        shared = self._cam.shape[0] == 1
+        with torch.cuda.device(self.device):
+            for s, nb, h in self.parts:
+                _lib.check(_lib.lib().psi_fit_begin(h, _lib.ptr(self._xhr[s:s + nb]), _lib.ptr(self._cam if shared else self._cam[s:s + nb]),
+                                                    0 if shared else 12, int(num_iter), _lib.stream_ptr()), "psi_fit_begin")
+
+    def end(self):
+        out = torch.empty_like(self._xhr)
+        losses = torch.empty(self.B, 4, dtype=torch.float32, device=self._xhr.device)
+        with torch.cuda.device(self.device):
+            for s, nb, h in self.parts:
+                _lib.check(_lib.lib().psi_fit_end(h, _lib.ptr(out[s:s + nb]), _lib.ptr(losses[s:s + nb]), _lib.stream_ptr()), "psi_fit_end")
+        return out, losses
+
     def run(self, xhr, cam_ext, num_iter):
         """xhr [B,75] device; cam_ext [B|1,4,4] -> (fitted xhr [B,75], losses [B,4])."""
         _lib.require_cuda(xhr, cam_ext)
@@ -176,7 +228,7 @@ class FusedFit:
                 nbytes = int(L.psi_fit_trace_bytes(h, code))
                 t = torch.empty(nbytes // 4, dtype=torch.int32 if is_int else torch.float32, device=self.device)
                 _lib.check(L.psi_fit_trace(h, code, _lib.ptr(t), nbytes, st), "psi_fit_trace")
-                outs.append(t if what == "query_ids" else t.view(nb, -1))
+                outs.append(t if what == "query_ids" else t.view(1, -1) if what == "exchange" else t.view(nb, -1))
         if what == "query_ids":
             return outs[0]
         return torch.cat(outs, 0)

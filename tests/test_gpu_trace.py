@@ -237,3 +237,37 @@ def test_fused_loop_at_baseline_size(full_model):
     a = op.fit(xh.cuda(), cam.cuda(), num_iter=300)
     b = op.fit(xh.cuda(), cam.cuda(), num_iter=300)
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_batch_coupled_loss_sharded_over_two_contexts_equals_the_union_batch(small_model):
+    """SURVEY.md 8(e) option 2: the batch-coupled loss with the batch cut into shards.  Two contexts of this process
+    (3 + 2 bodies, each on its own stream) exchange their penetration counts every iteration through each other's
+    exchange buffers inside the loop -- and must reproduce, bit for bit, one context fitting all 5 bodies.  (Across
+    GPUs the same buffers are opened through CUDA IPC: tools/probes/sharded_batch_check.py under torchrun.)"""
+    from psi_release_b200 import synthetic
+    from psi_release_b200.geometry import GeometryTransformer
+    scene = synthetic.make_scene(seed=1, dim=32, num_points=3000)
+    B = 5
+    xh = torch.tensor(synthetic.make_body_params(scene, B, seed=3)).cuda()
+    cid = synthetic.make_contact_ids(431, "parts")
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0).cuda()
+    union = _make(small_model, scene, cid, B, loss_mode="batch")
+    ref = union.fit(xh, cam, num_iter=6)
+    a = _make(small_model, scene, cid, 3, loss_mode="batch")
+    b = _make(small_model, scene, cid, 2, loss_mode="batch")
+    fa, fb = a._fused, b._fused
+    fa.connect_local([fa, fb], 0, B)
+    fb.connect_local([fa, fb], 1, B)
+    x6 = GeometryTransformer.convert_to_6D_rot(xh)
+    for _ in range(2):                                   # a second fit: the sequence number keeps stale slots from matching
+        fa.begin(x6[:3], cam, 6)
+        fb.begin(x6[3:], cam, 6)
+        (oa, la), (ob, lb) = fa.end(), fb.end()
+        torch.cuda.synchronize()
+        got = GeometryTransformer.convert_to_3D_rot(torch.cat([oa, ob]))
+        assert torch.equal(got, ref)
+        assert int(fa.trace("exchange")[0, 1]) == 0 and int(fb.trace("exchange")[0, 1]) == 0       # every count arrived in time
+        assert torch.equal(torch.cat([la, lb]).sum(0), union.last_losses)
+    # and it differs from two unconnected batch-mode shards (the coupling is real)
+    lone = _make(small_model, scene, cid, 3, loss_mode="batch").fit(xh[:3], cam, num_iter=6)
+    assert not torch.equal(lone, ref[:3])
