@@ -399,9 +399,11 @@ def run_ours(args):
     model, scene, _ = make_world(args, rank, scene_seed=my_scene)
     t_synth = time.perf_counter() - t0
     # the bodies of scene s, the same on every rank (a rank fits its slice of them)
-    # (two ranks share a scene and draw the same array; the other scenes' rows are never read by this rank)
-    xh_scene = [(torch.tensor(synthetic.make_body_params(scene, per_scene, seed=100 + s)) if s == my_scene
-                 else torch.zeros(per_scene, 72)) for s in range(ns)] if world > 1 else []
+    # scene s holds the bodies of its ranks back to back, rank r's drawn with seed r exactly as at N = 1 (rank 0 fits the
+    # same 64 bodies in the same scene whatever N is; the other scenes' rows are never read by this rank)
+    rps = world // ns                                       # ranks per scene
+    xh_scene = [(torch.tensor(np.concatenate([synthetic.make_body_params(scene, args.batch, seed=s * rps + k) for k in range(rps)]))
+                 if s == my_scene else torch.zeros(per_scene, 72)) for s in range(ns)] if world > 1 else []
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     cfg = dict(model_data=model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
