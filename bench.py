@@ -168,9 +168,11 @@ def nccl_init_lines():
         path = path.replace("%h", socket.gethostname())
     try:
         with open(path) as f:
-            return [l.strip()[-220:] for l in f if "nranks" in l][:4]
-    except OSError:
-        return []
+            lines = [l.strip() for l in f]
+    except OSError as e:
+        return ["(no NCCL debug file at %s: %s)" % (path, e.__class__.__name__)]
+    hits = [l[-220:] for l in lines if "nranks" in l.lower() or "init complete" in l.lower()]
+    return hits[:4] if hits else ["(%d NCCL debug lines, none naming the communicator size)" % len(lines)] + [l[-160:] for l in lines[:3]]
 
 
 # ------------------------------------------------------------------------------- rooflines
