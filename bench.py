@@ -148,14 +148,16 @@ def peaks():
 
 def init_dist(dev):
     """One process per GPU over NCCL.  NCCL's own init lines are the evidence of the communicator (nranks): whatever
-    NCCL_DEBUG / NCCL_DEBUG_FILE the environment sets is kept untouched; without one, INIT-level lines go to a
-    per-process file that `nccl_init_lines` reads back into the JSON line (stdout then carries only NCCL's version
+    an INFO / TRACE level the environment sets is kept untouched (with its NCCL_DEBUG_FILE, if any); otherwise (unset,
+    VERSION, WARN: no init lines) INIT-level lines go to a per-process file that `nccl_init_lines` reads back into the JSON line (stdout then carries only NCCL's version
     banner before the ONE JSON line, which is printed last)."""
     import torch.distributed as dist
-    if "NCCL_DEBUG" not in os.environ:
+    level = os.environ.get("NCCL_DEBUG", "").upper()
+    if level not in ("INFO", "TRACE"):
+        # unset, or a level (VERSION / WARN) that prints no init lines: INIT-level lines to a per-process file
         os.environ["NCCL_DEBUG"] = "INFO"
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/psi_bench_nccl_%p.log")
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+        os.environ["NCCL_DEBUG_FILE"] = "/tmp/psi_bench_nccl_%p.log"
     dist.init_process_group("nccl", device_id=dev)
     return dist
 
@@ -163,6 +165,9 @@ def init_dist(dev):
 def nccl_init_lines():
     """This process's NCCL init lines that name the communicator size (from the file init_dist pointed NCCL at)."""
     path = os.environ.get("NCCL_DEBUG_FILE", "").replace("%p", str(os.getpid()))
+    if not path:
+        return ["(NCCL_DEBUG=%s from the environment without NCCL_DEBUG_FILE: NCCL's init lines are on this run's stdout)"
+                % os.environ.get("NCCL_DEBUG")]
     if "%h" in path:
         import socket
         path = path.replace("%h", socket.gethostname())
@@ -513,6 +518,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_reference_gpu:
         ref_gpu = reference_gpu(args, op, model, scene, xh_dev, cam_dev, flush, dev, step_ms)
     nccl_lines = nccl_init_lines() if world > 1 else None
+    if nccl_lines and rank == 0:
+        for l in nccl_lines:                      # the communicator's own init lines, also in this run's log
+            print("[nccl] " + l, file=sys.stderr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

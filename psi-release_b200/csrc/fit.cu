@@ -41,14 +41,14 @@ struct psi_fit_ctx {
     psi_fit_config cfg;
     int B, V, J, NB, latent, hidden, nbody, ncomp, num_rot, nu, num_contact, D, np_sdf, nchunk;
     // constants: decoder weights as GEMM tiles (forward: W[out][in]; backward: W^T), biases, hands
-    float *Wf1, *Wf2, *Wf3, *Wb3, *Wb2, *Wb1, *b1, *b2, *b3, *hand_l, *hand_r, *pose_mean, *cweight;
+    float *W1p, *Wf2, *Wf3, *Wb3, *Wb2, *b1, *b2, *b3, *hand_l, *hand_r, *pose_mean, *cweight;
     int no_pad;                    // decoder outputs (nbody*6) padded to the GEMM's N / K granularity
     int *csel, *cslot;
     const float *sdf, *scene_pts;
     float gmin[3], gmax[3];
     // state + scratch.  *A buffers are GEMM A operands ([body group][K/32][64][32], rows >= B zero)
-    float *x0, *x, *am, *av, *cam, *rot6d, *pose, *shape, *transl, *zA, *h1pre, *h1A, *h2pre, *h2A,
-        *g6_root, *g6A, *dh2A, *dh1A, *dz, *verts, *saved, *sdfv, *sdfg, *partial, *nnd, *cpart,
+    float *x0, *x, *am, *av, *cam, *rot6d, *pose, *shape, *transl, *h1pre, *h1A, *h2pre, *h2A,
+        *g6_root, *g6A, *dh2A, *dh1, *verts, *saved, *sdfv, *sdfg, *partial, *nnd, *cpart,
         *gshape, *gpose, *gtransl, *lbs_ws, *losses, *gx, *xeval;
     int *nni, *step, *nnhint;
     psi::LbfgsState lb;            // optimizer 1: per-body L-BFGS state
@@ -81,6 +81,7 @@ namespace psi {
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.2f * v; }
 __device__ __forceinline__ float lrelu_grad(float pre) { return pre > 0.f ? 1.0f : 0.2f; }
 
+constexpr int kW1Row = 33;           // decoder layer 1 in shared memory: rows of 32 weights + 1 pad (conflict free both ways)
 constexpr int kDefaultUnroll = 15;   // iterations per pass of the WHILE body when psi_fit_config.loop_unroll == 0
 
 struct FitDims {
@@ -107,19 +108,31 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
                 const float *__restrict__ x0, float *__restrict__ x, float *__restrict__ am,
                 float *__restrict__ av, int *__restrict__ step, const float *__restrict__ hand_l,
                 const float *__restrict__ hand_r, const float *__restrict__ pose_mean,
-                const float *__restrict__ dz, const float *__restrict__ g6_root,
+                const float *__restrict__ g6_root,
                 const float *__restrict__ gpose, const float *__restrict__ gshape,
                 const float *__restrict__ gtransl, const float *__restrict__ partial,
-                const float *__restrict__ cpart, float *__restrict__ losses, float *__restrict__ zA,
+                const float *__restrict__ cpart, float *__restrict__ losses,
                 float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
                 float *__restrict__ transl, float *__restrict__ gx_out, float *__restrict__ xeval_out,
                 int *__restrict__ neg_cnt, const int *__restrict__ neg_tot, int batch_total, int *__restrict__ loop_left,
-                cudaGraphConditionalHandle loop_cond, const LbfgsParams lbp, const LbfgsState lbs) {
-    pdl_wait();
+                cudaGraphConditionalHandle loop_cond, const LbfgsParams lbp, const LbfgsState lbs,
+                const float *__restrict__ W1p, const float *__restrict__ b1, const float *__restrict__ dh1,
+                float *__restrict__ h1pre, float *__restrict__ h1A) {
+    extern __shared__ __align__(128) float sW[];      // decoder layer 1, W1[n][i] in rows of kW1Row floats
+    __shared__ __align__(8) uint64_t wbar;
     __shared__ float sx[96], g[96];
+    __shared__ float s_dh[512], s_dzp[4][32];
     __shared__ float s_loss;
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int Lz = d.latent;
+    const int Lz = d.latent, H = d.hidden;
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        mbar_fence_init();
+        // a constant: requested before the dependency wait, lands while the state below is read
+        mbar_arrive_expect_tx(&wbar, (uint32_t)(H * kW1Row * 4));
+        tma_load_1d(sW, W1p, (uint32_t)(H * kW1Row * 4), &wbar);
+    }
+    pdl_wait();
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;   // 75
     const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
     for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
@@ -129,6 +142,23 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     if (do_post) {
         t_prev = step[b];
         if (tid < xdim) { x0e = x0[(size_t)b * xdim + tid]; ame = am[(size_t)b * xdim + tid]; ave = av[(size_t)b * xdim + tid]; }
+        for (int k = tid; k < H; k += blockDim.x) s_dh[k] = dh1[(size_t)b * H + k];
+    }
+    __syncthreads();
+    mbar_wait(&wbar, 0);
+    if (do_post) {
+        // d z = W1^T d h1 (the decoder's last backward layer, 32 x 512 per body): lane = latent component, warp = a
+        // quarter of the hidden units, four interleaved chains each; fixed order
+        const int i = tid & 31, part = tid >> 5, k0 = part * (H / 4);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int k = k0; k < k0 + H / 4; k += 4) {
+            a0 = fmaf(s_dh[k], sW[k * kW1Row + i], a0);
+            a1 = fmaf(s_dh[k + 1], sW[(k + 1) * kW1Row + i], a1);
+            a2 = fmaf(s_dh[k + 2], sW[(k + 2) * kW1Row + i], a2);
+            a3 = fmaf(s_dh[k + 3], sW[(k + 3) * kW1Row + i], a3);
+        }
+        s_dzp[part][i] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     // loss_mode 1: the L1 / L2 terms are means over the whole batch (the contact and collision terms are scaled
@@ -138,7 +168,11 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
         if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
         else if (tid < 9) g[tid] = g6_root[(size_t)b * 6 + tid - 3];
         else if (tid < 19) g[tid] = gshape[(size_t)b * d.NB + tid - 9];
-        else if (tid < 19 + Lz) g[tid] = dz[(size_t)b * Lz + tid - zoff] + cfg.w_vposer * (2.0f * sx[tid] / ((float)Lz * bdiv));
+        else if (tid < 19 + Lz) {
+            const int i = tid - zoff;
+            const float dzi = (s_dzp[0][i] + s_dzp[1][i]) + (s_dzp[2][i] + s_dzp[3][i]);
+            g[tid] = dzi + cfg.w_vposer * (2.0f * sx[tid] / ((float)Lz * bdiv));
+        }
         else if (tid < xdim) {                       // hand PCA backward
             const int u = tid - lhoff, c = u % d.ncomp;
             const bool right = u >= d.ncomp;
@@ -218,7 +252,19 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     }
     pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     // inputs of the next evaluation
-    if (tid < Lz) zA[a_index(b, tid, Lz)] = sx[zoff + tid];
+    // decoder layer 1 for the new latent: h1 = lrelu(W1 z + b1), as the pre-activation (kept for the backward) and as
+    // the A operand of layer 2's GEMM
+    for (int n = tid; n < H; n += blockDim.x) {
+        float v0 = b1[n], v1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            v0 = fmaf(sW[n * kW1Row + i], sx[zoff + i], v0);
+            v1 = fmaf(sW[n * kW1Row + i + 1], sx[zoff + i + 1], v1);
+        }
+        const float v = v0 + v1;
+        h1pre[(size_t)b * H + n] = v;
+        h1A[a_index(b, n, H)] = lrelu(v);
+    }
     if (tid < 6) rot6d[(size_t)b * d.num_rot * 6 + tid] = sx[3 + tid];
     // axis-angle pose vector [J*3]: only joints >= num_rot are read by the LBS kernels
     const int hl0 = (d.J - 30) * 3, hr0 = (d.J - 15) * 3;
@@ -327,8 +373,8 @@ static int launch_linear(cudaStream_t st, int B, const float *A, const float *W,
     LinearParams p;
     p.A = A; p.W = W; p.bias = bias; p.gate = gate; p.pre_out = pre_out; p.out_rm = out_rm; p.outA = outA;
     p.K = K; p.N = N; p.B = B; p.n_valid = n_valid; p.ld = ld; p.outA_kpad = outA_kpad; p.act = act;
-    dim3 grid((unsigned)(N / kLT), (unsigned)((B + kBG - 1) / kBG));
-    if (K % kKC || K / kKC > kLMaxChunks || N % kLT) return PSI_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)(N / kLT), (unsigned)(2 * ((B + kBG - 1) / kBG)));
+    if (K % (2 * kKC) || K / kKC > kLMaxChunks || N % kLT) return PSI_ERR_UNSUPPORTED;
     (psi::skip_kernel("fit_linear") ? cudaSuccess : launch_pdl(fit_linear_kernel, dim3(grid), dim3(128), (size_t)(K / kKC) * kLChunkBytes, st, p));
     PSI_LAUNCHED_K("fit_linear");
     return PSI_OK;
@@ -337,12 +383,14 @@ static int launch_linear(cudaStream_t st, int B, const float *A, const float *W,
 static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
     const FitDims d = {c->B, c->V, c->J, c->NB, c->latent, c->hidden, c->nbody, c->ncomp, c->num_rot};
     auto go = [&](auto kernel) {
-        return launch_pdl(kernel, dim3(c->B), dim3(128), 0, st, d, c->cfg, do_post, c->np_sdf, c->nchunk, c->num_contact,
-                          c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->dz, c->g6_root, c->gpose,
-                          c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->zA, c->rot6d, c->pose, c->shape, c->transl,
+        return launch_pdl(kernel, dim3(c->B), dim3(128), (size_t)c->hidden * kW1Row * 4, st, d, c->cfg, do_post, c->np_sdf,
+                          c->nchunk, c->num_contact,
+                          c->x0, c->x, c->am, c->av, c->step, c->hand_l, c->hand_r, c->pose_mean, c->g6_root, c->gpose,
+                          c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->rot6d, c->pose, c->shape, c->transl,
                           c->gx, c->xeval, c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr,
                           c->cfg.loss_mode == 1 && c->world > 1 ? c->neg_tot : nullptr, c->batch_total,
-                          c->capturing_loop ? c->loop_left : nullptr, c->loop_cond, c->lbp, c->lb);
+                          c->capturing_loop ? c->loop_left : nullptr, c->loop_cond, c->lbp, c->lb, c->W1p, c->b1, c->dh1,
+                          c->h1pre, c->h1A);
     };
     if (!psi::skip_kernel("fit_step")) {
         if (c->cfg.optimizer == 1) go(fit_step_kernel<1>);
@@ -354,11 +402,10 @@ static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
 
 // one iteration = 15 launches; expects the per-body inputs of fit_step_kernel's second half
 static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
-    const int H = c->hidden, Lz = c->latent, NO = c->nbody * 6, NOp = c->no_pad, B = c->B;
+    const int H = c->hidden, NO = c->nbody * 6, NOp = c->no_pad, B = c->B;
     // VPoser decode: 32 -> 512 -> 512 -> nbody*6 (the 6D vectors land behind the root's in rot6d)
-    int rc = launch_linear(st, B, c->zA, c->Wf1, Lz, H, c->b1, nullptr, c->h1pre, nullptr, 0, H, c->h1A, H, 1);
-    if (rc) return rc;
-    rc = launch_linear(st, B, c->h1A, c->Wf2, H, H, c->b2, nullptr, c->h2pre, nullptr, 0, H, c->h2A, H, 1);
+    // (layer 1, 32 -> 512, is the tail of fit_step: per body, W1 in shared memory)
+    int rc = launch_linear(st, B, c->h1A, c->Wf2, H, H, c->b2, nullptr, c->h2pre, nullptr, 0, H, c->h2A, H, 1);
     if (rc) return rc;
     rc = launch_linear(st, B, c->h2A, c->Wf3, H, NOp, c->b3, nullptr, nullptr, c->rot6d + 6, c->num_rot * 6, NO,
                        nullptr, 0, 0);
@@ -410,11 +457,9 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     // decoder backward: d h2 = (d o . W3) * lrelu', d h1 = (d h2 . W2) * lrelu', d z = d h1 . W1
     rc = launch_linear(st, B, c->g6A, c->Wb3, NOp, H, nullptr, c->h2pre, nullptr, nullptr, 0, H, c->dh2A, H, 0);
     if (rc) return rc;
-    rc = launch_linear(st, B, c->dh2A, c->Wb2, H, H, nullptr, c->h1pre, nullptr, nullptr, 0, H, c->dh1A, H, 0);
+    rc = launch_linear(st, B, c->dh2A, c->Wb2, H, H, nullptr, c->h1pre, nullptr, c->dh1, H, H, nullptr, 0, 0);
     if (rc) return rc;
-    rc = launch_linear(st, B, c->dh1A, c->Wb1, H, Lz, nullptr, nullptr, nullptr, c->dz, Lz, Lz, nullptr, 0, 0);
-    if (rc) return rc;
-    return launch_step(c, 1, st);       // Adam, losses, and the next iteration's per-body inputs
+    return launch_step(c, 1, st);       // d z, Adam, losses, and the next iteration's per-body inputs + decoder layer 1
 }
 
 }  // namespace psi
@@ -471,7 +516,9 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         return PSI_ERR_ALLOC;
     }
     for (int a = 0; a < 3; ++a) { c->gmin[a] = h_grid_min[a]; c->gmax[a] = h_grid_max[a]; }
-    if (ensure_max_dyn_smem(fit_linear_kernel, (size_t)kLMaxChunks * kLChunkBytes) != PSI_OK) {
+    if (ensure_max_dyn_smem(fit_linear_kernel, (size_t)kLMaxChunks * kLChunkBytes) != PSI_OK ||
+        ensure_max_dyn_smem(fit_step_kernel<0>, (size_t)hidden * kW1Row * 4) != PSI_OK ||
+        ensure_max_dyn_smem(fit_step_kernel<1>, (size_t)hidden * kW1Row * 4) != PSI_OK) {
         psi_fit_destroy(c);
         return PSI_ERR_UNSUPPORTED;
     }
@@ -513,8 +560,10 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
             return T;
         };
         int np = 0, kp = 0;
-        std::vector<float> t1 = linear_weight_tiles(h_W1, H, latent, &np, &kp);
-        c->Wf1 = upload_f(t1);
+        std::vector<float> w1p((size_t)H * kW1Row, 0.f);            // layer 1 as fit_step stages it: W1[n][i], padded rows
+        for (int n = 0; n < H; ++n)
+            for (int i = 0; i < latent; ++i) w1p[(size_t)n * kW1Row + i] = h_W1[(size_t)n * latent + i];
+        c->W1p = upload_f(w1p);
         std::vector<float> t2 = linear_weight_tiles(h_W2, H, H, &np, &kp);
         c->Wf2 = upload_f(t2);
         std::vector<float> t3 = linear_weight_tiles(h_W3, NO, H, &np, &kp);
@@ -527,9 +576,6 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         const std::vector<float> tr2 = transpose(h_W2, H, H);
         std::vector<float> tb2 = linear_weight_tiles(tr2.data(), H, H, &np, &kp);
         c->Wb2 = upload_f(tb2);
-        const std::vector<float> tr1 = transpose(h_W1, H, latent);  // [latent][H]
-        std::vector<float> tb1 = linear_weight_tiles(tr1.data(), latent, H, &np, &kp);
-        c->Wb1 = upload_f(tb1);
         std::vector<float> v1(h_b1, h_b1 + H), v2(h_b2, h_b2 + H), v3(h_b3, h_b3 + NO),
             hl(h_hand_l, h_hand_l + (size_t)ncomp * 45), hr(h_hand_r, h_hand_r + (size_t)ncomp * 45),
             pm(h_pose_mean, h_pose_mean + (size_t)J * 3);
@@ -550,9 +596,9 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
     c->x0 = fbuf(B * xd); c->x = fbuf(B * xd); c->am = fbuf(B * xd); c->av = fbuf(B * xd);
     c->cam = fbuf(B * 12); c->rot6d = fbuf(B * c->num_rot * 6); c->pose = fbuf(B * J * 3); c->shape = fbuf(B * NB);
     c->transl = fbuf(B * 3); c->h1pre = fbuf(B * H); c->h2pre = fbuf(B * H);
-    c->zA = zbuf(Bp * latent); c->h1A = zbuf(Bp * H); c->h2A = zbuf(Bp * H);
-    c->g6A = zbuf(Bp * c->no_pad); c->dh2A = zbuf(Bp * H); c->dh1A = zbuf(Bp * H);
-    c->g6_root = fbuf(B * 6); c->dz = fbuf(B * latent);
+    c->h1A = zbuf(Bp * H); c->h2A = zbuf(Bp * H);
+    c->g6A = zbuf(Bp * c->no_pad); c->dh2A = zbuf(Bp * H); c->dh1 = fbuf(B * H);
+    c->g6_root = fbuf(B * 6);
     c->verts = fbuf(B * V * 3); c->saved = fbuf(psi_lbs_saved_floats(model, c->B) + 64);
     c->sdfv = fbuf(B * V); c->sdfg = fbuf(B * V * 3); c->partial = fbuf(B * c->np_sdf * 2);
     c->nnd = fbuf(B * c->nu); c->nni = (int *)dev_alloc(B * c->nu * sizeof(int));
@@ -778,7 +824,7 @@ int psi_fit_run(psi_fit_ctx *c, const float *xhr_init, const float *cam, long ca
     return psi_fit_end(c, xhr_out, losses_out, stream);
 }
 
-int psi_fit_launches_per_iteration(void) { return 15; }
+int psi_fit_launches_per_iteration(void) { return 13; }
 
 int psi_fit_exchange_handle(psi_fit_ctx *c, void *h_handle64) {
     if (!c || !h_handle64) return PSI_ERR_BAD_ARG;
