@@ -43,6 +43,7 @@
 namespace psi {
 
 constexpr int kMaxJ = 64;
+constexpr int kJdMaxNB = 32;     // shape coefficients up to which the pose kernels keep Jdirs in shared memory
 constexpr int kUnitLen = 16;      // entries per work unit of the dA partial sums (lbs_vertex_bwd)
 constexpr int kMaxUnits = 160;    // units per 256-vertex chunk held in shared memory; more -> per-joint loop
 constexpr int kFT = 72;         // forward tile: 72 vertex coordinates (9 n8 tiles); 3V/72 = 437 tiles at
@@ -65,7 +66,7 @@ struct psi_lbs_model {
     int *tree_buf;
     int V, J, NB, P, K, Kpad, Npad, KW, NC, NT, FT;   // NC coordinate chunks of 32 (Npad = 32 NC), NT forward tiles of 72
     long nnz;
-    float *basis_fwd, *basis_bwd, *v_template, *Jt, *Jdirs, *skin_w, *ch_w;
+    float *basis_fwd, *basis_bwd, *v_template, *Jt, *Jdirs, *Jdirs_p, *skin_w, *ch_w;
     unsigned short *basis_fwd3, *basis_bwd3;   // bf3 path: the basis as three bfloat16 terms (see psi_lbs_model_create)
     int *skin_j, *parents, *ch_seg, *ch_ju, *unit_desc;
     int max_units;                 // most work units in one chunk
@@ -161,52 +162,89 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ betas, const float *__restrict__ pose,
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
                     float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
-                    const float *__restrict__ rot6d, int split, const psi_lbs_tree tree) {
+                    const float *__restrict__ rot6d, int split, const psi_lbs_tree tree,
+                    const float *__restrict__ Jdirs_p) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
+    __shared__ __align__(16) float sJd[kMaxJ * 3 * (kJdMaxNB + 1)];
+    __shared__ float sbeta[kJdMaxNB];
+    __shared__ __align__(8) uint64_t jbar;
     __shared__ TreeSmem st;
     const int b = blockIdx.x, tid = threadIdx.x;
-    stage_tree(st, tree, parents, J);          // constants: before the dependency wait
+    const int S = NB | 1;
+    if (Jdirs_p && tid == 0) {                 // constants: requested before the dependency wait
+        const uint32_t bytes = (uint32_t)(((size_t)J * 3 * S + 3) / 4 * 16);
+        mbar_init(&jbar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(&jbar, bytes);
+        tma_load_1d(sJd, Jdirs_p, bytes, &jbar);
+    }
+    stage_tree(st, tree, parents, J);
+    float jt[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) jt[i] = tid + i * 128 < J * 3 ? Jt[tid + i * 128] : 0.f;
     pdl_wait();
-    for (int j = tid; j < J; j += blockDim.x) {
-        if (j < num_rot && rot6d) {   // 6D representation -> R by Gram-Schmidt (cvae.py:46-55), fused here
-            float R[9];
-            gs_fwd(rot6d + ((size_t)b * num_rot + j) * 6, R);
+    if (Jdirs_p && tid < NB) sbeta[tid] = betas[(size_t)b * NB + tid];
+    {
+        // joint rotations.  Axis-angle joints on the low threads, 6D / matrix joints from thread 64 on: the two code
+        // paths run in different warps instead of one after the other
+        int j = -1;
+        if (tid < J - num_rot) j = num_rot + tid;
+        else if (tid >= 64 && tid - 64 < num_rot) j = tid - 64;
+        if (j >= 0) {
+            if (j < num_rot && rot6d) {   // 6D representation -> R by Gram-Schmidt (cvae.py:46-55), fused here
+                float R[9];
+                gs_fwd(rot6d + ((size_t)b * num_rot + j) * 6, R);
 #pragma unroll
-            for (int e = 0; e < 9; ++e) sR[j * 9 + e] = R[e];
-        } else if (j < num_rot) {     // rotation matrices handed over directly (no axis-angle round trip)
+                for (int e = 0; e < 9; ++e) sR[j * 9 + e] = R[e];
+            } else if (j < num_rot) {     // rotation matrices handed over directly (no axis-angle round trip)
 #pragma unroll
-            for (int e = 0; e < 9; ++e) sR[j * 9 + e] = rot_in[((size_t)b * num_rot + j) * 9 + e];
-        } else {
-            rodrigues(pose + ((size_t)b * J + j) * 3, sR + j * 9);
+                for (int e = 0; e < 9; ++e) sR[j * 9 + e] = rot_in[((size_t)b * num_rot + j) * 9 + e];
+            } else {
+                rodrigues(pose + ((size_t)b * J + j) * 3, sR + j * 9);
+            }
         }
     }
-    for (int e = tid; e < J * 3; e += blockDim.x) {
-        float v = Jt[e];
-        for (int l = 0; l < NB; ++l) v = fmaf(Jdirs[(size_t)e * NB + l], betas[(size_t)b * NB + l], v);
-        sJ[e] = v;
+    if (Jdirs_p) {
+        __syncthreads();                       // sbeta, the barrier's initialisation
+        mbar_wait(&jbar, 0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int e = tid + i * 128;
+            if (e < J * 3) {
+                float v = jt[i];
+                for (int l = 0; l < NB; ++l) v = fmaf(sJd[e * S + l], sbeta[l], v);
+                sJ[e] = v;
+            }
+        }
+    } else {
+        for (int e = tid; e < J * 3; e += blockDim.x) {
+            float v = Jt[e];
+            for (int l = 0; l < NB; ++l) v = fmaf(Jdirs[(size_t)e * NB + l], betas[(size_t)b * NB + l], v);
+            sJ[e] = v;
+        }
     }
     __syncthreads();
-    // kinematic chain, one tree level at a time (joints of a level are independent)
+    // kinematic chain, one tree level at a time (joints of a level are independent), one thread per entry of
+    // [Gr | Gt] (12 per joint): a level costs one short dependent chain instead of 36 multiply-adds in one thread
     for (int l = 0; l < tree.nlev; ++l) {
-        for (int q = st.lvl_start[l] + tid; q < st.lvl_start[l + 1]; q += blockDim.x) {
-            const int j = st.lvl_joint[q];
+        const int q0 = st.lvl_start[l], nj = st.lvl_start[l + 1] - q0;
+        for (int u = tid; u < nj * 12; u += blockDim.x) {
+            const int j = st.lvl_joint[q0 + u / 12], o = u % 12;
             if (j == 0) {
-                for (int e = 0; e < 9; ++e) sGr[e] = sR[e];
-                for (int e = 0; e < 3; ++e) sGt[e] = sJ[e];
+                if (o < 9) sGr[o] = sR[o];
+                else sGt[o - 9] = sJ[o - 9];
                 continue;
             }
             const int p = st.parents[j];
-            const float *Gp = sGr + p * 9, *Rj = sR + j * 9;
-            float rel[3] = {sJ[j * 3] - sJ[p * 3], sJ[j * 3 + 1] - sJ[p * 3 + 1],
-                            sJ[j * 3 + 2] - sJ[p * 3 + 2]};
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    sGr[j * 9 + r * 3 + c] =
-                        Gp[r * 3] * Rj[c] + Gp[r * 3 + 1] * Rj[3 + c] + Gp[r * 3 + 2] * Rj[6 + c];
-                sGt[j * 3 + r] =
-                    Gp[r * 3] * rel[0] + Gp[r * 3 + 1] * rel[1] + Gp[r * 3 + 2] * rel[2] + sGt[p * 3 + r];
+            const float *Gp = sGr + p * 9;
+            if (o < 9) {
+                const int r = o / 3, c = o % 3;
+                const float *Rj = sR + j * 9;
+                sGr[j * 9 + o] = Gp[r * 3] * Rj[c] + Gp[r * 3 + 1] * Rj[3 + c] + Gp[r * 3 + 2] * Rj[6 + c];
+            } else {
+                const int r = o - 9;
+                const float rel[3] = {sJ[j * 3] - sJ[p * 3], sJ[j * 3 + 1] - sJ[p * 3 + 1], sJ[j * 3 + 2] - sJ[p * 3 + 2]};
+                sGt[j * 3 + r] = Gp[r * 3] * rel[0] + Gp[r * 3 + 1] * rel[1] + Gp[r * 3 + 2] * rel[2] + sGt[p * 3 + r];
             }
         }
         __syncthreads();
@@ -1519,20 +1557,32 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     float *__restrict__ gbetas, float *__restrict__ gpose,
                     float *__restrict__ gtransl, float *__restrict__ grot, int num_rot,
                     const float *__restrict__ rot6d, float *__restrict__ g6_root, float *__restrict__ g6A,
-                    int g6_kpad, const psi_lbs_tree tree) {
+                    int g6_kpad, const psi_lbs_tree tree, const float *__restrict__ Jdirs_p) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], drel_s[kMaxJ * 3];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
+    __shared__ float sdA[(kMaxJ + 1) * 12], dGtF[kMaxJ * 3];   // dGtF: dGt after the pull (what a parent reads)
     __shared__ float dbeta_direct[64], dbeta_part[6][32];
+    __shared__ __align__(16) float sJd[kMaxJ * 3 * (kJdMaxNB + 1)];
+    __shared__ __align__(8) uint64_t jbar;
     __shared__ TreeSmem st;
     const int b = blockIdx.x, tid = threadIdx.x;
-    stage_tree(st, tree, parents, J);          // constants: before the dependency wait
+    const int S = NB | 1;
+    if (Jdirs_p && tid == 0) {                 // constants: requested before the dependency wait
+        const uint32_t bytes = (uint32_t)(((size_t)J * 3 * S + 3) / 4 * 16);
+        mbar_init(&jbar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(&jbar, bytes);
+        tma_load_1d(sJd, Jdirs_p, bytes, &jbar);
+    }
+    stage_tree(st, tree, parents, J);
     pdl_wait();
     const float *dA = dAsum + (size_t)b * (J + 1) * 12;      // chunk partials already summed; row J = d translation
-    const float *dtr = dA + J * 12;
     const float *iR = saved + L.R + (size_t)b * J * 9, *iJ = saved + L.Jr + (size_t)b * J * 3;
     const float *iGr = saved + L.Gr + (size_t)b * J * 9;
+    // everything this body reads from global memory, in one round trip
     for (int e = tid; e < J * 9; e += blockDim.x) { sR[e] = iR[e]; sGr[e] = iGr[e]; }
     for (int e = tid; e < J * 3; e += blockDim.x) sJ[e] = iJ[e];
+    for (int e = tid; e < (J + 1) * 12; e += blockDim.x) sdA[e] = dA[e];
     // d pose-feature (added to dR below) and the direct d beta, summed over splits in order
     for (int k = tid; k < P + NB; k += blockDim.x) {
         const float s = part[(size_t)b * Kpad + k];          // already summed over the splits
@@ -1542,9 +1592,10 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     }
     if (tid < 9) dR[tid] = 0.f;
     __syncthreads();
+    const float *dtr = sdA + J * 12;
     // dGr = dAr - dAt J^T ; dGt = dAt (+ d posed joints) ; dJ = -Gr^T dAt
     for (int j = tid; j < J; j += blockDim.x) {
-        const float *a = dA + j * 12;
+        const float *a = sdA + j * 12;
         const float at[3] = {a[3], a[7], a[11]};
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -1557,57 +1608,55 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
             dJ[j * 3 + c] = -(sGr[j * 9 + c] * at[0] + sGr[j * 9 + 3 + c] * at[1] + sGr[j * 9 + 6 + c] * at[2]);
     }
     __syncthreads();
-    // chain backward, deepest tree level first.  A joint first PULLS from its children (fixed
-    // child order: deterministic, race free), then finishes its own dR / d rel.
+    // chain backward, deepest tree level first.  A joint first PULLS from its children (fixed child order:
+    // deterministic, race free), then finishes its own dR / d rel.  Three threads per joint, one per COLUMN cc of
+    // dGr[j]: column cc of the pulled sum is all that dR[j][.][cc] needs, so the three never exchange anything.
     for (int l = tree.nlev - 1; l >= 0; --l) {
-        for (int q = st.lvl_start[l] + tid; q < st.lvl_start[l + 1]; q += blockDim.x) {
-            const int j = st.lvl_joint[q];
-            float g[9], gt[3], dj[3];
+        const int q0 = st.lvl_start[l], nj = st.lvl_start[l + 1] - q0;
+        for (int u = tid; u < nj * 3; u += blockDim.x) {
+            const int j = st.lvl_joint[q0 + u / 3], cc = u % 3;
+            float g[3], gt[3], djc = dJ[j * 3 + cc];
 #pragma unroll
-            for (int e = 0; e < 9; ++e) g[e] = dGr[j * 9 + e];
-#pragma unroll
-            for (int e = 0; e < 3; ++e) { gt[e] = dGt[j * 3 + e]; dj[e] = dJ[j * 3 + e]; }
+            for (int r = 0; r < 3; ++r) { g[r] = dGr[j * 9 + r * 3 + cc]; gt[r] = dGt[j * 3 + r]; }
             for (int ci = st.child_start[j]; ci < st.child_start[j + 1]; ++ci) {
                 const int c = st.child_list[ci];
-                const float *Rc = sR + c * 9, *gc = dGr + c * 9, *gtc = dGt + c * 3;
-                const float rel[3] = {sJ[c * 3] - sJ[j * 3], sJ[c * 3 + 1] - sJ[j * 3 + 1], sJ[c * 3 + 2] - sJ[j * 3 + 2]};
+                const float *Rc = sR + c * 9, *gc = dGr + c * 9, *gtc = dGtF + c * 3;
+                const float relc = sJ[c * 3 + cc] - sJ[j * 3 + cc];
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc)   // dGr[j] += dGr[c] Rc^T + dGt[c] rel^T
-                        g[r * 3 + cc] += gc[r * 3] * Rc[cc * 3] + gc[r * 3 + 1] * Rc[cc * 3 + 1] +
-                                         gc[r * 3 + 2] * Rc[cc * 3 + 2] + gtc[r] * rel[cc];
+                for (int r = 0; r < 3; ++r) {      // dGr[j] += dGr[c] Rc^T + dGt[c] rel^T
+                    g[r] += gc[r * 3] * Rc[cc * 3] + gc[r * 3 + 1] * Rc[cc * 3 + 1] + gc[r * 3 + 2] * Rc[cc * 3 + 2] +
+                            gtc[r] * relc;
                     gt[r] += gtc[r];
-                    dj[r] -= drel_s[c * 3 + r];
                 }
+                djc -= drel_s[c * 3 + cc];
             }
-#pragma unroll
-            for (int e = 0; e < 9; ++e) dGr[j * 9 + e] = g[e];
+            float drel = 0.f;
             if (j == 0) {
 #pragma unroll
-                for (int e = 0; e < 9; ++e) dR[e] += g[e];
-#pragma unroll
-                for (int e = 0; e < 3; ++e) dj[e] += gt[e];
+                for (int r = 0; r < 3; ++r) dR[r * 3 + cc] += g[r];
+                djc += gt[cc];
             } else {
                 const float *Gp = sGr + st.parents[j] * 9;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc)   // dR[j] += Gp^T dGr[j]
-                        dR[j * 9 + r * 3 + cc] += Gp[r] * g[cc] + Gp[3 + r] * g[3 + cc] + Gp[6 + r] * g[6 + cc];
-                    const float drel = Gp[r] * gt[0] + Gp[3 + r] * gt[1] + Gp[6 + r] * gt[2];
-                    drel_s[j * 3 + r] = drel;
-                    dj[r] += drel;
-                }
+                for (int r = 0; r < 3; ++r)        // dR[j] += Gp^T dGr[j]
+                    dR[j * 9 + r * 3 + cc] += Gp[r] * g[0] + Gp[3 + r] * g[1] + Gp[6 + r] * g[2];
+                drel = Gp[cc] * gt[0] + Gp[3 + cc] * gt[1] + Gp[6 + cc] * gt[2];
+                djc += drel;
             }
+            // a thread overwrites only what no other thread of this level reads (its own column of dGr[j], its own
+            // entries of the other arrays; dGt[j], read by all three, stays as it was)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) { dGt[j * 3 + e] = gt[e]; dJ[j * 3 + e] = dj[e]; }
+            for (int r = 0; r < 3; ++r) dGr[j * 9 + r * 3 + cc] = g[r];
+            drel_s[j * 3 + cc] = drel;
+            dGtF[j * 3 + cc] = gt[cc];
+            dJ[j * 3 + cc] = djc;
         }
         __syncthreads();
     }
     pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     // Rodrigues backward (lbs.py:177-191); joints given as matrices export dR itself
-    for (int j = tid; j < J; j += blockDim.x) {
+    // (axis-angle joints on the low threads, 6D / matrix joints from thread 64 on: different warps, no divergence)
+    for (int j = tid < J - num_rot ? num_rot + tid : (tid >= 64 && tid - 64 < num_rot ? tid - 64 : J); j < J; j = J) {
         float *o = gpose + ((size_t)b * J + j) * 3;
         if (j < num_rot && rot6d) {
             // Gram-Schmidt backward fused here: joint 0 -> g6_root [B,6]; joints 1.. -> g6A, the
@@ -1666,8 +1715,25 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
         o[1] = dn1 / a + da * ey / a;
         o[2] = dn2 / a + da * ez / a;
     }
-    // d beta = direct term + Jdirs^T dJ: (l, slice of the joint coordinates) per thread, six slices summed in order
-    if (NB <= 32) {
+    // d beta = direct term + Jdirs^T dJ: (l, slice of the joint coordinates) per thread, slices summed in order
+    if (Jdirs_p) {
+        const int l = tid % 32, part = tid / 32;                 // one slice per warp, Jdirs from shared memory
+        mbar_wait(&jbar, 0);
+        float s0 = 0.f, s1 = 0.f;
+        if (l < NB) {
+            int e = part;
+            for (; e + 4 < J * 3; e += 8) {
+                s0 = fmaf(sJd[e * S + l], dJ[e], s0);
+                s1 = fmaf(sJd[(e + 4) * S + l], dJ[e + 4], s1);
+            }
+            if (e < J * 3) s0 = fmaf(sJd[e * S + l], dJ[e], s0);
+        }
+        dbeta_part[part][l] = s0 + s1;
+        __syncthreads();
+        if (tid < NB)
+            gbetas[(size_t)b * NB + tid] =
+                dbeta_direct[tid] + ((dbeta_part[0][tid] + dbeta_part[1][tid]) + (dbeta_part[2][tid] + dbeta_part[3][tid]));
+    } else if (NB <= 32) {
         const int l = tid % 32, part = tid / 32;                 // 128 threads: 4 slices active, parts 4, 5 done by a second pass
         for (int pp = part; pp < 6; pp += 4) {
             float s = 0.f;
@@ -1734,7 +1800,7 @@ extern "C" {
 
 void psi_lbs_model_destroy(psi_lbs_model *m) {
     if (!m) return;
-    cudaFree(m->basis_fwd); cudaFree(m->basis_bwd); cudaFree(m->basis_fwd3); cudaFree(m->basis_bwd3); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs);
+    cudaFree(m->basis_fwd); cudaFree(m->basis_bwd); cudaFree(m->basis_fwd3); cudaFree(m->basis_bwd3); cudaFree(m->v_template); cudaFree(m->Jt); cudaFree(m->Jdirs); cudaFree(m->Jdirs_p);
     cudaFree(m->skin_w); cudaFree(m->ch_w); cudaFree(m->skin_j); cudaFree(m->parents);
     cudaFree(m->ch_seg); cudaFree(m->ch_lv); cudaFree(m->tree_buf); cudaFree(m->ch_ju); cudaFree(m->unit_desc);
     delete m;
@@ -1923,6 +1989,13 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     if (rc == PSI_OK) rc = upload(&m->v_template, vt, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->Jt, Jt, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->Jdirs, Jdirs, st, &m->bytes);
+    if (NB <= kJdMaxNB) {       // rows of an odd length: the copy the pose kernels stage in shared memory (one TMA bulk copy)
+        const int S = NB | 1;
+        std::vector<float> jp(((size_t)J * 3 * S + 3) / 4 * 4, 0.f);
+        for (int e = 0; e < J * 3; ++e)
+            for (int l = 0; l < NB; ++l) jp[(size_t)e * S + l] = Jdirs[(size_t)e * NB + l];
+        if (rc == PSI_OK) rc = upload(&m->Jdirs_p, jp, st, &m->bytes);
+    }
     if (rc == PSI_OK) rc = upload(&m->skin_j, skin_j, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->skin_w, skin_w, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->parents, parents, st, &m->bytes);
@@ -1983,7 +2056,7 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
     const bool tc5 = lbs_gemm_tc5();
     const int gmode = lbs_gemm_mode();
     (psi::skip_kernel("lbs_pose_fwd") ? cudaSuccess : launch_pdl(lbs_pose_fwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, gmode, m->tree));
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, gmode, m->tree, m->Jdirs_p));
     PSI_LAUNCHED_K("lbs_pose_fwd");
     if (B % kBG && gmode == kGemmBf3) {
         (psi::skip_kernel("lbs_zero_coef_pad") ? cudaSuccess : launch_pdl(lbs_zero_coef_pad3_kernel, dim3(8), dim3(256), 0, st,
@@ -2134,7 +2207,7 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
     }
     (psi::skip_kernel("lbs_pose_bwd") ? cudaSuccess : launch_pdl(lbs_pose_bwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, W.Bpad, nsplit, m->Jdirs,
                m->parents, pose, saved, L, ws + W.dA, ws + W.dsum, grad_joints, grad_betas,
-               grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree));
+               grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree, m->Jdirs_p));
     PSI_LAUNCHED_K("lbs_pose_bwd");
     return PSI_OK;
 }
