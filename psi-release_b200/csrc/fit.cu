@@ -120,7 +120,7 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
                 float *__restrict__ h1pre, float *__restrict__ h1A) {
     extern __shared__ __align__(128) float sW[];      // decoder layer 1, W1[n][i] in rows of kW1Row floats
     __shared__ __align__(8) uint64_t wbar;
-    __shared__ float sx[96], g[96];
+    __shared__ float sx[96], g[96], sx0[96];
     __shared__ float s_dh[512], s_dzp[4][32];
     __shared__ float s_loss;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -132,17 +132,52 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
         mbar_arrive_expect_tx(&wbar, (uint32_t)(H * kW1Row * 4));
         tma_load_1d(sW, W1p, (uint32_t)(H * kW1Row * 4), &wbar);
     }
+    float b1r[4];              // layer 1's bias for this thread's four hidden units (H = 512): a constant too
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b1r[i] = b1[tid + i * 128];
     pdl_wait();
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;   // 75
     const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
     for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
-    // Adam state of this thread's component: requested now, consumed two barriers later
-    float x0e = 0.f, ame = 0.f, ave = 0.f;
+    // Everything the post-processing half reads from global memory is requested HERE, in one round trip: the Adam
+    // state of this thread's component, its raw gradient component (hand PCA backward included), the loss partial sums
+    // (warp 3) and d h1.  (Loads left inside run-time loops further down cost a dependent round trip each.)
+    float x0e = 0.f, ame = 0.f, ave = 0.f, gin = 0.f;
+    float pf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int t_prev = 0;
     if (do_post) {
         t_prev = step[b];
         if (tid < xdim) { x0e = x0[(size_t)b * xdim + tid]; ame = am[(size_t)b * xdim + tid]; ave = av[(size_t)b * xdim + tid]; }
-        for (int k = tid; k < H; k += blockDim.x) s_dh[k] = dh1[(size_t)b * H + k];
+        float t4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t4[i] = dh1[(size_t)b * H + tid + i * 128];
+        if (tid < 3) gin = gtransl[(size_t)b * 3 + tid];
+        else if (tid < 9) gin = g6_root[(size_t)b * 6 + tid - 3];
+        else if (tid < 19) gin = gshape[(size_t)b * d.NB + tid - 9];
+        else if (tid >= lhoff && tid < xdim) {       // hand PCA backward
+            const int u = tid - lhoff, c = u % d.ncomp;
+            const bool right = u >= d.ncomp;
+            const float *comp = (right ? hand_r : hand_l) + c * 45;
+            const float *gp = gpose + (size_t)b * d.J * 3 + (right ? (d.J - 15) * 3 : (d.J - 30) * 3);
+            float a = 0.f;
+            for (int k = 0; k < 45; ++k) a = fmaf(comp[k], gp[k], a);
+            gin = a;
+        }
+        if (tid >= 96) {
+            const int ln = tid - 96;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int i = ln + q * 32;
+                if (i < np_sdf) {
+                    pf[q * 2] = partial[((size_t)b * np_sdf + i) * 2];
+                    pf[q * 2 + 1] = partial[((size_t)b * np_sdf + i) * 2 + 1];
+                }
+                if (i < nchunk) pf[4 + q] = cpart[(size_t)b * nchunk + i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_dh[tid + i * 128] = t4[i];
+        if (tid < xdim) sx0[tid] = x0e;
     }
     __syncthreads();
     mbar_wait(&wbar, 0);
@@ -165,33 +200,27 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     // where their gradients are formed, lbs_vertex_bwd<FIT>)
     const float bdiv = cfg.loss_mode == 1 ? (float)(neg_tot ? batch_total : d.B) : 1.0f;   // sharded: bodies of the WHOLE batch
     if (do_post) {
-        if (tid < 3) g[tid] = gtransl[(size_t)b * 3 + tid];
-        else if (tid < 9) g[tid] = g6_root[(size_t)b * 6 + tid - 3];
-        else if (tid < 19) g[tid] = gshape[(size_t)b * d.NB + tid - 9];
-        else if (tid < 19 + Lz) {
+        if (tid >= zoff && tid < zoff + Lz) {
             const int i = tid - zoff;
             const float dzi = (s_dzp[0][i] + s_dzp[1][i]) + (s_dzp[2][i] + s_dzp[3][i]);
             g[tid] = dzi + cfg.w_vposer * (2.0f * sx[tid] / ((float)Lz * bdiv));
-        }
-        else if (tid < xdim) {                       // hand PCA backward
-            const int u = tid - lhoff, c = u % d.ncomp;
-            const bool right = u >= d.ncomp;
-            const float *comp = (right ? hand_r : hand_l) + c * 45;
-            const float *gp = gpose + (size_t)b * d.J * 3 + (right ? (d.J - 15) * 3 : (d.J - 30) * 3);
-            float a = 0.f;
-            for (int k = 0; k < 45; ++k) a = fmaf(comp[k], gp[k], a);
-            g[(right ? rhoff : lhoff) + c] = a;
+        } else if (tid < xdim) {
+            g[tid] = gin;
         }
         if (tid >= 96) {        // warp 3: loss values of the iteration just evaluated (x before the update)
             const int ln = tid - 96;
             float r = 0.f, zz = 0.f, sn = 0.f, cn = 0.f, cs = 0.f;
-            for (int e = ln; e < xdim; e += 32) r += fabsf(x0[(size_t)b * xdim + e] - sx[e]);
+            for (int e = ln; e < xdim; e += 32) r += fabsf(sx0[e] - sx[e]);
             for (int i = ln; i < Lz; i += 32) zz = fmaf(sx[zoff + i], sx[zoff + i], zz);
-            for (int i = ln; i < np_sdf; i += 32) {
+            sn += pf[0]; cn += pf[1];               // rows ln, ln + 32 (requested at the top), then the rest in order
+            sn += pf[2]; cn += pf[3];
+            for (int i = ln + 64; i < np_sdf; i += 32) {
                 sn += partial[((size_t)b * np_sdf + i) * 2];
                 cn += partial[((size_t)b * np_sdf + i) * 2 + 1];
             }
-            for (int i = ln; i < nchunk; i += 32) cs += cpart[(size_t)b * nchunk + i];
+            cs += pf[4];
+            cs += pf[5];
+            for (int i = ln + 64; i < nchunk; i += 32) cs += cpart[(size_t)b * nchunk + i];
             r = warp_sum(r); zz = warp_sum(zz); sn = warp_sum(sn); cn = warp_sum(cn); cs = warp_sum(cs);
             // loss_mode 1: this body's share of the batch means (the rows add up to the reference's scalars)
             if (cfg.loss_mode == 1) cn = (float)(neg_tot ? neg_tot : neg_cnt)[t_prev & 1];
@@ -254,8 +283,10 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     // inputs of the next evaluation
     // decoder layer 1 for the new latent: h1 = lrelu(W1 z + b1), as the pre-activation (kept for the backward) and as
     // the A operand of layer 2's GEMM
-    for (int n = tid; n < H; n += blockDim.x) {
-        float v0 = b1[n], v1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int n = tid + q * 128;
+        float v0 = b1r[q], v1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
             v0 = fmaf(sW[n * kW1Row + i], sx[zoff + i], v0);

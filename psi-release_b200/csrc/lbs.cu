@@ -1579,16 +1579,42 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     const float *dA = dAsum + (size_t)b * (J + 1) * 12;      // chunk partials already summed; row J = d translation
     const float *iR = saved + L.R + (size_t)b * J * 9, *iJ = saved + L.Jr + (size_t)b * J * 3;
     const float *iGr = saved + L.Gr + (size_t)b * J * 9;
-    // everything this body reads from global memory, in one round trip
-    for (int e = tid; e < J * 9; e += blockDim.x) { sR[e] = iR[e]; sGr[e] = iGr[e]; }
-    for (int e = tid; e < J * 3; e += blockDim.x) sJ[e] = iJ[e];
-    for (int e = tid; e < (J + 1) * 12; e += blockDim.x) sdA[e] = dA[e];
-    // d pose-feature (added to dR below) and the direct d beta, summed over splits in order
-    for (int k = tid; k < P + NB; k += blockDim.x) {
-        const float s = part[(size_t)b * Kpad + k];          // already summed over the splits
+    // everything this body reads from global memory in ONE round trip: all loads are issued before the first store
+    // (loops with run-time bounds are not unrolled across their loads: 16 dependent round trips before)
+    {
+        constexpr int n9 = (kMaxJ * 9 + 127) / 128, n3 = (kMaxJ * 3 + 127) / 128, nA = ((kMaxJ + 1) * 12 + 127) / 128,
+                      nP = ((kMaxJ - 1) * 9 + 64 + 127) / 128;
+        float rR[n9], rG[n9], rJ[n3], rA[nA], rP[nP];
+        const float *pb = part + (size_t)b * Kpad;           // already summed over the splits
         (void)nsplit; (void)Bpad;
-        if (k < P) dR[9 + k] = s;           // joint j = k/9+1, entry k%9
-        else dbeta_direct[k - P] = s;
+#pragma unroll
+        for (int i = 0; i < n9; ++i) {
+            const int e = tid + i * 128;
+            rR[i] = e < J * 9 ? iR[e] : 0.f;
+            rG[i] = e < J * 9 ? iGr[e] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < n3; ++i) { const int e = tid + i * 128; rJ[i] = e < J * 3 ? iJ[e] : 0.f; }
+#pragma unroll
+        for (int i = 0; i < nA; ++i) { const int e = tid + i * 128; rA[i] = e < (J + 1) * 12 ? dA[e] : 0.f; }
+#pragma unroll
+        for (int i = 0; i < nP; ++i) { const int k = tid + i * 128; rP[i] = k < P + NB ? pb[k] : 0.f; }
+#pragma unroll
+        for (int i = 0; i < n9; ++i) {
+            const int e = tid + i * 128;
+            if (e < J * 9) { sR[e] = rR[i]; sGr[e] = rG[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < n3; ++i) { const int e = tid + i * 128; if (e < J * 3) sJ[e] = rJ[i]; }
+#pragma unroll
+        for (int i = 0; i < nA; ++i) { const int e = tid + i * 128; if (e < (J + 1) * 12) sdA[e] = rA[i]; }
+        // d pose-feature (added to dR below) and the direct d beta
+#pragma unroll
+        for (int i = 0; i < nP; ++i) {
+            const int k = tid + i * 128;
+            if (k < P) dR[9 + k] = rP[i];           // joint j = k/9+1, entry k%9
+            else if (k < P + NB) dbeta_direct[k - P] = rP[i];
+        }
     }
     if (tid < 9) dR[tid] = 0.f;
     __syncthreads();

@@ -89,7 +89,8 @@ class FusedFit:
         md = body_model._model_data
         cid = _spatial_order(contact_ids, md["v_template"], md["weights"], np.asarray(md["kintree_table"])[0])
         if num_streams is None:
-            num_streams = 1     # measured: two half-batch contexts are not faster (kernels do not shrink with B)
+            # measured: two half-batch contexts are not faster (kernels do not shrink with B); PSI_FIT_STREAMS re-measures
+            num_streams = int(os.environ.get("PSI_FIT_STREAMS", "1"))
         num_streams = max(1, min(int(num_streams), self.B))
         if loss_mode not in ("independent", "batch"):
             raise ValueError("loss_mode must be 'independent' or 'batch'")
