@@ -122,7 +122,7 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     __shared__ __align__(8) uint64_t wbar;
     __shared__ float sx[96], g[96], sx0[96];
     __shared__ float s_dh[512], s_dzp[4][32];
-    __shared__ float s_loss;
+    __shared__ float s_loss, s_bc[2];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int Lz = d.latent, H = d.hidden;
     if (tid == 0) {
@@ -135,9 +135,19 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     float b1r[4];              // layer 1's bias for this thread's four hidden units (H = 512): a constant too
 #pragma unroll
     for (int i = 0; i < 4; ++i) b1r[i] = b1[tid + i * 128];
-    pdl_wait();
     const int xdim = 9 + 10 + Lz + 2 * d.ncomp;   // 75
     const int zoff = 19, lhoff = 19 + Lz, rhoff = lhoff + d.ncomp;
+    // ... and so are the hand PCA rows of the pose entry this thread writes at the end (entries tid and tid + 128 of
+    // [J*3]: at most one of the two is a hand entry)
+    const int hl0 = (d.J - 30) * 3, hr0 = (d.J - 15) * 3;
+    const int eh = tid >= hl0 ? tid : tid + 128;            // this thread's hand entry, if eh < J*3
+    float hc[16], pm2[2];
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+        hc[c] = (eh < d.J * 3 && c < d.ncomp) ? (eh >= hr0 ? hand_r[c * 45 + (eh - hr0)] : hand_l[c * 45 + (eh - hl0)]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) pm2[i] = tid + i * 128 < d.J * 3 ? pose_mean[tid + i * 128] : 0.f;
+    pdl_wait();
     for (int e = tid; e < xdim; e += blockDim.x) sx[e] = x[(size_t)b * xdim + e];
     // Everything the post-processing half reads from global memory is requested HERE, in one round trip: the Adam
     // state of this thread's component, its raw gradient component (hand PCA backward included), the loss partial sums
@@ -147,6 +157,13 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     int t_prev = 0;
     if (do_post) {
         t_prev = step[b];
+        if (OPT == 0 && tid == 96) {
+            // Adam's bias corrections (double, as torch computes them on the host): one thread, while the loads fly
+            const double bc1 = 1.0 - pow((double)cfg.beta1, (double)(t_prev + 1));
+            const double bc2 = 1.0 - pow((double)cfg.beta2, (double)(t_prev + 1));
+            s_bc[0] = (float)((double)cfg.lr / bc1);
+            s_bc[1] = (float)sqrt(bc2);
+        }
         if (tid < xdim) { x0e = x0[(size_t)b * xdim + tid]; ame = am[(size_t)b * xdim + tid]; ave = av[(size_t)b * xdim + tid]; }
         float t4[4];
 #pragma unroll
@@ -258,10 +275,8 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
             const float v = cfg.beta2 * ave + (1.0f - cfg.beta2) * ge * ge;
             am[o] = m;
             av[o] = v;
-            const double bc1 = 1.0 - pow((double)cfg.beta1, (double)t);
-            const double bc2 = 1.0 - pow((double)cfg.beta2, (double)t);
-            const float step_size = (float)((double)cfg.lr / bc1);
-            const float denom = sqrtf(v) / (float)sqrt(bc2) + cfg.eps;
+            const float step_size = s_bc[0];
+            const float denom = sqrtf(v) / s_bc[1] + cfg.eps;
             xn = xe - (m / denom) * step_size;
             x[o] = xn;
         }
@@ -298,13 +313,16 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     }
     if (tid < 6) rot6d[(size_t)b * d.num_rot * 6 + tid] = sx[3 + tid];
     // axis-angle pose vector [J*3]: only joints >= num_rot are read by the LBS kernels
-    const int hl0 = (d.J - 30) * 3, hr0 = (d.J - 15) * 3;
-    for (int e = tid; e < d.J * 3; e += blockDim.x) {
-        float v = pose_mean[e];
-        if (e >= hr0) {
-            for (int c = 0; c < d.ncomp; ++c) v = fmaf(sx[rhoff + c], hand_r[c * 45 + (e - hr0)], v);
-        } else if (e >= hl0) {
-            for (int c = 0; c < d.ncomp; ++c) v = fmaf(sx[lhoff + c], hand_l[c * 45 + (e - hl0)], v);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int e = tid + i * 128;
+        if (e >= d.J * 3) break;
+        float v = pm2[i];
+        if (e >= hl0) {        // e == eh
+            const int off = e >= hr0 ? rhoff : lhoff;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < d.ncomp) v = fmaf(sx[off + c], hc[c], v);
         } else if (e < d.num_rot * 3) {
             v = 0.f;
         }

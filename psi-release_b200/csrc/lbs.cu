@@ -61,8 +61,15 @@ struct psi_lbs_tree {          // kinematic tree by levels (root = level 0) + ch
     const int *lvl_start, *lvl_joint, *child_start, *child_list;
 };
 
+// the same tree BY VALUE (a kernel parameter: constant bank, no global round trip before the pose kernels can start)
+struct TreeParam {
+    int nlev;
+    unsigned char lvl_start[64 + 1], lvl_joint[64], child_start[64 + 1], child_list[64], parents[64];   // 64 = kMaxJ
+};
+
 struct psi_lbs_model {
     psi_lbs_tree tree;
+    TreeParam tp;
     int *tree_buf;
     int V, J, NB, P, K, Kpad, Npad, KW, NC, NT, FT;   // NC coordinate chunks of 32 (Npad = 32 NC), NT forward tiles of 72
     long nnz;
@@ -126,11 +133,11 @@ __host__ __device__ inline SavedLayout saved_layout(int B, int J, int V, int Kpa
 struct TreeSmem {
     int lvl_start[kMaxJ + 1], lvl_joint[kMaxJ], child_start[kMaxJ + 1], child_list[kMaxJ], parents[kMaxJ];
 };
-__device__ __forceinline__ void stage_tree(TreeSmem &t, const psi_lbs_tree &tree, const int *__restrict__ parents, int J) {
+__device__ __forceinline__ void stage_tree(TreeSmem &t, const TreeParam &tp, int J) {
     for (int i = threadIdx.x; i <= J; i += blockDim.x) {
-        t.lvl_start[i] = tree.lvl_start[i];
-        t.child_start[i] = tree.child_start[i];
-        if (i < J) { t.lvl_joint[i] = tree.lvl_joint[i]; t.child_list[i] = tree.child_list[i]; t.parents[i] = parents[i]; }
+        t.lvl_start[i] = tp.lvl_start[i];
+        t.child_start[i] = tp.child_start[i];
+        if (i < J) { t.lvl_joint[i] = tp.lvl_joint[i]; t.child_list[i] = tp.child_list[i]; t.parents[i] = tp.parents[i]; }
     }
 }
 
@@ -162,7 +169,7 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
                     const float *__restrict__ betas, const float *__restrict__ pose,
                     const float *__restrict__ transl, float *__restrict__ saved, SavedLayout L,
                     float *__restrict__ joints_out, const float *__restrict__ rot_in, int num_rot,
-                    const float *__restrict__ rot6d, int split, const psi_lbs_tree tree,
+                    const float *__restrict__ rot6d, int split, const TreeParam tree,
                     const float *__restrict__ Jdirs_p) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], sGt[kMaxJ * 3];
     __shared__ __align__(16) float sJd[kMaxJ * 3 * (kJdMaxNB + 1)];
@@ -178,7 +185,7 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
         mbar_arrive_expect_tx(&jbar, bytes);
         tma_load_1d(sJd, Jdirs_p, bytes, &jbar);
     }
-    stage_tree(st, tree, parents, J);
+    stage_tree(st, tree, J);
     float jt[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) jt[i] = tid + i * 128 < J * 3 ? Jt[tid + i * 128] : 0.f;
@@ -281,7 +288,7 @@ lbs_pose_fwd_kernel(int J, int NB, int P, int Kpad, const float *__restrict__ Jt
             const int j = k / 9 + 1, e = k % 9;
             v = sR[j * 9 + e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
         } else if (k < P + NB) {
-            v = betas[(size_t)b * NB + (k - P)];
+            v = Jdirs_p ? sbeta[k - P] : betas[(size_t)b * NB + (k - P)];
         }
         if (split == 2) {     // bf16x3 GEMM: three bfloat16 terms, 192-row tiles (common.cuh)
             unsigned short b1, b2, b3;
@@ -1557,7 +1564,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
                     float *__restrict__ gbetas, float *__restrict__ gpose,
                     float *__restrict__ gtransl, float *__restrict__ grot, int num_rot,
                     const float *__restrict__ rot6d, float *__restrict__ g6_root, float *__restrict__ g6A,
-                    int g6_kpad, const psi_lbs_tree tree, const float *__restrict__ Jdirs_p) {
+                    int g6_kpad, const TreeParam tree, const float *__restrict__ Jdirs_p) {
     __shared__ float sR[kMaxJ * 9], sJ[kMaxJ * 3], sGr[kMaxJ * 9], drel_s[kMaxJ * 3];
     __shared__ float dGr[kMaxJ * 9], dGt[kMaxJ * 3], dR[kMaxJ * 9], dJ[kMaxJ * 3];
     __shared__ float sdA[(kMaxJ + 1) * 12], dGtF[kMaxJ * 3];   // dGtF: dGt after the pull (what a parent reads)
@@ -1574,11 +1581,15 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
         mbar_arrive_expect_tx(&jbar, bytes);
         tma_load_1d(sJd, Jdirs_p, bytes, &jbar);
     }
-    stage_tree(st, tree, parents, J);
+    stage_tree(st, tree, J);
     pdl_wait();
     const float *dA = dAsum + (size_t)b * (J + 1) * 12;      // chunk partials already summed; row J = d translation
     const float *iR = saved + L.R + (size_t)b * J * 9, *iJ = saved + L.Jr + (size_t)b * J * 3;
     const float *iGr = saved + L.Gr + (size_t)b * J * 9;
+    // the joint whose rotation gradient this thread finishes at the end (axis-angle joints on the low threads, 6D /
+    // matrix joints from thread 64 on: different warps, no divergence), and that joint's input
+    const int jr = tid < J - num_rot ? num_rot + tid : (tid >= 64 && tid - 64 < num_rot ? tid - 64 : -1);
+    float pin[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     // everything this body reads from global memory in ONE round trip: all loads are issued before the first store
     // (loops with run-time bounds are not unrolled across their loads: 16 dependent round trips before)
     {
@@ -1587,6 +1598,13 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
         float rR[n9], rG[n9], rJ[n3], rA[nA], rP[nP];
         const float *pb = part + (size_t)b * Kpad;           // already summed over the splits
         (void)nsplit; (void)Bpad;
+        if (jr >= 0 && jr < num_rot && rot6d) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) pin[e] = rot6d[((size_t)b * num_rot + jr) * 6 + e];
+        } else if (jr >= num_rot) {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) pin[e] = pose[((size_t)b * J + jr) * 3 + e];
+        }
 #pragma unroll
         for (int i = 0; i < n9; ++i) {
             const int e = tid + i * 128;
@@ -1681,15 +1699,14 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
     }
     pdl_launch_dependents();   // the rest is this kernel's tail: let the next kernel's CTAs be scheduled
     // Rodrigues backward (lbs.py:177-191); joints given as matrices export dR itself
-    // (axis-angle joints on the low threads, 6D / matrix joints from thread 64 on: different warps, no divergence)
-    for (int j = tid < J - num_rot ? num_rot + tid : (tid >= 64 && tid - 64 < num_rot ? tid - 64 : J); j < J; j = J) {
+    for (int j = jr < 0 ? J : jr; j < J; j = J) {
         float *o = gpose + ((size_t)b * J + j) * 3;
         if (j < num_rot && rot6d) {
             // Gram-Schmidt backward fused here: joint 0 -> g6_root [B,6]; joints 1.. -> g6A, the
             // A operand ([chunk][64 bodies][32 k, swizzled], k = (j-1)*6+e, zero up to g6_kpad) of the
             // decoder's backward GEMM (fit.cu)
             float dx6[6];
-            gs_bwd(rot6d + ((size_t)b * num_rot + j) * 6, dR + j * 9, dx6);
+            gs_bwd(pin, dR + j * 9, dx6);
 #pragma unroll
             for (int e = 0; e < 6; ++e) {
                 if (j == 0) g6_root[(size_t)b * 6 + e] = dx6[e];
@@ -1706,7 +1723,7 @@ lbs_pose_bwd_kernel(int J, int NB, int P, int Kpad, int Bpad, int nsplit,
             o[0] = o[1] = o[2] = 0.f;
             continue;
         }
-        const float *r = pose + ((size_t)b * J + j) * 3;
+        const float *r = pin;
         const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
         const float a = sqrtf(ex * ex + ey * ey + ez * ez);
         const float nx = r[0] / a, ny = r[1] / a, nz = r[2] / a;
@@ -2031,6 +2048,19 @@ int psi_lbs_model_create(psi_lbs_model **out, int V, int J, int NB, const float 
     if (rc == PSI_OK) rc = upload(&m->ch_ju, ch_ju, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->unit_desc, unit_desc, st, &m->bytes);
     if (rc == PSI_OK) rc = upload(&m->tree_buf, treebuf, st, &m->bytes);
+    {
+        m->tp.nlev = nlev;
+        const int *tb = treebuf.data();
+        for (int i = 0; i <= J; ++i) {
+            m->tp.lvl_start[i] = (unsigned char)tb[i];
+            m->tp.child_start[i] = (unsigned char)tb[2 * J + 1 + i];
+        }
+        for (int i = 0; i < J; ++i) {
+            m->tp.lvl_joint[i] = (unsigned char)tb[J + 1 + i];
+            m->tp.child_list[i] = (unsigned char)tb[3 * J + 2 + i];
+            m->tp.parents[i] = (unsigned char)(parents[i] < 0 ? 0 : parents[i]);      // (the root's is never read)
+        }
+    }
     if (rc == PSI_OK) {
         m->tree.nlev = nlev;
         m->tree.lvl_start = m->tree_buf;
@@ -2082,7 +2112,7 @@ int lbs_fwd_impl(const psi_lbs_model *m, int B, const float *betas, const float 
     const bool tc5 = lbs_gemm_tc5();
     const int gmode = lbs_gemm_mode();
     (psi::skip_kernel("lbs_pose_fwd") ? cudaSuccess : launch_pdl(lbs_pose_fwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, m->Jt, m->Jdirs, m->parents,
-                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, gmode, m->tree, m->Jdirs_p));
+                                          B, betas, pose, transl, saved, L, joints, rot_in, num_rot, rot6d, gmode, m->tp, m->Jdirs_p));
     PSI_LAUNCHED_K("lbs_pose_fwd");
     if (B % kBG && gmode == kGemmBf3) {
         (psi::skip_kernel("lbs_zero_coef_pad") ? cudaSuccess : launch_pdl(lbs_zero_coef_pad3_kernel, dim3(8), dim3(256), 0, st,
@@ -2233,7 +2263,7 @@ int lbs_bwd_impl(const psi_lbs_model *m, int B, const float *pose, const float *
     }
     (psi::skip_kernel("lbs_pose_bwd") ? cudaSuccess : launch_pdl(lbs_pose_bwd_kernel, dim3(B), dim3(128), 0, st, m->J, m->NB, m->P, m->Kpad, W.Bpad, nsplit, m->Jdirs,
                m->parents, pose, saved, L, ws + W.dA, ws + W.dsum, grad_joints, grad_betas,
-               grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tree, m->Jdirs_p));
+               grad_pose, grad_transl, grad_rot, num_rot, rot6d, g6_root, g6A, g6_kpad, m->tp, m->Jdirs_p));
     PSI_LAUNCHED_K("lbs_pose_bwd");
     return PSI_OK;
 }
