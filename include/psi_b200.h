@@ -217,7 +217,7 @@ PSI_API int psi_lbs_bwd2(const psi_lbs_model *m, int B, const float *betas, cons
  * The fused fitting loop.
  * Replaces: FittingOP.cal_loss + loss.backward + optimizer.step, i.e. the body of the loop at
  * source/fitting_habitat.py:177-191 (cal_loss :103-164; Adam :76), for a batch of bodies in one
- * scene, as 15 kernel launches per iteration replayed from a CUDA graph.  Loss = the SUM over
+ * scene, as 13 kernel launches per iteration replayed from a CUDA graph.  Loss = the SUM over
  * bodies of the reference's B=1 loss (bodies never interact).
  * ---------------------------------------------------------------------------------------- */
 typedef struct psi_fit_config {

@@ -1,7 +1,7 @@
 // Fused scene-fitting loop: the whole iteration of FittingOP.cal_loss + backward + Adam
-// (source/fitting_habitat.py:103-164,177-191) as 15 kernel launches, captured once in a CUDA graph.
+// (source/fitting_habitat.py:103-164,177-191) as 13 kernel launches, captured once in a CUDA graph.
 //
-//   fit_linear x3    VPoser decode over the whole batch (MLP 32->512->512->126, leaky 0.2,
+//   fit_linear x2    VPoser decode, layers 2 and 3, over the whole batch (MLP 32->512->512->126, leaky 0.2,
 //                    vposer_smpl.py:107-121) as tensor-core GEMMs; the 21 x 6D outputs land behind the
 //                    root's 6D vector
 //   lbs_fwd_impl     (lbs.cu) pose kernel: 6D -> R by Gram-Schmidt (cvae.py:46-55) for joints 0..21 --
@@ -13,9 +13,10 @@
 //   lbs_bwd_impl     vertex kernel forms dL/dverts of the contact robustifier (fitting_habitat.py:141)
 //                    and the collision mean (:155-160) in place; -> d betas, d hand axis-angles,
 //                    d translation, d 6D (root) and the decoder-output gradient as a GEMM operand
-//   fit_linear x3    decoder backward
-//   fit_step         per body: loss-term gradients, Adam step (torch.optim.Adam defaults,
-//                    fitting_habitat.py:76), loss values, and the inputs of the next iteration
+//   fit_linear x2    decoder backward, layers 3 and 2
+//   fit_step         per body: decoder layer 1 backward (d z = W1^T d h1), loss-term gradients, Adam step
+//                    (torch.optim.Adam defaults, fitting_habitat.py:76), loss values, the inputs of the next
+//                    iteration and its decoder layer 1 (h1 = lrelu(W1 z + b1)); W1 sits in shared memory
 // Loss semantics: loss_mode 0 = the SUM over bodies of the reference's B=1 loss ('independent') -- every
 // body is optimised exactly as the shipped batch_size-1 scripts do, bodies never interact, results are
 // independent of B; loss_mode 1 = the reference's batch-coupled means (fitting_proxe.py:105,110,139,155-160
@@ -449,7 +450,7 @@ static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
     return PSI_OK;
 }
 
-// one iteration = 15 launches; expects the per-body inputs of fit_step_kernel's second half
+// one iteration = 13 launches; expects the per-body inputs of fit_step_kernel's second half
 static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     const int H = c->hidden, NO = c->nbody * 6, NOp = c->no_pad, B = c->B;
     // VPoser decode: 32 -> 512 -> 512 -> nbody*6 (the 6D vectors land behind the root's in rot6d)

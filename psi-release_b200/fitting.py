@@ -145,7 +145,7 @@ class FittingOP:
         self.contact_ids = torch.as_tensor(np.asarray(cid), dtype=torch.long, device=self.device)
         self._full_contact = bool(self.contact_ids.numel() == self.body_mesh_model.handle(self.device).V and
                                   torch.equal(self.contact_ids, torch.arange(self.contact_ids.numel(), device=self.device)))
-        # 'fused': the whole iteration in libpsi_b200 (psi_fit_run, 15 launches/iteration);
+        # 'fused': the whole iteration in libpsi_b200 (psi_fit_run, 13 launches/iteration);
         # 'autograd': torch autograd over the psi ops (any loss_mode, any nn mode)
         if self.loss_mode not in ("independent", "batch"):
             raise ValueError("fittingconfig['loss_mode'] must be 'independent' or 'batch'")

@@ -1,6 +1,6 @@
 """The fused fitting loop (psi_fit_* in include/psi_b200.h): one C call runs all iterations of
 source/fitting_habitat.py:177-191 for a batch of bodies -- VPoser decode, rotation chain, SMPL-X,
-contact NN, SDF, losses, backward and Adam as 15 kernel launches per iteration from a CUDA graph.
+contact NN, SDF, losses, backward and Adam as 13 kernel launches per iteration from a CUDA graph.
 
 A batch can be split over several contexts (`num_streams`), each with its own stream and graph:
 bodies are independent, so the per-body kernels of one half (64 CTAs on 148 SMs) overlap the

@@ -1,4 +1,4 @@
-"""The fused fitting loop (psi_fit_run: 15 launches per iteration, replayed by a CUDA graph) pinned NUMERICALLY
+"""The fused fitting loop (psi_fit_run: 13 launches per iteration, replayed by a CUDA graph) pinned NUMERICALLY
 against the CPU oracle through psi_fit_trace: the loop's own vertices, SDF samples, NN results, loss values and
 dL/dx (before Adam) of a chosen iteration -- not just the fitted vector after a few sign-like Adam steps.
 
