@@ -239,8 +239,9 @@ def roofline_fused(op, args, xh_dev, cam_dev, hbm_peak, peak_src, step_ms, clock
         tot, n = agg[name]
         per = tot / n
         ach = alg.get(name, 0) / (per * 1e-3) / 1e9
-        base = name.replace("lbs_skin_sdf_fwd", "lbs_skin_fwd").replace("lbs_vertex_bwd_fit", "lbs_vertex_bwd")
-        tr = next((v for k, v in ncu.items() if base in k), None)
+        bases = [name.replace("lbs_skin_sdf_fwd", "lbs_skin_sdf").replace("lbs_vertex_bwd_fit", "lbs_vertex_bwd"),
+                 name.replace("lbs_skin_sdf_fwd", "lbs_skin_fwd")]
+        tr = next((v for base in bases for k, v in ncu.items() if base in k), None)
         e = {"kernel": "psi::" + name + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
              "frac": ach / hbm_peak, "peak_source": peak_src,
              "traffic": None if tr is None else int(tr["dram_bytes_read"] + tr["dram_bytes_write"]),

@@ -31,6 +31,7 @@ for stage in "$@"; do
     bench_bf3) PSI_LBS_GEMM=bf3 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_bf3.json" 2> "$OUT/bench_bf3.err"; python tools/bench_brief.py "$OUT/bench_bf3.json" 2>/dev/null | head -12; tail -3 "$OUT/bench_bf3.err" ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; tail -c 600 "$OUT/bench_ref.json" ;;
     launches) PSI_FIT_LOOP=replay timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 90 --csv --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 3 --iters 30 --no-cpu-baseline --no-reference-gpu > "$OUT/launches.log" 2>&1; python tools/ncu_summary.py launches "$OUT/launches.csv" | tail -30 ;;
+    launches_warm) PSI_FIT_LOOP=replay timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 400 -c 65 --csv --log-file "$OUT/launches_warm.csv" python bench.py --steps 1 --warmup 3 --iters 30 --no-cpu-baseline --no-reference-gpu > "$OUT/launches_warm.log" 2>&1; python tools/ncu_summary.py launches "$OUT/launches_warm.csv" | tail -20 ;;
     ncu_full) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNELS:-nn_index_group|lbs_vertex_bwd|lbs_skin_fwd|lbs_blend_fwd_tc5|lbs_dcoef_tc5}" -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-10} -o "$OUT/prof" python bench.py --steps 1 --warmup 3 --iters 30 --no-cpu-baseline --no-reference-gpu > "$OUT/ncu_full.log" 2>&1; ls -la "$OUT" ;;
     report) timeout 900 python tools/parity_report.py > "$OUT/parity_report.json" 2> "$OUT/parity_report.err"; cat "$OUT/parity_report.json"; tail -3 "$OUT/parity_report.err" ;;
     smoke) timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > "$OUT/smoke.log" 2>&1; tail -3 "$OUT/smoke.log" ;;
