@@ -17,15 +17,22 @@ bool skip_kernel(const char *name) {
     return skip && name && strcmp(skip, name) == 0;
 }
 int pdl_mode() {
-    // PSI_PDL: 0 / unset = plain graph edges (default), 1 = programmatic dependent launch on every kernel of the chain,
-    // 2 = only on the kernels that have a long constant-only prologue before their dependency wait (the NN walk
-    // stages the top of the box tree, the vertex backward kernel its skinning entries).  Mode 1 measured SLOWER
-    // inside the captured graph three times (460 vs 535, 593 vs 630, 640 vs 663 bodies/s): the graph's programmatic
-    // edges cost more than the overlapped launch latency saves.
-    static const int mode = [] { const char *e = getenv("PSI_PDL"); return e ? atoi(e) : 0; }();
+    // PSI_PDL: programmatic dependent launch (griddepcontrol) between consecutive kernels of a chain.
+    //   3 (default) = only kernels whose grid has at most PSI_PDL_MAX (296) CTAs -- the per-body chain (decoder GEMMs,
+    //       pose kernels, fit_step) and the persistent blend GEMMs: their constant-only prologues (TMA of weights and
+    //       of Jdirs, barrier / TMEM set-up) run under the predecessor's tail.  797 vs 767 bodies/s.
+    //   0 = plain graph edges;  1 = every kernel;  2 = only the NN walk and the vertex backward kernel.
+    // Programmatic launch of the BIG grids is what made mode 1 slower every time it was measured (460 vs 535, 593 vs
+    // 630, 640 vs 663, 732 vs 767 bodies/s): with the skinning kernel (1344 CTAs) included the gain turns into a
+    // loss (734), without it (limits 100 ... 400) the loop runs at 786 ... 797.
+    static const int mode = [] { const char *e = getenv("PSI_PDL"); return e ? atoi(e) : 3; }();
     return mode;
 }
 bool pdl_enabled() { return pdl_mode() == 1; }
+int pdl_max_ctas() {
+    static const int v = [] { const char *e = getenv("PSI_PDL_MAX"); return e ? atoi(e) : 296; }();
+    return v;
+}
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs
 // through the C ABI has to opt every kernel in on every device it launches on.  (device, function) pairs that
 // already hold at least `bytes` are remembered; the map is the only mutable process-wide state besides the
