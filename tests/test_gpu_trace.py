@@ -271,3 +271,44 @@ def test_batch_coupled_loss_sharded_over_two_contexts_equals_the_union_batch(sma
     # and it differs from two unconnected batch-mode shards (the coupling is real)
     lone = _make(small_model, scene, cid, 3, loss_mode="batch").fit(xh[:3], cam, num_iter=6)
     assert not torch.equal(lone, ref[:3])
+
+
+@pytest.mark.gpu
+def test_fit_is_bit_identical_under_every_launch_mode_in_subprocesses():
+    """Programmatic dependent launch (PSI_PDL, read once per process: csrc/api.cu) lets a kernel's constant-only
+    prologue run under its predecessor's tail; every kernel waits (griddepcontrol.wait) before it touches anything
+    the predecessor writes.  The evidence that no wait is missing or misplaced: the same fit, Adam and L-BFGS,
+    per-body and batch-coupled loss, is bit-identical with plain graph edges (0), with every kernel programmatic
+    (1), with the NN walk + vertex backward only (2) and with the default (3, small grids only)."""
+    import hashlib, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+from psi_release_b200 import synthetic
+from psi_release_b200.fitting import FittingOP
+W = dict(weight_loss_rec=1.0, weight_loss_vposer=0.01, weight_contact=0.1, weight_collision=0.5)
+model = synthetic.make_smplx_model(seed=1234, num_verts=431)
+scene = synthetic.make_scene(seed=1, dim=32, num_points=3000)
+cam = torch.tensor(scene.cam_ext).unsqueeze(0).cuda()
+h = hashlib.sha256()
+for B, kw in ((5, dict()), (3, dict(loss_mode="batch")), (4, dict(optimizer_name="lbfgs")), (65, dict())):
+    xh = torch.tensor(synthetic.make_body_params(scene, B, seed=3)).cuda()
+    cfg = dict(model_data=model, scene=scene, vposer_weights=synthetic.make_vposer_weights(),
+               contact_ids=synthetic.make_contact_ids(431, "parts"), init_lr_h=0.1, num_iter=33, batch_size=B,
+               device="cuda", engine="fused")
+    cfg.update(kw)
+    op = FittingOP(cfg, W)
+    out = op.fit(xh, cam)
+    assert torch.isfinite(out).all()
+    h.update(out.cpu().numpy().tobytes())
+    h.update(op.trace("grad_x").cpu().numpy().tobytes())
+print("HASH", h.hexdigest())
+""" % (root,)
+    digests = {}
+    for mode in ("0", "1", "2", "3"):
+        env = dict(os.environ, PSI_PDL=mode)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (mode, r.stderr[-2000:])
+        digests[mode] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][-1]
+    assert len(set(digests.values())) == 1, digests
