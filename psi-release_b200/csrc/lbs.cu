@@ -1453,7 +1453,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) lbs_blend_fwd_bf3_kernel(const 
     const int nchunks = p.Kpad / kKC3, N = 3 * p.V;
     int g0 = 0, idx = 0;
     for (int item = blockIdx.x; item < p.ntiles * p.nbg; item += gridDim.x, g0 += nchunks, ++idx) {
-        const int tile = item % p.ntiles, bg = item / p.ntiles;
+        // body groups of one basis tile are neighbours in the item order: they run at the same time on neighbouring CTAs,
+        // so a batch of more than 64 bodies streams the basis from HBM once (the second group's reads hit L2)
+        const int bg = item % p.nbg, tile = item / p.nbg;
         T3Item it;
         it.basis = p.basis3 + (size_t)tile * nchunks * (3 * kTM * kKC3);
         it.basis_stride = (size_t)3 * kTM * kKC3;
@@ -1496,7 +1498,7 @@ lbs_dcoef_bf3_kernel(int Kpad, int NC3, int Bpad, const unsigned short *__restri
     const int nkt = Kpad / kTM, nbg = Bpad / kBG;
     int g0 = 0, idx = 0;
     for (int item = blockIdx.x; item < nkt * nsplit * nbg; item += gridDim.x) {
-        const int kt = item % nkt, ns = (item / nkt) % nsplit, bg = item / (nkt * nsplit);
+        const int bg = item % nbg, kt = (item / nbg) % nkt, ns = item / (nbg * nkt);     // body group fastest (see the forward GEMM)
         const int c_begin = (int)((long)ns * NC3 / nsplit), c_end = (int)((long)(ns + 1) * NC3 / nsplit);
         float *o = part + ((size_t)ns * Bpad + (size_t)bg * kBG) * Kpad + kt * kTM + (w & 3) * 32 + lane;
         if (c_end == c_begin) {                    // more splits than chunks (small models): an empty split

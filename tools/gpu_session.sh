@@ -13,7 +13,7 @@ for stage in "$@"; do
     tests) timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > "$OUT/tests.log" 2>&1; tail -25 "$OUT/tests.log" ;;
     tests_new) timeout 1200 python -m pytest tests/test_gpu_trace.py tests/test_gpu_edges.py -m gpu -q --tb=short -p no:cacheprovider > "$OUT/tests_new.log" 2>&1; tail -25 "$OUT/tests_new.log" ;;
     bench) timeout 900 python bench.py --steps 5 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; tail -c 600 "$OUT/bench.json"; tail -3 "$OUT/bench.err" ;;
-    bench_quick) timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_quick.json" 2> "$OUT/bench_quick.err"; python tools/bench_brief.py "$OUT/bench_quick.json"; tail -3 "$OUT/bench_quick.err" ;;
+    bench_quick) timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu ${BENCH_ARGS:-} > "$OUT/bench_quick.json" 2> "$OUT/bench_quick.err"; python tools/bench_brief.py "$OUT/bench_quick.json"; tail -3 "$OUT/bench_quick.err" ;;
     bench_replay) PSI_FIT_LOOP=replay timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_replay.json" 2> "$OUT/bench_replay.err"; python tools/bench_brief.py "$OUT/bench_replay.json"; tail -3 "$OUT/bench_replay.err" ;;
     bench_u*) U=${stage#bench_u}; PSI_FIT_UNROLL=$U timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/$stage.json" 2> "$OUT/$stage.err"; python tools/bench_brief.py "$OUT/$stage.json" | head -1; tail -3 "$OUT/$stage.err" ;;
     tests_k) timeout 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "$TESTS_K" > "$OUT/tests_k.log" 2>&1; tail -25 "$OUT/tests_k.log" ;;
@@ -28,7 +28,7 @@ for stage in "$@"; do
     bench_pdl2) PSI_PDL=2 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_pdl2.json" 2> "$OUT/bench_pdl2.err"; python tools/bench_brief.py "$OUT/bench_pdl2.json" 2>/dev/null | head -1 ;;
     bench_pdl) PSI_PDL=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_pdl.json" 2> "$OUT/bench_pdl.err"; python tools/bench_brief.py "$OUT/bench_pdl.json" | head -1 ;;
     bench_lbfgs) timeout 600 python bench.py --optimizer lbfgs --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_lbfgs.json" 2> "$OUT/bench_lbfgs.err"; python tools/bench_brief.py "$OUT/bench_lbfgs.json" | head -12; tail -3 "$OUT/bench_lbfgs.err" ;;
-    benchlib_*) V=${stage#benchlib_}; PSI_B200_LIB=$PWD/psi-release_b200/lib/variants/libpsi_b200_$V.so timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/$stage.json" 2> "$OUT/$stage.err"; python tools/bench_brief.py "$OUT/$stage.json" | head -12; tail -2 "$OUT/$stage.err" ;;
+    benchlib_*) V=${stage#benchlib_}; PSI_B200_LIB=$PWD/psi-release_b200/lib/variants/libpsi_b200_$V.so timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu ${BENCH_ARGS:-} > "$OUT/$stage.json" 2> "$OUT/$stage.err"; python tools/bench_brief.py "$OUT/$stage.json" | head -12; tail -2 "$OUT/$stage.err" ;;
     testlib_*) V=${stage#testlib_}; PSI_B200_LIB=$PWD/psi-release_b200/lib/variants/libpsi_b200_$V.so timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "${TESTS_K:-golden or baseline_size or fused_iteration}" > "$OUT/$stage.log" 2>&1; tail -4 "$OUT/$stage.log" ;;
     bench_bf3) PSI_LBS_GEMM=bf3 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_bf3.json" 2> "$OUT/bench_bf3.err"; python tools/bench_brief.py "$OUT/bench_bf3.json" 2>/dev/null | head -12; tail -3 "$OUT/bench_bf3.err" ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; tail -c 600 "$OUT/bench_ref.json" ;;
