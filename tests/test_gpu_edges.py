@@ -54,10 +54,11 @@ def test_cabi_error_codes():
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("B", [1, 3, 65])
+@pytest.mark.parametrize("B", [1, 3, 65, 130])
 def test_fused_fit_odd_batches_and_kbg_boundary(small_model, B):
-    """B = 1 (the reference's own batch size), a ragged body group, and one body past the 64-body
-    group boundary of the vertex kernel: fused == autograd within tolerance, finite, reproducible."""
+    """B = 1 (the reference's own batch size), a ragged body group, one body past the 64-body
+    group boundary of the vertex kernel, and three body groups (the blend GEMMs interleave the groups of a basis
+    tile over neighbouring CTAs): fused == autograd within tolerance, finite, reproducible."""
     from psi_release_b200 import synthetic
     from psi_release_b200.fitting import FittingOP
     scene = synthetic.make_scene(seed=2, dim=24, num_points=1500)
@@ -77,6 +78,11 @@ def test_fused_fit_odd_batches_and_kbg_boundary(small_model, B):
     if B > 1:
         one = FittingOP(dict(cfg, engine="fused", batch_size=1), W).fit(xh[B - 1:], cam)
         assert torch.equal(one, out[B - 1:])
+    if B > 64:      # ... nor on which 64-body group of the GEMM operands it lands in
+        first = FittingOP(dict(cfg, engine="fused", batch_size=64), W).fit(xh[:64], cam)
+        assert torch.equal(first, out[:64])
+        mid = FittingOP(dict(cfg, engine="fused", batch_size=B - 64), W).fit(xh[64:], cam)
+        assert torch.equal(mid, out[64:])
 
 
 def test_lbs_dense_skinning_weights_and_small_tree():
