@@ -56,6 +56,7 @@ struct psi_fit_ctx {
     psi::LbfgsParams lbp;
     int *lb_info;                  // trace staging [B,4]
     int *neg_cnt;                  // loss_mode 1: this shard's count of penetrating vertices, [2] by iteration parity
+    int *body_cnt;                 // loss_mode 0: per-body counts [2][B] by iteration parity
     // loss_mode 1 sharded over several contexts (psi_fit_set_peers): exchange buffer [2][16] of (tag << 32 | count)
     // written by the peers, the peers' buffers, the batch-wide count [2], a fit sequence number, an error flag
     unsigned long long *xbuf;
@@ -115,7 +116,8 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
                 const float *__restrict__ cpart, float *__restrict__ losses,
                 float *__restrict__ rot6d, float *__restrict__ pose, float *__restrict__ shape,
                 float *__restrict__ transl, float *__restrict__ gx_out, float *__restrict__ xeval_out,
-                int *__restrict__ neg_cnt, const int *__restrict__ neg_tot, int batch_total, int *__restrict__ loop_left,
+                int *__restrict__ neg_cnt, const int *__restrict__ neg_tot, int batch_total, int *__restrict__ body_cnt,
+                int *__restrict__ loop_left,
                 cudaGraphConditionalHandle loop_cond, const LbfgsParams lbp, const LbfgsState lbs,
                 const float *__restrict__ W1p, const float *__restrict__ b1, const float *__restrict__ dh1,
                 float *__restrict__ h1pre, float *__restrict__ h1A) {
@@ -283,7 +285,10 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
         }
         __syncthreads();           // everyone has read sx / step[b]
         if (OPT == 0 && tid < xdim) sx[tid] = xn;
-        if (tid == 0) step[b] = t;
+        if (tid == 0) {
+            step[b] = t;
+            if (body_cnt) body_cnt[(size_t)(t & 1) * d.B + b] = 0;     // the next iteration's counter of this body
+        }
         if (b == 0 && tid == 0) {
             // the next iteration's penetration counter (its parity is t & 1; nobody reads it during this kernel)
             if (neg_cnt) neg_cnt[t & 1] = 0;
@@ -333,11 +338,12 @@ fit_step_kernel(FitDims d, psi_fit_config cfg, int do_post, int np_sdf, int nchu
     if (tid < 3) transl[(size_t)b * 3 + tid] = sx[tid];
 }
 
-__global__ void fit_reset_kernel(float *am, float *av, int *step, long n, int B, int *neg_cnt) {
+__global__ void fit_reset_kernel(float *am, float *av, int *step, long n, int B, int *neg_cnt, int *body_cnt) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { am[i] = 0.f; av[i] = 0.f; }
     if (i < B) step[i] = 0;
     if (i < 2) neg_cnt[i] = 0;
+    if (i < 2 * B) body_cnt[i] = 0;
 }
 
 __global__ void fit_lbfgs_reset_kernel(LbfgsScalars *sc, int B) {
@@ -439,6 +445,7 @@ static int launch_step(psi_fit_ctx *c, int do_post, cudaStream_t st) {
                           c->gshape, c->gtransl, c->partial, c->cpart, c->losses, c->rot6d, c->pose, c->shape, c->transl,
                           c->gx, c->xeval, c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr,
                           c->cfg.loss_mode == 1 && c->world > 1 ? c->neg_tot : nullptr, c->batch_total,
+                          c->cfg.loss_mode == 0 ? c->body_cnt : nullptr,
                           c->capturing_loop ? c->loop_left : nullptr, c->loop_cond, c->lbp, c->lb, c->W1p, c->b1, c->dh1,
                           c->h1pre, c->h1A);
     };
@@ -472,6 +479,7 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     }
     sf.sdfv = c->sdfv; sf.sdfg = c->sdfg; sf.partial = c->partial;
     sf.neg_cnt = c->cfg.loss_mode == 1 ? c->neg_cnt : nullptr; sf.step = c->step;
+    sf.body_cnt = c->cfg.loss_mode == 0 ? c->body_cnt : nullptr; sf.nbodies = B;
     rc = lbs_fwd_impl(c->model, B, c->shape, c->pose, c->transl, c->cam, 12, nullptr, c->rot6d, c->num_rot,
                       c->verts, nullptr, c->saved, &sf, st);
     if (rc) return rc;
@@ -499,6 +507,7 @@ static int enqueue_iteration(psi_fit_ctx *c, cudaStream_t st) {
     vg.w_contact = c->cfg.w_contact; vg.w_coll = c->cfg.w_collision; vg.robust_c = c->cfg.robust_c;
     vg.nu = c->nu; vg.np_sdf = c->np_sdf; vg.num_contact = c->num_contact; vg.cpart = c->cpart;
     vg.neg_cnt = c->cfg.loss_mode == 1 ? (sharded ? c->neg_tot : c->neg_cnt) : nullptr; vg.step = c->step;
+    vg.body_cnt = c->cfg.loss_mode == 0 ? c->body_cnt : nullptr;
     vg.bdiv = c->cfg.loss_mode == 1 ? (float)(sharded ? c->batch_total : B) : 1.0f;
     rc = lbs_bwd_impl(c->model, B, c->pose, c->cam, 12, c->saved, nullptr, &vg, nullptr, c->gshape, c->gpose,
                       c->gtransl, nullptr, c->num_rot, c->rot6d, c->g6_root, c->g6A, NOp, c->lbs_ws,
@@ -680,6 +689,7 @@ int psi_fit_create(psi_fit_ctx **out, const psi_lbs_model *model, int V, int J, 
         c->lb_info = (int *)dev_alloc(B * 4 * sizeof(int));
     }
     c->neg_cnt = (int *)dev_alloc(2 * sizeof(int));
+    c->body_cnt = (int *)dev_alloc(2 * B * sizeof(int));
     c->rank = 0; c->world = 1; c->batch_total = c->B;
     for (int q = 0; q < PSI_FIT_MAX_SHARDS; ++q) { c->peer_buf[q] = nullptr; c->ipc_opened[q] = nullptr; }
     c->neg_tot = (int *)dev_alloc(2 * sizeof(int));
@@ -766,7 +776,7 @@ static int reset_state(psi_fit_ctx *c, const float *xhr_init, cudaStream_t st) {
     cudaError_t e = cudaMemcpyAsync(c->x, xhr_init, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->nnhint, 0xff, (size_t)c->B * c->nu * sizeof(int), st);   // -1: no hint yet
     if (e != cudaSuccess) return (int)e;
-    fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt);
+    fit_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->am, c->av, c->step, (long)n, c->B, c->neg_cnt, c->body_cnt);
     PSI_LAUNCHED();
     if (c->world > 1) {     // a new fit: the peers' stale slots of the last one must not match
         fit_seq_kernel<<<1, 1, 0, st>>>(c->xseq);

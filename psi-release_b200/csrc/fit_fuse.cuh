@@ -13,6 +13,10 @@ struct SdfFuse {
     // accumulated with integer atomics into neg_cnt[iteration & 1] (iteration = step[0]); NULL otherwise
     int *neg_cnt;
     const int *step;
+    // per-body count of penetrating vertices, [2][B] by iteration parity (integer atomics: order-independent): what
+    // lbs_vertex_bwd<FIT> divides by in loss_mode 0 -- one load instead of a sum over the chunk partials; NULL: not kept
+    int *body_cnt;
+    int nbodies;
 };
 
 // dL/dverts of the contact robustifier (fitting_habitat.py:133-141) and the collision mean
@@ -25,6 +29,7 @@ struct VGradFuse {
     int nu, np_sdf, num_contact;
     float *cpart;            // [B, vertex chunks]: contact-loss partial sums
     const int *neg_cnt;      // loss_mode 1: batch-wide penetration count [2] (see SdfFuse), else NULL
+    const int *body_cnt;     // loss_mode 0: per-body penetration counts [2][B] (see SdfFuse), or NULL (sum the partials)
     const int *step;
     float bdiv;              // loss_mode 1: bodies in the batch (the contact mean runs over B x Nc), else 1
 };

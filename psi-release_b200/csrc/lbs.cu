@@ -529,6 +529,7 @@ lbs_skin_fwd_kernel(int V, int J, int KW, const int *__restrict__ skin_j, const 
             sf.partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = s;
             sf.partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = c;
             if (sf.neg_cnt && c > 0.f) atomicAdd(sf.neg_cnt + (sf.step[0] & 1), (int)c);   // integer: order-independent
+            if (sf.body_cnt && c > 0.f) atomicAdd(sf.body_cnt + (size_t)(sf.step[0] & 1) * sf.nbodies + b, (int)c);
         }
     }
 }
@@ -641,6 +642,7 @@ lbs_skin_sdf2_kernel(int V, int J, const int *__restrict__ skin_j, const float *
             sf.partial[((size_t)b * np + chunk) * 2 + 0] = s_;
             sf.partial[((size_t)b * np + chunk) * 2 + 1] = c_;
             if (sf.neg_cnt && c_ > 0.f) atomicAdd(sf.neg_cnt + (sf.step[0] & 1), (int)c_);   // integer: order-independent
+            if (sf.body_cnt && c_ > 0.f) atomicAdd(sf.body_cnt + (size_t)(sf.step[0] & 1) * sf.nbodies + b, (int)c_);
         }
     }
 }
@@ -763,6 +765,8 @@ lbs_vertex_bwd_kernel(int V, int J, int KW, int Npad, int B, const int *__restri
     if (FIT) {
         if (fg.neg_cnt) {    // batch-coupled loss: penetrating vertices of the WHOLE batch (fitting_proxe.py:155-158)
             if (tid == 0) s_cnt = (float)fg.neg_cnt[fg.step[0] & 1];
+        } else if (fg.body_cnt) {   // the skinning kernel counted this body's penetrating vertices (same integer, one load)
+            if (tid == 0) s_cnt = (float)fg.body_cnt[(size_t)(fg.step[0] & 1) * B + b];
         } else if (tid < 32) {      // number of penetrating vertices of the body: lane-strided loads, shuffle tree (fixed order)
             float c = 0.f;
             for (int i = tid; i < fg.np_sdf; i += 32) c += fg.partial[((size_t)b * fg.np_sdf + i) * 2 + 1];
