@@ -21,7 +21,8 @@ int pdl_mode() {
     //   3 (default) = only kernels whose grid has at most PSI_PDL_MAX (296) CTAs -- the per-body chain (decoder GEMMs,
     //       pose kernels, fit_step) and the persistent blend GEMMs: their constant-only prologues (TMA of weights and
     //       of Jdirs, barrier / TMEM set-up) run under the predecessor's tail.  797 vs 767 bodies/s.
-    //   0 = plain graph edges;  1 = every kernel;  2 = only the NN walk and the vertex backward kernel.
+    //   0 = plain graph edges;  1 = every kernel;  2 = only the NN walk and the vertex backward kernel;
+    //   4 = 3 plus the NN walk and the vertex backward kernel (794.6 vs 796.9: nothing gained).
     // Programmatic launch of the BIG grids is what made mode 1 slower every time it was measured (460 vs 535, 593 vs
     // 630, 640 vs 663, 732 vs 767 bodies/s): with the skinning kernel (1344 CTAs) included the gain turns into a
     // loss (734), without it (limits 100 ... 400) the loop runs at 786 ... 797.

@@ -130,7 +130,7 @@ inline int ensure_max_dyn_smem(void (*kernel)(KArgs...), size_t bytes) {
 bool skip_kernel(const char *name);   // api.cu: measurement aid, PSI_SKIP_KERNEL=<name> drops that launch (results invalid)
 bool pdl_enabled();   // api.cu: true only when PSI_PDL=1 (measured slower, see api.cu)
 int pdl_max_ctas();   // api.cu: PSI_PDL_MAX (mode 3's grid-size limit, default 296)
-int pdl_mode();       // api.cu: PSI_PDL (0 off, 1 every kernel, 2 only launch_pdl_sel sites, 3 only grids of <= 296 CTAs)
+int pdl_mode();       // api.cu: PSI_PDL (0 off, 1 every kernel, 2 only launch_pdl_sel sites, 3 only grids of <= 296 CTAs, 4 = 2 + 3)
 // launch `kernel`; it MUST call pdl_wait() before touching global memory other than constants
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -146,7 +146,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.attrs = attr;
     // PSI_PDL=3: only the small kernels of the per-body chain (their constant prologues -- TMA of weights, barrier
     // initialisation -- then run under the predecessor's tail)
-    cfg.numAttrs = (pdl_enabled() || (pdl_mode() == 3 && (size_t)grid.x * grid.y * grid.z <= (size_t)pdl_max_ctas())) ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() || ((pdl_mode() == 3 || pdl_mode() == 4) && (size_t)grid.x * grid.y * grid.z <= (size_t)pdl_max_ctas())) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -163,7 +163,7 @@ inline cudaError_t launch_pdl_sel(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (pdl_mode() == 1 || pdl_mode() == 2) ? 1 : 0;
+    cfg.numAttrs = (pdl_mode() == 1 || pdl_mode() == 2 || pdl_mode() == 4) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
