@@ -312,3 +312,25 @@ print("HASH", h.hexdigest())
         assert r.returncode == 0, (mode, r.stderr[-2000:])
         digests[mode] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][-1]
     assert len(set(digests.values())) == 1, digests
+
+
+def test_launch_count_claim_matches_the_kernels_actually_launched(small_model):
+    """bench.py reports gpu_launches = psi_fit_launches_per_iteration() x iterations x steps.  The claim is checked
+    against the library's own launch counter on an eager run (one count per kernel launch; graph replays do not pass
+    through the counter): k iterations cost k x per_iteration launches + the opening fit_step + the reset kernels."""
+    from psi_release_b200 import _lib, synthetic
+    L = _lib.lib()
+    scene = synthetic.make_scene(seed=1, dim=32, num_points=3000)
+    B = 64                                   # a full body group: no padding-row kernels
+    xh = torch.tensor(synthetic.make_body_params(scene, B, seed=3)).cuda()
+    cam = torch.tensor(scene.cam_ext).unsqueeze(0).cuda()
+    op = _make(small_model, scene, synthetic.make_contact_ids(431, "parts"), B, use_cuda_graph=False)
+    per = int(L.psi_fit_launches_per_iteration())
+    assert per == 13
+    counts = []
+    for k in (1, 4):
+        c0 = L.psi_launch_count()
+        op.fit(xh, cam, num_iter=k)
+        torch.cuda.synchronize()
+        counts.append(L.psi_launch_count() - c0)
+    assert counts[1] - counts[0] == 3 * per, counts      # three more iterations = 3 x 13 launches
