@@ -217,6 +217,32 @@ class SMPLX(nn.Module):
                                         md["J_regressor"], md["weights"], self.parents.cpu().numpy(), device)
         return self._handle
 
+    def coherent_handle(self, device=None) -> _ModelHandle:
+        """The same model with its vertices RE-ORDERED so that consecutive vertices are skinned to the same joints
+        (dominant joint, joints depth-first along the tree, kd order of the template inside a joint).  The kernels
+        take one thread per vertex and gather the joints' transforms from a shared-memory table: with a vertex order
+        that scatters the joints (nothing in the file format promises otherwise) every warp hits most of the table
+        and its banks collide; in this order a warp reads one or two rows.  Per-vertex results come out in the new
+        order: `handle.perm[k]` = original index of new vertex k, `handle.inv` = its inverse.  Used by the fused
+        fitting loop, where vertices never leave the library (fused.py)."""
+        device = torch.device(device) if device is not None else self.pose_mean.device
+        h = getattr(self, "_chandle", None)
+        if h is None or h.device != device:
+            from .fused import _spatial_order
+            md = self._model_data
+            V = md["v_template"].shape[0]
+            parents = self.parents.cpu().numpy()
+            perm = _spatial_order(np.arange(V), md["v_template"], md["weights"], parents).astype(np.int64)
+            assert perm.shape == (V,) and np.array_equal(np.sort(perm), np.arange(V))
+            P = self._posedirs.shape[0]
+            pd = self._posedirs.reshape(P, V, 3)[:, perm, :].reshape(P, V * 3)
+            h = _ModelHandle(md["v_template"][perm], self._shapedirs[perm], pd, md["J_regressor"][:, perm],
+                             md["weights"][perm], parents, device)
+            h.perm = perm
+            h.inv = np.argsort(perm)
+            self._chandle = h
+        return h
+
     def _default(self, value, name, B, dim):
         if value is not None:
             return value

@@ -44,7 +44,8 @@ namespace psi {
 
 constexpr int kMaxJ = 64;
 constexpr int kJdMaxNB = 32;     // shape coefficients up to which the pose kernels keep Jdirs in shared memory
-constexpr int kUnitLen = 16;      // entries per work unit of the dA partial sums (lbs_vertex_bwd)
+constexpr int kUnitLen = 15;      // entries per work unit of the dA partial sums (lbs_vertex_bwd); ODD: with a joint-coherent vertex
+                                  // order a unit walks consecutive vertices, and units 16 apart would collide on the same banks
 constexpr int kMaxUnits = 160;    // units per 256-vertex chunk held in shared memory; more -> per-joint loop
 constexpr int kFT = 72;         // forward tile: 72 vertex coordinates (9 n8 tiles); 3V/72 = 437 tiles at
                                 // V = 10475 = 2.95 per SM -> one balanced wave at 3 CTAs per SM

@@ -143,7 +143,7 @@ class FittingOP:
         if cid is None:
             cid, _ = GeometryTransformer.get_contact_id(self.contact_id_folder, self.contact_part)
         self.contact_ids = torch.as_tensor(np.asarray(cid), dtype=torch.long, device=self.device)
-        self._full_contact = bool(self.contact_ids.numel() == self.body_mesh_model.handle(self.device).V and
+        self._full_contact = bool(self.contact_ids.numel() == self.body_mesh_model._model_data["v_template"].shape[0] and
                                   torch.equal(self.contact_ids, torch.arange(self.contact_ids.numel(), device=self.device)))
         # 'fused': the whole iteration in libpsi_b200 (psi_fit_run, 13 launches/iteration);
         # 'autograd': torch autograd over the psi ops (any loss_mode, any nn mode)
@@ -164,7 +164,7 @@ class FittingOP:
             from .fused import FusedFit
             lossw = {k: getattr(self, k) for k in ("weight_loss_rec", "weight_loss_vposer", "weight_contact",
                                                    "weight_collision")}
-            self._fused = FusedFit(B, self.body_mesh_model.handle(self.device), self.body_mesh_model,
+            self._fused = FusedFit(B, self.device, self.body_mesh_model,
                                    self.s_index, self.scene_sdf, self.vposer, self.contact_ids.cpu().numpy(),
                                    lossw, self.robust_c, self.init_lr_h, use_graph=self.use_cuda_graph,
                                    num_streams=getattr(self, "num_streams", None), loss_mode=self.loss_mode,

@@ -73,8 +73,26 @@ class FusedFit:
                  optimizer="adam", lbfgs=None):
         if scene_sdf.num_scenes != 1:
             raise ValueError("the fused loop fits one scene per context")
-        self.device = model_handle.device
+        # model_handle: a body_model._ModelHandle, or just the device (the handle is then made here, once, in the
+        # vertex order the loop wants)
+        dev_only = not hasattr(model_handle, "h")
+        self.device = torch.device(model_handle) if dev_only else model_handle.device
         self.B = int(batch_size)
+        # Vertices never leave the loop (only the fitted parameters do), so it runs on the joint-coherent vertex order
+        # (body_model.SMPLX.coherent_handle); trace() hands per-vertex buffers back in the file's order.
+        # PSI_FIT_VORDER=0 keeps the file's order.
+        self._perm = self._inv = None
+        md = body_model._model_data
+        vt, wts = md["v_template"], md["weights"]
+        if os.environ.get("PSI_FIT_VORDER", "1") != "0":
+            model_handle = body_model.coherent_handle(self.device)
+            perm, inv = model_handle.perm, model_handle.inv
+            self._perm = torch.as_tensor(perm, device=self.device)
+            self._inv = torch.as_tensor(inv, device=self.device)
+            contact_ids = inv[np.asarray(contact_ids, dtype=np.int64)]
+            vt, wts = vt[perm], wts[perm]
+        elif dev_only:
+            model_handle = body_model.handle(self.device)
         self._keep = (model_handle, scene_index, scene_sdf)     # borrowed device objects
         f32 = lambda t: np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32))
         sd = {k: f32(v) for k, v in vposer.state_dict().items()}
@@ -86,8 +104,7 @@ class FusedFit:
         # Query order = order of first appearance in the id list: spatially sorted ids make the 32
         # queries of a warp neighbours on the body (needed by the thread-per-query NN schedule);
         # the result does not depend on the order.
-        md = body_model._model_data
-        cid = _spatial_order(contact_ids, md["v_template"], md["weights"], np.asarray(md["kintree_table"])[0])
+        cid = _spatial_order(contact_ids, vt, wts, np.asarray(md["kintree_table"])[0])
         if num_streams is None:
             # measured: two half-batch contexts are not faster (kernels do not shrink with B); PSI_FIT_STREAMS re-measures
             num_streams = int(os.environ.get("PSI_FIT_STREAMS", "1"))
@@ -231,8 +248,12 @@ class FusedFit:
                 _lib.check(L.psi_fit_trace(h, code, _lib.ptr(t), nbytes, st), "psi_fit_trace")
                 outs.append(t if what == "query_ids" else t.view(1, -1) if what == "exchange" else t.view(nb, -1))
         if what == "query_ids":
-            return outs[0]
-        return torch.cat(outs, 0)
+            return outs[0] if self._perm is None else self._perm[outs[0].long()].to(torch.int32)
+        out = torch.cat(outs, 0)
+        if self._inv is not None and what in ("verts", "sdf", "sdf_grad"):      # back to the file's vertex order
+            V = self._inv.numel()
+            out = out.view(out.shape[0], V, -1)[:, self._inv].reshape(out.shape[0], -1)
+        return out
 
     def profile(self, xhr, cam_ext, warm_iters=20, timed_iters=50):
         """Per-kernel timing of one fitting iteration (psi_fit_profile: eager launches with a CUDA

@@ -24,6 +24,7 @@ for stage in "$@"; do
        timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG $EXTRA > "$OUT/$stage.n$NG.json" 2> "$OUT/$stage.n$NG.err"; grep '^{' "$OUT/$stage.n$NG.json" | tail -1 | cut -c1-1500; grep -i "nranks\|error\|Traceback" "$OUT/$stage.n$NG.err" | head -5 ;;
     bench_s*) NS=${stage#bench_s}; PSI_FIT_STREAMS=$NS timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/$stage.json" 2> "$OUT/$stage.err"; python tools/bench_brief.py "$OUT/$stage.json" | head -1; tail -3 "$OUT/$stage.err" ;;
     bench_pdlmax*) M=${stage#bench_pdlmax}; PSI_PDL=3 PSI_PDL_MAX=$M timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/$stage.json" 2> "$OUT/$stage.err"; python tools/bench_brief.py "$OUT/$stage.json" 2>/dev/null | head -1 ;;
+    bench_vo0) PSI_FIT_VORDER=0 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_vo0.json" 2> "$OUT/bench_vo0.err"; python tools/bench_brief.py "$OUT/bench_vo0.json" 2>/dev/null | head -12 ;;
     bench_pdl4) PSI_PDL=4 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_pdl4.json" 2> "$OUT/bench_pdl4.err"; python tools/bench_brief.py "$OUT/bench_pdl4.json" 2>/dev/null | head -1 ;;
     bench_pdl3) PSI_PDL=3 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_pdl3.json" 2> "$OUT/bench_pdl3.err"; python tools/bench_brief.py "$OUT/bench_pdl3.json" 2>/dev/null | head -1 ;;
     bench_pdl2) PSI_PDL=2 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-gpu > "$OUT/bench_pdl2.json" 2> "$OUT/bench_pdl2.err"; python tools/bench_brief.py "$OUT/bench_pdl2.json" 2>/dev/null | head -1 ;;
