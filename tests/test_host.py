@@ -348,3 +348,35 @@ def test_shims_route_only_the_reference_call_shape():
     with shims.routed_grid_sample():
         assert F.grid_sample is not orig
     assert F.grid_sample is orig
+
+
+def test_joint_coherent_vertex_order_is_a_consistent_relabelling():
+    """The fused loop runs on a re-ordered copy of the model (body_model.SMPLX.coherent_handle): the order is a
+    permutation of the vertices, it makes the vertices of a warp share their skinning joints, and permuting every
+    per-vertex constant of the model with it only relabels the output vertices (checked on the CPU restatement)."""
+    import numpy as np
+    import torch
+    from oracle import oracle
+    from psi_release_b200 import synthetic
+    from psi_release_b200.fused import _spatial_order
+    m = synthetic.make_smplx_model(seed=1234, num_verts=431)
+    V = 431
+    parents = np.asarray(m["kintree_table"])[0].astype(np.int64)
+    perm = _spatial_order(np.arange(V), m["v_template"], m["weights"], parents).astype(np.int64)
+    assert perm.shape == (V,) and np.array_equal(np.sort(perm), np.arange(V))
+    owner = m["weights"].argmax(1)
+    per_warp = lambda o: np.mean([len(set(o[i:i + 32])) for i in range(0, V - 31, 32)])
+    assert per_warp(owner[perm]) < 0.4 * per_warp(owner)           # 3-7 joints per warp instead of 22-26
+    mp = dict(m)
+    for k in ("v_template", "shapedirs", "posedirs", "weights"):
+        mp[k] = m[k][perm]
+    mp["J_regressor"] = m["J_regressor"][:, perm]
+    g = torch.Generator().manual_seed(0)
+    B = 3
+    kw = dict(body_pose=torch.randn(B, 63, generator=g) * 0.3, transl=torch.randn(B, 3, generator=g),
+              global_orient=torch.randn(B, 3, generator=g) * 0.5, betas=torch.randn(B, 10, generator=g),
+              left_hand_pose=torch.randn(B, 12, generator=g) * 0.3, right_hand_pose=torch.randn(B, 12, generator=g) * 0.3)
+    va, ja = oracle.SMPLXOracle(m)(**kw)
+    vb, jb = oracle.SMPLXOracle(mp)(**kw)
+    assert float((va[:, perm] - vb).abs().max()) < 1e-5
+    assert float((ja - jb).abs().max()) < 1e-5
