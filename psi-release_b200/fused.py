@@ -2,10 +2,12 @@
 source/fitting_habitat.py:177-191 for a batch of bodies -- VPoser decode, rotation chain, SMPL-X,
 contact NN, SDF, losses, backward and Adam as 13 kernel launches per iteration from a CUDA graph.
 
-A batch can be split over several contexts (`num_streams`), each with its own stream and graph:
-bodies are independent, so the per-body kernels of one half (64 CTAs on 148 SMs) overlap the
-big kernels of the other.  Results do not depend on the split (every kernel is per-body
-deterministic).
+The loop runs on a joint-coherent re-ordering of the model's vertices (body_model.SMPLX.coherent_handle): vertices
+never leave the library, only the fitted parameters do; `trace()` hands per-vertex buffers back in the file's order.
+
+A batch CAN be split over several contexts (`num_streams` / PSI_FIT_STREAMS), each with its own stream and graph;
+results do not depend on the split (every kernel is per-body deterministic), but it is slower (657 vs 761 bodies/s:
+the blend GEMMs stream the whole basis per context), so the default is one context.
 """
 from __future__ import annotations
 
